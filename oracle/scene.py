@@ -1,0 +1,414 @@
+"""ORACLE (test infrastructure): level lumps + texture directory -> compiled scene blob.
+
+Restates which surfaces a level contributes and how they are textured and lit, following the
+reference's one-and-only geometry emitter `LevelWalker` and its visitor in `game/`:
+
+* seg -> wall pieces, pegging, offsets        wad/src/visitor.rs:711-937
+* fake contrast + static light byte           wad/src/visitor.rs:887-901, wad/src/light.rs:27-115,
+                                              game/src/lights.rs:14-30
+* flats / sky flats                           wad/src/visitor.rs:939-985, wad/src/util.rs:8-10
+* player-1 start marker, sector_at            wad/src/visitor.rs:1010-1060, game/src/level.rs:757-762,
+                                              game/src/player.rs:72-92 (camera_height)
+* sky texture per level                       wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
+
+The blob layout ("B2DS" v1) is the contract shared with the product's scene compiler
+(rust-doom_b200/csrc/b2d_scene.cpp, written independently); tests compare the two byte-for-byte.
+All fields are little-endian int32 unless noted.
+
+header  : 32 x u32 (see H_* indices below)
+verts   : {x, y}                                                   8 B
+nodes   : {x, y, dx, dy, rbox[4], lbox[4], rchild, lchild, 0, 0}   64 B  (box = top,bottom,left,right;
+          child bit31 = subsector)
+ssectors: {first_seg, num_segs, sector, 0}                         16 B
+segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, light, otop, obot, back}  64 B
+sectors : {floor, ceil, floor_flat, ceil_flat, light, 0, 0, 0}     32 B  (flat: >=0 id, -1 sky, -2 missing)
+textures: {texel_off, w, h, hmagic, hbias, 0, 0, 0}                32 B
+texels  : u8 row-major, textures back to back (transparent texels stored as 0)
+flats   : n x 4096 u8
+colormap: 34 x 256 u8 (zero padded if the WAD has fewer)
+palette : 256 x u32  R | G<<8 | B<<16 | 0xFF<<24  from PLAYPAL[0]
+"""
+from __future__ import annotations
+
+import math
+import re
+import struct
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import wad as W
+
+MAGIC = 0x53443242
+VERSION = 1
+(H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
+ H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
+ H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
+ H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H) = range(30)
+
+SEG_TWO_SIDED = 1
+SEG_INVALID = 0x80
+LEAF = 0x80000000
+
+FLAT_SKY = -1
+FLAT_MISSING = -2
+TEX_NONE = -1
+
+# assets/meta/doom.toml:29-68 (first regex match wins, fallback = entry 0)
+SKY_TABLE = [
+    (r"E1M.", b"SKY1"), (r"E2M.", b"SKY2"), (r"E3M.", b"SKY3"), (r"E4M.", b"SKY4"),
+    (r"MAP(0[1-9]|10|11)", b"SKY1"), (r"MAP(1[2-9]|20)", b"SKY2"), (r"MAP(2[1-9]|32)", b"SKY3"),
+]
+
+
+def sky_for(level_name: bytes) -> bytes:
+    s = level_name.rstrip(b"\0").decode("ascii")
+    for pat, tex in SKY_TABLE:
+        if re.search(pat, s):          # regex `is_match` = unanchored search
+            return W.wad_name(tex)
+    return W.wad_name(SKY_TABLE[0][1])
+
+
+def _align16(n: int) -> int:
+    return (n + 15) & ~15
+
+
+def _floormod(a: int, b: int) -> int:
+    return a - b * (a // b)
+
+
+def sector_at(level: W.Level, x: float, y: float) -> int:
+    """LevelWalker::sector_at (visitor.rs:1028-1060).  Returns sector id or -1.  Works in WAD
+    coordinates; the reference's `signed_distance` sign is (py-oy)*dx - (px-ox)*dy > 0 => left."""
+    if len(level.nodes) == 0:
+        return -1
+    child = len(level.nodes) - 1
+    leaf = False
+    for _ in range(4096):
+        if leaf:
+            break
+        n = level.nodes[child]
+        sd = (y - float(n["y"])) * float(n["dx"]) - (x - float(n["x"])) * float(n["dy"])
+        nxt = int(n["left"]) if sd > 0.0 else int(n["right"])
+        child, leaf = nxt & 0x7FFF, bool(nxt & 0x8000)
+        if not leaf and child >= len(level.nodes):
+            return -1
+    if not leaf or child >= len(level.subsectors):
+        return -1
+    ss = level.subsectors[child]
+    first, num = int(ss["first_seg"]), int(ss["num_segs"])
+    if num == 0 or first + num > len(level.segs):
+        return -1
+    segs = level.segs[first:first + num]
+    side = level.seg_sidedef_index(segs[0])
+    if side < 0:
+        return -1
+    sector = int(level.sidedefs[side]["sector"])
+    if sector >= len(level.sectors):
+        return -1
+    for s in segs:
+        if s["v1"] >= len(level.vertices) or s["v2"] >= len(level.vertices):
+            continue
+        a, b = level.vertices[s["v1"]], level.vertices[s["v2"]]
+        dx, dy = float(b["x"]) - float(a["x"]), float(b["y"]) - float(a["y"])
+        ln = math.hypot(dx, dy)
+        if ln < 1e-14:
+            continue
+        sd = ((y - float(a["y"])) * dx - (x - float(a["x"])) * dy) / ln
+        if sd > 10.0:                       # SEG_TOLERANCE = 0.1 world units = 10 map units
+            return -1
+    return sector
+
+
+def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int) -> bytes:
+    level = W.Level(archive, level_index)
+    nverts, nsegs = len(level.vertices), len(level.segs)
+    nsect, nss, nnodes = len(level.sectors), len(level.subsectors), len(level.nodes)
+
+    # --- texture / flat id assignment in first-use order -------------------------------------
+    tex_ids: Dict[bytes, int] = {}
+    tex_list: List[np.ndarray] = []
+
+    def tex_id(name: bytes) -> int:
+        if W.is_untextured(name):
+            return TEX_NONE
+        if name in tex_ids:
+            return tex_ids[name]
+        img = tex.textures.get(name)
+        if img is None or img.shape[0] == 0 or img.shape[1] == 0:
+            return TEX_NONE                           # visitor.rs:857-860: skip + warn
+        tex_ids[name] = len(tex_list)
+        tex_list.append(img)
+        return tex_ids[name]
+
+    sky_tex = tex_id(sky_for(level.name))
+
+    flat_ids: Dict[bytes, int] = {}
+    flat_list: List[bytes] = []
+
+    def flat_id(name: bytes) -> int:
+        if W.is_sky_flat(name):
+            return FLAT_SKY
+        if name in flat_ids:
+            return flat_ids[name]
+        data = tex.flats.get(name)
+        if data is None or len(data) < 4096:
+            return FLAT_MISSING
+        flat_ids[name] = len(flat_list)
+        flat_list.append(data[:4096])
+        return flat_ids[name]
+
+    def raw_name(arr, i, field) -> bytes:
+        dt = arr.dtype
+        off = dt.fields[field][1]
+        b = arr.tobytes()[i * dt.itemsize + off:i * dt.itemsize + off + 8]
+        return W.wad_name(b)
+
+    # --- sectors --------------------------------------------------------------------------------
+    sectors = np.zeros((nsect, 8), dtype=np.int32)
+    sec_bytes = level.sectors.tobytes()
+    has_effect = []
+    for i in range(nsect):
+        s = level.sectors[i]
+        fname = W.wad_name(sec_bytes[i * 26 + 4:i * 26 + 12])
+        cname = W.wad_name(sec_bytes[i * 26 + 12:i * 26 + 20])
+        eff = False
+        if int(s["type"]) in W.EFFECT_TYPES:
+            eff = (level.sector_min_light(i) >> 3) != (int(s["light"]) >> 3)
+        has_effect.append(eff)
+        sectors[i] = [int(s["floor"]), int(s["ceil"]), flat_id(fname), flat_id(cname),
+                      W.light_byte(int(s["light"]), 0), 0, 0, 0]
+    if nsect:
+        min_h = int(level.sectors["floor"].min()) - 512      # visitor.rs:1173-1182
+        max_h = int(level.sectors["ceil"].max()) + 512
+    else:
+        min_h, max_h = -512, 512
+
+    # --- subsectors (sector = sector of the first seg's front sidedef, visitor.rs:636-643) -------
+    ssectors = np.zeros((nss, 4), dtype=np.int32)
+    seg_front = np.full(nsegs, -1, dtype=np.int64)
+    for i in range(nss):
+        first, num = int(level.subsectors[i]["first_seg"]), int(level.subsectors[i]["num_segs"])
+        sector = -1
+        if num > 0 and first + num <= nsegs:
+            side = level.seg_sidedef_index(level.segs[first])
+            if side >= 0 and int(level.sidedefs[side]["sector"]) < nsect:
+                sector = int(level.sidedefs[side]["sector"])
+            seg_front[first:first + num] = sector
+        else:
+            first, num = 0, 0
+        ssectors[i] = [first, num, sector, 0]
+
+    # --- segs ------------------------------------------------------------------------------------
+    segs = np.zeros((nsegs, 16), dtype=np.int32)
+    side_bytes = level.sidedefs.tobytes()
+
+    def side_name(idx: int, which: int) -> bytes:
+        o = idx * 30 + 4 + 8 * which          # 0 upper, 1 lower, 2 middle
+        return W.wad_name(side_bytes[o:o + 8])
+
+    for i in range(nsegs):
+        sg = level.segs[i]
+        rec = [0] * 16
+        rec[3] = SEG_INVALID
+        rec[6] = rec[9] = TEX_NONE
+        rec[15] = -1
+        v1, v2 = int(sg["v1"]), int(sg["v2"])
+        ok = v1 < nverts and v2 < nverts and int(sg["linedef"]) < len(level.linedefs)
+        side = level.seg_sidedef_index(sg) if ok else -1
+        front = int(seg_front[i])
+        if front < 0 and side >= 0 and int(level.sidedefs[side]["sector"]) < nsect:
+            front = int(level.sidedefs[side]["sector"])     # seg outside any subsector (never drawn)
+        if not ok or side < 0 or front < 0:
+            segs[i] = rec
+            continue
+        line = level.linedefs[sg["linedef"]]
+        sd = level.sidedefs[side]
+        fsec = level.sectors[front]
+        ff, fc = int(fsec["floor"]), int(fsec["ceil"])
+        a, b = level.vertices[v1], level.vertices[v2]
+        dx, dy = int(b["x"]) - int(a["x"]), int(b["y"]) - int(a["y"])
+        flags_line = int(line["flags"])
+        unpeg_upper = bool(flags_line & 0x0008)
+        unpeg_lower = bool(flags_line & 0x0010)
+        xoff, yoff = int(sd["xoff"]), int(sd["yoff"])
+        # light: sector light + fake contrast when the sector has no effect (visitor.rs:887-901).
+        # world X = -wad_y, world Z = -wad_x: "v1[0]==v2[0]" <=> wad dy == 0 => Brighten.
+        contrast = 0
+        if not has_effect[front]:
+            if dy == 0:
+                contrast = 1
+            elif dx == 0:
+                contrast = -1
+        light = W.light_byte(int(fsec["light"]), contrast)
+
+        back_side = level.seg_back_sidedef_index(sg)
+        back = -1
+        if back_side >= 0 and int(level.sidedefs[back_side]["sector"]) < nsect:
+            back = int(level.sidedefs[back_side]["sector"])
+
+        def piece(name: bytes, t_top_expr):
+            """-> (tex id, t row at anchor reduced mod texture height)."""
+            tid = tex_id(name)
+            if tid < 0:
+                return TEX_NONE, 0
+            th = int(tex_list[tid].shape[0])
+            return tid, _floormod(t_top_expr(th) + yoff, th)
+
+        rec[0], rec[1], rec[2] = v1, v2, front
+        rec[4] = int(sg["offset"]) + xoff                     # s1 (visitor.rs:904)
+        rec[5] = math.isqrt((dx * dx + dy * dy) << 24)        # |v2-v1| in Q12 (visitor.rs:905)
+        rec[12] = light
+        rec[15] = back
+        if back < 0:
+            # one-sided: full-height middle, Peg::Bottom if lower-unpegged else Peg::Top
+            # (visitor.rs:733-749; t at `high`: Top -> 0, Bottom -> texh - (ceil - floor), :909-912)
+            if unpeg_lower:
+                tid, t = piece(side_name(side, 2), lambda th: th - (fc - ff))
+            else:
+                tid, t = piece(side_name(side, 2), lambda th: 0)
+            rec[3] = 0
+            rec[6], rec[7], rec[8] = tid, t, fc
+            rec[13], rec[14] = fc, ff
+        else:
+            bsec = level.sectors[back]
+            bf, bc = int(bsec["floor"]), int(bsec["ceil"])
+            back_sky = W.is_sky_flat(raw_name(level.sectors, back, "ceil_tex"))
+            rec[3] = SEG_TWO_SIDED
+            # upper: exists iff back_ceil < ceil and the back ceiling is not sky (visitor.rs:791-807);
+            # Peg::Top if upper-unpegged else Peg::Bottom (t at `high`=ceil: 0 / texh - (ceil-back_ceil)).
+            otop = fc
+            if bc < fc and not back_sky:
+                otop = bc
+                if unpeg_upper:
+                    tid, t = piece(side_name(side, 0), lambda th: 0)
+                else:
+                    tid, t = piece(side_name(side, 0), lambda th: th - (fc - bc))
+                rec[6], rec[7] = tid, t
+            rec[8] = fc
+            # lower: exists iff back_floor > floor (visitor.rs:772-790); Peg::BottomLower if
+            # lower-unpegged (t at `high`=back_floor: texh - (back_floor-floor) + (ceil-floor)) else Top.
+            obot = ff
+            if bf > ff:
+                obot = bf
+                if unpeg_lower:
+                    tid, t = piece(side_name(side, 1), lambda th: th - (bf - ff) + (fc - ff))
+                else:
+                    tid, t = piece(side_name(side, 1), lambda th: 0)
+                rec[9], rec[10] = tid, t
+            rec[11] = obot
+            rec[13], rec[14] = otop, obot
+        segs[i] = rec
+
+    # --- nodes -----------------------------------------------------------------------------------
+    nodes = np.zeros((nnodes, 16), dtype=np.int64)
+
+    def child(c: int) -> int:
+        idx = c & 0x7FFF
+        return (idx | LEAF) if (c & 0x8000) else idx
+
+    for i in range(nnodes):
+        n = level.nodes[i]
+        rb, lb = [int(v) for v in n["rbox"]], [int(v) for v in n["lbox"]]
+        # on-disk order is top, bottom, left, right; be tolerant of swapped pairs
+        rb = [max(rb[0], rb[1]), min(rb[0], rb[1]), min(rb[2], rb[3]), max(rb[2], rb[3])]
+        lb = [max(lb[0], lb[1]), min(lb[0], lb[1]), min(lb[2], lb[3]), max(lb[2], lb[3])]
+        nodes[i, :14] = [int(n["x"]), int(n["y"]), int(n["dx"]), int(n["dy"])] + rb + lb + \
+                        [child(int(n["right"])), child(int(n["left"]))]
+
+    verts = np.zeros((nverts, 2), dtype=np.int32)
+    verts[:, 0] = level.vertices["x"]
+    verts[:, 1] = level.vertices["y"]
+
+    # --- textures ---------------------------------------------------------------------------------
+    ntex = len(tex_list)
+    texrec = np.zeros((ntex, 8), dtype=np.uint32)
+    texels = bytearray()
+    for i, img in enumerate(tex_list):
+        h, w = img.shape
+        px = np.where((img >> 8) != 0, 0, img & 0xFF).astype(np.uint8)
+        hmagic = (1 << 32) // h + 1
+        hbias = h * ((16384 + h - 1) // h)
+        texrec[i] = [len(texels), w, h, hmagic & 0xFFFFFFFF, hbias, 0, 0, 0]
+        texels += px.tobytes()
+        while len(texels) % 16:
+            texels += b"\0"
+
+    colormap = bytearray(34 * 256)
+    for k in range(min(34, len(tex.colormaps))):
+        colormap[k * 256:(k + 1) * 256] = tex.colormaps[k]
+    pal = np.frombuffer(tex.palettes[0], dtype=np.uint8).reshape(256, 3).astype(np.uint32)
+    palette = (pal[:, 0] | (pal[:, 1] << 8) | (pal[:, 2] << 16) | np.uint32(0xFF000000)).astype("<u4")
+
+    # --- player start (visitor.rs:1010-1026, game/src/level.rs:757-762) -------------------------
+    has_start, sx, sy, sz, sang = 0, 0, 0, 0, 0
+    for t in level.things:
+        if int(t["type"]) != 1:
+            continue
+        sec = sector_at(level, float(t["x"]), float(t["y"]))
+        if sec < 0:
+            continue
+        ang = float(np.round(np.float32(t["angle"]) / np.float32(45.0)) * np.float32(45.0))
+        has_start = 1
+        sx, sy = int(t["x"]) - 32, int(t["y"])
+        sz = int(level.sectors[sec]["floor"]) + 50 + 12
+        sang = int(ang) % 360
+        break   # visit_marker overwrites on every player-1 start; doom maps have exactly one
+
+    # --- assemble ---------------------------------------------------------------------------------
+    parts = [("verts", verts.astype("<i4").tobytes()), ("nodes", (nodes & 0xFFFFFFFF).astype("<u4").tobytes()),
+             ("ssectors", ssectors.astype("<i4").tobytes()), ("segs", segs.astype("<i4").tobytes()),
+             ("sectors", sectors.astype("<i4").tobytes()), ("tex", texrec.astype("<u4").tobytes()),
+             ("texels", bytes(texels)), ("flats", b"".join(flat_list)), ("colormap", bytes(colormap)),
+             ("palette", palette.tobytes())]
+    off = 128
+    offs = {}
+    for name, data in parts:
+        offs[name] = off
+        off = _align16(off + len(data))
+    total = off
+    hdr = [0] * 32
+    hdr[H_MAGIC], hdr[H_VERSION], hdr[H_TOTAL] = MAGIC, VERSION, total
+    hdr[H_NVERTS], hdr[H_NNODES], hdr[H_NSSECTORS], hdr[H_NSEGS] = nverts, nnodes, nss, nsegs
+    hdr[H_NSECTORS], hdr[H_NTEX], hdr[H_NFLATS] = nsect, ntex, len(flat_list)
+    hdr[H_OFF_VERTS], hdr[H_OFF_NODES], hdr[H_OFF_SSECTORS] = offs["verts"], offs["nodes"], offs["ssectors"]
+    hdr[H_OFF_SEGS], hdr[H_OFF_SECTORS], hdr[H_OFF_TEX] = offs["segs"], offs["sectors"], offs["tex"]
+    hdr[H_OFF_TEXELS], hdr[H_TEXEL_BYTES], hdr[H_OFF_FLATS] = offs["texels"], len(texels), offs["flats"]
+    hdr[H_OFF_COLORMAP], hdr[H_OFF_PALETTE] = offs["colormap"], offs["palette"]
+    if nnodes > 0:
+        hdr[H_ROOT] = nnodes - 1
+    else:
+        hdr[H_ROOT] = LEAF | 0
+    hdr[H_SKY_TEX] = sky_tex & 0xFFFFFFFF
+    hdr[H_START_X], hdr[H_START_Y], hdr[H_START_Z] = sx & 0xFFFFFFFF, sy & 0xFFFFFFFF, sz & 0xFFFFFFFF
+    hdr[H_START_ANGLE], hdr[H_HAS_START] = sang, has_start
+    hdr[H_MIN_H], hdr[H_MAX_H] = min_h & 0xFFFFFFFF, max_h & 0xFFFFFFFF
+    blob = bytearray(total)
+    blob[0:128] = struct.pack("<32I", *hdr)
+    for name, data in parts:
+        blob[offs[name]:offs[name] + len(data)] = data
+    return bytes(blob)
+
+
+def header(blob: bytes) -> List[int]:
+    return list(struct.unpack_from("<32I", blob, 0))
+
+
+def section(blob: bytes, which: str) -> np.ndarray:
+    """Convenience view of one section as an int32 (or u8) array."""
+    h = header(blob)
+    def arr(off, n, width, dt="<i4"):
+        return np.frombuffer(blob, dtype=dt, count=n * width, offset=off).reshape(n, width)
+    if which == "verts":
+        return arr(h[H_OFF_VERTS], h[H_NVERTS], 2)
+    if which == "nodes":
+        return arr(h[H_OFF_NODES], h[H_NNODES], 16)
+    if which == "ssectors":
+        return arr(h[H_OFF_SSECTORS], h[H_NSSECTORS], 4)
+    if which == "segs":
+        return arr(h[H_OFF_SEGS], h[H_NSEGS], 16)
+    if which == "sectors":
+        return arr(h[H_OFF_SECTORS], h[H_NSECTORS], 8)
+    if which == "textures":
+        return arr(h[H_OFF_TEX], h[H_NTEX], 8, "<u4")
+    raise KeyError(which)
