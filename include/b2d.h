@@ -1,0 +1,126 @@
+/*
+ * b2d.h -- C ABI of the B200-native Doom-WAD software renderer (libb2d.so).
+ *
+ * The reference (cristicbz/rust-doom) has no FFI or plugin ABI (100% safe Rust, README.md:39).
+ * Its renderer-facing seams are Rust-level only; each entry point below names the reference
+ * interface it stands in for, so that a Rust `GpuRenderer: engine::System` can bind these with
+ * a plain `extern "C"` block (INTEGRATION.md shows that binding):
+ *
+ *   wad::Archive::open / num_levels / level_lump(i).name()      wad/src/archive.rs:36-60,108-146
+ *   game::WadSystem (archive + textures + level)                game/src/wad_system.rs:18-114
+ *   wad::LevelWalker::walk + game::level::Builder               wad/src/visitor.rs:541-555,
+ *                                                               game/src/level.rs:330-511
+ *   game::GameShaders::load_palette / load_level                game/src/game_shaders.rs:123-280
+ *   engine::Renderer::update (the per-frame draw loop)          engine/src/renderer.rs:62-175
+ *   engine::Projection {fov, aspect, near, far}                 engine/src/projections.rs:7-13,93-101
+ *   player start marker                                         wad/src/visitor.rs:1010-1026,
+ *                                                               game/src/level.rs:757-762
+ *
+ * Conventions (mirroring the reference's): every call returns 0 on success or a negative
+ * B2D_ERR_* code (wad::ErrorKind::{CorruptWad, Io, ...}, wad/src/errors.rs:9-19); the message is
+ * available from b2d_last_error() (thread-local).  Handles are owned by the library and released
+ * by the matching *_destroy / *_close.  Input buffers are caller-owned and copied.  A handle may
+ * be used from one thread at a time (the reference is single-threaded); distinct handles are
+ * independent.  There is NO CPU rendering path in this library: every render entry point runs the
+ * CUDA kernels and fails with B2D_ERR_CUDA if no device is usable.
+ */
+#ifndef B2D_H
+#define B2D_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2D_OK 0
+#define B2D_ERR_CORRUPT_WAD (-1)
+#define B2D_ERR_IO (-2)
+#define B2D_ERR_CUDA (-3)
+#define B2D_ERR_INVALID_ARG (-4)
+#define B2D_ERR_NO_MEMORY (-5)
+
+typedef struct b2d_archive b2d_archive;     /* wad::Archive */
+typedef struct b2d_scene b2d_scene;         /* WadSystem's current level, compiled for the GPU */
+typedef struct b2d_renderer b2d_renderer;   /* engine::Renderer replacement, bound to one device */
+
+/* Camera pose.  Position in 16.16 fixed-point WAD map units (z = eye height, absolute);
+ * angle in BAM (2^32 = 360 deg, 0 = east / +x, counter-clockwise).  Pitch and roll are 0
+ * (a column/span renderer is exact only for upright cameras; SURVEY.md 7 "Pitch"). */
+typedef struct b2d_pose {
+    int32_t x, y, z;
+    uint32_t angle;
+} b2d_pose;
+
+/* Viewport + projection, all integers so that every consumer sees identical bits.
+ * F = round(2*focal_x), FY2 = round(2*focal_y) in pixels, where focal_y = (H/2)/tan(fovy/2) and
+ * focal_x = (H/2)/(1.2*tan(fovy/2))  (perspective(fovy, aspect=(W/H)*1.2): player.rs:84-89,339-343). */
+typedef struct b2d_view {
+    int32_t width, height, F, FY2;
+} b2d_view;
+
+typedef struct b2d_scene_info {
+    int32_t n_verts, n_nodes, n_ssectors, n_segs, n_sectors, n_textures, n_flats;
+    int32_t blob_bytes;
+    int32_t has_start;                       /* player-1 start found */
+    b2d_pose start;                          /* spawn camera pose (eye = floor + 62) */
+    int32_t min_height, max_height;          /* level height range +-512 (visitor.rs:1173-1182) */
+} b2d_scene_info;
+
+const char *b2d_last_error(void);
+
+/* ---- wad::Archive ----------------------------------------------------------------------- */
+int b2d_archive_open(const char *wad_path, b2d_archive **out);
+int b2d_archive_open_memory(const void *bytes, size_t size, b2d_archive **out);
+int b2d_archive_num_levels(const b2d_archive *a);
+int b2d_archive_level_name(const b2d_archive *a, int level_index, char name_out[9]);
+void b2d_archive_close(b2d_archive *a);
+
+/* WadName::from_bytes (wad/src/name.rs:41-75): 0 and the padded upper-cased name, or an error. */
+int b2d_wad_name(const void *bytes, size_t size, char name_out[8]);
+
+/* ---- scene (level + textures -> GPU-ready arrays) ------------------------------------------ */
+int b2d_scene_create(const b2d_archive *a, int level_index, b2d_scene **out);
+int b2d_scene_info_get(const b2d_scene *s, b2d_scene_info *out);
+/* Read-only access to the compiled "B2DS" blob (layout in DESIGN.md); valid until destroy. */
+const void *b2d_scene_blob(const b2d_scene *s, size_t *size_out);
+/* LevelWalker::sector_at (visitor.rs:1028-1060): sector id at a map position, -1 if outside. */
+int b2d_scene_sector_at(const b2d_scene *s, double x, double y, int32_t *floor_out, int32_t *ceil_out);
+void b2d_scene_destroy(b2d_scene *s);
+
+/* ---- view ------------------------------------------------------------------------------- */
+int b2d_view_init(b2d_view *v, int width, int height, double fov_y_degrees);
+
+/* ---- renderer --------------------------------------------------------------------------- */
+/* Uploads the scene to `device` and sizes per-batch work buffers for up to max_batch poses. */
+int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, int max_batch,
+                        b2d_renderer **out);
+void b2d_renderer_destroy(b2d_renderer *r);
+
+/* End-to-end: HOST poses in, HOST frames out (pinned staging + copies inside).  index_fb gets
+ * n*W*H palette indices, row-major, top row first; rgba_fb (nullable) gets n*W*H RGBA8
+ * (R in the low byte).  n may exceed max_batch; it is processed in batches. */
+int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_fb, uint32_t *rgba_fb);
+
+/* Device-resident: poses, index_fb and rgba_fb (nullable) are DEVICE pointers on the renderer's
+ * device; work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and NOT
+ * synchronised.  n <= max_batch. */
+int b2d_render_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, uint8_t *d_index_fb,
+                      uint32_t *d_rgba_fb, void *cuda_stream);
+
+/* Kernel 3 on its own: palette lookup index -> RGBA8 for n_pixels device bytes. */
+int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_rgba, size_t n_pixels,
+                           void *cuda_stream);
+
+/* Introspection for tests/profiling: copies the BSP-walk worklist of the LAST b2d_render_device
+ * batch to the host.  counts_out[n], and for frame i seg ids seg_ids_out[i*stride .. +counts[i]). */
+int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *seg_ids_out, size_t stride);
+
+/* Number of kernel launches issued by this renderer so far (bench.py's gpu_launches). */
+int64_t b2d_launch_count(const b2d_renderer *r);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2D_H */

@@ -1,6 +1,206 @@
 """b2d -- B200-native software renderer for the Doom-WAD visibility-and-raster hot path.
 
-Host-side mirror of the reference's renderer-facing surface (wad::Archive / WadSystem /
-engine::Renderer) over the C-ABI shared library `libb2d.so` (include/b2d.h).  See DESIGN.md.
+Host-side mirror of the reference's renderer-facing surface over the C-ABI shared library
+`libb2d.so` (include/b2d.h):
+
+    Archive      ~ wad::Archive             (wad/src/archive.rs:36-146)
+    Scene        ~ game::WadSystem's level  (game/src/wad_system.rs:18-114) compiled for the GPU
+    View         ~ engine::Projection       (engine/src/projections.rs:7-13)
+    Renderer     ~ engine::Renderer         (engine/src/renderer.rs:62-175)
+
+Errors surface as B2dError carrying the library's code + message (wad::ErrorKind analogue).
+All rendering runs in hand-written sm_100a CUDA kernels; there is no CPU fallback.
 """
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
 __version__ = "0.1.0"
+
+POSE_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("z", "<i4"), ("angle", "<u4")])
+DEFAULT_FOV_DEG = 65.0          # game/src/player.rs:84
+
+ERR_CORRUPT_WAD, ERR_IO, ERR_CUDA, ERR_INVALID_ARG, ERR_NO_MEMORY = -1, -2, -3, -4, -5
+
+
+class B2dError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__("b2d error %d: %s" % (code, message))
+        self.code = code
+        self.message = message
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise B2dError(rc, _lib.load().b2d_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def wad_name(value: bytes) -> bytes:
+    """WadName::from_bytes (wad/src/name.rs:41-75)."""
+    out = ctypes.create_string_buffer(8)
+    buf = ctypes.create_string_buffer(value, len(value)) if len(value) else ctypes.create_string_buffer(1)
+    _check(_lib.load().b2d_wad_name(ctypes.addressof(buf), len(value), out))
+    return out.raw
+
+
+def make_pose(x: float, y: float, z: float, angle_deg: float) -> np.ndarray:
+    """One pose record from map-unit floats (quantised to 16.16 / BAM on the host)."""
+    p = np.zeros(1, dtype=POSE_DTYPE)
+    p["x"] = int(round(x * 65536.0))
+    p["y"] = int(round(y * 65536.0))
+    p["z"] = int(round(z * 65536.0))
+    p["angle"] = int(round(angle_deg / 360.0 * 4294967296.0)) & 0xFFFFFFFF
+    return p
+
+
+class Archive:
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def open(cls, path: str) -> "Archive":
+        h = ctypes.c_void_p()
+        _check(_lib.load().b2d_archive_open(path.encode(), ctypes.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_bytes(cls, data: bytes) -> "Archive":
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_char * len(data)).from_buffer_copy(data) if len(data) else (ctypes.c_char * 1)()
+        _check(_lib.load().b2d_archive_open_memory(ctypes.addressof(buf), len(data), ctypes.byref(h)))
+        return cls(h)
+
+    def num_levels(self) -> int:
+        return _check(_lib.load().b2d_archive_num_levels(self._h))
+
+    def level_name(self, index: int) -> str:
+        out = ctypes.create_string_buffer(9)
+        _check(_lib.load().b2d_archive_level_name(self._h, index, out))
+        return out.value.decode("ascii")
+
+    def level_names(self):
+        return [self.level_name(i) for i in range(self.num_levels())]
+
+    def close(self):
+        if self._h:
+            _lib.load().b2d_archive_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class Scene:
+    def __init__(self, archive: Archive, level_index: int = 0):
+        h = ctypes.c_void_p()
+        _check(_lib.load().b2d_scene_create(archive._h, level_index, ctypes.byref(h)))
+        self._h = h
+        info = _lib.SceneInfo()
+        _check(_lib.load().b2d_scene_info_get(self._h, ctypes.byref(info)))
+        self.info = info
+
+    @property
+    def blob(self) -> bytes:
+        n = ctypes.c_size_t()
+        p = _lib.load().b2d_scene_blob(self._h, ctypes.byref(n))
+        return ctypes.string_at(p, n.value)
+
+    @property
+    def start_pose(self) -> Optional[np.ndarray]:
+        if not self.info.has_start:
+            return None
+        p = np.zeros(1, dtype=POSE_DTYPE)
+        s = self.info.start
+        p["x"], p["y"], p["z"], p["angle"] = s.x, s.y, s.z, s.angle
+        return p
+
+    def sector_at(self, x: float, y: float) -> Tuple[int, int, int]:
+        """(sector id or -1, floor, ceiling) -- LevelWalker::sector_at."""
+        f, c = ctypes.c_int32(), ctypes.c_int32()
+        sec = _lib.load().b2d_scene_sector_at(self._h, float(x), float(y), ctypes.byref(f), ctypes.byref(c))
+        return sec, f.value, c.value
+
+    def close(self):
+        if self._h:
+            _lib.load().b2d_scene_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def make_view(width: int, height: int, fov_deg: float = DEFAULT_FOV_DEG) -> "_lib.View":
+    v = _lib.View()
+    _check(_lib.load().b2d_view_init(ctypes.byref(v), width, height, float(fov_deg)))
+    return v
+
+
+class Renderer:
+    """Bound to one CUDA device; owns the scene copy in HBM and the per-batch work buffers."""
+
+    def __init__(self, scene: Scene, view, device: int = 0, max_batch: int = 64):
+        h = ctypes.c_void_p()
+        _check(_lib.load().b2d_renderer_create(scene._h, ctypes.byref(view), device, max_batch, ctypes.byref(h)))
+        self._h = h
+        self.view = view
+        self.width, self.height = view.width, view.height
+        self.max_batch = max_batch
+        self.device = device
+        self.n_segs = scene.info.n_segs
+
+    # -- end to end: host poses in, host frames out -------------------------------------------------
+    def render(self, poses: np.ndarray, rgba: bool = False, out_index: Optional[np.ndarray] = None,
+               out_rgba: Optional[np.ndarray] = None):
+        poses = np.ascontiguousarray(poses, dtype=POSE_DTYPE)
+        n = len(poses)
+        if out_index is None:
+            out_index = np.empty((n, self.height, self.width), dtype=np.uint8)
+        if rgba and out_rgba is None:
+            out_rgba = np.empty((n, self.height, self.width), dtype=np.uint32)
+        _check(_lib.load().b2d_render(self._h, poses.ctypes.data, n, out_index.ctypes.data,
+                                      out_rgba.ctypes.data if rgba else None))
+        return (out_index, out_rgba) if rgba else out_index
+
+    def render_ptr(self, poses_ptr: int, n: int, index_ptr: int, rgba_ptr: int = 0):
+        """b2d_render on raw host pointers (e.g. pinned torch tensors)."""
+        _check(_lib.load().b2d_render(self._h, poses_ptr, n, index_ptr, rgba_ptr or None))
+
+    # -- device resident ----------------------------------------------------------------------------
+    def render_device(self, poses_ptr: int, n: int, index_ptr: int, rgba_ptr: int = 0, stream: int = 0):
+        _check(_lib.load().b2d_render_device(self._h, poses_ptr, n, index_ptr, rgba_ptr or None, stream or None))
+
+    def palette_lut_device(self, index_ptr: int, rgba_ptr: int, n_pixels: int, stream: int = 0):
+        _check(_lib.load().b2d_palette_lut_device(self._h, index_ptr, rgba_ptr, n_pixels, stream or None))
+
+    def worklist(self, n: int):
+        counts = np.zeros(n, dtype=np.int32)
+        ids = np.full((n, max(self.n_segs, 1)), -1, dtype=np.int32)
+        _check(_lib.load().b2d_debug_worklist(self._h, n, counts.ctypes.data, ids.ctypes.data, ids.shape[1]))
+        return counts, ids
+
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.load().b2d_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.load().b2d_renderer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass

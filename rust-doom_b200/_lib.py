@@ -1,0 +1,79 @@
+"""ctypes binding of libb2d.so (include/b2d.h).  The product has no CPU path: if the library is
+missing we try to build it once with nvcc and otherwise fail loudly."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2d.so")
+
+
+class Pose(ctypes.Structure):
+    _fields_ = [("x", ctypes.c_int32), ("y", ctypes.c_int32), ("z", ctypes.c_int32), ("angle", ctypes.c_uint32)]
+
+
+class View(ctypes.Structure):
+    _fields_ = [("width", ctypes.c_int32), ("height", ctypes.c_int32), ("F", ctypes.c_int32), ("FY2", ctypes.c_int32)]
+
+
+class SceneInfo(ctypes.Structure):
+    _fields_ = [("n_verts", ctypes.c_int32), ("n_nodes", ctypes.c_int32), ("n_ssectors", ctypes.c_int32),
+                ("n_segs", ctypes.c_int32), ("n_sectors", ctypes.c_int32), ("n_textures", ctypes.c_int32),
+                ("n_flats", ctypes.c_int32), ("blob_bytes", ctypes.c_int32), ("has_start", ctypes.c_int32),
+                ("start", Pose), ("min_height", ctypes.c_int32), ("max_height", ctypes.c_int32)]
+
+
+EXPORTS = [
+    "b2d_last_error", "b2d_archive_open", "b2d_archive_open_memory", "b2d_archive_num_levels",
+    "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_info_get",
+    "b2d_scene_blob", "b2d_scene_sector_at", "b2d_scene_destroy", "b2d_view_init", "b2d_renderer_create",
+    "b2d_renderer_destroy", "b2d_render", "b2d_render_device", "b2d_palette_lut_device",
+    "b2d_debug_worklist", "b2d_launch_count",
+]
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise ImportError(
+                "libb2d.so is missing and could not be built with nvcc (%s). "
+                "Run `python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % e)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, ci, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    L.b2d_last_error.restype = ctypes.c_char_p
+    L.b2d_archive_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.b2d_archive_open_memory.argtypes = [vp, cs, ctypes.POINTER(vp)]
+    L.b2d_archive_num_levels.argtypes = [vp]
+    L.b2d_archive_level_name.argtypes = [vp, ci, ctypes.c_char_p]
+    L.b2d_archive_close.argtypes = [vp]
+    L.b2d_archive_close.restype = None
+    L.b2d_wad_name.argtypes = [vp, cs, ctypes.c_char_p]
+    L.b2d_scene_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    L.b2d_scene_info_get.argtypes = [vp, ctypes.POINTER(SceneInfo)]
+    L.b2d_scene_blob.argtypes = [vp, ctypes.POINTER(cs)]
+    L.b2d_scene_blob.restype = vp
+    L.b2d_scene_sector_at.argtypes = [vp, ctypes.c_double, ctypes.c_double, ctypes.POINTER(ctypes.c_int32),
+                                      ctypes.POINTER(ctypes.c_int32)]
+    L.b2d_scene_destroy.argtypes = [vp]
+    L.b2d_scene_destroy.restype = None
+    L.b2d_view_init.argtypes = [ctypes.POINTER(View), ci, ci, ctypes.c_double]
+    L.b2d_renderer_create.argtypes = [vp, ctypes.POINTER(View), ci, ci, ctypes.POINTER(vp)]
+    L.b2d_renderer_destroy.argtypes = [vp]
+    L.b2d_renderer_destroy.restype = None
+    L.b2d_render.argtypes = [vp, vp, cs, vp, vp]
+    L.b2d_render_device.argtypes = [vp, vp, cs, vp, vp, vp]
+    L.b2d_palette_lut_device.argtypes = [vp, vp, vp, cs, vp]
+    L.b2d_debug_worklist.argtypes = [vp, cs, vp, vp, cs]
+    L.b2d_launch_count.argtypes = [vp]
+    L.b2d_launch_count.restype = ctypes.c_int64
+    _lib = L
+    return L

@@ -1,0 +1,39 @@
+"""Build recipe for libb2d.so: nvcc, sm_100a only, in-tree output (rust-doom_b200/libb2d.so).
+
+`python -m rust_doom_b200.build` (or __graft_entry__.build()).  nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libb2d.so")
+SOURCES = ["b2d_api.cu", "b2d_kernels.cu", "b2d_wad.cpp", "b2d_scene.cpp"]
+HEADERS = ["b2d_math.cuh", "b2d_kernels.cuh", "b2d_scene.hpp", "b2d_wad.hpp", "../../include/b2d.h"]
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter", "-shared",
+              "-Xptxas", "-v" if os.environ.get("B2D_PTXAS_V") else "-warn-spills"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

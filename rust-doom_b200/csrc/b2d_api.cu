@@ -1,0 +1,364 @@
+// C-ABI of libb2d.so (declared in include/b2d.h).  Thin, exception-free boundary over the C++ host
+// side (WAD loader, scene compiler) and the CUDA kernels.  There is deliberately no CPU rendering
+// path here: every render entry point launches the sm_100a kernels or fails with B2D_ERR_CUDA.
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/b2d.h"
+#include "b2d_kernels.cuh"
+#include "b2d_scene.hpp"
+#include "b2d_wad.hpp"
+
+using namespace b2d;
+
+static_assert(sizeof(b2d_pose) == sizeof(Pose) && sizeof(b2d_view) == sizeof(View), "ABI structs");
+
+struct b2d_archive {
+    std::unique_ptr<Archive> wad;
+};
+
+struct b2d_scene {
+    std::vector<uint8_t> blob;
+    Level level;
+    b2d_scene_info info;
+};
+
+struct b2d_renderer {
+    int device = 0;
+    View view{};
+    int max_batch = 0;
+    int stride = 0;                 // worklist entries per frame (= n_segs)
+    uint8_t *d_blob = nullptr;
+    uint32_t *d_yslope = nullptr;
+    DeviceScene ds{};
+    Pose *d_poses = nullptr;
+    FrameConst *d_frames = nullptr;
+    SegFrame *d_work = nullptr;
+    // host-path staging (allocated on first b2d_render): double-buffered frame outputs
+    uint8_t *d_index[2] = {nullptr, nullptr};
+    uint32_t *d_rgba[2] = {nullptr, nullptr};
+    Pose *h_poses = nullptr;        // pinned
+    cudaStream_t render_stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    int64_t launches = 0;
+    int last_n = 0;
+};
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string &msg) {
+    g_error = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    return fail(B2D_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                         \
+    do {                                                 \
+        cudaError_t e_ = (call);                         \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+
+template <typename Fn>
+int guarded(Fn fn) {
+    try {
+        return fn();
+    } catch (const WadError &e) {
+        return fail(e.code == kErrIo ? B2D_ERR_IO : B2D_ERR_CORRUPT_WAD, e.what());
+    } catch (const std::bad_alloc &) {
+        return fail(B2D_ERR_NO_MEMORY, "out of host memory");
+    } catch (const std::exception &e) {
+        return fail(B2D_ERR_INVALID_ARG, e.what());
+    }
+}
+
+void free_renderer(b2d_renderer *r) {
+    if (!r) return;
+    cudaSetDevice(r->device);
+    for (int i = 0; i < 2; i++) {
+        if (r->d_index[i]) cudaFree(r->d_index[i]);
+        if (r->d_rgba[i]) cudaFree(r->d_rgba[i]);
+        if (r->rendered[i]) cudaEventDestroy(r->rendered[i]);
+        if (r->copied[i]) cudaEventDestroy(r->copied[i]);
+    }
+    if (r->h_poses) cudaFreeHost(r->h_poses);
+    if (r->render_stream) cudaStreamDestroy(r->render_stream);
+    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    if (r->d_work) cudaFree(r->d_work);
+    if (r->d_frames) cudaFree(r->d_frames);
+    if (r->d_poses) cudaFree(r->d_poses);
+    if (r->d_yslope) cudaFree(r->d_yslope);
+    if (r->d_blob) cudaFree(r->d_blob);
+    delete r;
+}
+
+int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
+                   cudaStream_t stream) {
+    CU(launch_walk(r->ds, r->view, d_poses, n, r->d_frames, r->d_work, r->stride, stream));
+    CU(launch_raster(r->ds, r->view, r->d_frames, r->d_work, r->stride, n, d_index, d_rgba, stream));
+    r->launches += 2;
+    r->last_n = n;
+    return B2D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *b2d_last_error(void) { return g_error.c_str(); }
+
+// ---- archive ---------------------------------------------------------------------------------
+int b2d_archive_open(const char *wad_path, b2d_archive **out) {
+    if (!wad_path || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        auto a = std::make_unique<b2d_archive>();
+        a->wad = std::make_unique<Archive>(Archive::open(wad_path));
+        *out = a.release();
+        return B2D_OK;
+    });
+}
+
+int b2d_archive_open_memory(const void *bytes, size_t size, b2d_archive **out) {
+    if (!bytes || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        const uint8_t *p = static_cast<const uint8_t *>(bytes);
+        auto a = std::make_unique<b2d_archive>();
+        a->wad = std::make_unique<Archive>(std::vector<uint8_t>(p, p + size));
+        *out = a.release();
+        return B2D_OK;
+    });
+}
+
+int b2d_archive_num_levels(const b2d_archive *a) {
+    if (!a) return fail(B2D_ERR_INVALID_ARG, "null archive");
+    return a->wad->num_levels();
+}
+
+int b2d_archive_level_name(const b2d_archive *a, int level_index, char name_out[9]) {
+    if (!a || !name_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        const Name &n = a->wad->level_name(level_index);
+        std::memcpy(name_out, n.data(), 8);
+        name_out[8] = 0;
+        return B2D_OK;
+    });
+}
+
+void b2d_archive_close(b2d_archive *a) { delete a; }
+
+int b2d_wad_name(const void *bytes, size_t size, char name_out[8]) {
+    if (!bytes || !name_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        Name n = make_name(static_cast<const uint8_t *>(bytes), size);
+        std::memcpy(name_out, n.data(), 8);
+        return B2D_OK;
+    });
+}
+
+// ---- scene -----------------------------------------------------------------------------------
+int b2d_scene_create(const b2d_archive *a, int level_index, b2d_scene **out) {
+    if (!a || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        auto s = std::make_unique<b2d_scene>();
+        TextureDirectory td = TextureDirectory::load(*a->wad);
+        s->blob = compile_scene(*a->wad, td, level_index);
+        s->level = Level::load(*a->wad, level_index);
+        const uint32_t *h = reinterpret_cast<const uint32_t *>(s->blob.data());
+        b2d_scene_info &i = s->info;
+        i.n_verts = (int32_t)h[H_NVERTS]; i.n_nodes = (int32_t)h[H_NNODES]; i.n_ssectors = (int32_t)h[H_NSSECTORS];
+        i.n_segs = (int32_t)h[H_NSEGS]; i.n_sectors = (int32_t)h[H_NSECTORS]; i.n_textures = (int32_t)h[H_NTEX];
+        i.n_flats = (int32_t)h[H_NFLATS]; i.blob_bytes = (int32_t)h[H_TOTAL];
+        i.has_start = (int32_t)h[H_HAS_START];
+        i.start.x = (int32_t)h[H_START_X] * 65536; i.start.y = (int32_t)h[H_START_Y] * 65536;
+        i.start.z = (int32_t)h[H_START_Z] * 65536;
+        i.start.angle = (uint32_t)(((uint64_t)h[H_START_ANGLE] << 32) / 360u);
+        i.min_height = (int32_t)h[H_MIN_H]; i.max_height = (int32_t)h[H_MAX_H];
+        *out = s.release();
+        return B2D_OK;
+    });
+}
+
+int b2d_scene_info_get(const b2d_scene *s, b2d_scene_info *out) {
+    if (!s || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    *out = s->info;
+    return B2D_OK;
+}
+
+const void *b2d_scene_blob(const b2d_scene *s, size_t *size_out) {
+    if (!s) return nullptr;
+    if (size_out) *size_out = s->blob.size();
+    return s->blob.data();
+}
+
+int b2d_scene_sector_at(const b2d_scene *s, double x, double y, int32_t *floor_out, int32_t *ceil_out) {
+    if (!s) return fail(B2D_ERR_INVALID_ARG, "null scene");
+    int sec = sector_at(s->level, x, y);
+    if (sec >= 0) {
+        if (floor_out) *floor_out = s->level.sectors[(size_t)sec].floor;
+        if (ceil_out) *ceil_out = s->level.sectors[(size_t)sec].ceil;
+    }
+    return sec;
+}
+
+void b2d_scene_destroy(b2d_scene *s) { delete s; }
+
+// ---- view ------------------------------------------------------------------------------------
+int b2d_view_init(b2d_view *v, int width, int height, double fov_y_degrees) {
+    if (!v) return fail(B2D_ERR_INVALID_ARG, "null view");
+    if (width < 1 || height < 2 || width > 4096 || height > 2160 || !(fov_y_degrees > 1.0 && fov_y_degrees < 170.0))
+        return fail(B2D_ERR_INVALID_ARG, "view out of range (width <= 4096, height <= 2160, 1 < fov < 170)");
+    const double t = std::tan(fov_y_degrees * 3.14159265358979323846 / 360.0);
+    v->width = width; v->height = height;
+    v->FY2 = (int32_t)((double)height / t + 0.5);
+    v->F = (int32_t)((double)height / (1.2 * t) + 0.5);     // aspect_ratio_correction (player.rs:87)
+    if (v->F < 2 || v->FY2 < 2) return fail(B2D_ERR_INVALID_ARG, "degenerate focal length");
+    return B2D_OK;
+}
+
+// ---- renderer --------------------------------------------------------------------------------
+int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, int max_batch, b2d_renderer **out) {
+    if (!s || !view || !out || max_batch < 1) return fail(B2D_ERR_INVALID_ARG, "bad renderer arguments");
+    if (view->width < 1 || view->width > 4096 || view->height < 2 || view->height > 2160 || view->F < 2 || view->FY2 < 2)
+        return fail(B2D_ERR_INVALID_ARG, "view out of range");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(B2D_ERR_CUDA, std::string("no usable CUDA device (this library has no CPU path): ") +
+                                      (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(B2D_ERR_INVALID_ARG, "device index out of range");
+    CU(cudaSetDevice(device));
+    b2d_renderer *r = new (std::nothrow) b2d_renderer();
+    if (!r) return fail(B2D_ERR_NO_MEMORY, "out of host memory");
+    r->device = device;
+    r->view = View{view->width, view->height, view->F, view->FY2};
+    r->max_batch = max_batch;
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(s->blob.data());
+    r->stride = (int)h[H_NSEGS] > 0 ? (int)h[H_NSEGS] : 1;
+    auto bail = [&](cudaError_t err, const char *what) { free_renderer(r); return cuda_fail(err, what); };
+#define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(e_, #call); } while (0)
+    CUR(cudaMalloc(&r->d_blob, s->blob.size()));
+    CUR(cudaMemcpy(r->d_blob, s->blob.data(), s->blob.size(), cudaMemcpyHostToDevice));
+    std::vector<uint32_t> ys((size_t)view->height);
+    for (int y = 0; y < view->height; y++) ys[(size_t)y] = yslope_entry(y, r->view);
+    CUR(cudaMalloc(&r->d_yslope, ys.size() * 4));
+    CUR(cudaMemcpy(r->d_yslope, ys.data(), ys.size() * 4, cudaMemcpyHostToDevice));
+    DeviceScene &d = r->ds;
+    d.verts = reinterpret_cast<const int32_t *>(r->d_blob + h[H_OFF_VERTS]);
+    d.nodes = reinterpret_cast<const NodeRec *>(r->d_blob + h[H_OFF_NODES]);
+    d.ssectors = reinterpret_cast<const SSectorRec *>(r->d_blob + h[H_OFF_SSECTORS]);
+    d.segs = reinterpret_cast<const SegRec *>(r->d_blob + h[H_OFF_SEGS]);
+    d.sectors = reinterpret_cast<const SectorRec *>(r->d_blob + h[H_OFF_SECTORS]);
+    d.tex = reinterpret_cast<const TexRec *>(r->d_blob + h[H_OFF_TEX]);
+    d.texels = r->d_blob + h[H_OFF_TEXELS];
+    d.flats = r->d_blob + h[H_OFF_FLATS];
+    d.colormap = r->d_blob + h[H_OFF_COLORMAP];
+    d.palette = reinterpret_cast<const uint32_t *>(r->d_blob + h[H_OFF_PALETTE]);
+    d.yslope = r->d_yslope;
+    d.nverts = (int32_t)h[H_NVERTS]; d.nnodes = (int32_t)h[H_NNODES]; d.nss = (int32_t)h[H_NSSECTORS];
+    d.nsegs = (int32_t)h[H_NSEGS]; d.nsectors = (int32_t)h[H_NSECTORS]; d.ntex = (int32_t)h[H_NTEX];
+    d.nflats = (int32_t)h[H_NFLATS]; d.sky_tex = (int32_t)h[H_SKY_TEX];
+    d.root = h[H_ROOT];
+    d.invF = (uint32_t)(4294967296ULL / (uint64_t)view->F);
+    if (d.nsegs > 65535) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level has more than 65535 segs"); }
+    if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
+    CUR(cudaMalloc(&r->d_poses, sizeof(Pose) * (size_t)max_batch));
+    CUR(cudaMalloc(&r->d_frames, sizeof(FrameConst) * (size_t)max_batch));
+    CUR(cudaMalloc(&r->d_work, sizeof(SegFrame) * (size_t)max_batch * (size_t)r->stride));
+#undef CUR
+    *out = r;
+    return B2D_OK;
+}
+
+void b2d_renderer_destroy(b2d_renderer *r) { free_renderer(r); }
+
+int b2d_render_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, uint8_t *d_index_fb,
+                      uint32_t *d_rgba_fb, void *cuda_stream) {
+    if (!r || !d_poses || !d_index_fb) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return B2D_OK;
+    if (n > (size_t)r->max_batch) return fail(B2D_ERR_INVALID_ARG, "n exceeds max_batch");
+    CU(cudaSetDevice(r->device));
+    return enqueue_frames(r, reinterpret_cast<const Pose *>(d_poses), (int)n, d_index_fb, d_rgba_fb,
+                          static_cast<cudaStream_t>(cuda_stream));
+}
+
+int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_fb, uint32_t *rgba_fb) {
+    if (!r || !poses || !index_fb) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    if (n == 0) return B2D_OK;
+    CU(cudaSetDevice(r->device));
+    const size_t npix = (size_t)r->view.W * r->view.H;
+    if (!r->render_stream) {
+        CU(cudaStreamCreateWithFlags(&r->render_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&r->rendered[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&r->copied[i], cudaEventDisableTiming));
+            CU(cudaMalloc(&r->d_index[i], npix * (size_t)r->max_batch));
+        }
+        CU(cudaMallocHost(&r->h_poses, sizeof(Pose) * (size_t)r->max_batch * 2));
+    }
+    if (rgba_fb && !r->d_rgba[0])
+        for (int i = 0; i < 2; i++) CU(cudaMalloc(&r->d_rgba[i], npix * 4 * (size_t)r->max_batch));
+    // Double-buffered pipeline: batch b renders into buffer b&1 on render_stream while the copy
+    // stream drains buffer (b-1)&1 to the caller's host memory.
+    size_t done = 0;
+    int b = 0;
+    while (done < n) {
+        const int cnt = (int)((n - done) < (size_t)r->max_batch ? (n - done) : (size_t)r->max_batch);
+        const int buf = b & 1;
+        if (b >= 2) CU(cudaEventSynchronize(r->copied[buf]));       // buffer + pose slot free again
+        Pose *hp = r->h_poses + (size_t)buf * r->max_batch;
+        std::memcpy(hp, poses + done, sizeof(Pose) * (size_t)cnt);
+        CU(cudaMemcpyAsync(r->d_poses, hp, sizeof(Pose) * (size_t)cnt, cudaMemcpyHostToDevice, r->render_stream));
+        int rc = enqueue_frames(r, r->d_poses, cnt, r->d_index[buf], rgba_fb ? r->d_rgba[buf] : nullptr, r->render_stream);
+        if (rc != B2D_OK) return rc;
+        CU(cudaEventRecord(r->rendered[buf], r->render_stream));
+        CU(cudaStreamWaitEvent(r->copy_stream, r->rendered[buf], 0));
+        CU(cudaMemcpyAsync(index_fb + done * npix, r->d_index[buf], npix * (size_t)cnt, cudaMemcpyDeviceToHost, r->copy_stream));
+        if (rgba_fb)
+            CU(cudaMemcpyAsync(rgba_fb + done * npix, r->d_rgba[buf], npix * 4 * (size_t)cnt, cudaMemcpyDeviceToHost, r->copy_stream));
+        CU(cudaEventRecord(r->copied[buf], r->copy_stream));
+        done += (size_t)cnt;
+        b++;
+    }
+    CU(cudaStreamSynchronize(r->copy_stream));
+    CU(cudaStreamSynchronize(r->render_stream));
+    return B2D_OK;
+}
+
+int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_rgba, size_t n_pixels, void *cuda_stream) {
+    if (!r || !d_index || !d_rgba) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(r->device));
+    CU(launch_palette(r->ds.palette, d_index, d_rgba, n_pixels, static_cast<cudaStream_t>(cuda_stream)));
+    r->launches += 1;
+    return B2D_OK;
+}
+
+int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *seg_ids_out, size_t stride) {
+    if (!r || !counts_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    if (n > (size_t)r->max_batch) return fail(B2D_ERR_INVALID_ARG, "n exceeds max_batch");
+    CU(cudaSetDevice(r->device));
+    CU(cudaDeviceSynchronize());
+    std::vector<FrameConst> frames(n);
+    CU(cudaMemcpy(frames.data(), r->d_frames, sizeof(FrameConst) * n, cudaMemcpyDeviceToHost));
+    std::vector<SegFrame> work;
+    for (size_t i = 0; i < n; i++) {
+        counts_out[i] = frames[i].status ? -frames[i].status : frames[i].count;
+        if (!seg_ids_out) continue;
+        size_t c = (size_t)frames[i].count;
+        work.resize(c);
+        if (c) CU(cudaMemcpy(work.data(), r->d_work + i * (size_t)r->stride, sizeof(SegFrame) * c, cudaMemcpyDeviceToHost));
+        for (size_t k = 0; k < c && k < stride; k++) seg_ids_out[i * stride + k] = work[k].seg;
+    }
+    return B2D_OK;
+}
+
+int64_t b2d_launch_count(const b2d_renderer *r) { return r ? r->launches : 0; }
+
+}  // extern "C"

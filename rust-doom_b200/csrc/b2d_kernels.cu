@@ -1,0 +1,496 @@
+// sm_100a kernels of the Doom-WAD software renderer.
+//
+//   b2d_walk_kernel    : one warp per frame.  Lane-parallel view transform of all vertices, per-seg
+//                        projection setup and per-node-child bounding-box ranges into shared memory,
+//                        then a front-to-back BSP walk with a warp-wide solid-column bitmask
+//                        (ballot / lane-striped words) that emits the compact seg worklist.
+//   b2d_raster_kernel  : one warp per (frame, 32-column strip); lane = screen column.  Consumes the
+//                        worklist front to back, keeps the per-column clip window in registers,
+//                        draws wall columns, floor/ceiling spans and sky with the light->colormap
+//                        lookup from shared memory; every pixel is written exactly once.
+//   b2d_palette_kernel : index -> RGBA8 with the 256-entry palette in shared memory, 128-bit I/O.
+//
+// There is no dense contraction anywhere on this path, so no tensor-core (tcgen05) work: the
+// kernels are integer/LSU bound and are tuned against the HBM write roofline.
+#include "b2d_kernels.cuh"
+
+namespace b2d {
+
+namespace {
+
+constexpr unsigned kFull = 0xFFFFFFFFu;
+constexpr int kMaskWords = 128;      // up to 4096 columns
+constexpr int kStackDepth = 128;
+
+// packed per-seg / per-box visibility word in shared memory
+constexpr uint32_t kVisBit = 1u << 25, kSolidBit = 1u << 24;
+__device__ __forceinline__ uint32_t pack_range(int lo, int hi, uint32_t bits) {
+    return (uint32_t)lo | ((uint32_t)hi << 12) | bits;
+}
+__device__ __forceinline__ int range_lo(uint32_t r) { return (int)(r & 0xFFFu); }
+__device__ __forceinline__ int range_hi(uint32_t r) { return (int)((r >> 12) & 0xFFFu); }
+
+// bits of columns [lo, hi] that fall into mask word w
+__device__ __forceinline__ uint32_t word_bits(int w, int lo, int hi) {
+    int a = max(lo, w * 32), b = min(hi, w * 32 + 31);
+    if (a > b) return 0u;
+    uint32_t m = 0xFFFFFFFFu >> (31 - (b - w * 32));
+    return m & (0xFFFFFFFFu << (a - w * 32));
+}
+
+// warp-wide: is any column of [lo, hi] still open?  (lane-striped words + ballot)
+__device__ __forceinline__ bool range_open(const uint32_t *mask, int lane, int lo, int hi) {
+    bool open = false;
+#pragma unroll
+    for (int k = 0; k < kMaskWords / 32; k++) {
+        int w = lane + 32 * k;
+        uint32_t bits = word_bits(w, lo, hi);
+        if (bits & ~mask[w]) open = true;
+    }
+    return __any_sync(kFull, open);
+}
+
+// single lane: same test over its own range (used for per-seg culling)
+__device__ __forceinline__ bool lane_range_open(const uint32_t *mask, int lo, int hi) {
+    for (int w = lo >> 5; w <= (hi >> 5); w++)
+        if (word_bits(w, lo, hi) & ~mask[w]) return true;
+    return false;
+}
+
+__device__ __forceinline__ void mark_solid(uint32_t *mask, int lane, int lo, int hi) {
+#pragma unroll
+    for (int k = 0; k < kMaskWords / 32; k++) {
+        int w = lane + 32 * k;
+        uint32_t bits = word_bits(w, lo, hi);
+        if (bits) mask[w] |= bits;
+    }
+}
+
+__host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
+
+struct WalkSmem {
+    size_t off_tx, off_tz, off_segr, off_boxr, off_mask, off_stack, off_list, total;
+};
+__host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnodes) {
+    WalkSmem L;
+    size_t o = 0;
+    L.off_tx = o; o = align16(o + 4 * (size_t)nverts);
+    L.off_tz = o; o = align16(o + 4 * (size_t)nverts);
+    L.off_segr = o; o = align16(o + 4 * (size_t)nsegs);
+    L.off_boxr = o; o = align16(o + 8 * (size_t)nnodes);
+    L.off_mask = o; o = align16(o + 4 * kMaskWords);
+    L.off_stack = o; o = align16(o + 4 * kStackDepth);
+    L.off_list = o; o = align16(o + 2 * (size_t)nsegs);
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: BSP walk -> worklist
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const Pose *__restrict__ poses, int n,
+                FrameConst *__restrict__ frames, SegFrame *__restrict__ work, int stride) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int frame = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (frame >= n) return;                       // warps are independent: no block barrier below
+
+    const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes);
+    uint8_t *base = smem + (size_t)warp * L.total;
+    int32_t *tx = reinterpret_cast<int32_t *>(base + L.off_tx);
+    int32_t *tz = reinterpret_cast<int32_t *>(base + L.off_tz);
+    uint32_t *segr = reinterpret_cast<uint32_t *>(base + L.off_segr);
+    uint32_t *boxr = reinterpret_cast<uint32_t *>(base + L.off_boxr);
+    uint32_t *mask = reinterpret_cast<uint32_t *>(base + L.off_mask);
+    uint32_t *stack = reinterpret_cast<uint32_t *>(base + L.off_stack);
+    uint16_t *list = reinterpret_cast<uint16_t *>(base + L.off_list);
+
+    FrameConst fc;
+    frame_setup(poses[frame], fc);
+
+    // 1. all vertices into view space (lane-parallel)
+    for (int i = lane; i < sc.nverts; i += 32) {
+        int32_t vx = sc.verts[2 * i], vy = sc.verts[2 * i + 1];
+        int32_t a, b;
+        to_view(fc, vx, vy, a, b);
+        tx[i] = a; tz[i] = b;
+    }
+    __syncwarp();
+
+    // 2. per-seg exact column interval + static/solid flags (lane-parallel, 64-bit setup)
+    for (int i = lane; i < sc.nsegs; i += 32) {
+        const SegRec &S = sc.segs[i];
+        uint32_t packed = 0;
+        int32_t flags = S.flags;
+        if (!(flags & kSegInvalid)) {
+            SegFrame sf;
+            if (seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf)) {
+                bool solid = (!(flags & kSegTwoSided) || S.otop <= S.obot) && (sf.flags & kSegFrameNoSkip);
+                packed = pack_range(sf.xlo, sf.xhi, kVisBit | (solid ? kSolidBit : 0u));
+            }
+        }
+        segr[i] = packed;
+    }
+    // 3. conservative column range of both child boxes of every node
+    for (int i = lane; i < 2 * sc.nnodes; i += 32) {
+        const NodeRec &N = sc.nodes[i >> 1];
+        const int32_t *box = (i & 1) ? N.lbox : N.rbox;
+        int32_t b4[4] = {box[0], box[1], box[2], box[3]};
+        int lo, hi;
+        boxr[i] = box_range(fc, vw, b4, lo, hi) ? pack_range(lo, hi, kVisBit) : 0u;
+    }
+    // solid-column mask: columns >= W start out solid
+#pragma unroll
+    for (int k = 0; k < kMaskWords / 32; k++) {
+        int w = lane + 32 * k;
+        mask[w] = ~word_bits(w, 0, vw.W - 1);
+    }
+    if (lane == 0) stack[0] = sc.root;
+    __syncwarp();
+
+    // 4. front-to-back traversal (control flow is warp-uniform)
+    int sp = 1, count = 0, status = 0;
+    while (sp > 0) {
+        uint32_t child = stack[--sp];
+        __syncwarp();
+        if (child & kLeaf) {
+            uint32_t id = child & 0x7FFFFFFFu;
+            if (id >= (uint32_t)sc.nss) continue;
+            const SSectorRec ss = sc.ssectors[id];
+            if (ss.sector < 0) continue;
+            for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {
+                int k = k0 + lane;
+                int si = ss.first_seg + k;
+                uint32_t r = k < ss.num_segs ? segr[si] : 0u;
+                bool vis = (r & kVisBit) && lane_range_open(mask, range_lo(r), range_hi(r));
+                unsigned m = __ballot_sync(kFull, vis);
+                int pos = count + __popc(m & ((1u << lane) - 1u));
+                if (vis && pos < sc.nsegs) list[pos] = (uint16_t)si;
+                count = min(count + __popc(m), sc.nsegs);
+                unsigned sm = __ballot_sync(kFull, vis && (r & kSolidBit));
+                __syncwarp();
+                while (sm) {
+                    int j = __ffs(sm) - 1;
+                    sm &= sm - 1;
+                    uint32_t rj = __shfl_sync(kFull, r, j);
+                    mark_solid(mask, lane, range_lo(rj), range_hi(rj));
+                }
+                __syncwarp();
+            }
+            if (!range_open(mask, lane, 0, vw.W - 1)) break;     // every column is closed
+        } else {
+            if (child >= (uint32_t)sc.nnodes) continue;
+            const NodeRec &N = sc.nodes[child];
+            int side = node_side(fc.pose, N.x, N.y, N.dx, N.dy);   // 1: left child is near
+            uint32_t near_c = N.child[side], far_c = N.child[side ^ 1];
+            uint32_t rn = boxr[2 * child + side], rf = boxr[2 * child + (side ^ 1)];
+            bool far_vis = (rf & kVisBit) && range_open(mask, lane, range_lo(rf), range_hi(rf));
+            bool near_vis = (rn & kVisBit) && range_open(mask, lane, range_lo(rn), range_hi(rn));
+            int need = (far_vis ? 1 : 0) + (near_vis ? 1 : 0);
+            if (sp + need > kStackDepth) { status = 1; break; }
+            if (lane == 0) {
+                int p = sp;
+                if (far_vis) stack[p++] = far_c;
+                if (near_vis) stack[p++] = near_c;
+            }
+            sp += need;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (count > stride) { count = stride; status |= 2; }
+
+    // 5. worklist records (lane-parallel): the projection coefficients of each emitted seg
+    for (int k = lane; k < count; k += 32) {
+        int si = list[k];
+        const SegRec &S = sc.segs[si];
+        SegFrame sf;
+        seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf);
+        sf.seg = si;
+        work[(size_t)frame * stride + k] = sf;
+    }
+    if (lane == 0) {
+        fc.count = count;
+        fc.status = status;
+#pragma unroll
+        for (int i = 0; i < 6; i++) fc.pad[i] = 0;
+        frames[frame] = fc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: raster
+// ------------------------------------------------------------------------------------------------
+struct RasterCtx {
+    const DeviceScene *sc;
+    const uint8_t *cmap;       // shared-memory colormap (32 x 256)
+    const uint32_t *pal;       // shared-memory palette (only when rgba)
+    uint8_t *fb;               // &index_fb[frame][0][x]
+    uint32_t *rgba;            // &rgba_fb[frame][0][x] or nullptr
+    int W, H, x, lane;
+    uint32_t skycol;
+};
+
+__device__ __forceinline__ void put_px(const RasterCtx &c, int y, uint8_t v) {
+    size_t o = (size_t)y * c.W;
+    c.fb[o] = v;
+    if (c.rgba) c.rgba[o] = c.pal[v];
+}
+
+// rows [ya, yb) of this lane's column := void (index 0); lanes with ya >= yb idle
+__device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int yb) {
+    bool act = ya < yb;
+    int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
+    int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+    for (int y = y0; y < y1; y++)
+        if (y >= ya && y < yb) put_px(c, y, 0);
+}
+
+__device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb) {
+    const DeviceScene &sc = *c.sc;
+    if (sc.sky_tex < 0) { fill_void_warp(c, ya, yb); return; }
+    const TexRec T = sc.tex[sc.sky_tex];
+    const uint8_t *px = sc.texels + T.texel_off;
+    bool act = ya < yb;
+    int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
+    int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+    for (int y = y0; y < y1; y++) {
+        int v = sky_row(y, c.H, (int32_t)T.h);
+        if (y >= ya && y < yb) put_px(c, y, c.cmap[px[(uint32_t)v * T.w + c.skycol]]);
+    }
+}
+
+__device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameConst &fc, const View &vw,
+                                                int ya, int yb, int32_t h, int32_t flat, int lightb,
+                                                bool visible) {
+    const DeviceScene &sc = *c.sc;
+    if (!__any_sync(kFull, ya < yb)) return;
+    if (!visible) { fill_void_warp(c, ya, yb); return; }
+    if (flat == kFlatSky) { draw_sky_warp(c, ya, yb); return; }
+    if (flat < 0 || flat >= sc.nflats) { fill_void_warp(c, ya, yb); return; }
+    const uint8_t *px = sc.flats + 4096u * (uint32_t)flat;
+    const uint32_t habs = plane_habs(h, fc.pose.z);
+    bool act = ya < yb;
+    int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
+    int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+    for (int y = y0; y < y1; y++) {
+        PlaneRow pr = plane_row(habs, sc.yslope[y], fc, vw, sc.invF);      // warp-uniform
+        const uint8_t *cm = c.cmap + 256 * light_row(lightb, pr.z8);
+        if (y >= ya && y < yb) {
+            uint32_t U = pr.baseU + (uint32_t)c.x * pr.stepU;
+            uint32_t V = pr.baseV + (uint32_t)c.x * pr.stepV;
+            put_px(c, y, cm[px[flat_index(U, V)]]);
+        }
+    }
+}
+
+__device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameConst &fc, int ya, int yb,
+                                               int32_t tex, int32_t tA, int32_t hA, int32_t ucol,
+                                               int32_t iscale, int row) {
+    const DeviceScene &sc = *c.sc;
+    if (!__any_sync(kFull, ya < yb)) return;
+    if (tex < 0 || tex >= sc.ntex) { fill_void_warp(c, ya, yb); return; }
+    const TexRec T = sc.tex[tex];
+    const uint8_t *px = sc.texels + T.texel_off;
+    bool act = ya < yb;
+    int32_t col = floormod32(ucol, (int32_t)T.w);
+    int32_t tbase = wall_tbase(tA, hA, fc.pose.z, c.H, iscale);
+    int32_t tstep = iscale >> 4;
+    const uint8_t *cm = c.cmap + 256 * row;
+    int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
+    int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+    for (int y = y0; y < y1; y++) {
+        if (y >= ya && y < yb) {
+            int32_t t = tbase + y * tstep;
+            uint32_t v = wall_row(t, T.h, T.hmagic, T.hbias);
+            put_px(c, y, cm[px[v * T.w + (uint32_t)col]]);
+        }
+    }
+}
+
+template <bool kRgba>
+__global__ void __launch_bounds__(128)
+b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
+                  const SegFrame *__restrict__ work, int stride, int n, int strips,
+                  uint8_t *__restrict__ index_fb, uint32_t *__restrict__ rgba_fb) {
+    __shared__ __align__(16) uint8_t s_cmap[32 * 256];
+    __shared__ uint32_t s_pal[kRgba ? 256 : 1];
+    {   // colormap rows 0..31 (and the palette) into shared memory, 128-bit loads
+        const uint4 *src = reinterpret_cast<const uint4 *>(sc.colormap);
+        uint4 *dst = reinterpret_cast<uint4 *>(s_cmap);
+        for (int i = threadIdx.x; i < 32 * 256 / 16; i += blockDim.x) dst[i] = src[i];
+        if (kRgba)
+            for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pal[i] = sc.palette[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (gw >= (long long)n * strips) return;
+    const int frame = (int)(gw / strips), strip = (int)(gw % strips);
+    const int W = vw.W, H = vw.H;
+    const int x0 = strip * 32, x = x0 + lane;
+    const bool inside = x < W;
+
+    const FrameConst fc = frames[frame];
+    RasterCtx c;
+    c.sc = &sc; c.cmap = s_cmap; c.pal = s_pal;
+    c.fb = index_fb + (size_t)frame * W * H + (inside ? x : 0);
+    c.rgba = kRgba ? rgba_fb + (size_t)frame * W * H + (inside ? x : 0) : nullptr;
+    c.W = W; c.H = H; c.x = x; c.lane = lane;
+    c.skycol = 0;
+    if (sc.sky_tex >= 0 && inside) c.skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
+
+    int ct = 0, cb = inside ? H : 0;              // open window [ct, cb) of this lane's column
+    const SegFrame *wl = work + (size_t)frame * stride;
+    const int count = fc.count;
+    bool done = false;
+
+    for (int k0 = 0; k0 < count && !done; k0 += 32) {
+        int k = k0 + lane;
+        bool overlap = false;
+        if (k < count) {
+            int xlo = wl[k].xlo, xhi = wl[k].xhi;
+            overlap = xhi >= x0 && xlo <= x0 + 31;
+        }
+        unsigned m = __ballot_sync(kFull, overlap);
+        while (m) {
+            int j = __ffs(m) - 1;
+            m &= m - 1;
+            if (!__any_sync(kFull, ct < cb)) { done = true; break; }
+            const SegFrame sf = wl[k0 + j];                              // warp-uniform 64 B
+            bool in = inside && ct < cb && x >= sf.xlo && x <= sf.xhi;
+            if (!__any_sync(kFull, in)) continue;
+            ColumnEval ce = {0u, 1, 1, 0};
+            bool ok = in && column_eval(sf, vw, x, ce);
+            if (!__any_sync(kFull, ok)) continue;
+
+            const SegRec S = sc.segs[sf.seg];
+            const SectorRec SF = sc.sectors[S.front];
+            const int32_t fcl = SF.ceil, ffl = SF.floor;
+            const bool two = S.flags & kSegTwoSided;
+            const bool ceil_vis = ((int64_t)fcl << 16) > fc.pose.z || SF.ceil_flat == kFlatSky;
+            const bool floor_vis = ((int64_t)ffl << 16) < fc.pose.z || SF.floor_flat == kFlatSky;
+
+            // per-lane rows: y1 wall top, y2 end of upper, y3 start of lower, y4 start of floor
+            int y1 = ct, y2 = ct, y3 = ct, y4 = ct, yend = ct, row = 0;
+            int32_t ucol = 0;
+            if (ok) {
+                row = light_row(S.light, ce.z8);
+                ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+                int yfc = yrow(fcl, ce.scale, fc.pose.z, H), yff = yrow(ffl, ce.scale, fc.pose.z, H);
+                y1 = clampv(yfc, ct, cb);
+                if (!two) {
+                    y2 = clampv(yff, y1, cb);       // one-sided: [y1,y2) is the middle texture
+                    y3 = y2; y4 = y2;
+                } else {
+                    int yot = yrow(S.otop, ce.scale, fc.pose.z, H), yob = yrow(S.obot, ce.scale, fc.pose.z, H);
+                    y2 = clampv(yot, y1, cb);
+                    y3 = clampv(yob, y2, cb);
+                    y4 = clampv(yff, y3, cb);
+                }
+                yend = cb;
+            }
+            // ceiling region [ct, y1)
+            draw_plane_warp(c, fc, vw, ok ? ct : 0, ok ? y1 : 0, fcl, SF.ceil_flat, SF.light, ceil_vis);
+            if (!two) {
+                draw_wall_warp(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+            } else {
+                if (S.otop < fcl)
+                    draw_wall_warp(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                if (S.obot > ffl)
+                    draw_wall_warp(c, fc, ok ? y3 : 0, ok ? y4 : 0, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
+            }
+            // floor region [y4, cb)
+            draw_plane_warp(c, fc, vw, ok ? y4 : 0, ok ? yend : 0, ffl, SF.floor_flat, SF.light, floor_vis);
+            if (ok) {
+                if (!two || y2 >= y3) { ct = H; cb = 0; }
+                else { ct = y2; cb = y3; }
+            }
+        }
+    }
+    // whatever is still open is void
+    fill_void_warp(c, inside ? ct : 0, inside ? cb : 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 3: palette LUT
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+b2d_palette_kernel(const uint32_t *__restrict__ palette, const uint8_t *__restrict__ index,
+                   uint32_t *__restrict__ rgba, size_t n_pixels) {
+    __shared__ uint32_t s_pal[256];
+    s_pal[threadIdx.x] = palette[threadIdx.x];
+    __syncthreads();
+    const size_t nvec = n_pixels / 16;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        uint4 in = __ldcs(reinterpret_cast<const uint4 *>(index) + i);
+        uint32_t wds[4] = {in.x, in.y, in.z, in.w};
+        uint4 *out = reinterpret_cast<uint4 *>(rgba) + 4 * i;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint4 o;
+            o.x = s_pal[wds[q] & 0xFF];
+            o.y = s_pal[(wds[q] >> 8) & 0xFF];
+            o.z = s_pal[(wds[q] >> 16) & 0xFF];
+            o.w = s_pal[wds[q] >> 24];
+            __stcs(out + q, o);
+        }
+    }
+    // tail (n_pixels not a multiple of 16)
+    for (size_t p = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pixels; p += stride)
+        rgba[p] = s_pal[index[p]];
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts, sc.nsegs, sc.nnodes).total; }
+
+cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
+                        FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const size_t per_warp = walk_smem_per_warp(sc);
+    int warps = 4;
+    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
+    if (per_warp * warps > 227 * 1024) return cudaErrorInvalidValue;
+    const size_t smem = per_warp * warps;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(b2d_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    const int blocks = (n + warps - 1) / warps;
+    b2d_walk_kernel<<<blocks, warps * 32, smem, stream>>>(sc, vw, d_poses, n, d_frames, d_work, stride);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameConst *d_frames,
+                          const SegFrame *d_work, int stride, int n, uint8_t *d_index_fb,
+                          uint32_t *d_rgba, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int strips = (vw.W + 31) / 32;
+    const long long warps = (long long)n * strips;
+    const int blocks = (int)((warps + 3) / 4);
+    if (d_rgba)
+        b2d_raster_kernel<true><<<blocks, 128, 0, stream>>>(sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba);
+    else
+        b2d_raster_kernel<false><<<blocks, 128, 0, stream>>>(sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, nullptr);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_palette(const uint32_t *d_palette, const uint8_t *d_index, uint32_t *d_rgba,
+                           size_t n_pixels, cudaStream_t stream) {
+    if (n_pixels == 0) return cudaSuccess;
+    size_t nvec = n_pixels / 16 + 1;
+    int blocks = (int)((nvec + 255) / 256);
+    const int cap = 148 * 16;
+    if (blocks > cap) blocks = cap;
+    b2d_palette_kernel<<<blocks, 256, 0, stream>>>(d_palette, d_index, d_rgba, n_pixels);
+    return cudaGetLastError();
+}
+
+}  // namespace b2d

@@ -1,0 +1,47 @@
+// Device-side scene view + kernel launchers (implemented in b2d_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "b2d_math.cuh"
+#include "b2d_scene.hpp"
+
+namespace b2d {
+
+// Pointers into the scene blob resident in HBM (one cudaMalloc, uploaded once per level).
+struct DeviceScene {
+    const int32_t *verts;
+    const NodeRec *nodes;
+    const SSectorRec *ssectors;
+    const SegRec *segs;
+    const SectorRec *sectors;
+    const TexRec *tex;
+    const uint8_t *texels;
+    const uint8_t *flats;
+    const uint8_t *colormap;     // 34 x 256
+    const uint32_t *palette;     // 256 RGBA8
+    const uint32_t *yslope;      // per view: H entries
+    int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex;
+    uint32_t root;
+    uint32_t invF;               // floor(2^32 / F)
+};
+
+// Bytes of dynamic shared memory one BSP-walk warp needs for this scene.
+size_t walk_smem_per_warp(const DeviceScene &sc);
+
+// Kernel 1: front-to-back BSP walk, one warp per frame.  Writes frames[i] and up to `stride`
+// worklist entries per frame at work[i*stride ...].
+cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
+                        FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream);
+
+// Kernel 2: wall-column / flat-span / sky rasteriser, one warp per (frame, 32-column strip).
+// Writes every pixel of d_index_fb exactly once; if d_rgba != nullptr also the palette-mapped RGBA8.
+cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameConst *d_frames,
+                          const SegFrame *d_work, int stride, int n, uint8_t *d_index_fb,
+                          uint32_t *d_rgba, cudaStream_t stream);
+
+// Kernel 3: palette LUT on its own (index -> RGBA8), 16 pixels per thread.
+cudaError_t launch_palette(const uint32_t *d_palette, const uint8_t *d_index, uint32_t *d_rgba,
+                           size_t n_pixels, cudaStream_t stream);
+
+}  // namespace b2d

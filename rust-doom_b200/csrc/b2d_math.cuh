@@ -1,0 +1,318 @@
+// Integer pixel-contract arithmetic shared by the CUDA kernels (DESIGN.md "Pixel contract").
+//
+// Every function is exact integer math so that the palette-index framebuffer is reproducible bit
+// for bit.  The functions are __host__ __device__ so that tests/hostcheck can run the very same
+// code on the CPU (one lane at a time) and compare it with the oracle before any GPU time is spent;
+// the shipped library contains no CPU rendering path.
+//
+// Reference semantics restated here (cristicbz/rust-doom):
+//   BSP side rule                      math/src/line.rs:41-43, wad/src/visitor.rs:1051-1057
+//   wall texel floor-mod sampling      assets/shaders/static.frag:19-22
+//   flat texel rule                    game/src/level.rs:537-549
+//   light -> colormap row              assets/shaders/static.vert:41-43, static.frag:15-27
+//   sky lookup                         assets/shaders/sky.vert:9-16, sky.frag:12-26
+//   projection constants               game/src/player.rs:84-89, engine/src/projections.rs:93-101
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2D_HD __host__ __device__ __forceinline__
+#else
+#define B2D_HD inline
+#endif
+
+namespace b2d {
+
+struct Pose { int32_t x, y, z; uint32_t angle; };     // == b2d_pose
+struct View { int32_t W, H, F, FY2; };                // == b2d_view
+
+// Per-frame constants produced by the BSP-walk kernel and consumed by the raster kernel.
+struct FrameConst {
+    Pose pose;
+    int32_t cosq, sinq;        // Q30
+    int32_t px8, py8;          // camera position, Q8
+    int32_t count;             // worklist length
+    int32_t status;            // 0 ok, 1 = traversal stack overflow
+    int32_t pad[6];
+};
+static_assert(sizeof(FrameConst) == 64, "FrameConst");
+
+// One worklist entry: a front-facing seg that may be visible, with its per-frame projection
+// coefficients.  N(x) = Nc + Nx*x and D(x) = Dc + Dx*x are the numerator / denominator of the
+// seg parameter s = N/D at screen column x; 1/depth is proportional to D.
+struct SegFrame {
+    int64_t Nc, Nx, Dc, Dx;
+    int64_t Dmax;              // D clamp: depth >= 1 map unit
+    uint32_t Rm;               // floor(2^62 / normalised(F*C))
+    int16_t sh, e;             // normalisation shift of N,D; scale exponent
+    int32_t seg;
+    int16_t xlo, xhi;          // exact visible column interval
+    int32_t flags;             // bit0: every column in [xlo,xhi] passes column_eval
+    int32_t pad;
+};
+static_assert(sizeof(SegFrame) == 64, "SegFrame");
+
+constexpr int32_t kSegFrameNoSkip = 1;
+
+// ------------------------------------------------------------------------------------------------
+B2D_HD int bitlen64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return 64 - __clzll((long long)v);
+#else
+    return v ? 64 - __builtin_clzll(v) : 0;
+#endif
+}
+B2D_HD int64_t floordiv64(int64_t a, int64_t b) {      // b > 0
+    int64_t q = a / b;
+    return (a % b != 0 && a < 0) ? q - 1 : q;
+}
+B2D_HD int32_t floormod32(int32_t a, int32_t b) {      // b > 0
+    int32_t r = a % b;
+    return r < 0 ? r + b : r;
+}
+template <typename T> B2D_HD T clampv(T v, T lo, T hi) { return v < lo ? lo : (v > hi ? hi : v); }
+B2D_HD uint32_t umulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (uint32_t)(((uint64_t)a * b) >> 32);
+#endif
+}
+
+// sin/cos of a BAM angle, Q30, integer Taylor series on [0, pi/4] with octant folding.
+B2D_HD void sincos_q30(uint32_t angle, int32_t &cosq, int32_t &sinq) {
+    const int64_t one = (int64_t)1 << 30;
+    uint32_t quad = angle >> 30;
+    uint32_t r = angle & 0x3FFFFFFFu;
+    bool swap = false;
+    if (r > 0x20000000u) { r = 0x40000000u - r; swap = true; }
+    int64_t x = ((int64_t)r * 1686629713LL) >> 30;
+    int64_t x2 = (x * x) >> 30;
+    int64_t t = one - x2 / 72;
+    t = one - ((x2 * t) >> 30) / 42;
+    t = one - ((x2 * t) >> 30) / 20;
+    t = one - ((x2 * t) >> 30) / 6;
+    int64_t s = (x * t) >> 30;
+    t = one - x2 / 90;
+    t = one - ((x2 * t) >> 30) / 56;
+    t = one - ((x2 * t) >> 30) / 30;
+    t = one - ((x2 * t) >> 30) / 12;
+    int64_t c = one - ((x2 * t) >> 30) / 2;
+    if (swap) { int64_t tmp = s; s = c; c = tmp; }
+    int64_t cc, ss;
+    if (quad == 0) { cc = c; ss = s; }
+    else if (quad == 1) { cc = -s; ss = c; }
+    else if (quad == 2) { cc = -c; ss = -s; }
+    else { cc = s; ss = -c; }
+    cosq = (int32_t)cc; sinq = (int32_t)ss;
+}
+
+B2D_HD void frame_setup(const Pose &p, FrameConst &f) {
+    f.pose = p;
+    sincos_q30(p.angle, f.cosq, f.sinq);
+    f.px8 = p.x >> 8;
+    f.py8 = p.y >> 8;
+    f.count = 0;
+    f.status = 0;
+}
+
+// world (map units) -> view space Q8: tx to the right, tz forward.
+B2D_HD void to_view(const FrameConst &f, int32_t wx, int32_t wy, int32_t &tx, int32_t &tz) {
+    int64_t dx = ((int64_t)wx << 8) - f.px8;
+    int64_t dy = ((int64_t)wy << 8) - f.py8;
+    tx = (int32_t)((dx * f.sinq - dy * f.cosq) >> 30);
+    tz = (int32_t)((dx * f.cosq + dy * f.sinq) >> 30);
+}
+
+// BSP side: 1 = left child is on the camera's side (sd > 0), 0 = right child.
+B2D_HD int node_side(const Pose &p, int32_t nx, int32_t ny, int32_t ndx, int32_t ndy) {
+    int64_t sd = ((int64_t)p.y - ((int64_t)ny << 16)) * ndx - ((int64_t)p.x - ((int64_t)nx << 16)) * ndy;
+    return sd > 0 ? 1 : 0;
+}
+
+// a + b*x >= c over integer x, intersected into [lo, hi]
+B2D_HD void constrain(int64_t &lo, int64_t &hi, int64_t a, int64_t b, int64_t c) {
+    if (b > 0) { int64_t v = -floordiv64(-(c - a), b); if (v > lo) lo = v; }
+    else if (b < 0) { int64_t v = floordiv64(a - c, -b); if (v < hi) hi = v; }
+    else if (a < c) { hi = lo - 1; }
+}
+
+struct ColumnEval {
+    uint32_t s24;      // seg parameter s in Q24
+    int32_t scale;     // pixels per map unit, Q18
+    int32_t iscale;    // map units per pixel, Q20, clamped to [1, 2^23]
+    int32_t z8;        // view depth in 1/8 map units, <= 65535
+};
+
+// Per-frame projection setup of one seg from its view-space endpoints.  Returns false if the seg is
+// back-facing / degenerate or covers no screen column.
+B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx_, int32_t bz_, SegFrame &sf);
+
+// Column predicate + per-column projection values.  Exact: does not rely on xlo/xhi.
+B2D_HD bool column_eval(const SegFrame &sf, const View &vw, int x, ColumnEval &out) {
+    int64_t N = sf.Nc + sf.Nx * x, D = sf.Dc + sf.Dx * x;
+    if (D <= 0 || N < 0 || N > D) return false;
+    int64_t Dt = D >> sf.sh;
+    if (Dt < 1) return false;
+    uint64_t Nn = (uint64_t)(N >> sf.sh);
+    out.s24 = (uint32_t)((Nn << 24) / (uint64_t)Dt);
+    int64_t Dcl = D < sf.Dmax ? D : sf.Dmax;
+    uint64_t Dn = (uint64_t)(Dcl >> sf.sh);
+    if (Dn < 1) return false;
+    uint64_t P = (Dn * (uint64_t)sf.Rm) >> 32;
+    uint64_t prod = (uint64_t)vw.FY2 * P;
+    const int64_t cap = (int64_t)vw.FY2 << 17;
+    int e = sf.e;
+    int64_t scale;
+    if (e >= 0) scale = e > 63 ? 0 : (int64_t)(prod >> e);
+    else scale = (-e) >= 20 ? cap : (int64_t)(prod << (-e));
+    if (scale > cap) scale = cap;
+    if (scale < 1) return false;
+    out.scale = (int32_t)scale;
+    int64_t isc = ((int64_t)1 << 38) / scale;
+    out.iscale = (int32_t)clampv<int64_t>(isc, 1, 1 << 23);
+    int64_t z8 = ((int64_t)out.iscale * vw.FY2) >> 18;
+    out.z8 = z8 > 65535 ? 65535 : (int32_t)z8;
+    return true;
+}
+
+B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx_, int32_t bz_, SegFrame &sf) {
+    const int64_t ax = ax_, az = az_, bx = bx_, bz = bz_;
+    const int64_t F = vw.F, W = vw.W;
+    int64_t dxs = bx - ax, dzs = bz - az;
+    int64_t C = az * dxs - ax * dzs;
+    if (C <= 0) return false;
+    sf.Nx = 2 * az; sf.Nc = az * (1 - W) - ax * F;
+    sf.Dx = -2 * dzs; sf.Dc = dxs * F - dzs * (1 - W);
+    int64_t lo = 0, hi = W - 1;
+    constrain(lo, hi, sf.Dc, sf.Dx, 1);
+    constrain(lo, hi, sf.Nc, sf.Nx, 0);
+    constrain(lo, hi, sf.Dc - sf.Nc, sf.Dx - sf.Nx, 0);
+    if (lo > hi) return false;
+    sf.xlo = (int16_t)lo; sf.xhi = (int16_t)hi;
+    int64_t Dbound = (dxs < 0 ? -dxs : dxs) * F + (dzs < 0 ? -dzs : dzs) * W;
+    int sh = bitlen64((uint64_t)Dbound) - 31;
+    if (sh < 0) sh = 0;
+    int64_t M = F * C;
+    int shm = bitlen64((uint64_t)M) - 31;
+    uint64_t Mn = shm >= 0 ? ((uint64_t)M >> shm) : ((uint64_t)M << (-shm));
+    uint64_t Rm = ((uint64_t)1 << 62) / Mn;
+    if (Rm > 0xFFFFFFFFull) Rm = 0xFFFFFFFFull;
+    sf.Rm = (uint32_t)Rm;
+    sf.sh = (int16_t)sh;
+    sf.e = (int16_t)(5 - sh + shm);
+    sf.Dmax = M >> 8;
+    // no-skip guarantee: column_eval's early-outs are monotone in D, so the endpoints decide
+    ColumnEval ce;
+    bool ok = column_eval(sf, vw, (int)lo, ce) && column_eval(sf, vw, (int)hi, ce);
+    sf.flags = ok ? kSegFrameNoSkip : 0;
+    sf.pad = 0;
+    return true;
+}
+
+// colormap row from light byte b and depth z8: clamp(floor(64(255-b)/255 - 2880/(z+90)), 0, 31)
+B2D_HD int light_row(int b, int32_t z8) {
+    uint32_t Z = (uint32_t)z8 + 720u;
+    int32_t num = (int32_t)(64u * (uint32_t)(255 - b) * Z) - 5875200;    // < 2^31
+    if (num <= 0) return 0;
+    uint32_t r = (uint32_t)num / (255u * Z);
+    return r > 31u ? 31 : (int)r;
+}
+
+// first row whose centre lies at or below the projection of height h (map units): ceil(Y - 1/2)
+B2D_HD int yrow(int32_t h, int32_t scale, int32_t pose_z, int32_t H) {
+    int64_t hrel8 = ((int64_t)h << 8) - (int64_t)(pose_z >> 8);
+    int64_t Y = ((int64_t)H << 25) - hrel8 * scale;
+    int64_t r = (Y + ((int64_t)1 << 25) - 1) >> 26;
+    return (int)clampv<int64_t>(r, 0, H);
+}
+
+B2D_HD uint32_t yslope_entry(int y, const View &vw) {
+    int32_t r2 = 2 * y + 1 - vw.H;
+    if (r2 < 0) r2 = -r2;
+    if (r2 == 0) r2 = 1;
+    return (uint32_t)(((uint64_t)vw.FY2 << 16) / (uint32_t)r2);
+}
+
+// |h*2^16 - eye_z| clamped to 2048 map units
+B2D_HD uint32_t plane_habs(int32_t h, int32_t pose_z) {
+    int64_t hrel = clampv<int64_t>(((int64_t)h << 16) - pose_z, -((int64_t)1 << 27), (int64_t)1 << 27);
+    return (uint32_t)(hrel < 0 ? -hrel : hrel);
+}
+B2D_HD int32_t wall_hrel(int32_t h, int32_t pose_z) {
+    return (int32_t)clampv<int64_t>(((int64_t)h << 16) - pose_z, -((int64_t)1 << 27), (int64_t)1 << 27);
+}
+
+// Texture mapping of one screen row of a horizontal plane: U(x) = baseU + x*stepU (wad x, Q26 mod 64),
+// V likewise for wad y; z8 = depth of the row for lighting.
+struct PlaneRow { uint32_t baseU, stepU, baseV, stepV; int32_t z8; };
+B2D_HD PlaneRow plane_row(uint32_t habs, uint32_t yslope, const FrameConst &f, const View &vw, uint32_t invF) {
+    PlaneRow pr;
+    uint64_t zz = ((uint64_t)habs * yslope) >> 16;
+    int32_t z16 = zz > 0x7FFFFFFFull ? 0x7FFFFFFF : (int32_t)zz;
+    int32_t fxw = (int32_t)(((int64_t)z16 * f.cosq) >> 30);
+    int32_t fyw = (int32_t)(((int64_t)z16 * f.sinq) >> 30);
+    int64_t Rx = fyw, Ry = -(int64_t)fxw;
+    pr.stepU = (uint32_t)(uint64_t)((Rx * (int64_t)invF) >> 21);
+    uint32_t halfU = (uint32_t)(uint64_t)((Rx * (int64_t)invF) >> 22);
+    pr.stepV = (uint32_t)(uint64_t)((Ry * (int64_t)invF) >> 21);
+    uint32_t halfV = (uint32_t)(uint64_t)((Ry * (int64_t)invF) >> 22);
+    pr.baseU = ((uint32_t)(f.pose.x + fxw) << 10) + (uint32_t)(1 - vw.W) * halfU;
+    pr.baseV = ((uint32_t)(f.pose.y + fyw) << 10) + (uint32_t)(1 - vw.W) * halfV;
+    int32_t z8 = z16 >> 13;
+    pr.z8 = z8 > 65535 ? 65535 : z8;
+    return pr;
+}
+B2D_HD uint32_t flat_index(uint32_t U, uint32_t V) { return ((U >> 26) << 6) | (V >> 26); }
+
+// wall texture row: t(y) = tbase + y*tstep (Q16); row index = floor-mod of t>>16 by the height,
+// evaluated with the per-texture magic reciprocal (exact for |t>>16| < 2^14, h <= 4096).
+B2D_HD int32_t wall_tbase(int32_t tA, int32_t hA, int32_t pose_z, int32_t H, int32_t iscale) {
+    int64_t t = ((int64_t)tA << 16) + wall_hrel(hA, pose_z) + (((int64_t)(1 - H) * iscale) >> 5);
+    return (int32_t)t;
+}
+B2D_HD uint32_t wall_row(int32_t t, uint32_t h, uint32_t hmagic, uint32_t hbias) {
+    uint32_t n = ((uint32_t)t + (hbias << 16)) >> 16;
+    uint32_t q = umulhi32(n, hmagic);
+    return n - q * h;
+}
+
+// sky: column from yaw + screen x (one texture width per NDC unit, 8 widths per turn); row mirrored
+// below the horizon.
+B2D_HD uint32_t sky_u32(int x, const View &vw, uint32_t angle) {
+    uint64_t num = ((uint64_t)(2 * x + 1)) << 32;
+    return (uint32_t)(num / (uint32_t)vw.W) - (angle << 3);
+}
+B2D_HD int32_t sky_row(int y, int32_t H, int32_t skyh) {
+    int32_t r = 2 * y + 1;
+    if (r < H) return (r * skyh) / H;
+    return floormod32(((2 * H - r) * skyh) / H, skyh);
+}
+
+// Conservative screen-column range of an axis-aligned map box (top, bottom, left, right).
+// false => nothing inside the box can be visible.  Boxes that come within 32 map units of the
+// camera plane are treated as covering the whole screen.
+constexpr int32_t kBoxNearQ8 = 32 * 256;
+B2D_HD bool box_range(const FrameConst &f, const View &vw, const int32_t box[4], int &lo, int &hi) {
+    bool all_behind = true, any_near = false;
+    int64_t mn = 0x7FFFFFFFFFFFFFFFLL, mx = -0x7FFFFFFFFFFFFFFFLL;
+    for (int i = 0; i < 4; i++) {
+        int32_t tx, tz;
+        to_view(f, box[2 + (i & 1)], box[i >> 1], tx, tz);
+        if (tz >= -256) all_behind = false;
+        if (tz < kBoxNearQ8) { any_near = true; continue; }
+        int64_t c = floordiv64((int64_t)tx * vw.F, tz);
+        int64_t xc = floordiv64(c - 1 + vw.W, 2);
+        if (xc < mn) mn = xc;
+        if (xc > mx) mx = xc;
+    }
+    if (all_behind) return false;
+    if (any_near) { lo = 0; hi = vw.W - 1; return true; }
+    mn -= 2; mx += 2;
+    if (mx < 0 || mn > vw.W - 1) return false;
+    lo = (int)(mn < 0 ? 0 : mn);
+    hi = (int)(mx > vw.W - 1 ? vw.W - 1 : mx);
+    return true;
+}
+
+}  // namespace b2d

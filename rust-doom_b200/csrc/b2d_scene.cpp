@@ -1,0 +1,345 @@
+// See b2d_scene.hpp for the reference citations.
+#include "b2d_scene.hpp"
+
+#include <cmath>
+#include <cstring>
+
+namespace b2d {
+
+namespace {
+
+// ---- sky table (assets/meta/doom.toml:29-68): first match wins, fallback = first entry ----------
+bool match_episode(const std::string &s, char episode) {       // unanchored "E<d>M."
+    for (size_t i = 0; i + 3 < s.size(); i++)
+        if (s[i] == 'E' && s[i + 1] == episode && s[i + 2] == 'M') return true;
+    return false;
+}
+
+int map_number(const std::string &s, size_t at) {               // two digits after "MAP", else -1
+    if (at + 5 > s.size()) return -1;
+    char a = s[at + 3], b = s[at + 4];
+    if (a < '0' || a > '9' || b < '0' || b > '9') return -1;
+    return (a - '0') * 10 + (b - '0');
+}
+
+Name sky_for(const Name &level_name) {
+    std::string s = name_str(level_name);
+    for (char e = '1'; e <= '4'; e++)
+        if (match_episode(s, e)) return make_name((std::string("SKY") + e).c_str());
+    auto any_map = [&](auto pred) {
+        for (size_t i = 0; i + 5 <= s.size(); i++)
+            if (s.compare(i, 3, "MAP") == 0) {
+                int n = map_number(s, i);
+                if (n >= 0 && pred(n)) return true;
+            }
+        return false;
+    };
+    if (any_map([](int n) { return n >= 1 && n <= 11; })) return make_name("SKY1");
+    if (any_map([](int n) { return n >= 12 && n <= 20; })) return make_name("SKY2");
+    if (any_map([](int n) { return (n >= 21 && n <= 29) || n == 32; })) return make_name("SKY3");
+    return make_name("SKY1");
+}
+
+int32_t floormod(int32_t a, int32_t b) {
+    int32_t r = a % b;
+    return r < 0 ? r + b : r;
+}
+
+uint64_t isqrt64(uint64_t v) {
+    if (v == 0) return 0;
+    uint64_t r = (uint64_t)std::sqrt((double)v);
+    while (r * r > v) r--;
+    while ((r + 1) * (r + 1) <= v) r++;
+    return r;
+}
+
+struct BlobWriter {
+    std::vector<uint8_t> bytes;
+    BlobWriter() : bytes(128, 0) {}
+    uint32_t append(const void *p, size_t n) {
+        uint32_t off = (uint32_t)bytes.size();
+        const uint8_t *b = static_cast<const uint8_t *>(p);
+        bytes.insert(bytes.end(), b, b + n);
+        while (bytes.size() % 16) bytes.push_back(0);
+        return off;
+    }
+};
+
+}  // namespace
+
+uint8_t light_byte(int16_t light, int contrast) {
+    volatile float level = (float)(int16_t)(light >> 3) / 31.0f;          // light.rs:113-115
+    if (contrast) {
+        volatile float c = contrast > 0 ? 2.0f / 31.0f : -2.0f / 31.0f;    // light.rs:82-91
+        level = level + c;
+        if (level > 1.0f) level = 1.0f; else if (level < 0.0f) level = 0.0f;
+    }
+    if (level > 1.0f) level = 1.0f; else if (level < 0.0f) level = 0.0f;   // lights.rs:26-29
+    volatile float scaled = level * 255.0f;
+    return (uint8_t)(int)scaled;
+}
+
+int sector_at(const Level &lv, double x, double y) {
+    if (lv.nodes.empty()) return -1;
+    unsigned child = (unsigned)lv.nodes.size() - 1;
+    bool leaf = false;
+    for (int guard = 0; guard < 4096 && !leaf; guard++) {
+        const Node &n = lv.nodes[child];
+        double sd = (y - (double)n.y) * (double)n.dx - (x - (double)n.x) * (double)n.dy;
+        unsigned next = sd > 0.0 ? n.left : n.right;
+        child = next & 0x7FFFu;
+        leaf = (next & 0x8000u) != 0;
+        if (!leaf && child >= lv.nodes.size()) return -1;
+    }
+    if (!leaf || child >= lv.subsectors.size()) return -1;
+    const Subsector &ss = lv.subsectors[child];
+    if (ss.num_segs == 0 || (size_t)ss.first_seg + ss.num_segs > lv.segs.size()) return -1;
+    int side = lv.seg_sidedef(lv.segs[ss.first_seg]);
+    if (side < 0) return -1;
+    int sector = lv.sidedefs[(size_t)side].sector;
+    if (sector >= (int)lv.sectors.size()) return -1;
+    for (unsigned i = 0; i < ss.num_segs; i++) {
+        const Seg &s = lv.segs[(size_t)ss.first_seg + i];
+        if (s.v1 >= lv.vertices.size() || s.v2 >= lv.vertices.size()) continue;
+        const Vertex &a = lv.vertices[s.v1], &b = lv.vertices[s.v2];
+        double dx = (double)b.x - (double)a.x, dy = (double)b.y - (double)a.y;
+        double len = std::hypot(dx, dy);
+        if (len < 1e-14) continue;
+        double sd = ((y - (double)a.y) * dx - (x - (double)a.x) * dy) / len;
+        if (sd > 10.0) return -1;           // SEG_TOLERANCE 0.1 world units (visitor.rs:1159)
+    }
+    return sector;
+}
+
+std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &td, int level_index) {
+    const Level lv = Level::load(wad, level_index);
+    const int nverts = (int)lv.vertices.size(), nsegs = (int)lv.segs.size();
+    const int nsect = (int)lv.sectors.size(), nss = (int)lv.subsectors.size(), nnodes = (int)lv.nodes.size();
+
+    // ids are handed out in first-use order: sky, then segs (A before B), flats by sector order
+    std::unordered_map<Name, int, NameHash> tex_ids, flat_ids;
+    std::vector<const Image *> tex_list;
+    std::vector<const uint8_t *> flat_list;
+    auto tex_id = [&](const Name &n) -> int32_t {
+        if (is_untextured(n)) return kTexNone;
+        auto it = tex_ids.find(n);
+        if (it != tex_ids.end()) return it->second;
+        const Image *img = td.texture(n);
+        if (!img || img->w == 0 || img->h == 0) return kTexNone;       // visitor.rs:857-860
+        int id = (int)tex_list.size();
+        tex_ids[n] = id;
+        tex_list.push_back(img);
+        return id;
+    };
+    auto flat_id = [&](const Name &n) -> int32_t {
+        if (is_sky_flat(n)) return kFlatSky;
+        auto it = flat_ids.find(n);
+        if (it != flat_ids.end()) return it->second;
+        const uint8_t *p = td.flat(n);
+        if (!p) return kFlatMissing;
+        int id = (int)flat_list.size();
+        flat_ids[n] = id;
+        flat_list.push_back(p);
+        return id;
+    };
+
+    const int32_t sky_tex = tex_id(sky_for(lv.name));
+
+    static const int kEffectTypes[] = {1, 2, 4, 13, 3, 12, 8, 17};    // light.rs:127-134
+    std::vector<SectorRec> sectors((size_t)nsect);
+    std::vector<char> has_effect((size_t)nsect, 0);
+    int32_t min_h = 32767, max_h = -32768;
+    for (int i = 0; i < nsect; i++) {
+        const Sector &s = lv.sectors[(size_t)i];
+        bool eff = false;
+        for (int t : kEffectTypes)
+            if (s.type == t) eff = (lv.sector_min_light(i) >> 3) != (s.light >> 3);
+        has_effect[(size_t)i] = eff;
+        SectorRec r{};
+        r.floor = s.floor; r.ceil = s.ceil;
+        r.floor_flat = flat_id(s.floor_tex);
+        r.ceil_flat = flat_id(s.ceil_tex);
+        r.light = light_byte(s.light, 0);
+        sectors[(size_t)i] = r;
+        if (s.floor < min_h) min_h = s.floor;
+        if (s.ceil > max_h) max_h = s.ceil;
+    }
+    if (nsect == 0) { min_h = 0; max_h = 0; }
+    min_h -= 512; max_h += 512;                                         // visitor.rs:1173-1182
+
+    // subsector sector = front sector of its first seg (visitor.rs:636-643); that sector is the
+    // `sector` every seg of the subsector is emitted with (visitor.rs:666).
+    std::vector<SSectorRec> ssectors((size_t)nss);
+    std::vector<int> seg_front((size_t)nsegs, -1);
+    for (int i = 0; i < nss; i++) {
+        const Subsector &ss = lv.subsectors[(size_t)i];
+        SSectorRec r{};
+        r.sector = -1;
+        if (ss.num_segs > 0 && (int)ss.first_seg + (int)ss.num_segs <= nsegs) {
+            r.first_seg = ss.first_seg; r.num_segs = ss.num_segs;
+            int side = lv.seg_sidedef(lv.segs[ss.first_seg]);
+            if (side >= 0 && lv.sidedefs[(size_t)side].sector < nsect) r.sector = lv.sidedefs[(size_t)side].sector;
+            for (int k = 0; k < ss.num_segs; k++) seg_front[(size_t)ss.first_seg + (size_t)k] = r.sector;
+        }
+        ssectors[(size_t)i] = r;
+    }
+
+    std::vector<SegRec> segs((size_t)nsegs);
+    for (int i = 0; i < nsegs; i++) {
+        const Seg &sg = lv.segs[(size_t)i];
+        SegRec r{};
+        r.flags = kSegInvalid; r.texA = r.texB = kTexNone; r.back = -1;
+        bool ok = sg.v1 < nverts && sg.v2 < nverts && sg.linedef < lv.linedefs.size();
+        int side = ok ? lv.seg_sidedef(sg) : -1;
+        int front = seg_front[(size_t)i];
+        if (front < 0 && side >= 0 && lv.sidedefs[(size_t)side].sector < nsect)
+            front = lv.sidedefs[(size_t)side].sector;
+        if (!ok || side < 0 || front < 0) { segs[(size_t)i] = r; continue; }
+        const Linedef &line = lv.linedefs[sg.linedef];
+        const Sidedef &sd = lv.sidedefs[(size_t)side];
+        const Sector &fs = lv.sectors[(size_t)front];
+        const int32_t ff = fs.floor, fc = fs.ceil;
+        const Vertex &a = lv.vertices[sg.v1], &b = lv.vertices[sg.v2];
+        const int64_t dx = (int64_t)b.x - a.x, dy = (int64_t)b.y - a.y;
+        const bool unpeg_upper = line.flags & 0x0008, unpeg_lower = line.flags & 0x0010;
+        // world X = -wad_y/100, world Z = -wad_x/100: "v1[0]==v2[0]" <=> dy==0 => Brighten,
+        // "v1[1]==v2[1]" <=> dx==0 => Darken (visitor.rs:887-901)
+        int contrast = 0;
+        if (!has_effect[(size_t)front]) contrast = dy == 0 ? 1 : (dx == 0 ? -1 : 0);
+        int back = -1;
+        int bside = lv.seg_back_sidedef(sg);
+        if (bside >= 0 && lv.sidedefs[(size_t)bside].sector < nsect) back = lv.sidedefs[(size_t)bside].sector;
+
+        // texture row at the piece's top edge, reduced modulo the texture height
+        auto piece = [&](const Name &nm, int32_t &tex_out, int32_t &t_out, auto top_row) {
+            tex_out = tex_id(nm);
+            t_out = 0;
+            if (tex_out < 0) return;
+            int32_t th = tex_list[(size_t)tex_out]->h;
+            t_out = floormod(top_row(th) + sd.yoff, th);
+        };
+
+        r.v1 = sg.v1; r.v2 = sg.v2; r.front = front; r.back = back;
+        r.uoff = (int32_t)sg.offset + sd.xoff;                                   // visitor.rs:904
+        r.len_q12 = (int32_t)isqrt64((uint64_t)(dx * dx + dy * dy) << 24);       // visitor.rs:905
+        r.light = light_byte(fs.light, contrast);
+        if (back < 0) {
+            // one-sided: full-height middle (visitor.rs:733-749); Peg::Bottom -> texture bottom at
+            // the floor, Peg::Top -> texture top at the ceiling (visitor.rs:909-912)
+            r.flags = 0;
+            if (unpeg_lower) piece(sd.middle, r.texA, r.tA, [&](int32_t th) { return th - (fc - ff); });
+            else piece(sd.middle, r.texA, r.tA, [&](int32_t) { return 0; });
+            r.hA = fc;
+            r.otop = fc; r.obot = ff;
+        } else {
+            const Sector &bs = lv.sectors[(size_t)back];
+            const int32_t bf = bs.floor, bc = bs.ceil;
+            r.flags = kSegTwoSided;
+            r.otop = fc;
+            if (bc < fc && !is_sky_flat(bs.ceil_tex)) {                          // visitor.rs:791-807
+                r.otop = bc;
+                if (unpeg_upper) piece(sd.upper, r.texA, r.tA, [&](int32_t) { return 0; });
+                else piece(sd.upper, r.texA, r.tA, [&](int32_t th) { return th - (fc - bc); });
+            }
+            r.hA = fc;
+            r.obot = ff;
+            if (bf > ff) {                                                       // visitor.rs:772-790
+                r.obot = bf;
+                if (unpeg_lower)
+                    piece(sd.lower, r.texB, r.tB, [&](int32_t th) { return th - (bf - ff) + (fc - ff); });
+                else piece(sd.lower, r.texB, r.tB, [&](int32_t) { return 0; });
+            }
+            r.hB = r.obot;
+        }
+        segs[(size_t)i] = r;
+    }
+
+    std::vector<NodeRec> nodes((size_t)nnodes);
+    auto child = [](uint16_t c) -> uint32_t { return (c & 0x8000u) ? ((c & 0x7FFFu) | kLeaf) : (c & 0x7FFFu); };
+    auto fix_box = [](const int16_t in[4], int32_t out[4]) {   // disk order: top, bottom, left, right
+        out[0] = in[0] > in[1] ? in[0] : in[1];
+        out[1] = in[0] > in[1] ? in[1] : in[0];
+        out[2] = in[2] < in[3] ? in[2] : in[3];
+        out[3] = in[2] < in[3] ? in[3] : in[2];
+    };
+    for (int i = 0; i < nnodes; i++) {
+        const Node &n = lv.nodes[(size_t)i];
+        NodeRec r{};
+        r.x = n.x; r.y = n.y; r.dx = n.dx; r.dy = n.dy;
+        fix_box(n.rbox, r.rbox);
+        fix_box(n.lbox, r.lbox);
+        r.child[0] = child(n.right);
+        r.child[1] = child(n.left);
+        nodes[(size_t)i] = r;
+    }
+
+    std::vector<int32_t> verts((size_t)nverts * 2);
+    for (int i = 0; i < nverts; i++) { verts[2 * (size_t)i] = lv.vertices[(size_t)i].x; verts[2 * (size_t)i + 1] = lv.vertices[(size_t)i].y; }
+
+    // textures: u8 row-major, transparent texels (high byte set) become 0
+    std::vector<TexRec> texrec(tex_list.size());
+    std::vector<uint8_t> texels;
+    for (size_t i = 0; i < tex_list.size(); i++) {
+        const Image &im = *tex_list[i];
+        TexRec t{};
+        t.texel_off = (uint32_t)texels.size();
+        t.w = (uint32_t)im.w; t.h = (uint32_t)im.h;
+        t.hmagic = (uint32_t)((((uint64_t)1 << 32) / (uint64_t)im.h + 1) & 0xFFFFFFFFu);
+        t.hbias = (uint32_t)im.h * (uint32_t)((16384 + im.h - 1) / im.h);
+        texrec[i] = t;
+        for (uint16_t v : im.px) texels.push_back((v >> 8) ? 0 : (uint8_t)(v & 0xFF));
+        while (texels.size() % 16) texels.push_back(0);
+    }
+    std::vector<uint8_t> flats(flat_list.size() * 4096);
+    for (size_t i = 0; i < flat_list.size(); i++) std::memcpy(&flats[i * 4096], flat_list[i], 4096);
+    std::vector<uint8_t> colormap(34 * 256, 0);
+    for (size_t k = 0; k < td.colormaps.size() && k < 34; k++) std::memcpy(&colormap[k * 256], td.colormaps[k].data(), 256);
+    std::vector<uint32_t> palette(256, 0xFF000000u);
+    if (!td.palettes.empty())
+        for (int i = 0; i < 256; i++) {
+            const uint8_t *c = &td.palettes[0][(size_t)i * 3];
+            palette[(size_t)i] = (uint32_t)c[0] | ((uint32_t)c[1] << 8) | ((uint32_t)c[2] << 16) | 0xFF000000u;
+        }
+
+    // player-1 start (visitor.rs:1010-1026; game/src/level.rs:757-762; player.rs:88 camera_height)
+    int32_t has_start = 0, sx = 0, sy = 0, sz = 0, sang = 0;
+    for (const Thing &t : lv.things) {
+        if (t.type != 1) continue;
+        int sec = sector_at(lv, (double)t.x, (double)t.y);
+        if (sec < 0) continue;
+        float yaw = std::round((float)t.angle / 45.0f) * 45.0f;
+        has_start = 1;
+        sx = t.x - 32; sy = t.y;
+        sz = lv.sectors[(size_t)sec].floor + 50 + 12;
+        sang = (((int)yaw % 360) + 360) % 360;
+        break;
+    }
+
+    BlobWriter w;
+    uint32_t hdr[H_COUNT] = {0};
+    hdr[H_MAGIC] = kSceneMagic; hdr[H_VERSION] = kSceneVersion;
+    hdr[H_NVERTS] = (uint32_t)nverts; hdr[H_NNODES] = (uint32_t)nnodes; hdr[H_NSSECTORS] = (uint32_t)nss;
+    hdr[H_NSEGS] = (uint32_t)nsegs; hdr[H_NSECTORS] = (uint32_t)nsect;
+    hdr[H_NTEX] = (uint32_t)tex_list.size(); hdr[H_NFLATS] = (uint32_t)flat_list.size();
+    hdr[H_OFF_VERTS] = w.append(verts.data(), verts.size() * 4);
+    hdr[H_OFF_NODES] = w.append(nodes.data(), nodes.size() * sizeof(NodeRec));
+    hdr[H_OFF_SSECTORS] = w.append(ssectors.data(), ssectors.size() * sizeof(SSectorRec));
+    hdr[H_OFF_SEGS] = w.append(segs.data(), segs.size() * sizeof(SegRec));
+    hdr[H_OFF_SECTORS] = w.append(sectors.data(), sectors.size() * sizeof(SectorRec));
+    hdr[H_OFF_TEX] = w.append(texrec.data(), texrec.size() * sizeof(TexRec));
+    hdr[H_OFF_TEXELS] = w.append(texels.data(), texels.size());
+    hdr[H_TEXEL_BYTES] = (uint32_t)texels.size();
+    hdr[H_OFF_FLATS] = w.append(flats.data(), flats.size());
+    hdr[H_OFF_COLORMAP] = w.append(colormap.data(), colormap.size());
+    hdr[H_OFF_PALETTE] = w.append(palette.data(), palette.size() * 4);
+    hdr[H_TOTAL] = (uint32_t)w.bytes.size();
+    hdr[H_ROOT] = nnodes > 0 ? (uint32_t)(nnodes - 1) : kLeaf;
+    hdr[H_SKY_TEX] = (uint32_t)sky_tex;
+    hdr[H_START_X] = (uint32_t)sx; hdr[H_START_Y] = (uint32_t)sy; hdr[H_START_Z] = (uint32_t)sz;
+    hdr[H_START_ANGLE] = (uint32_t)sang; hdr[H_HAS_START] = (uint32_t)has_start;
+    hdr[H_MIN_H] = (uint32_t)min_h; hdr[H_MAX_H] = (uint32_t)max_h;
+    std::memcpy(w.bytes.data(), hdr, sizeof hdr);
+    return std::move(w.bytes);
+}
+
+}  // namespace b2d

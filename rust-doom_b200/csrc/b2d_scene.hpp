@@ -1,0 +1,56 @@
+// Scene compiler: raw level lumps + texture directory -> one flat "B2DS" blob that is uploaded to
+// HBM as-is and indexed by the kernels (layout: DESIGN.md "Scene blob"; records below).
+//
+// What is pre-resolved here is the reference's geometry emitter, per seg instead of per triangle:
+//   which wall pieces a seg has, their texture, pegging anchor and offsets   wad/src/visitor.rs:711-937
+//   fake contrast and the static light byte   visitor.rs:887-901, wad/src/light.rs:27-115,
+//                                              game/src/lights.rs:14-30
+//   flats / sky flats per sector               visitor.rs:939-985
+//   sky texture of the level                   wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
+//   player-1 start                             visitor.rs:1010-1060, game/src/level.rs:757-762
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "b2d_wad.hpp"
+
+namespace b2d {
+
+constexpr uint32_t kSceneMagic = 0x53443242u;   // "B2DS"
+constexpr uint32_t kSceneVersion = 1;
+constexpr uint32_t kLeaf = 0x80000000u;
+
+enum HeaderField : int {
+    H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
+    H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
+    H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
+    H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_COUNT = 32
+};
+
+// 64-byte records; all int32.
+struct NodeRec { int32_t x, y, dx, dy, rbox[4], lbox[4]; uint32_t child[2]; int32_t pad[2]; };  // child[0]=right
+struct SSectorRec { int32_t first_seg, num_segs, sector, pad; };
+struct SegRec {
+    int32_t v1, v2, front, flags;
+    int32_t uoff, len_q12;
+    int32_t texA, tA, hA;      // upper (two-sided) or full-height middle (one-sided)
+    int32_t texB, tB, hB;      // lower
+    int32_t light, otop, obot, back;
+};
+struct SectorRec { int32_t floor, ceil, floor_flat, ceil_flat, light, pad[3]; };
+struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, pad[3]; };
+static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec) == 32 &&
+              sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16, "record layout");
+
+constexpr int32_t kSegTwoSided = 1, kSegInvalid = 0x80;
+constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
+
+std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &tex, int level_index);
+
+// LevelWalker::sector_at on the raw level (visitor.rs:1028-1060); -1 if outside.
+int sector_at(const Level &level, double x, double y);
+
+// (light >> 3)/31 (+-2/31, clamped) * 255 truncated to u8, in the reference's float32 arithmetic.
+uint8_t light_byte(int16_t light, int contrast);
+
+}  // namespace b2d

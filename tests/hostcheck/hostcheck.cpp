@@ -1,0 +1,250 @@
+// TEST-ONLY: runs the product's pixel-contract arithmetic (rust-doom_b200/csrc/b2d_math.cuh) and the
+// exact algorithms of the CUDA kernels on the CPU, one lane at a time, so that the maths can be
+// checked against the oracle without a GPU.  This file is compiled into tests/hostcheck/
+// libb2d_hostcheck.so by tests/conftest.py; it is NOT part of libb2d.so and no product code calls it.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../rust-doom_b200/csrc/b2d_math.cuh"
+#include "../../rust-doom_b200/csrc/b2d_scene.hpp"
+
+using namespace b2d;
+
+namespace {
+
+struct HostScene {
+    const uint32_t *hdr;
+    const int32_t *verts;
+    const NodeRec *nodes;
+    const SSectorRec *ssectors;
+    const SegRec *segs;
+    const SectorRec *sectors;
+    const TexRec *tex;
+    const uint8_t *texels, *flats, *colormap;
+    int nverts, nnodes, nss, nsegs, ntex, nflats, sky_tex;
+    uint32_t root;
+};
+
+HostScene bind(const uint8_t *blob) {
+    HostScene s;
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    s.hdr = h;
+    s.verts = reinterpret_cast<const int32_t *>(blob + h[H_OFF_VERTS]);
+    s.nodes = reinterpret_cast<const NodeRec *>(blob + h[H_OFF_NODES]);
+    s.ssectors = reinterpret_cast<const SSectorRec *>(blob + h[H_OFF_SSECTORS]);
+    s.segs = reinterpret_cast<const SegRec *>(blob + h[H_OFF_SEGS]);
+    s.sectors = reinterpret_cast<const SectorRec *>(blob + h[H_OFF_SECTORS]);
+    s.tex = reinterpret_cast<const TexRec *>(blob + h[H_OFF_TEX]);
+    s.texels = blob + h[H_OFF_TEXELS];
+    s.flats = blob + h[H_OFF_FLATS];
+    s.colormap = blob + h[H_OFF_COLORMAP];
+    s.nverts = (int)h[H_NVERTS]; s.nnodes = (int)h[H_NNODES]; s.nss = (int)h[H_NSSECTORS];
+    s.nsegs = (int)h[H_NSEGS]; s.ntex = (int)h[H_NTEX]; s.nflats = (int)h[H_NFLATS];
+    s.sky_tex = (int32_t)h[H_SKY_TEX];
+    s.root = h[H_ROOT];
+    return s;
+}
+
+struct Range { int lo = 0, hi = -1; bool vis = false, solid = false; };
+
+// mirrors b2d_walk_kernel
+void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc, std::vector<SegFrame> &out) {
+    frame_setup(pose, fc);
+    std::vector<int32_t> tx((size_t)sc.nverts), tz((size_t)sc.nverts);
+    for (int i = 0; i < sc.nverts; i++) to_view(fc, sc.verts[2 * i], sc.verts[2 * i + 1], tx[(size_t)i], tz[(size_t)i]);
+    std::vector<Range> segr((size_t)sc.nsegs), boxr((size_t)sc.nnodes * 2);
+    for (int i = 0; i < sc.nsegs; i++) {
+        const SegRec &S = sc.segs[i];
+        if (S.flags & kSegInvalid) continue;
+        SegFrame sf;
+        if (seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf)) {
+            Range &r = segr[(size_t)i];
+            r.vis = true; r.lo = sf.xlo; r.hi = sf.xhi;
+            r.solid = (!(S.flags & kSegTwoSided) || S.otop <= S.obot) && (sf.flags & kSegFrameNoSkip);
+        }
+    }
+    for (int i = 0; i < 2 * sc.nnodes; i++) {
+        const NodeRec &N = sc.nodes[i >> 1];
+        const int32_t *box = (i & 1) ? N.lbox : N.rbox;
+        int lo, hi;
+        Range &r = boxr[(size_t)i];
+        r.vis = box_range(fc, vw, box, lo, hi);
+        if (r.vis) { r.lo = lo; r.hi = hi; }
+    }
+    std::vector<char> solid((size_t)vw.W, 0);
+    auto range_open = [&](int lo, int hi) {
+        for (int x = lo; x <= hi; x++) if (!solid[(size_t)x]) return true;
+        return false;
+    };
+    std::vector<uint32_t> stack;
+    stack.push_back(sc.root);
+    std::vector<int> list;
+    int status = 0;
+    while (!stack.empty()) {
+        uint32_t child = stack.back();
+        stack.pop_back();
+        if (child & kLeaf) {
+            uint32_t id = child & 0x7FFFFFFFu;
+            if (id >= (uint32_t)sc.nss) continue;
+            const SSectorRec &ss = sc.ssectors[id];
+            if (ss.sector < 0) continue;
+            for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {
+                std::vector<int> emitted;
+                for (int lane = 0; lane < 32 && k0 + lane < ss.num_segs; lane++) {
+                    int si = ss.first_seg + k0 + lane;
+                    const Range &r = segr[(size_t)si];
+                    if (r.vis && range_open(r.lo, r.hi)) { list.push_back(si); emitted.push_back(si); }
+                }
+                for (int si : emitted) {
+                    const Range &r = segr[(size_t)si];
+                    if (r.solid) for (int x = r.lo; x <= r.hi; x++) solid[(size_t)x] = 1;
+                }
+            }
+            if (!range_open(0, vw.W - 1)) break;
+        } else {
+            if (child >= (uint32_t)sc.nnodes) continue;
+            const NodeRec &N = sc.nodes[child];
+            int side = node_side(fc.pose, N.x, N.y, N.dx, N.dy);
+            const Range &rn = boxr[2 * (size_t)child + (size_t)side], &rf = boxr[2 * (size_t)child + (size_t)(side ^ 1)];
+            bool far_vis = rf.vis && range_open(rf.lo, rf.hi);
+            bool near_vis = rn.vis && range_open(rn.lo, rn.hi);
+            if (stack.size() + (far_vis ? 1 : 0) + (near_vis ? 1 : 0) > 128) { status = 1; break; }
+            if (far_vis) stack.push_back(N.child[side ^ 1]);
+            if (near_vis) stack.push_back(N.child[side]);
+        }
+    }
+    out.clear();
+    for (int si : list) {
+        const SegRec &S = sc.segs[si];
+        SegFrame sf;
+        seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf);
+        sf.seg = si;
+        out.push_back(sf);
+    }
+    fc.count = (int)out.size();
+    fc.status = status;
+}
+
+struct Lane { int ct, cb; uint32_t skycol; };
+
+// mirrors b2d_raster_kernel, lanes executed one after the other
+void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std::vector<SegFrame> &wl,
+            const std::vector<uint32_t> &yslope, uint32_t invF, uint8_t *fb) {
+    const int W = vw.W, H = vw.H;
+    auto put = [&](int x, int y, uint8_t v) { fb[(size_t)y * W + x] = v; };
+    auto fill_void = [&](int x, int ya, int yb) { for (int y = ya; y < yb; y++) put(x, y, 0); };
+    auto draw_sky = [&](int x, const Lane &ln, int ya, int yb) {
+        if (sc.sky_tex < 0) { fill_void(x, ya, yb); return; }
+        const TexRec &T = sc.tex[sc.sky_tex];
+        const uint8_t *px = sc.texels + T.texel_off;
+        for (int y = ya; y < yb; y++) {
+            int v = sky_row(y, H, (int32_t)T.h);
+            put(x, y, sc.colormap[px[(uint32_t)v * T.w + ln.skycol]]);
+        }
+    };
+    auto draw_plane = [&](int x, const Lane &ln, int ya, int yb, int32_t h, int32_t flat, int lightb, bool visible) {
+        if (ya >= yb) return;
+        if (!visible) { fill_void(x, ya, yb); return; }
+        if (flat == kFlatSky) { draw_sky(x, ln, ya, yb); return; }
+        if (flat < 0 || flat >= sc.nflats) { fill_void(x, ya, yb); return; }
+        const uint8_t *px = sc.flats + 4096u * (uint32_t)flat;
+        uint32_t habs = plane_habs(h, fc.pose.z);
+        for (int y = ya; y < yb; y++) {
+            PlaneRow pr = plane_row(habs, yslope[(size_t)y], fc, vw, invF);
+            const uint8_t *cm = sc.colormap + 256 * light_row(lightb, pr.z8);
+            uint32_t U = pr.baseU + (uint32_t)x * pr.stepU, V = pr.baseV + (uint32_t)x * pr.stepV;
+            put(x, y, cm[px[flat_index(U, V)]]);
+        }
+    };
+    auto draw_wall = [&](int x, int ya, int yb, int32_t tex, int32_t tA, int32_t hA, int32_t ucol, int32_t iscale, int row) {
+        if (ya >= yb) return;
+        if (tex < 0 || tex >= sc.ntex) { fill_void(x, ya, yb); return; }
+        const TexRec &T = sc.tex[tex];
+        const uint8_t *px = sc.texels + T.texel_off;
+        int32_t col = floormod32(ucol, (int32_t)T.w);
+        int32_t tbase = wall_tbase(tA, hA, fc.pose.z, H, iscale), tstep = iscale >> 4;
+        const uint8_t *cm = sc.colormap + 256 * row;
+        for (int y = ya; y < yb; y++) {
+            int32_t t = tbase + y * tstep;
+            uint32_t v = wall_row(t, T.h, T.hmagic, T.hbias);
+            put(x, y, cm[px[v * T.w + (uint32_t)col]]);
+        }
+    };
+
+    const int strips = (W + 31) / 32;
+    for (int strip = 0; strip < strips; strip++) {
+        const int x0 = strip * 32;
+        Lane lanes[32];
+        for (int l = 0; l < 32; l++) {
+            int x = x0 + l;
+            lanes[l].ct = 0; lanes[l].cb = x < W ? H : 0; lanes[l].skycol = 0;
+            if (sc.sky_tex >= 0 && x < W) lanes[l].skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
+        }
+        for (size_t k = 0; k < wl.size(); k++) {
+            const SegFrame &sf = wl[k];
+            if (!(sf.xhi >= x0 && sf.xlo <= x0 + 31)) continue;
+            bool any_open = false;
+            for (int l = 0; l < 32; l++) any_open |= lanes[l].ct < lanes[l].cb;
+            if (!any_open) break;
+            const SegRec &S = sc.segs[sf.seg];
+            const SectorRec &SF = sc.sectors[S.front];
+            const int32_t fcl = SF.ceil, ffl = SF.floor;
+            const bool two = S.flags & kSegTwoSided;
+            const bool ceil_vis = ((int64_t)fcl << 16) > fc.pose.z || SF.ceil_flat == kFlatSky;
+            const bool floor_vis = ((int64_t)ffl << 16) < fc.pose.z || SF.floor_flat == kFlatSky;
+            for (int l = 0; l < 32; l++) {
+                int x = x0 + l;
+                Lane &ln = lanes[l];
+                if (!(x < W && ln.ct < ln.cb && x >= sf.xlo && x <= sf.xhi)) continue;
+                ColumnEval ce;
+                if (!column_eval(sf, vw, x, ce)) continue;
+                int ct = ln.ct, cb = ln.cb;
+                int row = light_row(S.light, ce.z8);
+                int32_t ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+                int yfc = yrow(fcl, ce.scale, fc.pose.z, H), yff = yrow(ffl, ce.scale, fc.pose.z, H);
+                int y1 = clampv(yfc, ct, cb), y2, y3, y4;
+                if (!two) { y2 = clampv(yff, y1, cb); y3 = y2; y4 = y2; }
+                else {
+                    int yot = yrow(S.otop, ce.scale, fc.pose.z, H), yob = yrow(S.obot, ce.scale, fc.pose.z, H);
+                    y2 = clampv(yot, y1, cb); y3 = clampv(yob, y2, cb); y4 = clampv(yff, y3, cb);
+                }
+                draw_plane(x, ln, ct, y1, fcl, SF.ceil_flat, SF.light, ceil_vis);
+                if (!two) draw_wall(x, y1, y2, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                else {
+                    if (S.otop < fcl) draw_wall(x, y1, y2, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                    if (S.obot > ffl) draw_wall(x, y3, y4, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
+                }
+                draw_plane(x, ln, y4, cb, ffl, SF.floor_flat, SF.light, floor_vis);
+                if (!two || y2 >= y3) { ln.ct = H; ln.cb = 0; }
+                else { ln.ct = y2; ln.cb = y3; }
+            }
+        }
+        for (int l = 0; l < 32; l++)
+            if (x0 + l < W) fill_void(x0 + l, lanes[l].ct, lanes[l].cb);
+    }
+}
+
+}  // namespace
+
+extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
+                                int32_t *counts, int32_t *seg_ids, int stride) {
+    HostScene sc = bind(blob);
+    std::vector<uint32_t> yslope((size_t)vw->H);
+    for (int y = 0; y < vw->H; y++) yslope[(size_t)y] = yslope_entry(y, *vw);
+    uint32_t invF = (uint32_t)(4294967296ULL / (uint64_t)vw->F);
+    const size_t npix = (size_t)vw->W * vw->H;
+    for (int i = 0; i < n; i++) {
+        FrameConst fc;
+        std::vector<SegFrame> wl;
+        walk(sc, *vw, poses[i], fc, wl);
+        // poison the frame first: the raster must overwrite every pixel exactly like the GPU does
+        std::memset(fb + npix * (size_t)i, 0xAB, npix);
+        raster(sc, *vw, fc, wl, yslope, invF, fb + npix * (size_t)i);
+        if (counts) counts[i] = fc.status ? -fc.status : fc.count;
+        if (seg_ids) for (int k = 0; k < fc.count && k < stride; k++) seg_ids[(size_t)i * stride + k] = wl[(size_t)k].seg;
+    }
+    return 0;
+}
+
+extern "C" void hostcheck_sincos(uint32_t angle, int32_t *c, int32_t *s) { sincos_q30(angle, *c, *s); }
