@@ -117,6 +117,12 @@ int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_
  * batch to the host.  counts_out[n], and for frame i seg ids seg_ids_out[i*stride .. +counts[i]). */
 int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *seg_ids_out, size_t stride);
 
+/* Per-kernel device timing for the roofline report: while enabled, every batch records CUDA events
+ * around the walk and raster launches on the launching stream.  b2d_profile_read synchronises the
+ * device, returns the summed milliseconds and batch count since the last read, and resets them. */
+int b2d_profile_enable(b2d_renderer *r, int enable);
+int b2d_profile_read(b2d_renderer *r, double *walk_ms, double *raster_ms, int64_t *batches);
+
 /* Number of kernel launches issued by this renderer so far (bench.py's gpu_launches). */
 int64_t b2d_launch_count(const b2d_renderer *r);
 

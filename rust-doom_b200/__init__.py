@@ -190,6 +190,15 @@ class Renderer:
         _check(_lib.load().b2d_debug_worklist(self._h, n, counts.ctypes.data, ids.ctypes.data, ids.shape[1]))
         return counts, ids
 
+    def profile(self, enable: bool):
+        _check(_lib.load().b2d_profile_enable(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """(walk_ms, raster_ms, batches) summed since the last read; synchronises the device."""
+        w, r, b = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        _check(_lib.load().b2d_profile_read(self._h, ctypes.byref(w), ctypes.byref(r), ctypes.byref(b)))
+        return w.value, r.value, b.value
+
     @property
     def launch_count(self) -> int:
         return int(_lib.load().b2d_launch_count(self._h))

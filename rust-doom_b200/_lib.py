@@ -29,7 +29,7 @@ EXPORTS = [
     "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_info_get",
     "b2d_scene_blob", "b2d_scene_sector_at", "b2d_scene_destroy", "b2d_view_init", "b2d_renderer_create",
     "b2d_renderer_destroy", "b2d_render", "b2d_render_device", "b2d_palette_lut_device",
-    "b2d_debug_worklist", "b2d_launch_count",
+    "b2d_debug_worklist", "b2d_launch_count", "b2d_profile_enable", "b2d_profile_read",
 ]
 
 _lib = None
@@ -73,6 +73,9 @@ def load() -> ctypes.CDLL:
     L.b2d_render_device.argtypes = [vp, vp, cs, vp, vp, vp]
     L.b2d_palette_lut_device.argtypes = [vp, vp, vp, cs, vp]
     L.b2d_debug_worklist.argtypes = [vp, cs, vp, vp, cs]
+    L.b2d_profile_enable.argtypes = [vp, ci]
+    L.b2d_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                   ctypes.POINTER(ctypes.c_int64)]
     L.b2d_launch_count.argtypes = [vp]
     L.b2d_launch_count.restype = ctypes.c_int64
     _lib = L

@@ -45,6 +45,8 @@ struct b2d_renderer {
     cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     int64_t launches = 0;
     int last_n = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // triples: before walk, between, after raster
 };
 
 namespace {
@@ -88,6 +90,7 @@ void free_renderer(b2d_renderer *r) {
         if (r->rendered[i]) cudaEventDestroy(r->rendered[i]);
         if (r->copied[i]) cudaEventDestroy(r->copied[i]);
     }
+    for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
     if (r->h_poses) cudaFreeHost(r->h_poses);
     if (r->render_stream) cudaStreamDestroy(r->render_stream);
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
@@ -101,8 +104,18 @@ void free_renderer(b2d_renderer *r) {
 
 int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
                    cudaStream_t stream) {
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (r->profiling) {
+        for (auto &e : ev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(ev[0], stream));
+    }
     CU(launch_walk(r->ds, r->view, d_poses, n, r->d_frames, r->d_work, r->stride, stream));
+    if (r->profiling) CU(cudaEventRecord(ev[1], stream));
     CU(launch_raster(r->ds, r->view, r->d_frames, r->d_work, r->stride, n, d_index, d_rgba, stream));
+    if (r->profiling) {
+        CU(cudaEventRecord(ev[2], stream));
+        for (auto e : ev) r->prof_events.push_back(e);
+    }
     r->launches += 2;
     r->last_n = n;
     return B2D_OK;
@@ -356,6 +369,31 @@ int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *
         if (c) CU(cudaMemcpy(work.data(), r->d_work + i * (size_t)r->stride, sizeof(SegFrame) * c, cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < c && k < stride; k++) seg_ids_out[i * stride + k] = work[k].seg;
     }
+    return B2D_OK;
+}
+
+int b2d_profile_enable(b2d_renderer *r, int enable) {
+    if (!r) return fail(B2D_ERR_INVALID_ARG, "null renderer");
+    r->profiling = enable != 0;
+    return B2D_OK;
+}
+
+int b2d_profile_read(b2d_renderer *r, double *walk_ms, double *raster_ms, int64_t *batches) {
+    if (!r) return fail(B2D_ERR_INVALID_ARG, "null renderer");
+    CU(cudaSetDevice(r->device));
+    CU(cudaDeviceSynchronize());
+    double w = 0.0, ra = 0.0;
+    for (size_t i = 0; i + 2 < r->prof_events.size(); i += 3) {
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, r->prof_events[i], r->prof_events[i + 1]));
+        CU(cudaEventElapsedTime(&b, r->prof_events[i + 1], r->prof_events[i + 2]));
+        w += a; ra += b;
+    }
+    if (walk_ms) *walk_ms = w;
+    if (raster_ms) *raster_ms = ra;
+    if (batches) *batches = (int64_t)(r->prof_events.size() / 3);
+    for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
+    r->prof_events.clear();
     return B2D_OK;
 }
 

@@ -1,0 +1,71 @@
+"""Multi-GPU sharding of independent camera poses.
+
+Frames for distinct poses are independent and the scene (< a few MB) is replicated on every GPU, so the
+path shards with NO data-path collective: pose i goes to rank i // ceil(n / world) (contiguous blocks).
+The only exchange the north star names is an optional all-gather of finished frames (config 5); it is an
+NVLink-bound step that is reported separately from render throughput and runs through
+torch.distributed (NCCL on GPUs, gloo in the CPU tests), chunked so that the gathered buffer of a chunk
+-- not of the whole job -- has to fit in HBM.
+"""
+from __future__ import annotations
+
+from typing import Iterator, Optional, Tuple
+
+import numpy as np
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int, int]:
+    """(start, end, per_rank) of this rank's contiguous block; the last blocks may be short/empty."""
+    per = (n + world - 1) // world
+    start = min(n, rank * per)
+    end = min(n, start + per)
+    return start, end, per
+
+
+def shard_poses(poses: np.ndarray, rank: int, world: int) -> np.ndarray:
+    s, e, _ = shard_bounds(len(poses), rank, world)
+    return poses[s:e]
+
+
+def gather_chunks(per_rank: int, chunk_frames: int) -> Iterator[Tuple[int, int]]:
+    c0 = 0
+    while c0 < per_rank:
+        yield c0, min(per_rank, c0 + chunk_frames)
+        c0 += chunk_frames
+
+
+def all_gather_frames(local, n_total: int, chunk_frames: int = 256, group=None, out=None):
+    """All-gather per-rank frame blocks [per_rank_valid, H, W] (torch uint8) into global pose order.
+
+    Returns a tensor [n_total, H, W] on every rank (or fills `out`).  Works chunk by chunk: each step moves
+    `chunk_frames` frames per rank, i.e. world * chunk_frames frames of receive buffer.
+    """
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    H, W = local.shape[1], local.shape[2]
+    if out is None:
+        out = torch.empty((n_total, H, W), dtype=local.dtype, device=local.device)
+    use_into = dist.get_backend(group) == "nccl"
+    for c0, c1 in gather_chunks(per, chunk_frames):
+        cnt = c1 - c0
+        send = torch.zeros((cnt, H, W), dtype=local.dtype, device=local.device)
+        have = max(0, min(local.shape[0], c1) - c0)
+        if have > 0:
+            send[:have] = local[c0:c0 + have]
+        if use_into:
+            recv = torch.empty((world * cnt, H, W), dtype=local.dtype, device=local.device)
+            dist.all_gather_into_tensor(recv, send, group=group)
+            parts = recv.view(world, cnt, H, W)
+        else:
+            lst = [torch.empty_like(send) for _ in range(world)]
+            dist.all_gather(lst, send, group=group)
+            parts = torch.stack(lst)
+        for r in range(world):
+            g0 = r * per + c0
+            g1 = min(n_total, r * per + c1)
+            if g1 > g0:
+                out[g0:g1] = parts[r, :g1 - g0]
+    return out

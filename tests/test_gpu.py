@@ -1,0 +1,150 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the oracle, plus size-independent
+properties at BASELINE.json's full sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import render
+from tests.conftest import sample_poses
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames.json")
+
+
+def _assert_same(ofb, gfb, what=""):
+    bad = [(i, int((ofb[i] != gfb[i]).sum())) for i in range(len(ofb)) if not np.array_equal(ofb[i], gfb[i])]
+    assert not bad, "%s: frames differ (index, pixels): %s" % (what, bad[:6])
+
+
+def _loaded_native():
+    from rust_doom_b200 import _lib
+    maps = open("/proc/self/maps").read()
+    assert _lib.LIB_PATH in maps, "libb2d.so is not mapped into this process"
+
+
+def test_gpu_matches_oracle_320x200(b2d, product_scene):
+    poses = sample_poses(b2d, product_scene, 96, 31)
+    r = b2d.Renderer(product_scene, b2d.make_view(320, 200), max_batch=40)     # forces 3 batches
+    gfb = r.render(poses)
+    _loaded_native()
+    ofb = render.render(product_scene.blob, render.make_view(320, 200), poses, threads=8)
+    _assert_same(ofb, gfb, "320x200")
+    assert r.launch_count == 6
+
+
+def test_gpu_matches_oracle_odd_width(b2d, product_scene):
+    poses = sample_poses(b2d, product_scene, 12, 32)
+    for (w, h) in ((333, 187), (64, 48), (1000, 10)):
+        gfb = b2d.Renderer(product_scene, b2d.make_view(w, h), max_batch=16).render(poses)
+        ofb = render.render(product_scene.blob, render.make_view(w, h), poses, threads=8)
+        _assert_same(ofb, gfb, "%dx%d" % (w, h))
+
+
+def test_gpu_matches_oracle_1080p_and_4k(b2d, product_scene):
+    poses = sample_poses(b2d, product_scene, 10, 33)
+    gfb = b2d.Renderer(product_scene, b2d.make_view(1920, 1080), max_batch=16).render(poses)
+    ofb = render.render(product_scene.blob, render.make_view(1920, 1080), poses, threads=8)
+    _assert_same(ofb, gfb, "1080p")
+    gfb = b2d.Renderer(product_scene, b2d.make_view(3840, 2160), max_batch=4).render(poses[:3])
+    ofb = render.render(product_scene.blob, render.make_view(3840, 2160), poses[:3], threads=8)
+    _assert_same(ofb, gfb, "4K")
+
+
+@pytest.mark.parametrize("seed,maps,level", [(7, ("E2M3",), 0), (21, ("MAP01", "MAP12"), 1), (3, ("E1M1", "E1M2", "E1M3"), 2)])
+def test_gpu_matches_oracle_other_maps(b2d, seed, maps, level):
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, maps)), level)
+    poses = sample_poses(b2d, sc, 48, seed)
+    gfb = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=64).render(poses)
+    ofb = render.render(sc.blob, render.make_view(320, 200), poses, threads=8)
+    _assert_same(ofb, gfb, str(maps))
+
+
+def test_gpu_micro_level_extremes(b2d):
+    from tests.test_scene import _micro_level
+    sc = b2d.Scene(b2d.Archive.from_bytes(_micro_level()), 0)
+    poses = np.concatenate([
+        b2d.make_pose(-0.01, 128, 60, 0), b2d.make_pose(0, 128, 60, 180), b2d.make_pose(-255.99, 0.01, 1, 45),
+        b2d.make_pose(-128, 128, 127.99, 270), b2d.make_pose(-5000, 9000, 60, 300), b2d.make_pose(128, 128, 30, 123.4),
+    ])
+    gfb = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=8).render(poses)
+    ofb = render.render(sc.blob, render.make_view(320, 200), poses)
+    _assert_same(ofb, gfb, "micro")
+
+
+def test_gpu_golden_crcs(b2d):
+    from rust_doom_b200 import synthwad
+    for c in json.load(open(GOLDEN)):
+        sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(c["seed"], c["maps"])), c["level"])
+        poses = np.array([tuple(p) for p in c["poses"]], dtype=b2d.POSE_DTYPE)
+        gfb = b2d.Renderer(sc, b2d.make_view(c["w"], c["h"]), max_batch=max(1, len(poses))).render(poses)
+        assert [render.crc32(gfb[i]) for i in range(len(poses))] == c["frame_crc"], c["name"]
+
+
+def test_gpu_worklist_matches_hostcheck(b2d, hostcheck, product_scene):
+    import torch
+    poses = sample_poses(b2d, product_scene, 24, 35)
+    view = b2d.make_view(640, 400)
+    r = b2d.Renderer(product_scene, view, max_batch=32)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    out = torch.empty((len(poses), 400, 640), dtype=torch.uint8, device="cuda")
+    r.render_device(dp.data_ptr(), len(poses), out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    counts, ids = r.worklist(len(poses))
+    hfb, hcounts, hids = hostcheck(product_scene.blob, view, poses)
+    assert counts.tolist() == hcounts.tolist()
+    for i in range(len(poses)):
+        assert ids[i, :counts[i]].tolist() == hids[i, :hcounts[i]].tolist()
+    assert np.array_equal(out.cpu().numpy(), hfb)
+
+
+def test_gpu_rgba_and_palette_kernel(b2d, product_scene):
+    import torch
+    poses = sample_poses(b2d, product_scene, 6, 36)
+    r = b2d.Renderer(product_scene, b2d.make_view(640, 400), max_batch=8)
+    idx, rgba = r.render(poses, rgba=True)
+    ofb, orgba = render.render(product_scene.blob, render.make_view(640, 400), poses, rgba=True)
+    assert np.array_equal(idx, ofb) and np.array_equal(rgba, orgba)
+    # stand-alone palette kernel, incl. a pixel count that is not a multiple of 16
+    for npx in (640 * 400 * 6, 1003):
+        di = torch.from_numpy(ofb.reshape(-1)[:npx].copy()).cuda()
+        do = torch.zeros(npx, dtype=torch.int32, device="cuda")
+        r.palette_lut_device(di.data_ptr(), do.data_ptr(), npx, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(do.cpu().numpy().view(np.uint32), orgba.reshape(-1)[:npx])
+
+
+def test_gpu_every_pixel_written_once_full_size(b2d, product_scene):
+    """Full-size property: the raster never leaves a byte of the frame untouched -- two runs over
+    differently poisoned buffers must agree everywhere (1920x1080, 64 poses)."""
+    import torch
+    poses = sample_poses(b2d, product_scene, 64, 37)
+    r = b2d.Renderer(product_scene, b2d.make_view(1920, 1080), max_batch=64)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    outs = []
+    for poison in (0x5A, 0xC3):
+        out = torch.full((64, 1080, 1920), poison, dtype=torch.uint8, device="cuda")
+        r.render_device(dp.data_ptr(), 64, out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        outs.append(out)
+    assert torch.equal(outs[0], outs[1])
+    # determinism + checksum-of-checksums against the oracle on a subsample
+    ofb = render.render(product_scene.blob, render.make_view(1920, 1080), poses[::16], threads=8)
+    assert np.array_equal(outs[0][::16].cpu().numpy(), ofb)
+
+
+def test_gpu_device_and_host_paths_agree(b2d, product_scene):
+    import torch
+    poses = sample_poses(b2d, product_scene, 20, 38)
+    r = b2d.Renderer(product_scene, b2d.make_view(320, 200), max_batch=7)
+    host = r.render(poses)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    out = torch.empty((7, 200, 320), dtype=torch.uint8, device="cuda")
+    r.render_device(dp.data_ptr(), 7, out.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), host[:7])
+    with pytest.raises(b2d.B2dError):
+        r.render_device(dp.data_ptr(), 8, out.data_ptr())          # n > max_batch

@@ -1,0 +1,58 @@
+"""The product's device maths (b2d_math.cuh) and the kernels' exact algorithms, executed on the CPU by
+tests/hostcheck, must reproduce the oracle's framebuffer bit for bit.  This is the no-GPU gate for the
+pixel contract; the -m gpu tests repeat it through the real kernels."""
+import numpy as np
+import pytest
+
+from oracle import render
+from tests.conftest import sample_poses
+
+
+def _compare(b2d, hostcheck, scene, w, h, n, seed):
+    blob = scene.blob
+    poses = sample_poses(b2d, scene, n, seed)
+    ofb, hits = render.render(blob, render.make_view(w, h), poses, threads=4, seg_hits=True)
+    hfb, counts, ids = hostcheck(blob, b2d.make_view(w, h), poses)
+    bad = [(i, int((ofb[i] != hfb[i]).sum())) for i in range(len(poses)) if not np.array_equal(ofb[i], hfb[i])]
+    assert not bad, "frames differ (index, pixels): %s" % bad[:5]
+    for i in range(len(poses)):
+        assert counts[i] >= 0
+        drawn = set(np.nonzero(hits[i] > 0)[0].tolist())
+        listed = ids[i, :counts[i]].tolist()
+        assert drawn <= set(listed), "culling dropped a seg the oracle drew"
+        assert len(listed) == len(set(listed))
+
+
+def test_hostcheck_320x200(b2d, hostcheck, product_scene):
+    _compare(b2d, hostcheck, product_scene, 320, 200, 40, 11)
+
+
+def test_hostcheck_odd_sizes(b2d, hostcheck, product_scene):
+    _compare(b2d, hostcheck, product_scene, 333, 187, 8, 12)      # width not a multiple of 32
+    _compare(b2d, hostcheck, product_scene, 64, 48, 8, 13)
+
+
+def test_hostcheck_1080p_and_4k(b2d, hostcheck, product_scene):
+    _compare(b2d, hostcheck, product_scene, 1920, 1080, 3, 14)
+    _compare(b2d, hostcheck, product_scene, 3840, 2160, 1, 15)
+
+
+@pytest.mark.parametrize("seed,maps,level", [(7, ("E2M3",), 0), (21, ("MAP01", "MAP12"), 1)])
+def test_hostcheck_other_maps(b2d, hostcheck, seed, maps, level):
+    from rust_doom_b200 import synthwad
+    a = b2d.Archive.from_bytes(synthwad.build_iwad(seed, maps))
+    _compare(b2d, hostcheck, b2d.Scene(a, level), 320, 200, 16, seed)
+
+
+def test_hostcheck_micro_level_extremes(b2d, hostcheck):
+    """Camera almost touching a wall, on a BSP partition line, and far outside the level."""
+    from tests.test_scene import _micro_level
+    a = b2d.Archive.from_bytes(_micro_level())
+    sc = b2d.Scene(a, 0)
+    poses = np.concatenate([
+        b2d.make_pose(-0.01, 128, 60, 0), b2d.make_pose(0, 128, 60, 180), b2d.make_pose(-255.99, 0.01, 1, 45),
+        b2d.make_pose(-128, 128, 127.99, 270), b2d.make_pose(-5000, 9000, 60, 300), b2d.make_pose(128, 128, 30, 123.4),
+    ])
+    ofb = render.render(sc.blob, render.make_view(320, 200), poses)
+    hfb, counts, _ = hostcheck(sc.blob, b2d.make_view(320, 200), poses)
+    assert np.array_equal(ofb, hfb)

@@ -1,0 +1,122 @@
+"""Oracle rasteriser: golden CRCs, a hand-checked micro level, and structural properties."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import render, scene, wad
+from tests.test_scene import _micro_level
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frames.json")
+
+
+def _cases():
+    with open(GOLDEN) as f:
+        return json.load(f)
+
+
+def _case_inputs(c):
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(c["seed"], c["maps"])
+    a = wad.Archive(data)
+    blob = scene.compile_scene(a, wad.TextureDirectory(a), c["level"])
+    poses = np.array([tuple(p) for p in c["poses"]], dtype=render.POSE)
+    return data, blob, poses
+
+
+@pytest.mark.parametrize("c", _cases(), ids=lambda c: c["name"])
+def test_golden_frames(c):
+    data, blob, poses = _case_inputs(c)
+    assert render.crc32(np.frombuffer(data, np.uint8)) == c["wad_crc"], "synthetic IWAD bytes changed"
+    assert render.crc32(np.frombuffer(blob, np.uint8)) == c["blob_crc"], "compiled scene changed"
+    fb = render.render(blob, render.make_view(c["w"], c["h"]), poses, threads=4)
+    assert [render.crc32(fb[i]) for i in range(len(poses))] == c["frame_crc"]
+
+
+def test_sincos_table_accuracy():
+    for k in range(0, 1 << 32, (1 << 32) // 997):
+        c, s = render.sincos_q30(k)
+        a = k / 2 ** 32 * 2 * math.pi
+        assert abs(c / 2 ** 30 - math.cos(a)) < 4e-9 and abs(s / 2 ** 30 - math.sin(a)) < 4e-9
+    assert render.sincos_q30(0) == (1 << 30, 0)
+    assert render.sincos_q30(1 << 30) == (0, 1 << 30)
+    assert render.sincos_q30(1 << 31) == (-(1 << 30), 0)
+
+
+def test_micro_level_hand_checked():
+    """Camera in room A at (-128,128,z=60) looking east at the two-sided line x=0, 128 units ahead.
+    With 320x200, fovy 65 deg: FY2=314 (focal_y 157 px).  A wall perpendicular to the view direction has the
+    same depth in every column, so row boundaries follow from  Y(h) = 100 - (h-60)*157/128  and the rule
+    'first row whose centre is at or below Y' = ceil(Y - 1/2)."""
+    data = _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(24, 96))
+    a = wad.Archive(data)
+    td = wad.TextureDirectory(a)
+    blob = scene.compile_scene(a, td, 0)
+    v = render.make_view(320, 200)
+    assert (v.F, v.FY2) == (262, 314)
+    pose = render.make_pose(-128, 128, 60, 0)
+    fb, hits = render.render(blob, v, pose, seg_hits=True)
+    fb = fb[0]
+    scale = 157.0 / 128.0
+    rows = {h: math.ceil(100 - (h - 60) * scale - 0.5) for h in (128, 96, 24, 0)}
+    assert rows == {128: 17, 96: 56, 24: 144, 0: 174}
+    x = 160
+    cmap = np.frombuffer(td.colormaps[0], np.uint8)
+    cm = np.stack([np.frombuffer(td.colormaps[k], np.uint8) for k in range(32)])
+    brick2 = td.textures[wad.wad_name(b"BRICK2")] & 0xFF
+    step2 = td.textures[wad.wad_name(b"STEP2")] & 0xFF
+    b = wad.light_byte(160, -1)                       # the line is vertical in the map: darkened
+    row = int(math.floor(64 * (255 - b) / 255.0 - 2880.0 / (128 + 90)))
+    assert 0 < row < 31
+    # texture column: seg runs (0,256)->(0,0); the centre ray hits ~128.5 along it; + x_offset 8
+    col = (8 + 128) % 64
+    for y in range(rows[128], rows[96]):              # upper texture, pegged to the back ceiling
+        hy = 60 - (y + 0.5 - 100) / scale
+        t = int(math.floor((128 - 32) % 128 + (128 - hy)))
+        assert fb[y, x] == cm[row][brick2[t % 128, col]], ("upper", y)
+    for y in range(rows[24], rows[0]):                # lower texture, top at the back floor
+        hy = 60 - (y + 0.5 - 100) / scale
+        t = int(math.floor(0 + (24 - hy)))
+        assert fb[y, x] == cm[row][step2[t % 24, col]], ("lower", y)
+    # the floor of room A directly below: texel rule flat[(wad_y mod 64) + 64*(wad_x mod 64)]
+    floor1 = np.frombuffer(td.flats[wad.wad_name(b"FLOOR1")], np.uint8)
+    bf = wad.light_byte(160, 0)
+    for y in (180, 190, 199):
+        z = 60 * 157.0 / (y + 0.5 - 100)              # depth of the floor point seen in this row
+        wx, wy = -128 + z, 128 - z * (1 / (2 * 131.0))    # centre column: c2 = 1, F = 262
+        rowf = max(0, min(31, int(math.floor(64 * (255 - bf) / 255.0 - 2880.0 / (z + 90)))))
+        texel = floor1[(int(math.floor(wy)) % 64) + 64 * (int(math.floor(wx)) % 64)]
+        assert fb[y, x] == cm[rowf][texel], ("floor", y)
+    # rows of the opening show room B (drawn by other segs); the shared seg drew upper+lower+planes only
+    assert hits[0][3] > 0 and hits[0][7] == 0         # B's side of the line is back-facing
+
+
+def test_every_pixel_is_covered_in_closed_levels(oracle_scene):
+    v = render.make_view(320, 200)
+    h = scene.header(oracle_scene)
+    pose = render.make_pose(h[scene.H_START_X] - (1 << 32) if h[scene.H_START_X] >> 31 else h[scene.H_START_X],
+                            h[scene.H_START_Y] - (1 << 32) if h[scene.H_START_Y] >> 31 else h[scene.H_START_Y],
+                            h[scene.H_START_Z], 0)
+    poses = np.concatenate([pose] * 8)
+    poses["angle"] = (np.arange(8, dtype=np.uint64) * (1 << 29)).astype(np.uint32)
+    fb, hits = render.render(oracle_scene, v, poses, seg_hits=True)
+    assert hits.sum(axis=1).tolist() == [320 * 200] * 8      # each pixel written exactly once
+
+
+def test_rgba_is_palette_of_index(oracle_scene):
+    v = render.make_view(160, 100)
+    pose = render.make_pose(0, 0, 41, 33)
+    fb, rgba = render.render(oracle_scene, v, pose, rgba=True)
+    h = scene.header(oracle_scene)
+    pal = np.frombuffer(oracle_scene, dtype="<u4", count=256, offset=h[scene.H_OFF_PALETTE])
+    assert np.array_equal(rgba, pal[fb])
+
+
+def test_threads_do_not_change_output(oracle_scene):
+    v = render.make_view(200, 120)
+    poses = np.concatenate([render.make_pose(10 * i, -20 * i, 41, 37 * i) for i in range(9)])
+    a = render.render(oracle_scene, v, poses, threads=1)
+    b = render.render(oracle_scene, v, poses, threads=4)
+    assert np.array_equal(a, b)

@@ -1,0 +1,143 @@
+"""Scene compiler: the product's C++ compiler must emit the same bytes as the oracle's restatement of
+LevelWalker (wad/src/visitor.rs:711-937) for every map, plus spot checks of the pegging rules."""
+import numpy as np
+import pytest
+
+from oracle import scene as S
+from oracle import wad as W
+
+
+@pytest.mark.parametrize("seed,maps", [(1, ("E1M1", "E1M2")), (7, ("E2M3",)), (21, ("MAP01", "MAP12", "MAP25"))])
+def test_blob_identical(b2d, seed, maps):
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(seed, maps)
+    oa = W.Archive(data)
+    ot = W.TextureDirectory(oa)
+    pa = b2d.Archive.from_bytes(data)
+    for i in range(len(maps)):
+        ob = S.compile_scene(oa, ot, i)
+        ps = b2d.Scene(pa, i)
+        pb = ps.blob
+        if ob != pb:
+            A, B = np.frombuffer(ob, np.uint8), np.frombuffer(pb, np.uint8)
+            n = min(len(A), len(B))
+            first = int(np.nonzero(A[:n] != B[:n])[0][0]) if (A[:n] != B[:n]).any() else n
+            pytest.fail("blob differs for %s at byte %d (sizes %d / %d)" % (maps[i], first, len(A), len(B)))
+
+
+def test_sky_table():
+    assert S.sky_for(W.wad_name(b"E1M1")) == W.wad_name(b"SKY1")
+    assert S.sky_for(W.wad_name(b"E3M7")) == W.wad_name(b"SKY3")
+    assert S.sky_for(W.wad_name(b"MAP11")) == W.wad_name(b"SKY1")
+    assert S.sky_for(W.wad_name(b"MAP12")) == W.wad_name(b"SKY2")
+    assert S.sky_for(W.wad_name(b"MAP32")) == W.wad_name(b"SKY3")
+    assert S.sky_for(W.wad_name(b"MAP30")) == W.wad_name(b"SKY1")      # no match -> entry 0
+
+
+def test_light_byte_matches_integer_rule():
+    # (light>>3)/31 (+-2/31 clamped) * 255 truncated, in float32 (light.rs:82-115, lights.rs:26-29)
+    for light in range(0, 256):
+        for c in (-1, 0, 1):
+            l5 = min(31, max(0, (light >> 3) + 2 * c))
+            assert W.light_byte(light, c) == (l5 * 255) // 31, (light, c)
+
+
+def test_sector_at_agrees(b2d, synth_wad, product_scene):
+    oa = W.Archive(synth_wad)
+    lv = W.Level(oa, 0)
+    rng = np.random.default_rng(3)
+    inside = 0
+    for _ in range(400):
+        x, y = rng.uniform(-1400, 1400), rng.uniform(-1300, 1300)
+        so = S.sector_at(lv, float(x), float(y))
+        sp, fl, ce = product_scene.sector_at(float(x), float(y))
+        assert so == sp
+        if so >= 0:
+            inside += 1
+            assert (fl, ce) == (int(lv.sectors[so]["floor"]), int(lv.sectors[so]["ceil"]))
+    assert inside > 100
+
+
+def test_view_constants(b2d):
+    from oracle import render
+    for (w, h, fov) in ((320, 200, 65.0), (1920, 1080, 65.0), (3840, 2160, 65.0), (1280, 720, 90.0)):
+        pv, ov = b2d.make_view(w, h, fov), render.make_view(w, h, fov)
+        assert (pv.width, pv.height, pv.F, pv.FY2) == (ov.W, ov.H, ov.F, ov.FY2)
+    v = b2d.make_view(1920, 1080)
+    assert (v.F, v.FY2) == (1413, 1695)     # 2*focal: fovy 65 deg, aspect correction 1.2
+
+
+def _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(24, 96), tex_h=128, yoff=0):
+    """Two square rooms A (x<0) and B (x>0) sharing the edge x=0; returns seg records of the shared line."""
+    from rust_doom_b200 import synthwad as G
+    import struct
+    rng = G.SplitMix64(9)
+    playpal = G.make_playpal()
+    patches, tex, flats = G.make_graphics(rng)
+    pn, t1 = G.make_pnames_texture1(list(patches.keys()), tex)
+    V = [(-256, 0), (0, 0), (0, 256), (-256, 256), (256, 0), (256, 256)]
+    secs = [G.Sector(front[0], front[1], "FLOOR1", "CEIL1", 160), G.Sector(back[0], back[1], "FLOOR2", "F_SKY1" if back[1] == -1 else "CEIL2", 160)]
+    sides = [G.Sidedef(0, 0, "-", "-", "BRICK1", 0) for _ in range(3)] + \
+            [G.Sidedef(0, 0, "-", "-", "BRICK1", 1) for _ in range(3)] + \
+            [G.Sidedef(8, yoff, "PANEL72" if tex_h == 72 else "BRICK2", "STEP2", "-", 0),
+             G.Sidedef(8, yoff, "BRICK2", "STEP2", "-", 1)]
+    # room A walls: clockwise so the room is on the right
+    L = [G.Linedef(0, 3, 1, 0, 0, 0, -1), G.Linedef(3, 2, 1, 0, 0, 1, -1), G.Linedef(1, 0, 1, 0, 0, 2, -1),
+         G.Linedef(2, 5, 1, 0, 0, 3, -1), G.Linedef(5, 4, 1, 0, 0, 4, -1), G.Linedef(4, 1, 1, 0, 0, 5, -1),
+         G.Linedef(2, 1, two_sided_flags, 0, 0, 6, 7)]     # 2->1 points south: A (west) is on the right
+    segsA = [(0, 3, 0, 0), (3, 2, 1, 0), (1, 0, 2, 0), (2, 1, 6, 0)]
+    segsB = [(2, 5, 3, 0), (5, 4, 4, 0), (4, 1, 5, 0), (1, 2, 6, 1)]
+    lb = struct.pack
+    lumps = [("PLAYPAL", playpal), ("COLORMAP", G.make_colormap(playpal)), ("E1M1", b""),
+             ("THINGS", lb("<hhhHH", -128, 128, 0, 1, 7)),
+             ("LINEDEFS", b"".join(lb("<HHHHHhh", l.v1, l.v2, l.flags, 0, 0, l.right, l.left) for l in L)),
+             ("SIDEDEFS", b"".join(lb("<hh8s8s8sH", s.xoff, s.yoff, G._name8(s.upper), G._name8(s.lower), G._name8(s.middle), s.sector) for s in sides)),
+             ("VERTEXES", b"".join(lb("<hh", *v) for v in V)),
+             ("SEGS", b"".join(lb("<HHHHHH", a, b, 0, l, d, 0) for (a, b, l, d) in segsA + segsB)),
+             ("SSECTORS", lb("<HH", 4, 0) + lb("<HH", 4, 4)),
+             # partition x=0 pointing north: right = east = B (subsector 1), left = A (subsector 0)
+             ("NODES", lb("<hhhh4h4hHH", 0, 0, 0, 256, 256, 0, 0, 256, 256, 0, -256, 0, 0x8001, 0x8000)),
+             ("SECTORS", b"".join(lb("<hh8s8shHH", s.floor, s.ceil, G._name8(s.floor_flat), G._name8(s.ceil_flat), s.light, 0, 0) for s in secs)),
+             ("TEXTURE1", t1), ("PNAMES", pn)] + list(patches.items()) + \
+            [("S_START", b""), ("S_END", b""), ("F_START", b"")] + list(flats.items()) + [("F_END", b"")]
+    return G.assemble_wad(lumps)
+
+
+def test_pegging_rules(b2d):
+    # visitor.rs:772-807,909-913 with texture BRICK2/STEP2 heights 128 / 24
+    data = _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(24, 96))
+    oa = W.Archive(data)
+    blob = S.compile_scene(oa, W.TextureDirectory(oa), 0)
+    assert blob == b2d.Scene(b2d.Archive.from_bytes(data), 0).blob
+    segs = S.section(blob, "segs")
+    tex = S.section(blob, "textures")
+    s = segs[3]                      # A's side of the shared line
+    assert s[3] == S.SEG_TWO_SIDED and s[2] == 0 and s[15] == 1
+    assert (s[13], s[14]) == (96, 24)                      # opening: back ceil / back floor
+    hA, hB = int(tex[s[6]][2]), int(tex[s[9]][2])
+    assert (hA, hB) == (128, 24)
+    assert s[7] == (hA - (128 - 96)) % hA and s[8] == 128  # upper, pegged: bottom of texture at back ceil
+    assert s[10] == 0 and s[11] == 24                      # lower, pegged: top of texture at back floor
+    assert s[4] == 8 and s[5] == 256 << 12                 # x offset, length Q12
+    # unpegged variants
+    data = _micro_level(two_sided_flags=0x0004 | 0x0008 | 0x0010, front=(0, 128), back=(24, 96), yoff=5)
+    oa = W.Archive(data)
+    blob = S.compile_scene(oa, W.TextureDirectory(oa), 0)
+    assert blob == b2d.Scene(b2d.Archive.from_bytes(data), 0).blob
+    s = S.section(blob, "segs")[3]
+    assert s[7] == 5                                       # upper unpegged: top of texture at front ceil
+    assert s[10] == (24 - 24 + 128 + 5) % 24               # lower unpegged: aligned to the front ceiling
+    # the B side sees no upper/lower (its floor is higher, ceiling lower)
+    sb = S.section(blob, "segs")[7]
+    assert sb[6] == -1 and sb[9] == -1 and (sb[13], sb[14]) == (96, 24)
+
+
+def test_contrast_rule(b2d):
+    # visitor.rs:887-901: wad dy == 0 -> brighten (+2/31), dx == 0 -> darken (-2/31)
+    data = _micro_level()
+    oa = W.Archive(data)
+    segs = S.section(S.compile_scene(oa, W.TextureDirectory(oa), 0), "segs")
+    base = W.light_byte(160, 0)
+    assert segs[0][12] == W.light_byte(160, -1)     # (-256,0)->(-256,256): dx == 0
+    assert segs[1][12] == W.light_byte(160, +1)     # horizontal
+    assert W.light_byte(160, -1) < base < W.light_byte(160, +1)
