@@ -1,0 +1,78 @@
+"""`b2d` command line, mirroring rs_doom's flags (reference src/main.rs:17-80,89-124):
+
+    python -m rust_doom_b200.cli --iwad doom1.wad --level 0 --resolution 1920x1080 [--fov 65]
+                                 [--poses N] [--dump frame.ppm] [--device 0]
+    python -m rust_doom_b200.cli --iwad doom1.wad list-levels
+    python -m rust_doom_b200.cli --iwad doom1.wad check
+
+`list-levels` prints "<index> <name>" per level (main.rs:116-121); `check` loads and compiles every level
+(the reference's smoke test, main.rs:99-115 / game/src/game.rs:118-129) without needing a GPU.  Without
+--iwad a synthetic IWAD is generated (no WAD ships with either project).  Unlike the reference, --fov is
+honoured (its value is parsed but never read there: main.rs:131 vs game/src/game.rs:72)."""
+from __future__ import annotations
+
+import argparse
+import sys
+import time
+
+import numpy as np
+
+
+def main(argv=None) -> int:
+    import rust_doom_b200 as b2d
+    from rust_doom_b200 import poses as P
+    from rust_doom_b200 import synthwad
+
+    ap = argparse.ArgumentParser(prog="b2d")
+    ap.add_argument("-i", "--iwad", default=None, help="initial WAD file (default: generated synthetic IWAD)")
+    ap.add_argument("-m", "--metadata", default=None, help="accepted for compatibility; the sky table is built in")
+    ap.add_argument("-r", "--resolution", default="1280x720")
+    ap.add_argument("-l", "--level", type=int, default=0)
+    ap.add_argument("-f", "--fov", type=float, default=65.0)
+    ap.add_argument("--poses", type=int, default=1, help="1 = spawn pose, N>1 = N-pose fly-through")
+    ap.add_argument("--dump", default=None, help="write the first frame as a binary PPM")
+    ap.add_argument("--device", type=int, default=0)
+    ap.add_argument("command", nargs="?", choices=["check", "list-levels"], default=None)
+    args = ap.parse_args(argv)
+
+    try:
+        w, h = (int(v) for v in args.resolution.lower().split("x"))
+    except ValueError:
+        print("resolution format is WIDTHxHEIGHT", file=sys.stderr)
+        return 2
+    try:
+        arch = b2d.Archive.open(args.iwad) if args.iwad else b2d.Archive.from_bytes(synthwad.build_iwad(1, synthwad.E1_MAPS[:3]))
+        if args.command == "list-levels":
+            for i, name in enumerate(arch.level_names()):
+                print("%3d %8s" % (i, name))
+            return 0
+        if args.command == "check":
+            for i, name in enumerate(arch.level_names()):
+                sc = b2d.Scene(arch, i)
+                print("Level %d (%s): %d segs, %d subsectors, %d sectors, %d textures: ok"
+                      % (i, name, sc.info.n_segs, sc.info.n_ssectors, sc.info.n_sectors, sc.info.n_textures))
+            return 0
+        scene = b2d.Scene(arch, args.level)
+        view = b2d.make_view(w, h, args.fov)
+        if args.poses <= 1:
+            poses = scene.start_pose if scene.start_pose is not None else P.random_poses(scene, 1, 1)
+        else:
+            poses = P.flythrough_poses(scene, args.poses, 2)
+        r = b2d.Renderer(scene, view, device=args.device, max_batch=min(len(poses), 256))
+        t0 = time.perf_counter()
+        idx, rgba = r.render(poses, rgba=True)
+        dt = time.perf_counter() - t0
+        print("rendered %d frame(s) %dx%d in %.2f ms (%.0f frames/s end to end)" % (len(poses), w, h, dt * 1e3, len(poses) / dt))
+        if args.dump:
+            rgb = rgba[0].view(np.uint8).reshape(h, w, 4)[:, :, :3]
+            with open(args.dump, "wb") as f:
+                f.write(b"P6\n%d %d\n255\n" % (w, h))
+                f.write(np.ascontiguousarray(rgb).tobytes())
+        return 0
+    except b2d.B2dError as e:
+        print("Fatal error: %s" % e, file=sys.stderr)
+        return 1
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -33,6 +33,7 @@ struct b2d_renderer {
     int stride = 0;                 // worklist entries per frame (= n_segs)
     uint8_t *d_blob = nullptr;
     uint32_t *d_yslope = nullptr;
+    uint16_t *d_skyrow = nullptr;
     DeviceScene ds{};
     Pose *d_poses = nullptr;
     FrameConst *d_frames = nullptr;
@@ -98,6 +99,7 @@ void free_renderer(b2d_renderer *r) {
     if (r->d_frames) cudaFree(r->d_frames);
     if (r->d_poses) cudaFree(r->d_poses);
     if (r->d_yslope) cudaFree(r->d_yslope);
+    if (r->d_skyrow) cudaFree(r->d_skyrow);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
 }
@@ -262,6 +264,16 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     for (int y = 0; y < view->height; y++) ys[(size_t)y] = yslope_entry(y, r->view);
     CUR(cudaMalloc(&r->d_yslope, ys.size() * 4));
     CUR(cudaMemcpy(r->d_yslope, ys.data(), ys.size() * 4, cudaMemcpyHostToDevice));
+    {   // sky texture row per screen row (sky.frag:12-26 at pitch 0)
+        std::vector<uint16_t> sr((size_t)view->height, 0);
+        int32_t sky = (int32_t)h[H_SKY_TEX];
+        if (sky >= 0) {
+            const TexRec *tr = reinterpret_cast<const TexRec *>(s->blob.data() + h[H_OFF_TEX]) + sky;
+            for (int y = 0; y < view->height; y++) sr[(size_t)y] = (uint16_t)sky_row(y, view->height, (int32_t)tr->h);
+        }
+        CUR(cudaMalloc(&r->d_skyrow, sr.size() * 2));
+        CUR(cudaMemcpy(r->d_skyrow, sr.data(), sr.size() * 2, cudaMemcpyHostToDevice));
+    }
     DeviceScene &d = r->ds;
     d.verts = reinterpret_cast<const int32_t *>(r->d_blob + h[H_OFF_VERTS]);
     d.nodes = reinterpret_cast<const NodeRec *>(r->d_blob + h[H_OFF_NODES]);
@@ -274,6 +286,7 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.colormap = r->d_blob + h[H_OFF_COLORMAP];
     d.palette = reinterpret_cast<const uint32_t *>(r->d_blob + h[H_OFF_PALETTE]);
     d.yslope = r->d_yslope;
+    d.skyrow = r->d_skyrow;
     d.nverts = (int32_t)h[H_NVERTS]; d.nnodes = (int32_t)h[H_NNODES]; d.nss = (int32_t)h[H_NSSECTORS];
     d.nsegs = (int32_t)h[H_NSEGS]; d.nsectors = (int32_t)h[H_NSECTORS]; d.ntex = (int32_t)h[H_NTEX];
     d.nflats = (int32_t)h[H_NFLATS]; d.sky_tex = (int32_t)h[H_SKY_TEX];

@@ -222,100 +222,171 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // Kernel 2: raster
 // ------------------------------------------------------------------------------------------------
+// shared-memory accesses by 32-bit shared-window address: keeps the per-pixel address arithmetic to one
+// add (the generic-pointer form re-derives the window base for every access)
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4_volatile(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+
 struct RasterCtx {
     const DeviceScene *sc;
-    const uint8_t *cmap;       // shared-memory colormap (32 x 256)
-    const uint32_t *pal;       // shared-memory palette (only when rgba)
+    uint32_t cmap_s;           // shared-window address of the colormap (32 x 256)
+    uint32_t pal_s;            // ... of the palette (rgba only)
+    uint32_t row4_s, row1_s;   // ... of this warp's 32-entry staging of per-row plane constants
+    uint4 *row4;               // generic pointers to the same staging (for the lane-parallel writes)
+    uint32_t *row1;
     uint8_t *fb;               // &index_fb[frame][0][x]
     uint32_t *rgba;            // &rgba_fb[frame][0][x] or nullptr
     int W, H, x, lane;
     uint32_t skycol;
 };
 
-__device__ __forceinline__ void put_px(const RasterCtx &c, int y, uint8_t v) {
-    size_t o = (size_t)y * c.W;
-    c.fb[o] = v;
-    if (c.rgba) c.rgba[o] = c.pal[v];
+template <bool kRgba>
+__device__ __forceinline__ void put_px(const RasterCtx &c, uint8_t *p8, uint32_t *p32, bool on, uint32_t v) {
+    if (on) {
+        *p8 = (uint8_t)v;
+        if (kRgba) *p32 = lds_u32(c.pal_s + 4u * v);
+    }
 }
 
 // rows [ya, yb) of this lane's column := void (index 0); lanes with ya >= yb idle
+template <bool kRgba>
 __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int yb) {
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
-    for (int y = y0; y < y1; y++)
-        if (y >= ya && y < yb) put_px(c, y, 0);
+    if (y0 >= y1) return;
+    uint8_t *p8 = c.fb + (size_t)y0 * c.W;
+    uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * c.W : nullptr;
+    for (int y = y0; y < y1; y++, p8 += c.W, p32 += c.W) put_px<kRgba>(c, p8, p32, y >= ya && y < yb, 0u);
 }
 
+template <bool kRgba>
 __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb) {
     const DeviceScene &sc = *c.sc;
-    if (sc.sky_tex < 0) { fill_void_warp(c, ya, yb); return; }
+    if (sc.sky_tex < 0) { fill_void_warp<kRgba>(c, ya, yb); return; }
     const TexRec T = sc.tex[sc.sky_tex];
-    const uint8_t *px = sc.texels + T.texel_off;
+    const uint8_t *px = sc.texels + T.texel_off + c.skycol;
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
-    for (int y = y0; y < y1; y++) {
-        int v = sky_row(y, c.H, (int32_t)T.h);
-        if (y >= ya && y < yb) put_px(c, y, c.cmap[px[(uint32_t)v * T.w + c.skycol]]);
+    if (y0 >= y1) return;
+    uint8_t *p8 = c.fb + (size_t)y0 * c.W;
+    uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * c.W : nullptr;
+#pragma unroll 4
+    for (int y = y0; y < y1; y++, p8 += c.W, p32 += c.W) {
+        uint32_t v = sc.skyrow[y];                                        // warp-uniform table entry
+        uint32_t texel = px[v * T.w];
+        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(c.cmap_s + texel));
     }
 }
 
+template <bool kRgba>
 __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameConst &fc, const View &vw,
                                                 int ya, int yb, int32_t h, int32_t flat, int lightb,
                                                 bool visible) {
     const DeviceScene &sc = *c.sc;
     if (!__any_sync(kFull, ya < yb)) return;
-    if (!visible) { fill_void_warp(c, ya, yb); return; }
-    if (flat == kFlatSky) { draw_sky_warp(c, ya, yb); return; }
-    if (flat < 0 || flat >= sc.nflats) { fill_void_warp(c, ya, yb); return; }
+    if (!visible) { fill_void_warp<kRgba>(c, ya, yb); return; }
+    if (flat == kFlatSky) { draw_sky_warp<kRgba>(c, ya, yb); return; }
+    if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba>(c, ya, yb); return; }
     const uint8_t *px = sc.flats + 4096u * (uint32_t)flat;
     const uint32_t habs = plane_habs(h, fc.pose.z);
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
-    for (int y = y0; y < y1; y++) {
-        PlaneRow pr = plane_row(habs, sc.yslope[y], fc, vw, sc.invF);      // warp-uniform
-        const uint8_t *cm = c.cmap + 256 * light_row(lightb, pr.z8);
-        if (y >= ya && y < yb) {
-            uint32_t U = pr.baseU + (uint32_t)c.x * pr.stepU;
-            uint32_t V = pr.baseV + (uint32_t)c.x * pr.stepV;
-            put_px(c, y, cm[px[flat_index(U, V)]]);
+    uint8_t *p8 = c.fb + (size_t)y0 * c.W;
+    uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * c.W : nullptr;
+    const uint32_t xx = (uint32_t)c.x;
+    for (int yc = y0; yc < y1; yc += 32) {
+        // lane j prepares the texture-mapping constants of row yc+j (64-bit maths, once per row per warp)
+        int yy = yc + c.lane;
+        if (yy < y1) {
+            PlaneRow pr = plane_row(habs, sc.yslope[yy], fc, vw, sc.invF);
+            c.row4[c.lane] = make_uint4(pr.baseU, pr.stepU, pr.baseV, pr.stepV);
+            c.row1[c.lane] = c.cmap_s + 256u * (uint32_t)light_row(lightb, pr.z8);
         }
+        __syncwarp();
+        const int rows = min(32, y1 - yc);
+#pragma unroll 4
+        for (int j = 0; j < rows; j++, p8 += c.W, p32 += c.W) {
+            const uint4 r4 = lds_v4_volatile(c.row4_s + 16u * (uint32_t)j);   // shared-memory broadcast
+            const uint32_t cm = lds_u32_volatile(c.row1_s + 4u * (uint32_t)j);
+            const int y = yc + j;
+            uint32_t U = r4.x + xx * r4.y;
+            uint32_t V = r4.z + xx * r4.w;
+            uint32_t texel = px[flat_index(U, V)];                         // always in bounds: unconditional
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
+        }
+        __syncwarp();
     }
 }
 
+template <bool kRgba>
 __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameConst &fc, int ya, int yb,
                                                int32_t tex, int32_t tA, int32_t hA, int32_t ucol,
                                                int32_t iscale, int row) {
     const DeviceScene &sc = *c.sc;
     if (!__any_sync(kFull, ya < yb)) return;
-    if (tex < 0 || tex >= sc.ntex) { fill_void_warp(c, ya, yb); return; }
+    if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba>(c, ya, yb); return; }
     const TexRec T = sc.tex[tex];
-    const uint8_t *px = sc.texels + T.texel_off;
     bool act = ya < yb;
-    int32_t col = floormod32(ucol, (int32_t)T.w);
-    int32_t tbase = wall_tbase(tA, hA, fc.pose.z, c.H, iscale);
-    int32_t tstep = iscale >> 4;
-    const uint8_t *cm = c.cmap + 256 * row;
+    const uint8_t *px = sc.texels + T.texel_off + (uint32_t)floormod32(ucol, (int32_t)T.w);
+    const int32_t tstep = iscale >> 4;
+    const uint32_t cm = c.cmap_s + 256u * (uint32_t)row;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
-    for (int y = y0; y < y1; y++) {
-        if (y >= ya && y < yb) {
-            int32_t t = tbase + y * tstep;
-            uint32_t v = wall_row(t, T.h, T.hmagic, T.hbias);
-            put_px(c, y, cm[px[v * T.w + (uint32_t)col]]);
+    uint32_t t = (uint32_t)wall_tbase(tA, hA, fc.pose.z, c.H, iscale) + (uint32_t)y0 * (uint32_t)tstep;
+    uint8_t *p8 = c.fb + (size_t)y0 * c.W;
+    uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * c.W : nullptr;
+    // Texel loads are unconditional (t is a bounded linear function of y for every lane, so the row index
+    // is always inside the texture); only the store is predicated.  That keeps the loop branch-free.
+    if (((T.h & (T.h - 1u)) | (T.w & (T.w - 1u))) == 0u) {
+        // power-of-two texture: row*w = ((t >> 16) & (h-1)) << log2(w) as one shift + one mask
+        const int lw = 31 - __clz((int)T.w);
+        const uint32_t mask = (T.h - 1u) << lw;
+        const int sh = 16 - lw;            // w <= 4096 -> sh >= 4
+#pragma unroll 4
+        for (int y = y0; y < y1; y++, p8 += c.W, p32 += c.W, t += (uint32_t)tstep) {
+            uint32_t texel = px[(t >> sh) & mask];
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
+        }
+    } else {
+#pragma unroll 4
+        for (int y = y0; y < y1; y++, p8 += c.W, p32 += c.W, t += (uint32_t)tstep) {
+            uint32_t v = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
+            uint32_t texel = px[v * T.w];
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
         }
     }
 }
 
 template <bool kRgba>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
                   const SegFrame *__restrict__ work, int stride, int n, int strips,
                   uint8_t *__restrict__ index_fb, uint32_t *__restrict__ rgba_fb) {
     __shared__ __align__(16) uint8_t s_cmap[32 * 256];
     __shared__ uint32_t s_pal[kRgba ? 256 : 1];
+    __shared__ uint4 s_row4[4][32];
+    __shared__ uint32_t s_row1[4][32];
     {   // colormap rows 0..31 (and the palette) into shared memory, 128-bit loads
         const uint4 *src = reinterpret_cast<const uint4 *>(sc.colormap);
         uint4 *dst = reinterpret_cast<uint4 *>(s_cmap);
@@ -335,7 +406,12 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
 
     const FrameConst fc = frames[frame];
     RasterCtx c;
-    c.sc = &sc; c.cmap = s_cmap; c.pal = s_pal;
+    c.sc = &sc;
+    c.cmap_s = (uint32_t)__cvta_generic_to_shared(s_cmap);
+    c.pal_s = (uint32_t)__cvta_generic_to_shared(s_pal);
+    c.row4 = s_row4[threadIdx.x >> 5]; c.row1 = s_row1[threadIdx.x >> 5];
+    c.row4_s = (uint32_t)__cvta_generic_to_shared(c.row4);
+    c.row1_s = (uint32_t)__cvta_generic_to_shared(c.row1);
     c.fb = index_fb + (size_t)frame * W * H + (inside ? x : 0);
     c.rgba = kRgba ? rgba_fb + (size_t)frame * W * H + (inside ? x : 0) : nullptr;
     c.W = W; c.H = H; c.x = x; c.lane = lane;
@@ -393,17 +469,17 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 yend = cb;
             }
             // ceiling region [ct, y1)
-            draw_plane_warp(c, fc, vw, ok ? ct : 0, ok ? y1 : 0, fcl, SF.ceil_flat, SF.light, ceil_vis);
+            draw_plane_warp<kRgba>(c, fc, vw, ok ? ct : 0, ok ? y1 : 0, fcl, SF.ceil_flat, SF.light, ceil_vis);
             if (!two) {
-                draw_wall_warp(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                draw_wall_warp<kRgba>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
             } else {
                 if (S.otop < fcl)
-                    draw_wall_warp(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                    draw_wall_warp<kRgba>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
                 if (S.obot > ffl)
-                    draw_wall_warp(c, fc, ok ? y3 : 0, ok ? y4 : 0, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
+                    draw_wall_warp<kRgba>(c, fc, ok ? y3 : 0, ok ? y4 : 0, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
             }
             // floor region [y4, cb)
-            draw_plane_warp(c, fc, vw, ok ? y4 : 0, ok ? yend : 0, ffl, SF.floor_flat, SF.light, floor_vis);
+            draw_plane_warp<kRgba>(c, fc, vw, ok ? y4 : 0, ok ? yend : 0, ffl, SF.floor_flat, SF.light, floor_vis);
             if (ok) {
                 if (!two || y2 >= y3) { ct = H; cb = 0; }
                 else { ct = y2; cb = y3; }
@@ -411,7 +487,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
         }
     }
     // whatever is still open is void
-    fill_void_warp(c, inside ? ct : 0, inside ? cb : 0);
+    fill_void_warp<kRgba>(c, inside ? ct : 0, inside ? cb : 0);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -21,6 +21,7 @@ struct DeviceScene {
     const uint8_t *colormap;     // 34 x 256
     const uint32_t *palette;     // 256 RGBA8
     const uint32_t *yslope;      // per view: H entries
+    const uint16_t *skyrow;      // per view: H entries, sky texture row of each screen row
     int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex;
     uint32_t root;
     uint32_t invF;               // floor(2^32 / F)
