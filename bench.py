@@ -9,7 +9,7 @@ environment -- set B2D_IWAD=/path/doom1.wad to use one), 1000-pose fly-through, 
 one pass of the hot path (BSP walk + raster) over the 1000-pose batch.  `value` is device-resident
 throughput (poses already in HBM, frames written to HBM); `e2e` goes through b2d_render with pinned HOST
 buffers -- host poses in, host frames out, both copies inside the timed region.  Multi-GPU: independent pose
-blocks per rank (weak scaling: every rank renders its own 1000-pose fly-through), no data-path collective;
+blocks per rank (weak scaling: every rank renders the 1000-pose fly-through, rotated by rank), no data-path collective;
 the optional frame all-gather is timed separately under "allgather" and never blended into `value`.
 """
 from __future__ import annotations
@@ -189,7 +189,9 @@ def main():
 
     scene, scene_name = load_scene(b2d)
     n = args.poses
-    poses_np = P.flythrough_poses(scene, n, 2 + rank)               # every rank flies its own path
+    # every rank renders the same 1000-pose fly-through, cyclically rotated by rank: identical work per GPU
+    # (clean weak-scaling efficiency) while no two ranks are on the same pose at the same time
+    poses_np = np.roll(P.flythrough_poses(scene, n, 2), -(rank * n // max(world, 1)))
     view = b2d.make_view(WIDTH, HEIGHT)
     r = b2d.Renderer(scene, view, device=local_rank, max_batch=n)
     npix = WIDTH * HEIGHT

@@ -148,3 +148,51 @@ def test_gpu_device_and_host_paths_agree(b2d, product_scene):
     assert np.array_equal(out.cpu().numpy(), host[:7])
     with pytest.raises(b2d.B2dError):
         r.render_device(dp.data_ptr(), 8, out.data_ptr())          # n > max_batch
+
+
+# ---- BASELINE.json configs as parity cases (sizes the oracle finishes in seconds) ---------------------
+def test_config3_all_e1_maps_batched_1080p(b2d):
+    """configs[2]: every E1 map, 1920x1080, one renderer per map, frames vs oracle."""
+    from rust_doom_b200 import poses as P
+    from rust_doom_b200 import synthwad
+    arch = b2d.Archive.from_bytes(synthwad.build_iwad(1, synthwad.E1_MAPS, map_seeds=list(range(11, 20))))
+    assert arch.num_levels() == 9
+    view = b2d.make_view(1920, 1080)
+    for lvl in range(9):
+        sc = b2d.Scene(arch, lvl)
+        poses = P.flythrough_poses(sc, 3, 2)
+        gfb = b2d.Renderer(sc, view, max_batch=4).render(poses)
+        ofb = render.render(sc.blob, render.make_view(1920, 1080), poses, threads=8)
+        _assert_same(ofb, gfb, "E1M%d" % (lvl + 1))
+
+
+def test_config4_doom2_maps_4k(b2d):
+    """configs[3]: MAP01-MAP10 stand-ins at 3840x2160 (one map per GPU in the real config)."""
+    from rust_doom_b200 import poses as P
+    from rust_doom_b200 import synthwad
+    arch = b2d.Archive.from_bytes(synthwad.build_iwad(2, synthwad.MAP_NAMES_DOOM2, map_seeds=list(range(21, 31))))
+    view = b2d.make_view(3840, 2160)
+    for lvl in (0, 4, 9):
+        sc = b2d.Scene(arch, lvl)
+        poses = P.flythrough_poses(sc, 2, 2)
+        gfb = b2d.Renderer(sc, view, max_batch=2).render(poses)
+        ofb = render.render(sc.blob, render.make_view(3840, 2160), poses, threads=8)
+        _assert_same(ofb, gfb, "MAP%02d" % (lvl + 1))
+
+
+def test_config5_random_poses_1080p(b2d, product_scene):
+    """configs[4]: random poses (splitmix64, sector_at acceptance); 512 rendered, every 32nd checked vs oracle,
+    all checked for determinism across two launches."""
+    import torch
+    from rust_doom_b200 import poses as P
+    poses = P.random_poses(product_scene, 512, 5)
+    r = b2d.Renderer(product_scene, b2d.make_view(1920, 1080), max_batch=512)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    a = torch.empty((512, 1080, 1920), dtype=torch.uint8, device="cuda")
+    bb = torch.full((512, 1080, 1920), 7, dtype=torch.uint8, device="cuda")
+    r.render_device(dp.data_ptr(), 512, a.data_ptr())
+    r.render_device(dp.data_ptr(), 512, bb.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(a, bb)
+    ofb = render.render(product_scene.blob, render.make_view(1920, 1080), poses[::32], threads=8)
+    assert np.array_equal(a[::32].cpu().numpy(), ofb)
