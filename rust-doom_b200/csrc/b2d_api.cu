@@ -34,6 +34,7 @@ struct b2d_renderer {
     uint8_t *d_blob = nullptr;
     uint32_t *d_yslope = nullptr;
     uint16_t *d_skyrow = nullptr;
+    int32_t *d_status = nullptr;
     DeviceScene ds{};
     Pose *d_poses = nullptr;
     FrameConst *d_frames = nullptr;
@@ -100,12 +101,17 @@ void free_renderer(b2d_renderer *r) {
     if (r->d_poses) cudaFree(r->d_poses);
     if (r->d_yslope) cudaFree(r->d_yslope);
     if (r->d_skyrow) cudaFree(r->d_skyrow);
+    if (r->d_status) cudaFree(r->d_status);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
 }
 
 int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
                    cudaStream_t stream) {
+    // walk -> raster on the caller's stream.  (Measured on B200: splitting a batch so that the second
+    // half's BSP walk runs on an auxiliary stream under the first half's raster is *slower* -- the walk is
+    // a single latency-bound wave of ~0.15 ms whatever the batch size, and two raster launches pay two
+    // tails: 456 k vs 488 k frames/s at 1000 frames per batch.  See profiles/README.md.)
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     if (r->profiling) {
         for (auto &e : ev) CU(cudaEventCreate(&e));
@@ -287,6 +293,9 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.palette = reinterpret_cast<const uint32_t *>(r->d_blob + h[H_OFF_PALETTE]);
     d.yslope = r->d_yslope;
     d.skyrow = r->d_skyrow;
+    CUR(cudaMalloc(&r->d_status, sizeof(int32_t)));
+    CUR(cudaMemset(r->d_status, 0, sizeof(int32_t)));
+    d.status_flag = r->d_status;
     d.nverts = (int32_t)h[H_NVERTS]; d.nnodes = (int32_t)h[H_NNODES]; d.nss = (int32_t)h[H_NSSECTORS];
     d.nsegs = (int32_t)h[H_NSEGS]; d.nsectors = (int32_t)h[H_NSECTORS]; d.ntex = (int32_t)h[H_NTEX];
     d.nflats = (int32_t)h[H_NFLATS]; d.sky_tex = (int32_t)h[H_SKY_TEX];
@@ -355,6 +364,13 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
     }
     CU(cudaStreamSynchronize(r->copy_stream));
     CU(cudaStreamSynchronize(r->render_stream));
+    int32_t status = 0;
+    CU(cudaMemcpy(&status, r->d_status, sizeof status, cudaMemcpyDeviceToHost));
+    if (status) {
+        CU(cudaMemset(r->d_status, 0, sizeof(int32_t)));
+        return fail(B2D_ERR_INVALID_ARG, status & 1 ? "BSP traversal stack overflow (tree deeper than 128 pending nodes): frames incomplete"
+                                                    : "worklist overflow: frames incomplete");
+    }
     return B2D_OK;
 }
 

@@ -213,6 +213,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         work[(size_t)frame * stride + k] = sf;
     }
     if (lane == 0) {
+        if (status) atomicOr(sc.status_flag, status);
         fc.count = count;
         fc.status = status;
 #pragma unroll

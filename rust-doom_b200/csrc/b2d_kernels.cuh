@@ -25,6 +25,7 @@ struct DeviceScene {
     int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex;
     uint32_t root;
     uint32_t invF;               // floor(2^32 / F)
+    int32_t *status_flag;        // device int: OR of per-frame walk status bits (0 = all frames complete)
 };
 
 // Bytes of dynamic shared memory one BSP-walk warp needs for this scene.

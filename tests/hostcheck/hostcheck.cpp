@@ -129,8 +129,10 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
 struct Lane { int ct, cb; uint32_t skycol; };
 
 // mirrors b2d_raster_kernel, lanes executed one after the other
+struct RasterStats { long long iters = 0, pixels = 0, entries = 0, evals = 0; };
+
 void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std::vector<SegFrame> &wl,
-            const std::vector<uint32_t> &yslope, uint32_t invF, uint8_t *fb) {
+            const std::vector<uint32_t> &yslope, uint32_t invF, uint8_t *fb, int SW = 32, RasterStats *st = nullptr) {
     const int W = vw.W, H = vw.H;
     auto put = [&](int x, int y, uint8_t v) { fb[(size_t)y * W + x] = v; };
     auto fill_void = [&](int x, int ya, int yb) { for (int y = ya; y < yb; y++) put(x, y, 0); };
@@ -172,20 +174,20 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
         }
     };
 
-    const int strips = (W + 31) / 32;
+    const int strips = (W + SW - 1) / SW;
     for (int strip = 0; strip < strips; strip++) {
-        const int x0 = strip * 32;
-        Lane lanes[32];
-        for (int l = 0; l < 32; l++) {
+        const int x0 = strip * SW;
+        std::vector<Lane> lanes((size_t)SW);
+        for (int l = 0; l < SW; l++) {
             int x = x0 + l;
             lanes[l].ct = 0; lanes[l].cb = x < W ? H : 0; lanes[l].skycol = 0;
             if (sc.sky_tex >= 0 && x < W) lanes[l].skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
         }
         for (size_t k = 0; k < wl.size(); k++) {
             const SegFrame &sf = wl[k];
-            if (!(sf.xhi >= x0 && sf.xlo <= x0 + 31)) continue;
+            if (!(sf.xhi >= x0 && sf.xlo <= x0 + SW - 1)) continue;
             bool any_open = false;
-            for (int l = 0; l < 32; l++) any_open |= lanes[l].ct < lanes[l].cb;
+            for (int l = 0; l < SW; l++) any_open |= lanes[l].ct < lanes[l].cb;
             if (!any_open) break;
             const SegRec &S = sc.segs[sf.seg];
             const SectorRec &SF = sc.sectors[S.front];
@@ -193,12 +195,16 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
             const bool two = S.flags & kSegTwoSided;
             const bool ceil_vis = ((int64_t)fcl << 16) > fc.pose.z || SF.ceil_flat == kFlatSky;
             const bool floor_vis = ((int64_t)ffl << 16) < fc.pose.z || SF.floor_flat == kFlatSky;
-            for (int l = 0; l < 32; l++) {
+            // lock-step extents of the five draws (ceiling, A, B, floor) over the strip, for statistics
+            int lo[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, hi[4] = {0, 0, 0, 0};
+            if (st) st->entries++;
+            for (int l = 0; l < SW; l++) {
                 int x = x0 + l;
                 Lane &ln = lanes[l];
                 if (!(x < W && ln.ct < ln.cb && x >= sf.xlo && x <= sf.xhi)) continue;
                 ColumnEval ce;
                 if (!column_eval(sf, vw, x, ce)) continue;
+                if (st) st->evals++;
                 int ct = ln.ct, cb = ln.cb;
                 int row = light_row(S.light, ce.z8);
                 int32_t ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
@@ -208,6 +214,13 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 else {
                     int yot = yrow(S.otop, ce.scale, fc.pose.z, H), yob = yrow(S.obot, ce.scale, fc.pose.z, H);
                     y2 = clampv(yot, y1, cb); y3 = clampv(yob, y2, cb); y4 = clampv(yff, y3, cb);
+                }
+                if (st) {
+                    auto acc = [&](int d, int a, int b) { if (a < b) { if (a < lo[d]) lo[d] = a; if (b > hi[d]) hi[d] = b; st->pixels += b - a; } };
+                    acc(0, ct, y1);
+                    if (!two || S.otop < fcl) acc(1, y1, y2);
+                    if (two && S.obot > ffl) acc(2, y3, y4);
+                    acc(3, y4, cb);
                 }
                 draw_plane(x, ln, ct, y1, fcl, SF.ceil_flat, SF.light, ceil_vis);
                 if (!two) draw_wall(x, y1, y2, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
@@ -219,8 +232,9 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 if (!two || y2 >= y3) { ln.ct = H; ln.cb = 0; }
                 else { ln.ct = y2; ln.cb = y3; }
             }
+            if (st) for (int d = 0; d < 4; d++) if (hi[d] > lo[d]) st->iters += hi[d] - lo[d];
         }
-        for (int l = 0; l < 32; l++)
+        for (int l = 0; l < SW; l++)
             if (x0 + l < W) fill_void(x0 + l, lanes[l].ct, lanes[l].cb);
     }
 }
@@ -248,3 +262,22 @@ extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose 
 }
 
 extern "C" void hostcheck_sincos(uint32_t angle, int32_t *c, int32_t *s) { sincos_q30(angle, *c, *s); }
+
+// lock-step iteration statistics for a strip width (design exploration; test-only)
+extern "C" int hostcheck_stats(const uint8_t *blob, const View *vw, const Pose *poses, int n, int strip_width,
+                               long long *out4) {
+    HostScene sc = bind(blob);
+    std::vector<uint32_t> yslope((size_t)vw->H);
+    for (int y = 0; y < vw->H; y++) yslope[(size_t)y] = yslope_entry(y, *vw);
+    uint32_t invF = (uint32_t)(4294967296ULL / (uint64_t)vw->F);
+    std::vector<uint8_t> fb((size_t)vw->W * vw->H);
+    RasterStats st;
+    for (int i = 0; i < n; i++) {
+        FrameConst fc;
+        std::vector<SegFrame> wl;
+        walk(sc, *vw, poses[i], fc, wl);
+        raster(sc, *vw, fc, wl, yslope, invF, fb.data(), strip_width, &st);
+    }
+    out4[0] = st.iters; out4[1] = st.pixels; out4[2] = st.entries; out4[3] = st.evals;
+    return 0;
+}

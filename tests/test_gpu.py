@@ -32,7 +32,7 @@ def test_gpu_matches_oracle_320x200(b2d, product_scene):
     _loaded_native()
     ofb = render.render(product_scene.blob, render.make_view(320, 200), poses, threads=8)
     _assert_same(ofb, gfb, "320x200")
-    assert r.launch_count == 6
+    assert r.launch_count == 6          # 3 batches of <= 40 frames: walk + raster each
 
 
 def test_gpu_matches_oracle_odd_width(b2d, product_scene):
@@ -196,3 +196,25 @@ def test_config5_random_poses_1080p(b2d, product_scene):
     assert torch.equal(a, bb)
     ofb = render.render(product_scene.blob, render.make_view(1920, 1080), poses[::32], threads=8)
     assert np.array_equal(a[::32].cpu().numpy(), ofb)
+
+
+def test_gpu_edge_sizes(b2d, product_scene):
+    """Empty pose list, 1x2 and the maximum 4096x2160 view."""
+    poses = sample_poses(b2d, product_scene, 3, 41)
+    r = b2d.Renderer(product_scene, b2d.make_view(320, 200), max_batch=4)
+    assert r.render(poses[:0]).shape == (0, 200, 320)
+    for (w, h) in ((1, 2), (31, 3), (4096, 2160)):
+        gfb = b2d.Renderer(product_scene, b2d.make_view(w, h), max_batch=2).render(poses[:2])
+        ofb = render.render(product_scene.blob, render.make_view(w, h), poses[:2], threads=2)
+        _assert_same(ofb, gfb, "%dx%d" % (w, h))
+
+
+def test_gpu_large_batch(b2d, product_scene):
+    poses = sample_poses(b2d, product_scene, 130, 42)
+    r = b2d.Renderer(product_scene, b2d.make_view(320, 200), max_batch=130)
+    gfb = r.render(poses)
+    assert r.launch_count == 2
+    ofb = render.render(product_scene.blob, render.make_view(320, 200), poses, threads=8)
+    _assert_same(ofb, gfb, "batch of 130")
+    counts, ids = r.worklist(130)
+    assert (counts > 0).all()
