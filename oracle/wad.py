@@ -137,7 +137,7 @@ class Archive:
         _, pos, size = self.lumps[index]
         if size == 0:
             return b""
-        if pos < 0 or pos + size > len(self.data):
+        if pos < 0 or size < 0 or pos + size > len(self.data):   # i32 -> usize wrap makes the read fail
             raise WadError("lump %d out of file bounds" % index)
         return self.data[pos:pos + size]
 
@@ -310,10 +310,11 @@ class TextureDirectory:
         s0 = wad.required(b"S_START") + 1
         s1 = wad.required(b"S_END")
         for i in range(s0, s1):
+            buf = wad.read(i)                       # a read failure fails the load (tex.rs:484-485)
             try:
-                px, _, _ = decode_picture(wad.read(i))
+                px, _, _ = decode_picture(buf)
             except WadError:
-                continue
+                continue                            # a decode failure skips the sprite (tex.rs:486-493)
             self.textures[wad.lumps[i][0]] = px
 
     @staticmethod
@@ -335,8 +336,9 @@ class TextureDirectory:
             if idx is None:
                 out.append((name, None))
                 continue
+            pbuf = wad.read(idx)                    # read errors propagate (tex.rs:384-385)
             try:
-                px, _, _ = decode_picture(wad.read(idx))
+                px, _, _ = decode_picture(pbuf)
                 out.append((name, px))
             except WadError:
                 out.append((name, None))

@@ -369,7 +369,8 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
     if (status) {
         CU(cudaMemset(r->d_status, 0, sizeof(int32_t)));
         return fail(B2D_ERR_INVALID_ARG, status & 1 ? "BSP traversal stack overflow (tree deeper than 128 pending nodes): frames incomplete"
-                                                    : "worklist overflow: frames incomplete");
+                                            : (status & 4 ? "BSP traversal did not terminate (cyclic node graph): frames incomplete"
+                                                          : "worklist overflow: frames incomplete"));
     }
     return B2D_OK;
 }

@@ -127,8 +127,9 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         int32_t flags = S.flags;
         if (!(flags & kSegInvalid)) {
             SegFrame sf;
-            if (seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf)) {
-                bool solid = (!(flags & kSegTwoSided) || S.otop <= S.obot) && (sf.flags & kSegFrameNoSkip);
+            const bool closes = !(flags & kSegTwoSided) || S.otop <= S.obot;   // every column it covers closes
+            if (seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf, closes)) {
+                bool solid = closes && (sf.flags & kSegFrameNoSkip);
                 packed = pack_range(sf.xlo, sf.xhi, kVisBit | (solid ? kSolidBit : 0u));
             }
         }
@@ -153,7 +154,9 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
 
     // 4. front-to-back traversal (control flow is warp-uniform)
     int sp = 1, count = 0, status = 0;
+    int budget = 2 * (sc.nnodes + sc.nss) + 64;      // a corrupt BSP with a cycle must not hang the GPU
     while (sp > 0) {
+        if (--budget < 0) { status |= 4; break; }
         uint32_t child = stack[--sp];
         __syncwarp();
         if (child & kLeaf) {
@@ -208,7 +211,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         int si = list[k];
         const SegRec &S = sc.segs[si];
         SegFrame sf;
-        seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf);
+        seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf, false);
         sf.seg = si;
         work[(size_t)frame * stride + k] = sf;
     }

@@ -146,7 +146,8 @@ struct ColumnEval {
 
 // Per-frame projection setup of one seg from its view-space endpoints.  Returns false if the seg is
 // back-facing / degenerate or covers no screen column.
-B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx_, int32_t bz_, SegFrame &sf);
+B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx_, int32_t bz_, SegFrame &sf,
+                            bool want_noskip = true);
 
 // Column predicate + per-column projection values.  Exact: does not rely on xlo/xhi.
 B2D_HD bool column_eval(const SegFrame &sf, const View &vw, int x, ColumnEval &out) {
@@ -176,14 +177,22 @@ B2D_HD bool column_eval(const SegFrame &sf, const View &vw, int x, ColumnEval &o
     return true;
 }
 
-B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx_, int32_t bz_, SegFrame &sf) {
+B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx_, int32_t bz_, SegFrame &sf,
+                            bool want_noskip) {
     const int64_t ax = ax_, az = az_, bx = bx_, bz = bz_;
     const int64_t F = vw.F, W = vw.W;
+    if (az_ <= 0 && bz_ <= 0) return false;       // wholly behind the camera plane: no column can see it
     int64_t dxs = bx - ax, dzs = bz - az;
     int64_t C = az * dxs - ax * dzs;
     if (C <= 0) return false;
     sf.Nx = 2 * az; sf.Nc = az * (1 - W) - ax * F;
     sf.Dx = -2 * dzs; sf.Dc = dxs * F - dzs * (1 - W);
+    {   // division-free rejects: a linear function that is negative at both screen edges is negative on
+        // the whole screen (exact; the interval solve below would come out empty)
+        const int64_t xr = W - 1;
+        const int64_t n0 = sf.Nc, n1 = sf.Nc + sf.Nx * xr, d0 = sf.Dc, d1 = sf.Dc + sf.Dx * xr;
+        if ((n0 < 0 && n1 < 0) || (d0 < 1 && d1 < 1) || (d0 - n0 < 0 && d1 - n1 < 0)) return false;
+    }
     int64_t lo = 0, hi = W - 1;
     constrain(lo, hi, sf.Dc, sf.Dx, 1);
     constrain(lo, hi, sf.Nc, sf.Nx, 0);
@@ -202,10 +211,14 @@ B2D_HD bool seg_frame_setup(const View &vw, int32_t ax_, int32_t az_, int32_t bx
     sf.sh = (int16_t)sh;
     sf.e = (int16_t)(5 - sh + shm);
     sf.Dmax = M >> 8;
-    // no-skip guarantee: column_eval's early-outs are monotone in D, so the endpoints decide
-    ColumnEval ce;
-    bool ok = column_eval(sf, vw, (int)lo, ce) && column_eval(sf, vw, (int)hi, ce);
-    sf.flags = ok ? kSegFrameNoSkip : 0;
+    // no-skip guarantee (only solid segs need it): column_eval's early-outs are monotone in D, so the
+    // two endpoints decide for the whole interval
+    sf.flags = 0;
+    if (want_noskip) {
+        ColumnEval ce;
+        bool ok = column_eval(sf, vw, (int)lo, ce) && column_eval(sf, vw, (int)hi, ce);
+        sf.flags = ok ? kSegFrameNoSkip : 0;
+    }
     sf.pad = 0;
     return true;
 }

@@ -315,8 +315,9 @@ TextureDirectory TextureDirectory::load(const Archive &wad) {
             int li = wad.find(nm);
             int img = -1;
             if (li >= 0) {
+                const uint8_t *bytes = wad.lump_data(li);      // a read failure fails the load (tex.rs:384-385)
                 try {
-                    Image im = Image::decode(wad.lump_data(li), (size_t)wad.lump(li).size);
+                    Image im = Image::decode(bytes, (size_t)wad.lump(li).size);
                     img = (int)td.patch_images.size();
                     td.patch_images.push_back(std::move(im));
                 } catch (const WadError &) { img = -1; }
@@ -361,13 +362,17 @@ TextureDirectory TextureDirectory::load(const Archive &wad) {
     {   // flats (tex.rs:594-606)
         int s = wad.require("F_START"), e = wad.require("F_END");
         for (int i = s; i < e; i++)
-            if (wad.lump(i).size != 0) td.flat_index[wad.lump(i).name] = i;
+            if (wad.lump(i).size != 0) {
+                (void)wad.lump_data(i);                        // read_bytes()? : out-of-file lumps fail the load
+                td.flat_index[wad.lump(i).name] = i;
+            }
     }
     {   // sprites share the texture name space and may shadow a texture (tex.rs:475-497)
         int s = wad.require("S_START") + 1, e = wad.require("S_END");
         for (int i = s; i < e; i++) {
+            const uint8_t *bytes = wad.lump_data(i);           // read failure propagates (tex.rs:484-485)
             try {
-                Image im = Image::decode(wad.lump_data(i), (size_t)wad.lump(i).size);
+                Image im = Image::decode(bytes, (size_t)wad.lump(i).size);
                 const Name &nm = wad.lump(i).name;
                 auto found = td.texture_index.find(nm);
                 if (found != td.texture_index.end()) td.textures[(size_t)found->second] = std::move(im);

@@ -58,10 +58,11 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
         const SegRec &S = sc.segs[i];
         if (S.flags & kSegInvalid) continue;
         SegFrame sf;
-        if (seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf)) {
+        const bool closes = !(S.flags & kSegTwoSided) || S.otop <= S.obot;
+        if (seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf, closes)) {
             Range &r = segr[(size_t)i];
             r.vis = true; r.lo = sf.xlo; r.hi = sf.xhi;
-            r.solid = (!(S.flags & kSegTwoSided) || S.otop <= S.obot) && (sf.flags & kSegFrameNoSkip);
+            r.solid = closes && (sf.flags & kSegFrameNoSkip);
         }
     }
     for (int i = 0; i < 2 * sc.nnodes; i++) {
@@ -81,7 +82,9 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
     stack.push_back(sc.root);
     std::vector<int> list;
     int status = 0;
+    int budget = 2 * (sc.nnodes + sc.nss) + 64;
     while (!stack.empty()) {
+        if (--budget < 0) { status |= 4; break; }
         uint32_t child = stack.back();
         stack.pop_back();
         if (child & kLeaf) {
@@ -118,7 +121,7 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
     for (int si : list) {
         const SegRec &S = sc.segs[si];
         SegFrame sf;
-        seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf);
+        seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf, false);
         sf.seg = si;
         out.push_back(sf);
     }

@@ -218,3 +218,45 @@ def test_gpu_large_batch(b2d, product_scene):
     _assert_same(ofb, gfb, "batch of 130")
     counts, ids = r.worklist(130)
     assert (counts > 0).all()
+
+
+def test_gpu_fuzzed_levels_match_oracle(b2d):
+    """Corrupt level lumps (random bytes in SEGS/NODES/SECTORS/...) that still load must render identically
+    on the GPU and in the oracle, or be reported incomplete by the walk -- and never fault the device."""
+    import struct
+    import torch
+    from oracle import scene as S
+    from oracle import wad as W
+    from rust_doom_b200 import synthwad
+    base = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(gx=4, gy=3, origin=(-512, -384)))
+    oa0 = W.Archive(base)
+    rng = synthwad.SplitMix64(77)
+    view, oview = b2d.make_view(160, 100), render.make_view(160, 100)
+    poses = np.concatenate([b2d.make_pose(-300 + 150 * i, -100 + 60 * i, 30 + 7 * i, 47 * i) for i in range(4)])
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    compared = 0
+    for it in range(60):
+        data = bytearray(base)
+        idx = oa0.levels[0] + 2 + rng.below(7)            # LINEDEFS .. SECTORS
+        _, pos, size = oa0.lumps[idx]
+        for _ in range(1 + rng.below(5)):
+            data[pos + rng.below(size)] = rng.below(256)
+        data = bytes(data)
+        try:
+            oa = W.Archive(data)
+            ob = S.compile_scene(oa, W.TextureDirectory(oa), 0)
+            sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+        except (W.WadError, b2d.B2dError):
+            continue
+        assert sc.blob == ob
+        r = b2d.Renderer(sc, view, max_batch=4)
+        out = torch.full((4, 100, 160), 0xEE, dtype=torch.uint8, device="cuda")
+        r.render_device(dp.data_ptr(), 4, out.data_ptr())
+        torch.cuda.synchronize()
+        counts, _ = r.worklist(4)
+        if (counts < 0).any():
+            continue                                      # walk reported an incomplete traversal (cyclic BSP)
+        ofb = render.render(ob, oview, poses)
+        _assert_same(ofb, out.cpu().numpy(), "fuzz iteration %d" % it)
+        compared += 1
+    assert compared > 20
