@@ -307,12 +307,77 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
         idx = c & 0x7FFF
         return (idx | LEAF) if (c & 0x8000) else idx
 
+    # Child bounding boxes are NOT taken from the file: they are recomputed from the segs each subtree
+    # actually holds, so that bounding-box culling stays conservative for any (even inconsistent) map.
+    # box = (top, bottom, left, right); an empty subtree gets (0,0,0,0); a cyclic reference gets the
+    # whole coordinate range.  Iterative post-order, identical in the product's compiler.
+    FULL = (32767, -32768, -32768, 32767)
+    EMPTY = (0, 0, 0, 0)
+
+    def leaf_box(ss_id: int):
+        if ss_id >= nss:
+            return None
+        first, num = int(ssectors[ss_id, 0]), int(ssectors[ss_id, 1])
+        box = None
+        for k in range(first, first + num):
+            if segs[k, 3] & SEG_INVALID:
+                continue
+            for v in (int(segs[k, 0]), int(segs[k, 1])):
+                x, y = int(level.vertices[v]["x"]), int(level.vertices[v]["y"])
+                box = (y, y, x, x) if box is None else (max(box[0], y), min(box[1], y), min(box[2], x), max(box[3], x))
+        return box
+
+    def union(a, b):
+        if a is None:
+            return b
+        if b is None:
+            return a
+        return (max(a[0], b[0]), min(a[1], b[1]), min(a[2], b[2]), max(a[3], b[3]))
+
+    state = [0] * nnodes            # 0 unvisited, 1 on the stack, 2 done
+    node_box = [None] * nnodes      # union of both children once done
+    child_box = [[None, None] for _ in range(nnodes)]
+
+    def resolve(c: int):
+        """box of child id c if already known, else the node index that must be visited first"""
+        if c & LEAF:
+            return leaf_box(c & 0x7FFFFFFF), -1
+        if c >= nnodes:
+            return None, -1
+        if state[c] == 2:
+            return node_box[c], -1
+        if state[c] == 1:
+            return FULL, -1
+        return None, c
+
+    if nnodes > 0:
+        stack = [nnodes - 1]
+        state[nnodes - 1] = 1
+        while stack:
+            i = stack[-1]
+            n = level.nodes[i]
+            pending = -1
+            for side, raw in ((0, int(n["right"])), (1, int(n["left"]))):
+                box, need = resolve(child(raw))
+                if need >= 0:
+                    pending = need
+                    break
+                child_box[i][side] = box
+            if pending >= 0:
+                state[pending] = 1
+                stack.append(pending)
+                continue
+            node_box[i] = union(child_box[i][0], child_box[i][1])
+            state[i] = 2
+            stack.pop()
+
     for i in range(nnodes):
         n = level.nodes[i]
-        rb, lb = [int(v) for v in n["rbox"]], [int(v) for v in n["lbox"]]
-        # on-disk order is top, bottom, left, right; be tolerant of swapped pairs
-        rb = [max(rb[0], rb[1]), min(rb[0], rb[1]), min(rb[2], rb[3]), max(rb[2], rb[3])]
-        lb = [max(lb[0], lb[1]), min(lb[0], lb[1]), min(lb[2], lb[3]), max(lb[2], lb[3])]
+        if state[i] == 2:
+            rb = list(child_box[i][0] or EMPTY)
+            lb = list(child_box[i][1] or EMPTY)
+        else:                       # unreachable from the root: never traversed
+            rb, lb = list(EMPTY), list(EMPTY)
         nodes[i, :14] = [int(n["x"]), int(n["y"]), int(n["dx"]), int(n["dy"])] + rb + lb + \
                         [child(int(n["right"])), child(int(n["left"]))]
 

@@ -256,18 +256,72 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
 
     std::vector<NodeRec> nodes((size_t)nnodes);
     auto child = [](uint16_t c) -> uint32_t { return (c & 0x8000u) ? ((c & 0x7FFFu) | kLeaf) : (c & 0x7FFFu); };
-    auto fix_box = [](const int16_t in[4], int32_t out[4]) {   // disk order: top, bottom, left, right
-        out[0] = in[0] > in[1] ? in[0] : in[1];
-        out[1] = in[0] > in[1] ? in[1] : in[0];
-        out[2] = in[2] < in[3] ? in[2] : in[3];
-        out[3] = in[2] < in[3] ? in[3] : in[2];
+    // Child bounding boxes are recomputed from the segs each subtree actually holds (never trusted from the
+    // file), so that bounding-box culling in the walk kernel stays conservative for inconsistent maps.
+    // box = {top, bottom, left, right}; empty subtree -> {0,0,0,0}; cyclic reference -> whole range.
+    struct Box { bool valid; int32_t b[4]; };
+    const Box kFull{true, {32767, -32768, -32768, 32767}};
+    auto unite = [](const Box &a, const Box &c) -> Box {
+        if (!a.valid) return c;
+        if (!c.valid) return a;
+        Box r{true, {a.b[0] > c.b[0] ? a.b[0] : c.b[0], a.b[1] < c.b[1] ? a.b[1] : c.b[1],
+                     a.b[2] < c.b[2] ? a.b[2] : c.b[2], a.b[3] > c.b[3] ? a.b[3] : c.b[3]}};
+        return r;
     };
+    auto leaf_box = [&](uint32_t ss_id) -> Box {
+        Box box{false, {0, 0, 0, 0}};
+        if (ss_id >= (uint32_t)nss) return box;
+        const SSectorRec &ss = ssectors[ss_id];
+        for (int k = ss.first_seg; k < ss.first_seg + ss.num_segs; k++) {
+            const SegRec &sg = segs[(size_t)k];
+            if (sg.flags & kSegInvalid) continue;
+            for (int32_t v : {sg.v1, sg.v2}) {
+                int32_t x = lv.vertices[(size_t)v].x, y = lv.vertices[(size_t)v].y;
+                Box p{true, {y, y, x, x}};
+                box = unite(box, p);
+            }
+        }
+        return box;
+    };
+    std::vector<char> state((size_t)nnodes, 0);              // 0 unvisited, 1 on the stack, 2 done
+    std::vector<Box> node_box((size_t)nnodes, Box{false, {0, 0, 0, 0}});
+    std::vector<std::array<Box, 2>> child_box((size_t)nnodes, {Box{false, {0, 0, 0, 0}}, Box{false, {0, 0, 0, 0}}});
+    if (nnodes > 0) {
+        std::vector<int> stack{nnodes - 1};
+        state[(size_t)nnodes - 1] = 1;
+        while (!stack.empty()) {
+            const int i = stack.back();
+            const Node &n = lv.nodes[(size_t)i];
+            int pending = -1;
+            const uint16_t raw[2] = {n.right, n.left};
+            for (int side = 0; side < 2 && pending < 0; side++) {
+                uint32_t c = child(raw[side]);
+                Box box{false, {0, 0, 0, 0}};
+                if (c & kLeaf) box = leaf_box(c & 0x7FFFFFFFu);
+                else if ((int)c >= nnodes) box = Box{false, {0, 0, 0, 0}};
+                else if (state[c] == 2) box = node_box[c];
+                else if (state[c] == 1) box = kFull;
+                else { pending = (int)c; break; }
+                child_box[(size_t)i][(size_t)side] = box;
+            }
+            if (pending >= 0) {
+                state[(size_t)pending] = 1;
+                stack.push_back(pending);
+                continue;
+            }
+            node_box[(size_t)i] = unite(child_box[(size_t)i][0], child_box[(size_t)i][1]);
+            state[(size_t)i] = 2;
+            stack.pop_back();
+        }
+    }
     for (int i = 0; i < nnodes; i++) {
         const Node &n = lv.nodes[(size_t)i];
         NodeRec r{};
         r.x = n.x; r.y = n.y; r.dx = n.dx; r.dy = n.dy;
-        fix_box(n.rbox, r.rbox);
-        fix_box(n.lbox, r.lbox);
+        if (state[(size_t)i] == 2) {
+            const Box &rb = child_box[(size_t)i][0], &lb = child_box[(size_t)i][1];
+            for (int k = 0; k < 4; k++) { r.rbox[k] = rb.valid ? rb.b[k] : 0; r.lbox[k] = lb.valid ? lb.b[k] : 0; }
+        }
         r.child[0] = child(n.right);
         r.child[1] = child(n.left);
         nodes[(size_t)i] = r;

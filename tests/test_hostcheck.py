@@ -56,3 +56,36 @@ def test_hostcheck_micro_level_extremes(b2d, hostcheck):
     ofb = render.render(sc.blob, render.make_view(320, 200), poses)
     hfb, counts, _ = hostcheck(sc.blob, b2d.make_view(320, 200), poses)
     assert np.array_equal(ofb, hfb)
+
+
+def test_hostcheck_fuzzed_levels(b2d, hostcheck):
+    """Inconsistent maps (random bytes in LINEDEFS..SECTORS that still load): bounding-box / solid-column
+    culling must stay conservative because the scene compiler recomputes child boxes from the segs."""
+    from oracle import scene as S
+    from oracle import wad as W
+    from rust_doom_b200 import synthwad
+    base = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(gx=4, gy=3, origin=(-512, -384)))
+    oa0 = W.Archive(base)
+    rng = synthwad.SplitMix64(77)
+    view, oview = b2d.make_view(160, 100), render.make_view(160, 100)
+    poses = np.ascontiguousarray(np.concatenate(
+        [b2d.make_pose(-300 + 150 * i, -100 + 60 * i, 30 + 7 * i, 47 * i) for i in range(4)]))
+    compared = 0
+    for it in range(80):
+        data = bytearray(base)
+        idx = oa0.levels[0] + 2 + rng.below(7)
+        _, pos, size = oa0.lumps[idx]
+        for _ in range(1 + rng.below(5)):
+            data[pos + rng.below(size)] = rng.below(256)
+        try:
+            oa = W.Archive(bytes(data))
+            ob = S.compile_scene(oa, W.TextureDirectory(oa), 0)
+        except W.WadError:
+            continue
+        ofb = render.render(ob, oview, poses)
+        hfb, counts, _ = hostcheck(ob, view, poses)
+        if (counts < 0).any():
+            continue
+        assert np.array_equal(ofb, hfb), "fuzz iteration %d" % it
+        compared += 1
+    assert compared > 30
