@@ -273,7 +273,7 @@ __device__ __forceinline__ void put_px(const RasterCtx &c, uint8_t *p8, uint32_t
 }
 
 // rows [ya, yb) of this lane's column := void (index 0); lanes with ya >= yb idle
-template <bool kRgba, int kW>
+template <bool kRgba, int kW, int kUnroll>
 __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int yb) {
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
@@ -285,10 +285,10 @@ __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int y
     for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) put_px<kRgba>(c, p8, p32, y >= ya && y < yb, 0u);
 }
 
-template <bool kRgba, int kW>
+template <bool kRgba, int kW, int kUnroll>
 __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb) {
     const DeviceScene &sc = *c.sc;
-    if (sc.sky_tex < 0) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
+    if (sc.sky_tex < 0) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const TexRec T = sc.tex[sc.sky_tex];
     const uint8_t *px = sc.texels + T.texel_off + c.skycol;
     bool act = ya < yb;
@@ -298,7 +298,7 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
-#pragma unroll 4
+#pragma unroll(kUnroll)
     for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) {
         uint32_t v = sc.skyrow[y];                                        // warp-uniform table entry
         uint32_t texel = px[v * T.w];
@@ -306,15 +306,15 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     }
 }
 
-template <bool kRgba, int kW>
+template <bool kRgba, int kW, int kUnroll>
 __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameConst &fc, const View &vw,
                                                 int ya, int yb, int32_t h, int32_t flat, int lightb,
                                                 bool visible) {
     const DeviceScene &sc = *c.sc;
     if (!__any_sync(kFull, ya < yb)) return;
-    if (!visible) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
-    if (flat == kFlatSky) { draw_sky_warp<kRgba, kW>(c, ya, yb); return; }
-    if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
+    if (!visible) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
+    if (flat == kFlatSky) { draw_sky_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
+    if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const uint8_t *px = sc.flats + 4096u * (uint32_t)flat;
     const uint32_t habs = plane_habs(h, fc.pose.z);
     bool act = ya < yb;
@@ -334,7 +334,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         }
         __syncwarp();
         const int rows = min(32, y1 - yc);
-#pragma unroll 4
+#pragma unroll(kUnroll)
         for (int j = 0; j < rows; j++, p8 += Wc, p32 += Wc) {
             const uint4 r4 = lds_v4_volatile(c.row4_s + 16u * (uint32_t)j);   // shared-memory broadcast
             const uint32_t cm = lds_u32_volatile(c.row1_s + 4u * (uint32_t)j);
@@ -348,13 +348,13 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
     }
 }
 
-template <bool kRgba, int kW>
+template <bool kRgba, int kW, int kUnroll>
 __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameConst &fc, int ya, int yb,
                                                int32_t tex, int32_t tA, int32_t hA, int32_t ucol,
                                                int32_t iscale, int row) {
     const DeviceScene &sc = *c.sc;
     if (!__any_sync(kFull, ya < yb)) return;
-    if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
+    if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const TexRec T = sc.tex[tex];
     bool act = ya < yb;
     const uint8_t *px = sc.texels + T.texel_off + (uint32_t)floormod32(ucol, (int32_t)T.w);
@@ -373,13 +373,13 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
         const int lw = 31 - __clz((int)T.w);
         const uint32_t mask = (T.h - 1u) << lw;
         const int sh = 16 - lw;            // w <= 4096 -> sh >= 4
-#pragma unroll 4
+#pragma unroll(kUnroll)
         for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
             uint32_t texel = px[(t >> sh) & mask];
             put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
         }
     } else {
-#pragma unroll 4
+#pragma unroll(kUnroll)
         for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
             uint32_t v = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
             uint32_t texel = px[v * T.w];
@@ -388,15 +388,15 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
     }
 }
 
-template <bool kRgba, int kMinBlocks, int kW>
-__global__ void __launch_bounds__(128, kMinBlocks)
+template <bool kRgba, int kMinBlocks, int kW, int kUnroll, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
                   const SegFrame *__restrict__ work, int stride, int n, int strips,
                   uint8_t *__restrict__ index_fb, uint32_t *__restrict__ rgba_fb) {
     __shared__ __align__(16) uint8_t s_cmap[32 * 256];
     __shared__ uint32_t s_pal[kRgba ? 256 : 1];
-    __shared__ uint4 s_row4[4][32];
-    __shared__ uint32_t s_row1[4][32];
+    __shared__ uint4 s_row4[kWarps][32];
+    __shared__ uint32_t s_row1[kWarps][32];
     {   // colormap rows 0..31 (and the palette) into shared memory, 128-bit loads
         const uint4 *src = reinterpret_cast<const uint4 *>(sc.colormap);
         uint4 *dst = reinterpret_cast<uint4 *>(s_cmap);
@@ -479,17 +479,17 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 yend = cb;
             }
             // ceiling region [ct, y1)
-            draw_plane_warp<kRgba, kW>(c, fc, vw, ok ? ct : 0, ok ? y1 : 0, fcl, SF.ceil_flat, SF.light, ceil_vis);
+            draw_plane_warp<kRgba, kW, kUnroll>(c, fc, vw, ok ? ct : 0, ok ? y1 : 0, fcl, SF.ceil_flat, SF.light, ceil_vis);
             if (!two) {
-                draw_wall_warp<kRgba, kW>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
             } else {
                 if (S.otop < fcl)
-                    draw_wall_warp<kRgba, kW>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
+                    draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
                 if (S.obot > ffl)
-                    draw_wall_warp<kRgba, kW>(c, fc, ok ? y3 : 0, ok ? y4 : 0, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
+                    draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? y3 : 0, ok ? y4 : 0, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
             }
             // floor region [y4, cb)
-            draw_plane_warp<kRgba, kW>(c, fc, vw, ok ? y4 : 0, ok ? yend : 0, ffl, SF.floor_flat, SF.light, floor_vis);
+            draw_plane_warp<kRgba, kW, kUnroll>(c, fc, vw, ok ? y4 : 0, ok ? yend : 0, ffl, SF.floor_flat, SF.light, floor_vis);
             if (ok) {
                 if (!two || y2 >= y3) { ct = H; cb = 0; }
                 else { ct = y2; cb = y3; }
@@ -497,7 +497,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
         }
     }
     // whatever is still open is void
-    fill_void_warp<kRgba, kW>(c, inside ? ct : 0, inside ? cb : 0);
+    fill_void_warp<kRgba, kW, kUnroll>(c, inside ? ct : 0, inside ? cb : 0);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -559,29 +559,20 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
                           uint32_t *d_rgba, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     const int strips = (vw.W + 31) / 32;
-    const long long warps = (long long)n * strips;
-    const int blocks = (int)((warps + 3) / 4);
-    // Variants: registers/thread are capped by the min-blocks launch bound (8 CTAs x 4 warps per SM measured
-    // fastest on B200: the kernel is latency bound at lower occupancy), and the frame width is a
-    // compile-time constant for the benchmark resolution so that unrolled row stores use immediate offsets.
-    static int variant = -1;
-    if (variant < 0) {
-        const char *e = getenv("B2D_RASTER_MINBLOCKS");
-        variant = e ? atoi(e) : 8;
-    }
-#define B2D_LAUNCH_RASTER(RGBA, MB, KW) \
-    b2d_raster_kernel<RGBA, MB, KW><<<blocks, 128, 0, stream>>>(sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba)
+    // Launch shape (tuned on B200, profiles/README.md): 4 warps per CTA and 64 registers/thread, i.e. 8 CTAs =
+    // 32 warps resident per SM (the kernel is latency bound below that; 8- and 16-warp CTAs lose 5-15 % to
+    // intra-CTA imbalance); row loops unrolled x8; the frame width is a compile-time constant for the
+    // benchmark resolution so that the unrolled row stores use immediate offsets.
+    constexpr int kWarps = 4;
+    const long long total_warps = (long long)n * strips;
+    const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
     const bool w1920 = vw.W == 1920 && !getenv("B2D_RASTER_GENERIC_W");
-    if (d_rgba) {
-        if (w1920) B2D_LAUNCH_RASTER(true, 8, 1920); else B2D_LAUNCH_RASTER(true, 8, 0);
-    } else if (variant >= 8) {
-        if (w1920) B2D_LAUNCH_RASTER(false, 8, 1920); else B2D_LAUNCH_RASTER(false, 8, 0);
-    } else if (variant >= 6) {
-        B2D_LAUNCH_RASTER(false, 6, 0);
-    } else {
-        B2D_LAUNCH_RASTER(false, 5, 0);
-    }
-#undef B2D_LAUNCH_RASTER
+#define B2D_RASTER_GO(RGBA, KW) \
+    b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps><<<nblocks, kWarps * 32, 0, stream>>>( \
+        sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba)
+    if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
+    else { if (w1920) B2D_RASTER_GO(false, 1920); else B2D_RASTER_GO(false, 0); }
+#undef B2D_RASTER_GO
     return cudaGetLastError();
 }
 
