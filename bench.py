@@ -133,7 +133,7 @@ def cpu_reference(blob, poses, threads, steps, warmup, sample):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2d", choices=["b2d", "reference"])
     ap.add_argument("--poses", type=int, default=POSES_PER_STEP)
@@ -307,7 +307,7 @@ def main():
         fps, ms = cpu_reference(scene.blob, poses_np, cores, reps, 1, sample)
         # keep the CPU leg near 10-30 s: repeat if it was very quick
         if ms < 3000:
-            reps = int(min(10, max(1, 10000 // max(ms, 1))))
+            reps = int(min(100, max(1, 10000 // max(ms, 1))))
             fps, ms = cpu_reference(scene.blob, poses_np, cores, reps, 0, sample)
         cpu_baseline = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "%d of the %d poses x %d passes at %dx%d, OpenMP over poses (oracle/b2d_oracle.c)" % (sample, n, reps, WIDTH, HEIGHT)}
