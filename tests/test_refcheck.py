@@ -1,0 +1,49 @@
+"""Scene-semantics pin for the oracle.  The reference has no CPU renderer to compare pixels with, but its
+pipeline is well defined: a static triangle soup + depth test + the GLSL in assets/shaders/.  With a depth
+test the visible surface at a pixel is the nearest one along the pixel's ray, so tests/refcheck/glcaster.py
+ray-casts the level in float64 straight from the reference's geometry and shader rules (no BSP order, no column
+clipping, no fixed point).  The oracle -- a completely different algorithm -- must agree with it on almost every
+pixel; the residue is float-vs-fixed-point rounding at texel / colormap-row / silhouette boundaries."""
+import numpy as np
+import pytest
+
+from oracle import render, scene, wad
+from tests.refcheck import glcaster
+
+
+def _poses_in(level, want_sky, n, seed):
+    rng = np.random.default_rng(seed)
+    sec_bytes = level.sectors.tobytes()
+    out = []
+    while len(out) < n:
+        x, y = rng.uniform(-1280, 1280), rng.uniform(-1152, 1152)
+        sec = scene.sector_at(level, x, y)
+        if sec < 0:
+            continue
+        s = level.sectors[sec]
+        is_sky = wad.is_sky_flat(wad.wad_name(sec_bytes[sec * 26 + 12:sec * 26 + 20]))
+        if is_sky != want_sky or int(s["ceil"]) - int(s["floor"]) < 56:
+            continue
+        out.append((round(x * 4) / 4, round(y * 4) / 4, int(s["floor"]) + 41, float(rng.integers(0, 720)) / 2))
+    return out
+
+
+@pytest.mark.parametrize("want_sky", [False, True])
+def test_oracle_agrees_with_reference_semantics_raycaster(synth_wad, oracle_scene, want_sky):
+    a = wad.Archive(synth_wad)
+    tex = wad.TextureDirectory(a)
+    level = wad.Level(a, 0)
+    W_, H_ = 320, 200
+    view = render.make_view(W_, H_)
+    fracs, sky_share = [], []
+    for (x, y, z, ang) in _poses_in(level, want_sky, 5, 7 + want_sky):
+        g, kind = glcaster.render(a, tex, 0, W_, H_, x, y, z, ang, focal2=(view.F, view.FY2))
+        o = render.render(oracle_scene, view, render.make_pose(x, y, z, ang))[0]
+        fracs.append(float((g == o).mean()))
+        sky_share.append(float((kind == 3).mean()))
+        if (kind == 3).any():
+            assert (g == o)[kind == 3].mean() > 0.97, "sky mapping disagrees"
+    assert min(fracs) > 0.985, fracs
+    assert float(np.mean(fracs)) > 0.992, fracs
+    if want_sky:
+        assert max(sky_share) > 0.05, "no pose actually saw the sky"
