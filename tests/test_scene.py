@@ -141,3 +141,43 @@ def test_contrast_rule(b2d):
     assert segs[0][12] == W.light_byte(160, -1)     # (-256,0)->(-256,256): dx == 0
     assert segs[1][12] == W.light_byte(160, +1)     # horizontal
     assert W.light_byte(160, -1) < base < W.light_byte(160, +1)
+
+
+def test_wad_layout_quirks(b2d):
+    """IWAD layout variations real files have: TEXTURE2, nested F1_START/F1_END markers (virtual lumps inside
+    F_START..F_END), a duplicated lump name (the later one wins, archive.rs:85), lower-case texture names in
+    sidedefs (upper-cased on read, name.rs:41-75) and a sprite that shadows a texture name (tex.rs:475-497)."""
+    import struct
+    from rust_doom_b200 import synthwad as G
+    rng = G.SplitMix64(5)
+    playpal = G.make_playpal()
+    patches, tex, flats = G.make_graphics(rng)
+    names = list(patches.keys())
+    pn, t1 = G.make_pnames_texture1(names, tex[:9])
+    _, t2 = G.make_pnames_texture1(names, tex[9:])
+    lvl = G.LevelBuilder("E1M1", 42, G.SynthConfig(gx=4, gy=3, origin=(-512, -384))).generate()
+    lumps = lvl.lumps()
+    # lower-case the texture names of the first 20 sidedefs
+    sd = bytearray(dict(lumps)["SIDEDEFS"])
+    for i in range(20):
+        for f in range(3):
+            o = i * 30 + 4 + 8 * f
+            sd[o:o + 8] = bytes(sd[o:o + 8]).lower()
+    lumps = [(n, bytes(sd) if n == "SIDEDEFS" else d) for n, d in lumps]
+    flat_items = list(flats.items())
+    wadlumps = [("PLAYPAL", playpal), ("COLORMAP", G.make_colormap(playpal))] + lumps + \
+               [("TEXTURE1", t1), ("TEXTURE2", t2), ("PNAMES", pn)] + list(patches.items()) + \
+               [("S_START", b""), ("BRICK1", G.encode_picture(G._img_gradient(rng, 64, 128, 9))), ("S_END", b""),
+                ("F_START", b""), ("F1_START", b"")] + flat_items[:6] + [("F1_END", b""), ("F2_START", b"")] + \
+               flat_items[6:] + [("F2_END", b""), ("FLOOR1", flat_items[3][1]), ("F_END", b"")]
+    data = G.assemble_wad(wadlumps)
+    oa = W.Archive(data)
+    ot = W.TextureDirectory(oa)
+    assert len(ot.textures) >= len(tex)                       # TEXTURE1 + TEXTURE2 (+ the sprite)
+    assert ot.flats[W.wad_name(b"FLOOR1")] == flat_items[3][1]       # later duplicate wins
+    assert ot.textures[W.wad_name(b"BRICK1")].shape == (128, 64)      # sprite shadows the texture
+    ob = S.compile_scene(oa, ot, 0)
+    pb = b2d.Scene(b2d.Archive.from_bytes(data), 0).blob
+    assert ob == pb
+    segs = S.section(ob, "segs")
+    assert (segs[:, 6] >= 0).sum() > 10                       # lower-case names resolved to textures
