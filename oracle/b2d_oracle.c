@@ -36,7 +36,8 @@ typedef struct { int32_t W, H, F, FY2; } b2o_view;                  /* F = round
 
 enum { H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX,
        H_NFLATS, H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX,
-       H_OFF_TEXELS, H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX };
+       H_OFF_TEXELS, H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX,
+       H_NMIDS = 30, H_OFF_MIDS = 31 };
 
 #define LEAF 0x80000000u
 #define SEG_TWO_SIDED 1
@@ -45,16 +46,16 @@ enum { H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_
 
 typedef struct {
     const uint32_t *hdr;
-    const int32_t *verts, *nodes, *ssectors, *segs, *sectors;
+    const int32_t *verts, *nodes, *ssectors, *segs, *sectors, *mids;
     const uint32_t *tex;
     const uint8_t *texels, *flats, *colormap;
     const uint32_t *palette;
-    int nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex;
+    int nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids;
 } Scene;
 
 static int scene_bind(Scene *s, const uint8_t *blob) {
     const uint32_t *h = (const uint32_t *)blob;
-    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 1) return -1;
+    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 2) return -1;
     s->hdr = h;
     s->verts = (const int32_t *)(blob + h[H_OFF_VERTS]);
     s->nodes = (const int32_t *)(blob + h[H_OFF_NODES]);
@@ -62,6 +63,8 @@ static int scene_bind(Scene *s, const uint8_t *blob) {
     s->segs = (const int32_t *)(blob + h[H_OFF_SEGS]);
     s->sectors = (const int32_t *)(blob + h[H_OFF_SECTORS]);
     s->tex = (const uint32_t *)(blob + h[H_OFF_TEX]);
+    s->mids = (const int32_t *)(blob + h[H_OFF_MIDS]);
+    s->nmids = (int)h[H_NMIDS];
     s->texels = blob + h[H_OFF_TEXELS];
     s->flats = blob + h[H_OFF_FLATS];
     s->colormap = blob + h[H_OFF_COLORMAP];
@@ -133,6 +136,10 @@ static inline int light_row(int b, int32_t z8) {
 }
 
 /* ---------------------------------------------------------------- per-frame state ------------ */
+/* one screen column of a masked two-sided middle texture, with the clip window that was open behind the
+ * seg when the front-to-back pass reached it (Doom's drawseg silhouette, per column) */
+struct Masked { int seg, x, ya, yb, row; int32_t scale, iscale, ucol; };
+
 typedef struct {
     const Scene *sc;
     b2o_view vw;
@@ -146,6 +153,8 @@ typedef struct {
     uint8_t *fb;
     int32_t *seg_hits;        /* optional: pixels drawn per seg (may be NULL) */
     int cur_seg;
+    struct Masked *masked;    /* masked middle-texture columns met during the solid pass, front to back */
+    int n_masked, cap_masked;
 } Frame;
 
 static inline void put(Frame *f, int x, int y, uint8_t v) {
@@ -313,7 +322,50 @@ static void draw_seg(Frame *f, int si) {
             if (obot > ff) draw_wall(f, x, y3, y4, S[9], S[10], S[11], ucol, iscale, row);
             if (floor_vis) draw_plane(f, x, y4, cb, ff, SF[2], SF[4]);
             if (y2 >= y3) { f->ctop[x] = H; f->cbot[x] = 0; f->open_cols--; }
-            else { f->ctop[x] = y2; f->cbot[x] = y3; }
+            else {
+                f->ctop[x] = y2; f->cbot[x] = y3;
+                if (S[15] >= 0 && S[15] < sc->nmids) {       /* masked middle: drawn after the solid pass */
+                    if (f->n_masked == f->cap_masked) {
+                        f->cap_masked = f->cap_masked ? 2 * f->cap_masked : 1024;
+                        f->masked = (struct Masked *)realloc(f->masked, (size_t)f->cap_masked * sizeof *f->masked);
+                    }
+                    struct Masked *m = &f->masked[f->n_masked++];
+                    m->seg = si; m->x = x; m->ya = y2; m->yb = y3; m->row = row;
+                    m->scale = (int32_t)scale; m->iscale = iscale; m->ucol = ucol;
+                }
+            }
+        }
+    }
+}
+
+/* back-to-front pass over the recorded masked columns: texture rows [yrow(high), yrow(low)) clipped to the
+ * recorded window; transparent texels (opacity plane 0) leave the pixel untouched (static.frag:21-22) */
+static void draw_masked(Frame *f) {
+    const Scene *sc = f->sc;
+    for (int i = f->n_masked - 1; i >= 0; i--) {
+        const struct Masked *m = &f->masked[i];
+        const int32_t *S = sc->segs + 16 * m->seg;
+        const int32_t *M = sc->mids + 8 * S[15];
+        if (M[0] < 0 || M[0] >= sc->ntex) continue;
+        const uint32_t *T = sc->tex + 8 * M[0];
+        int32_t w = (int32_t)T[1], h = (int32_t)T[2];
+        const uint8_t *px = sc->texels + T[0];
+        const uint8_t *opaque = T[5] != 0xFFFFFFFFu ? sc->texels + T[5] : NULL;
+        int ya = yrow(f, M[3], m->scale), yb = yrow(f, M[2], m->scale);
+        if (ya < m->ya) ya = m->ya;
+        if (yb > m->yb) yb = m->yb;
+        if (ya >= yb) continue;
+        f->cur_seg = m->seg;
+        int32_t col = floormod32(m->ucol, w);
+        int64_t hrel = clamp64(((int64_t)M[3] << 16) - f->pose.z, -((int64_t)1 << 27), (int64_t)1 << 27);
+        int64_t tbase = ((int64_t)M[1] << 16) + hrel + asr64((int64_t)(1 - f->vw.H) * m->iscale, 5);
+        int32_t tstep = m->iscale >> 4;
+        const uint8_t *cm = sc->colormap + 256 * m->row;
+        for (int y = ya; y < yb; y++) {
+            int32_t t = (int32_t)(tbase + (int64_t)y * tstep);
+            int32_t v = floormod32((int32_t)asr64(t, 16), h);
+            if (opaque && !opaque[v * w + col]) continue;
+            put(f, m->x, y, cm[px[v * w + col]]);
         }
     }
 }
@@ -363,7 +415,10 @@ static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *po
         f.yslope[y] = (uint32_t)(((uint64_t)vw->FY2 << 16) / (uint32_t)r2);
     }
     f.open_cols = W;
+    f.masked = NULL; f.n_masked = 0; f.cap_masked = 0;
     walk(&f, sc->hdr[H_ROOT], 0);
+    draw_masked(&f);
+    free(f.masked);
 }
 
 /* ---------------------------------------------------------------- public entry points -------- */

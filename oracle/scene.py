@@ -11,7 +11,7 @@ reference's one-and-only geometry emitter `LevelWalker` and its visitor in `game
                                               game/src/player.rs:72-92 (camera_height)
 * sky texture per level                       wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
 
-The blob layout ("B2DS" v1) is the contract shared with the product's scene compiler
+The blob layout ("B2DS" v2) is the contract shared with the product's scene compiler
 (rust-doom_b200/csrc/b2d_scene.cpp, written independently); tests compare the two byte-for-byte.
 All fields are little-endian int32 unless noted.
 
@@ -20,10 +20,14 @@ verts   : {x, y}                                                   8 B
 nodes   : {x, y, dx, dy, rbox[4], lbox[4], rchild, lchild, 0, 0}   64 B  (box = top,bottom,left,right;
           child bit31 = subsector)
 ssectors: {first_seg, num_segs, sector, 0}                         16 B
-segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, light, otop, obot, back}  64 B
+segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, light, otop, obot, mid}   64 B
+          (mid = index into mids or -1)
+mids    : {tex, t_high, low, high, 0, 0, 0, 0}                     32 B  masked two-sided middle texture:
+          vertical extent [low, high) in map units and the texture row at `high` (visitor.rs:808-836,875-919)
 sectors : {floor, ceil, floor_flat, ceil_flat, light, 0, 0, 0}     32 B  (flat: >=0 id, -1 sky, -2 missing)
-textures: {texel_off, w, h, hmagic, hbias, 0, 0, 0}                32 B
-texels  : u8 row-major, textures back to back (transparent texels stored as 0)
+textures: {texel_off, w, h, hmagic, hbias, mask_off, 0, 0}         32 B  (mask_off = 0xFFFFFFFF: fully opaque)
+texels  : u8 row-major, textures back to back (transparent texels stored as 0); a texture with holes is
+          followed by its opacity plane (1 = opaque), same layout, at mask_off
 flats   : n x 4096 u8
 colormap: 34 x 256 u8 (zero padded if the WAD has fewer)
 palette : 256 x u32  R | G<<8 | B<<16 | 0xFF<<24  from PLAYPAL[0]
@@ -40,11 +44,11 @@ import numpy as np
 from . import wad as W
 
 MAGIC = 0x53443242
-VERSION = 1
+VERSION = 2
 (H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
  H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
  H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
- H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H) = range(30)
+ H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS) = range(32)
 
 SEG_TWO_SIDED = 1
 SEG_INVALID = 0x80
@@ -201,6 +205,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
 
     # --- segs ------------------------------------------------------------------------------------
     segs = np.zeros((nsegs, 16), dtype=np.int32)
+    mids: List[List[int]] = []
     side_bytes = level.sidedefs.tobytes()
 
     def side_name(idx: int, which: int) -> bytes:
@@ -298,6 +303,26 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
                 rec[9], rec[10] = tid, t
             rec[11] = obot
             rec[13], rec[14] = otop, obot
+            # masked middle (visitor.rs:808-836): between max(floors) and min(ceilings); float pegs clamp the
+            # quad to the texture height (visitor.rs:875-885); t at `high`: Top/Floats 0, Bottom texh-height
+            low0, high0 = obot, (bc if bc < fc else fc)
+            mname = side_name(side, 2)
+            mtid = tex_id(mname) if low0 < high0 else TEX_NONE
+            rec[15] = -1
+            if mtid >= 0:
+                th = int(tex_list[mtid].shape[0])
+                if unpeg_lower:
+                    peg = "topfloat" if W.is_untextured(side_name(side, 0)) else "bottom"
+                else:
+                    peg = "bottomfloat" if W.is_untextured(side_name(side, 1)) else "top"
+                low, high = low0, high0
+                if peg == "topfloat":
+                    low, high = low0 + yoff, low0 + th + yoff
+                elif peg == "bottomfloat":
+                    low, high = high0 + yoff - th, high0 + yoff
+                t_high = (th - (high - low)) if peg == "bottom" else 0
+                rec[15] = len(mids)
+                mids.append([mtid, _floormod(t_high + yoff, th), low, high, 0, 0, 0, 0])
         segs[i] = rec
 
     # --- nodes -----------------------------------------------------------------------------------
@@ -391,13 +416,19 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     texels = bytearray()
     for i, img in enumerate(tex_list):
         h, w = img.shape
-        px = np.where((img >> 8) != 0, 0, img & 0xFF).astype(np.uint8)
+        holes = (img >> 8) != 0
+        px = np.where(holes, 0, img & 0xFF).astype(np.uint8)
         hmagic = (1 << 32) // h + 1
         hbias = h * ((16384 + h - 1) // h)
-        texrec[i] = [len(texels), w, h, hmagic & 0xFFFFFFFF, hbias, 0, 0, 0]
+        texrec[i] = [len(texels), w, h, hmagic & 0xFFFFFFFF, hbias, 0xFFFFFFFF, 0, 0]
         texels += px.tobytes()
         while len(texels) % 16:
             texels += b"\0"
+        if holes.any():
+            texrec[i][5] = len(texels)
+            texels += (~holes).astype(np.uint8).tobytes()
+            while len(texels) % 16:
+                texels += b"\0"
 
     colormap = bytearray(34 * 256)
     for k in range(min(34, len(tex.colormaps))):
@@ -424,6 +455,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     parts = [("verts", verts.astype("<i4").tobytes()), ("nodes", (nodes & 0xFFFFFFFF).astype("<u4").tobytes()),
              ("ssectors", ssectors.astype("<i4").tobytes()), ("segs", segs.astype("<i4").tobytes()),
              ("sectors", sectors.astype("<i4").tobytes()), ("tex", texrec.astype("<u4").tobytes()),
+             ("mids", np.array(mids, dtype="<i4").reshape(-1, 8).tobytes()),
              ("texels", bytes(texels)), ("flats", b"".join(flat_list)), ("colormap", bytes(colormap)),
              ("palette", palette.tobytes())]
     off = 128
@@ -448,6 +480,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     hdr[H_START_X], hdr[H_START_Y], hdr[H_START_Z] = sx & 0xFFFFFFFF, sy & 0xFFFFFFFF, sz & 0xFFFFFFFF
     hdr[H_START_ANGLE], hdr[H_HAS_START] = sang, has_start
     hdr[H_MIN_H], hdr[H_MAX_H] = min_h & 0xFFFFFFFF, max_h & 0xFFFFFFFF
+    hdr[H_NMIDS], hdr[H_OFF_MIDS] = len(mids), offs["mids"]
     blob = bytearray(total)
     blob[0:128] = struct.pack("<32I", *hdr)
     for name, data in parts:
@@ -476,4 +509,6 @@ def section(blob: bytes, which: str) -> np.ndarray:
         return arr(h[H_OFF_SECTORS], h[H_NSECTORS], 8)
     if which == "textures":
         return arr(h[H_OFF_TEX], h[H_NTEX], 8, "<u4")
+    if which == "mids":
+        return arr(h[H_OFF_MIDS], h[H_NMIDS], 8)
     raise KeyError(which)

@@ -35,6 +35,7 @@ struct b2d_renderer {
     uint32_t *d_yslope = nullptr;
     uint16_t *d_skyrow = nullptr;
     int32_t *d_status = nullptr;
+    uint32_t *d_masked = nullptr;
     DeviceScene ds{};
     Pose *d_poses = nullptr;
     FrameConst *d_frames = nullptr;
@@ -102,6 +103,7 @@ void free_renderer(b2d_renderer *r) {
     if (r->d_yslope) cudaFree(r->d_yslope);
     if (r->d_skyrow) cudaFree(r->d_skyrow);
     if (r->d_status) cudaFree(r->d_status);
+    if (r->d_masked) cudaFree(r->d_masked);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
 }
@@ -287,6 +289,14 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.segs = reinterpret_cast<const SegRec *>(r->d_blob + h[H_OFF_SEGS]);
     d.sectors = reinterpret_cast<const SectorRec *>(r->d_blob + h[H_OFF_SECTORS]);
     d.tex = reinterpret_cast<const TexRec *>(r->d_blob + h[H_OFF_TEX]);
+    d.mids = reinterpret_cast<const MidRec *>(r->d_blob + h[H_OFF_MIDS]);
+    d.nmids = (int32_t)h[H_NMIDS];
+    d.masked_list = nullptr;
+    if (d.nmids > 0) {   // deferred masked-texture lists: one per raster warp of a full batch
+        const size_t strips = (size_t)(view->width + 31) / 32;
+        CUR(cudaMalloc(&r->d_masked, sizeof(uint32_t) * 33 * kMaskedCap * strips * (size_t)max_batch));
+        d.masked_list = r->d_masked;
+    }
     d.texels = r->d_blob + h[H_OFF_TEXELS];
     d.flats = r->d_blob + h[H_OFF_FLATS];
     d.colormap = r->d_blob + h[H_OFF_COLORMAP];
@@ -370,7 +380,8 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
         CU(cudaMemset(r->d_status, 0, sizeof(int32_t)));
         return fail(B2D_ERR_INVALID_ARG, status & 1 ? "BSP traversal stack overflow (tree deeper than 128 pending nodes): frames incomplete"
                                             : (status & 4 ? "BSP traversal did not terminate (cyclic node graph): frames incomplete"
-                                                          : "worklist overflow: frames incomplete"));
+                                              : (status & 8 ? "more than 16 masked middle textures deferred in one 32-column strip: frames incomplete"
+                                                            : "worklist overflow: frames incomplete")));
     }
     return B2D_OK;
 }

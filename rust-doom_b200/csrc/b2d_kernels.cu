@@ -388,6 +388,60 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
     }
 }
 
+// Back-to-front pass over the masked middle textures this strip deferred during the solid pass.  Each entry
+// holds the worklist index and, per lane, the clip window [ya, yb) that was open behind the seg when the
+// front-to-back walk reached it (the per-column silhouette of everything nearer).  Texels whose opacity plane
+// is 0 leave the pixel as the solid pass drew it (static.frag:21-22).  Kept out of line so that the
+// register allocation of the solid pass is not affected.
+template <bool kRgba, int kW>
+__device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, int32_t pose_z, uint8_t *fb,
+                                         uint32_t *rgba, uint32_t cmap_s, uint32_t pal_s, int x, int lane,
+                                         const SegFrame *wl, const uint32_t *ml, int count) {
+    // everything arrives by value (or points at kernel parameters): taking the address of the solid pass's
+    // register-resident context would force it into local memory
+    RasterCtx c;
+    c.sc = &sc; c.cmap_s = cmap_s; c.pal_s = pal_s; c.fb = fb; c.rgba = rgba;
+    c.W = vw.W; c.H = vw.H; c.x = x; c.lane = lane;
+    const int Wc = kW ? kW : c.W;
+    for (int e = count - 1; e >= 0; e--) {
+        const uint32_t k = ml[33 * e];
+        const uint32_t packed = ml[33 * e + 1 + c.lane];
+        int ya = (int)(packed & 0xFFFFu), yb = (int)(packed >> 16);
+        const SegFrame sf = wl[k];
+        const SegRec S = sc.segs[sf.seg];
+        if (S.mid < 0 || S.mid >= sc.nmids) continue;
+        const MidRec M = sc.mids[S.mid];
+        if (M.tex < 0 || M.tex >= sc.ntex) continue;
+        const TexRec T = sc.tex[M.tex];
+        ColumnEval ce = {0u, 1, 1, 0};
+        if (ya < yb && column_eval(sf, vw, c.x, ce)) {
+            ya = max(ya, yrow(M.high, ce.scale, pose_z, c.H));
+            yb = min(yb, yrow(M.low, ce.scale, pose_z, c.H));
+        } else {
+            ya = yb = 0;
+        }
+        const bool act = ya < yb;
+        int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
+        int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+        if (y0 >= y1) continue;
+        const int32_t ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+        const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
+        const uint8_t *px = sc.texels + T.texel_off + col;
+        const bool has_mask = T.mask_off != 0xFFFFFFFFu;
+        const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
+        const int32_t tstep = ce.iscale >> 4;
+        const uint32_t cm = c.cmap_s + 256u * (uint32_t)light_row(S.light, ce.z8);
+        uint32_t t = (uint32_t)wall_tbase(M.t_high, M.high, pose_z, c.H, ce.iscale) + (uint32_t)y0 * (uint32_t)tstep;
+        uint8_t *p8 = c.fb + (size_t)y0 * Wc;
+        uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
+        for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
+            uint32_t idx = wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w;
+            bool on = y >= ya && y < yb && (!has_mask || mk[idx] != 0);
+            put_px<kRgba>(c, p8, p32, on, lds_u8(cm + px[idx]));
+        }
+    }
+}
+
 template <bool kRgba, int kMinBlocks, int kW, int kUnroll, int kWarps>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
@@ -429,6 +483,8 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     if (sc.sky_tex >= 0 && inside) c.skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
 
     int ct = 0, cb = inside ? H : 0;              // open window [ct, cb) of this lane's column
+    uint32_t *ml = sc.masked_list ? sc.masked_list + (size_t)gw * (33 * kMaskedCap) : nullptr;
+    int mcount = 0;
     const SegFrame *wl = work + (size_t)frame * stride;
     const int count = fc.count;
     bool done = false;
@@ -494,10 +550,27 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 if (!two || y2 >= y3) { ct = H; cb = 0; }
                 else { ct = y2; cb = y3; }
             }
+            if (two && S.mid >= 0 && ml != nullptr) {
+                // defer the masked middle texture: remember the window that is open behind this seg
+                const bool keep = ok && y2 < y3;
+                if (__any_sync(kFull, keep)) {
+                    if (mcount < kMaskedCap) {
+                        if (lane == 0) ml[33 * mcount] = (uint32_t)(k0 + j);
+                        ml[33 * mcount + 1 + lane] = keep ? ((uint32_t)y2 | ((uint32_t)y3 << 16)) : 0u;
+                        mcount++;
+                    } else if (lane == 0) {
+                        atomicOr(sc.status_flag, 8);
+                    }
+                }
+            }
         }
     }
     // whatever is still open is void
     fill_void_warp<kRgba, kW, kUnroll>(c, inside ? ct : 0, inside ? cb : 0);
+    if (mcount > 0) {
+        __syncwarp();
+        masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.cmap_s, c.pal_s, x, lane, wl, ml, mcount);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -16,17 +16,22 @@ struct DeviceScene {
     const SegRec *segs;
     const SectorRec *sectors;
     const TexRec *tex;
+    const MidRec *mids;          // masked two-sided middle textures (SegRec::mid indexes this)
     const uint8_t *texels;
     const uint8_t *flats;
     const uint8_t *colormap;     // 34 x 256
     const uint32_t *palette;     // 256 RGBA8
     const uint32_t *yslope;      // per view: H entries
     const uint16_t *skyrow;      // per view: H entries, sky texture row of each screen row
-    int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex;
+    int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids;
     uint32_t root;
     uint32_t invF;               // floor(2^32 / F)
     int32_t *status_flag;        // device int: OR of per-frame walk status bits (0 = all frames complete)
+    uint32_t *masked_list;       // per raster warp: kMaskedCap x 33 words (worklist index + 32 packed windows)
 };
+
+// masked middle textures one 32-column strip can defer per frame (more -> status bit 8, frames incomplete)
+constexpr int kMaskedCap = 16;
 
 // Bytes of dynamic shared memory one BSP-walk warp needs for this scene.
 size_t walk_smem_per_warp(const DeviceScene &sc);

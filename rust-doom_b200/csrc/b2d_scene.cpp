@@ -185,10 +185,11 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     }
 
     std::vector<SegRec> segs((size_t)nsegs);
+    std::vector<MidRec> mids;
     for (int i = 0; i < nsegs; i++) {
         const Seg &sg = lv.segs[(size_t)i];
         SegRec r{};
-        r.flags = kSegInvalid; r.texA = r.texB = kTexNone; r.back = -1;
+        r.flags = kSegInvalid; r.texA = r.texB = kTexNone; r.mid = -1;
         bool ok = sg.v1 < nverts && sg.v2 < nverts && sg.linedef < lv.linedefs.size();
         int side = ok ? lv.seg_sidedef(sg) : -1;
         int front = seg_front[(size_t)i];
@@ -219,7 +220,7 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
             t_out = floormod(top_row(th) + sd.yoff, th);
         };
 
-        r.v1 = sg.v1; r.v2 = sg.v2; r.front = front; r.back = back;
+        r.v1 = sg.v1; r.v2 = sg.v2; r.front = front; r.mid = -1;
         r.uoff = (int32_t)sg.offset + sd.xoff;                                   // visitor.rs:904
         r.len_q12 = (int32_t)isqrt64((uint64_t)(dx * dx + dy * dy) << 24);       // visitor.rs:905
         r.light = light_byte(fs.light, contrast);
@@ -250,6 +251,24 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
                 else piece(sd.lower, r.texB, r.tB, [&](int32_t) { return 0; });
             }
             r.hB = r.obot;
+            // masked middle (visitor.rs:808-836): spans max(floors)..min(ceilings); float pegs clamp the quad to
+            // the texture height (visitor.rs:875-885); t at `high`: Top/Floats 0, Bottom texh-height (:909-919)
+            const int32_t low0 = r.obot, high0 = bc < fc ? bc : fc;
+            int32_t mtex = low0 < high0 ? tex_id(sd.middle) : kTexNone;
+            if (mtex >= 0) {
+                const int32_t th = tex_list[(size_t)mtex]->h;
+                enum { kTop, kBottom, kTopFloat, kBottomFloat } peg;
+                if (unpeg_lower) peg = is_untextured(sd.upper) ? kTopFloat : kBottom;
+                else peg = is_untextured(sd.lower) ? kBottomFloat : kTop;
+                int32_t low = low0, high = high0;
+                if (peg == kTopFloat) { low = low0 + sd.yoff; high = low0 + th + sd.yoff; }
+                else if (peg == kBottomFloat) { low = high0 + sd.yoff - th; high = high0 + sd.yoff; }
+                const int32_t t_high = peg == kBottom ? th - (high - low) : 0;
+                MidRec m{};
+                m.tex = mtex; m.t_high = floormod(t_high + sd.yoff, th); m.low = low; m.high = high;
+                r.mid = (int32_t)mids.size();
+                mids.push_back(m);
+            }
         }
         segs[(size_t)i] = r;
     }
@@ -340,9 +359,16 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         t.w = (uint32_t)im.w; t.h = (uint32_t)im.h;
         t.hmagic = (uint32_t)((((uint64_t)1 << 32) / (uint64_t)im.h + 1) & 0xFFFFFFFFu);
         t.hbias = (uint32_t)im.h * (uint32_t)((16384 + im.h - 1) / im.h);
-        texrec[i] = t;
-        for (uint16_t v : im.px) texels.push_back((v >> 8) ? 0 : (uint8_t)(v & 0xFF));
+        t.mask_off = 0xFFFFFFFFu;
+        bool holes = false;
+        for (uint16_t v : im.px) { texels.push_back((v >> 8) ? 0 : (uint8_t)(v & 0xFF)); holes |= (v >> 8) != 0; }
         while (texels.size() % 16) texels.push_back(0);
+        if (holes) {            // opacity plane (1 = opaque) right behind the texels
+            t.mask_off = (uint32_t)texels.size();
+            for (uint16_t v : im.px) texels.push_back((v >> 8) ? 0 : 1);
+            while (texels.size() % 16) texels.push_back(0);
+        }
+        texrec[i] = t;
     }
     std::vector<uint8_t> flats(flat_list.size() * 4096);
     for (size_t i = 0; i < flat_list.size(); i++) std::memcpy(&flats[i * 4096], flat_list[i], 4096);
@@ -381,6 +407,8 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     hdr[H_OFF_SEGS] = w.append(segs.data(), segs.size() * sizeof(SegRec));
     hdr[H_OFF_SECTORS] = w.append(sectors.data(), sectors.size() * sizeof(SectorRec));
     hdr[H_OFF_TEX] = w.append(texrec.data(), texrec.size() * sizeof(TexRec));
+    hdr[H_OFF_MIDS] = w.append(mids.data(), mids.size() * sizeof(MidRec));
+    hdr[H_NMIDS] = (uint32_t)mids.size();
     hdr[H_OFF_TEXELS] = w.append(texels.data(), texels.size());
     hdr[H_TEXEL_BYTES] = (uint32_t)texels.size();
     hdr[H_OFF_FLATS] = w.append(flats.data(), flats.size());

@@ -17,14 +17,14 @@
 namespace b2d {
 
 constexpr uint32_t kSceneMagic = 0x53443242u;   // "B2DS"
-constexpr uint32_t kSceneVersion = 1;
+constexpr uint32_t kSceneVersion = 2;
 constexpr uint32_t kLeaf = 0x80000000u;
 
 enum HeaderField : int {
     H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
     H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
     H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
-    H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_COUNT = 32
+    H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_COUNT = 32
 };
 
 // 64-byte records; all int32.
@@ -35,12 +35,15 @@ struct SegRec {
     int32_t uoff, len_q12;
     int32_t texA, tA, hA;      // upper (two-sided) or full-height middle (one-sided)
     int32_t texB, tB, hB;      // lower
-    int32_t light, otop, obot, back;
+    int32_t light, otop, obot, mid;   // mid: index into the mids section, -1 = no masked middle texture
 };
+// masked two-sided middle texture (visitor.rs:808-836,875-919): vertical extent [low, high) and the
+// texture row at `high` (pegging and y offset folded in)
+struct MidRec { int32_t tex, t_high, low, high, pad[4]; };
 struct SectorRec { int32_t floor, ceil, floor_flat, ceil_flat, light, pad[3]; };
-struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, pad[3]; };
+struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, mask_off, pad[2]; };   // mask_off = ~0u: opaque
 static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec) == 32 &&
-              sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16, "record layout");
+              sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16 && sizeof(MidRec) == 32, "record layout");
 
 constexpr int32_t kSegTwoSided = 1, kSegInvalid = 0x80;
 constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;

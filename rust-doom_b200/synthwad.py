@@ -174,7 +174,7 @@ def _img_grate(rng: SplitMix64, w: int, h: int, hue: int) -> np.ndarray:
     noise = rng.bytes2d(h, w)
     ys, xs = np.mgrid[0:h, 0:w]
     bars = ((xs % 8) < 2) | ((ys % 12) < 2)
-    img = np.where(bars, hue * 16 + 5 + noise % 4, -1)
+    img = np.where(bars, (hue * 16 + 5 + noise % 4).astype(np.int16), np.int16(-1))
     return img.astype(np.int16)
 
 
@@ -235,7 +235,7 @@ class TexDef:
     patches: List[Tuple[int, int, str]]  # (origin_x, origin_y, patch name)
 
 
-def make_graphics(rng: SplitMix64):
+def make_graphics(rng: SplitMix64, masked: bool = False):
     """Returns (patch lumps {name: bytes} in order, texture defs, flats {name: 4096 bytes})."""
     patches: Dict[str, bytes] = {}
 
@@ -278,6 +278,13 @@ def make_graphics(rng: SplitMix64):
         TexDef("SKY1", 256, 128, [(0, 0, "SKY1")]),
     ]
 
+    if masked:
+        # single-patch textures whose first (opaque-copied) patch has holes -> transparent texels survive
+        add("WGRATE2", _img_grate(rng, 32, 64, 7))
+        add("WFENCE1", np.where(_img_grate(rng, 64, 72, 3) < 0, -1, _img_bricks(rng, 64, 72, 9, 16, 12)).astype(np.int16))
+        tex += [TexDef("GRATE1", 64, 128, [(0, 0, "WGRATE1")]), TexDef("GRATE2", 32, 64, [(0, 0, "WGRATE2")]),
+                TexDef("FENCE72", 64, 72, [(0, 0, "WFENCE1")])]
+
     flats: Dict[str, bytes] = {}
 
     def addflat(name, img):
@@ -304,6 +311,7 @@ WALL_TEX = ["BRICK1", "BRICK2", "BRICK3", "PANEL1", "PANEL2", "PANEL72", "GRAD1"
 STEP_TEX = ["STEP1", "STEP2", "TECH1", "BRICK2", "PANEL72"]
 FLOOR_FLATS = ["FLOOR1", "FLOOR2", "FLOOR3", "FLOOR4", "FLOOR5", "FLOOR6", "NUKAGE1"]
 CEIL_FLATS = ["CEIL1", "CEIL2", "CEIL3", "CEIL4", "FLOOR3"]
+MASKED_TEX = ["GRATE1", "GRATE2", "FENCE72"]
 
 
 def make_pnames_texture1(patch_names: Sequence[str], tex: Sequence[TexDef]) -> Tuple[bytes, bytes]:
@@ -379,6 +387,7 @@ class SynthConfig:
     sky_pct: int = 18
     wall_pct: int = 18
     door_pct: int = 22
+    mid_pct: int = 0            # % of two-sided lines that carry a masked middle texture (0 keeps legacy bytes)
 
 
 # inner convex polygons, CCW, in cell-local coordinates for a 256 cell (scaled by cell/256);
@@ -511,8 +520,25 @@ class LevelBuilder:
                 flags |= 0x0010
             xo = rng.pick([0, 0, 8, 32])
             yo = rng.pick([0, 0, 0, 4, -12])
-            s1 = self.side(sa, upper=wall_tex(), lower=rng.pick(STEP_TEX + WALL_TEX), xoff=xo, yoff=yo)
-            s2 = self.side(sb, upper=wall_tex(), lower=rng.pick(STEP_TEX + WALL_TEX), xoff=xo, yoff=yo)
+            up1, lo1, up2, lo2 = wall_tex(), rng.pick(STEP_TEX + WALL_TEX), wall_tex(), rng.pick(STEP_TEX + WALL_TEX)
+            mid = "-"
+            if cfg.mid_pct and rng.below(100) < cfg.mid_pct:
+                mid = rng.pick(MASKED_TEX)
+                style = rng.below(4)          # which of upper/lower are untextured decides the peg (float vs tiled)
+                A, B = self.sectors[sa], self.sectors[sb]
+                # leave a piece untextured only on a side that does not need it (well-formed map)
+                if style in (0, 2):
+                    if not (B.ceil < A.ceil):
+                        up1 = "-"
+                    if not (A.ceil < B.ceil):
+                        up2 = "-"
+                if style in (1, 2):
+                    if not (B.floor > A.floor):
+                        lo1 = "-"
+                    if not (A.floor > B.floor):
+                        lo2 = "-"
+            s1 = self.side(sa, upper=up1, lower=lo1, middle=mid, xoff=xo, yoff=yo)
+            s2 = self.side(sb, upper=up2, lower=lo2, middle=mid, xoff=xo, yoff=yo)
             li = self.line(a, b, s1, s2, flags=flags)
             add_seg(keyA, li, 0, a, b)
             add_seg(keyB, li, 1, b, a)
@@ -839,7 +865,7 @@ def build_iwad(seed: int = 1, maps: Sequence[str] = ("E1M1",), cfg: Optional[Syn
     rng = SplitMix64(seed)
     playpal = make_playpal()
     colormap = make_colormap(playpal)
-    patches, tex, flats = make_graphics(rng)
+    patches, tex, flats = make_graphics(rng, masked=cfg.mid_pct > 0)
     pnames, texture1 = make_pnames_texture1(list(patches.keys()), tex)
     lumps: List[Tuple[str, bytes]] = [("PLAYPAL", playpal), ("COLORMAP", colormap)]
     for k, name in enumerate(maps):

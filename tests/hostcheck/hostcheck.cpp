@@ -3,6 +3,7 @@
 // checked against the oracle without a GPU.  This file is compiled into tests/hostcheck/
 // libb2d_hostcheck.so by tests/conftest.py; it is NOT part of libb2d.so and no product code calls it.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -21,8 +22,9 @@ struct HostScene {
     const SegRec *segs;
     const SectorRec *sectors;
     const TexRec *tex;
+    const MidRec *mids;
     const uint8_t *texels, *flats, *colormap;
-    int nverts, nnodes, nss, nsegs, ntex, nflats, sky_tex;
+    int nverts, nnodes, nss, nsegs, ntex, nflats, sky_tex, nmids;
     uint32_t root;
 };
 
@@ -36,6 +38,8 @@ HostScene bind(const uint8_t *blob) {
     s.segs = reinterpret_cast<const SegRec *>(blob + h[H_OFF_SEGS]);
     s.sectors = reinterpret_cast<const SectorRec *>(blob + h[H_OFF_SECTORS]);
     s.tex = reinterpret_cast<const TexRec *>(blob + h[H_OFF_TEX]);
+    s.mids = reinterpret_cast<const MidRec *>(blob + h[H_OFF_MIDS]);
+    s.nmids = (int)h[H_NMIDS];
     s.texels = blob + h[H_OFF_TEXELS];
     s.flats = blob + h[H_OFF_FLATS];
     s.colormap = blob + h[H_OFF_COLORMAP];
@@ -186,6 +190,8 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
             lanes[l].ct = 0; lanes[l].cb = x < W ? H : 0; lanes[l].skycol = 0;
             if (sc.sky_tex >= 0 && x < W) lanes[l].skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
         }
+        struct Deferred { size_t k; std::vector<uint32_t> win; };
+        std::vector<Deferred> deferred;
         for (size_t k = 0; k < wl.size(); k++) {
             const SegFrame &sf = wl[k];
             if (!(sf.xhi >= x0 && sf.xlo <= x0 + SW - 1)) continue;
@@ -198,6 +204,8 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
             const bool two = S.flags & kSegTwoSided;
             const bool ceil_vis = ((int64_t)fcl << 16) > fc.pose.z || SF.ceil_flat == kFlatSky;
             const bool floor_vis = ((int64_t)ffl << 16) < fc.pose.z || SF.floor_flat == kFlatSky;
+            Deferred dfr{k, std::vector<uint32_t>((size_t)SW, 0u)};
+            bool any_deferred = false;
             // lock-step extents of the five draws (ceiling, A, B, floor) over the strip, for statistics
             int lo[4] = {1 << 30, 1 << 30, 1 << 30, 1 << 30}, hi[4] = {0, 0, 0, 0};
             if (st) st->entries++;
@@ -234,11 +242,42 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 draw_plane(x, ln, y4, cb, ffl, SF.floor_flat, SF.light, floor_vis);
                 if (!two || y2 >= y3) { ln.ct = H; ln.cb = 0; }
                 else { ln.ct = y2; ln.cb = y3; }
+                if (two && S.mid >= 0 && y2 < y3) { dfr.win[(size_t)l] = (uint32_t)y2 | ((uint32_t)y3 << 16); any_deferred = true; }
             }
+            if (any_deferred && deferred.size() < 16) deferred.push_back(dfr);
             if (st) for (int d = 0; d < 4; d++) if (hi[d] > lo[d]) st->iters += hi[d] - lo[d];
         }
         for (int l = 0; l < SW; l++)
             if (x0 + l < W) fill_void(x0 + l, lanes[l].ct, lanes[l].cb);
+        // masked middle textures, back to front (mirrors masked_pass in b2d_kernels.cu)
+        for (size_t e = deferred.size(); e-- > 0;) {
+            const SegFrame &sf = wl[deferred[e].k];
+            const SegRec &S = sc.segs[sf.seg];
+            if (S.mid < 0 || S.mid >= sc.nmids) continue;
+            const MidRec &M = sc.mids[S.mid];
+            if (M.tex < 0 || M.tex >= sc.ntex) continue;
+            const TexRec &T = sc.tex[M.tex];
+            for (int l = 0; l < SW; l++) {
+                uint32_t packed = deferred[e].win[(size_t)l];
+                int ya = (int)(packed & 0xFFFFu), yb = (int)(packed >> 16), x = x0 + l;
+                ColumnEval ce;
+                if (!(ya < yb) || !column_eval(sf, vw, x, ce)) continue;
+                ya = std::max(ya, yrow(M.high, ce.scale, fc.pose.z, H));
+                yb = std::min(yb, yrow(M.low, ce.scale, fc.pose.z, H));
+                int32_t ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+                uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
+                const uint8_t *px = sc.texels + T.texel_off + col;
+                const bool has_mask = T.mask_off != 0xFFFFFFFFu;
+                const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
+                int32_t tbase = wall_tbase(M.t_high, M.high, fc.pose.z, H, ce.iscale), tstep = ce.iscale >> 4;
+                const uint8_t *cm = sc.colormap + 256 * light_row(S.light, ce.z8);
+                for (int y = ya; y < yb; y++) {
+                    uint32_t idx = wall_row(tbase + y * tstep, T.h, T.hmagic, T.hbias) * T.w;
+                    if (has_mask && !mk[idx]) continue;
+                    put(x, y, cm[px[idx]]);
+                }
+            }
+        }
     }
 }
 

@@ -10,7 +10,8 @@ algorithmically independent check of the oracle's *scene semantics* (which surfa
 colormap row).  Agreement cannot be bit-exact (float vs fixed point at texel/row boundaries, silhouette
 pixels), so tests assert a high identical-pixel fraction instead.
 
-Not modelled (same as the oracle in round 1): masked two-sided middle textures, sprites, POLY_BIAS.
+Masked two-sided middle textures are modelled (transparent texels let the ray through, static.frag:21-22).
+Not modelled (same as the oracle): sprites, POLY_BIAS.
 """
 from __future__ import annotations
 
@@ -184,6 +185,22 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
                 img = tex.textures.get(name)
                 th = img.shape[0] if img is not None else 0
                 pieces.append((bc, fc, name, 0.0 if unpeg_upper else (th - (fc - bc))))
+            # middle (visitor.rs:808-836,875-919): drawn last, so lower/upper win at equal depth (IfLess)
+            low0, high0 = (bf if bf > ff else ff), (bc if bc < fc else fc)
+            mname = side_name(side, 2)
+            mimg = None if W.is_untextured(mname) else tex.textures.get(mname)
+            if mimg is not None and low0 < high0:
+                th = mimg.shape[0]
+                if unpeg_lower:
+                    peg = "topfloat" if W.is_untextured(side_name(side, 0)) else "bottom"
+                else:
+                    peg = "bottomfloat" if W.is_untextured(side_name(side, 1)) else "top"
+                low, high = low0, high0
+                if peg == "topfloat":
+                    low, high = low0 + yoff, low0 + th + yoff
+                elif peg == "bottomfloat":
+                    low, high = high0 + yoff - th, high0 + yoff
+                pieces.append((low, high, mname, (th - (high - low)) if peg == "bottom" else 0.0))
         for (low, high, name, t_high) in pieces:
             if low >= high:
                 continue

@@ -260,3 +260,17 @@ def test_gpu_fuzzed_levels_match_oracle(b2d):
         _assert_same(ofb, out.cpu().numpy(), "fuzz iteration %d" % it)
         compared += 1
     assert compared > 20
+
+
+def test_gpu_masked_middle_textures(b2d):
+    """Masked two-sided middle textures: deferred per-strip lists + back-to-front pass, index and RGBA."""
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=45))), 0)
+    poses = sample_poses(b2d, sc, 48, 61)
+    for (w, h) in ((320, 200), (1920, 1080)):
+        p = poses if w == 320 else poses[:6]
+        r = b2d.Renderer(sc, b2d.make_view(w, h), max_batch=48)
+        idx, rgba = r.render(p, rgba=True)
+        ofb, orgba = render.render(sc.blob, render.make_view(w, h), p, rgba=True, threads=8)
+        _assert_same(ofb, idx, "masked %dx%d" % (w, h))
+        assert np.array_equal(rgba, orgba)

@@ -89,3 +89,14 @@ def test_hostcheck_fuzzed_levels(b2d, hostcheck):
         assert np.array_equal(ofb, hfb), "fuzz iteration %d" % it
         compared += 1
     assert compared > 30
+
+
+def test_hostcheck_masked_middle_textures(b2d, hostcheck):
+    """Levels with masked two-sided middle textures (all four pegging variants): deferred back-to-front pass."""
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=45))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    from oracle import scene as S
+    assert S.header(sc.blob)[S.H_NMIDS] > 50
+    _compare(b2d, hostcheck, sc, 320, 200, 40, 51)
+    _compare(b2d, hostcheck, sc, 1920, 1080, 2, 52)

@@ -47,3 +47,24 @@ def test_oracle_agrees_with_reference_semantics_raycaster(synth_wad, oracle_scen
     assert float(np.mean(fracs)) > 0.992, fracs
     if want_sky:
         assert max(sky_share) > 0.05, "no pose actually saw the sky"
+
+
+def test_masked_middle_textures_agree_with_raycaster():
+    """Two-sided middle textures with holes (visitor.rs:808-836; transparent texels discarded,
+    static.frag:21-22): the oracle's deferred back-to-front pass vs rays that pass through the holes."""
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=45))
+    a = wad.Archive(data)
+    tex = wad.TextureDirectory(a)
+    blob = scene.compile_scene(a, tex, 0)
+    level = wad.Level(a, 0)
+    assert scene.header(blob)[scene.H_NMIDS] > 50
+    view = render.make_view(320, 200)
+    fracs, twice = [], 0
+    for (x, y, z, ang) in _poses_in(level, False, 6, 17) + _poses_in(level, True, 4, 18):
+        g, _ = glcaster.render(a, tex, 0, 320, 200, x, y, z, ang, focal2=(view.F, view.FY2))
+        o, hits = render.render(blob, view, render.make_pose(x, y, z, ang), seg_hits=True)
+        fracs.append(float((g == o[0]).mean()))
+        twice += int(hits.sum()) - 320 * 200          # pixels overdrawn by masked textures
+    assert min(fracs) > 0.985 and float(np.mean(fracs)) > 0.992, fracs
+    assert twice > 5000, "the poses never looked through a masked texture"
