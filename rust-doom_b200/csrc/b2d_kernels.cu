@@ -442,7 +442,7 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
     }
 }
 
-template <bool kRgba, int kMinBlocks, int kW, int kUnroll, int kWarps>
+template <bool kRgba, int kMinBlocks, int kW, int kUnroll, int kWarps, bool kMasked>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
                   const SegFrame *__restrict__ work, int stride, int n, int strips,
@@ -483,7 +483,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     if (sc.sky_tex >= 0 && inside) c.skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
 
     int ct = 0, cb = inside ? H : 0;              // open window [ct, cb) of this lane's column
-    uint32_t *ml = sc.masked_list ? sc.masked_list + (size_t)gw * (33 * kMaskedCap) : nullptr;
+    uint32_t *ml = (kMasked && sc.masked_list) ? sc.masked_list + (size_t)gw * (33 * kMaskedCap) : nullptr;
     int mcount = 0;
     const SegFrame *wl = work + (size_t)frame * stride;
     const int count = fc.count;
@@ -550,7 +550,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 if (!two || y2 >= y3) { ct = H; cb = 0; }
                 else { ct = y2; cb = y3; }
             }
-            if (two && S.mid >= 0 && ml != nullptr) {
+            if (kMasked && two && S.mid >= 0 && ml != nullptr) {
                 // defer the masked middle texture: remember the window that is open behind this seg
                 const bool keep = ok && y2 < y3;
                 if (__any_sync(kFull, keep)) {
@@ -567,7 +567,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     }
     // whatever is still open is void
     fill_void_warp<kRgba, kW, kUnroll>(c, inside ? ct : 0, inside ? cb : 0);
-    if (mcount > 0) {
+    if (kMasked && mcount > 0) {
         __syncwarp();
         masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.cmap_s, c.pal_s, x, lane, wl, ml, mcount);
     }
@@ -640,9 +640,13 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     const long long total_warps = (long long)n * strips;
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
     const bool w1920 = vw.W == 1920 && !getenv("B2D_RASTER_GENERIC_W");
-#define B2D_RASTER_GO(RGBA, KW) \
-    b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps><<<nblocks, kWarps * 32, 0, stream>>>( \
-        sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba)
+#define B2D_RASTER_GO(RGBA, KW) do { \
+    if (sc.nmids > 0 && sc.masked_list) \
+        b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
+            sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); \
+    else \
+        b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
+            sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); } while (0)
     if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
     else { if (w1920) B2D_RASTER_GO(false, 1920); else B2D_RASTER_GO(false, 0); }
 #undef B2D_RASTER_GO

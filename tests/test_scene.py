@@ -112,7 +112,7 @@ def test_pegging_rules(b2d):
     segs = S.section(blob, "segs")
     tex = S.section(blob, "textures")
     s = segs[3]                      # A's side of the shared line
-    assert s[3] == S.SEG_TWO_SIDED and s[2] == 0 and s[15] == 1
+    assert s[3] == S.SEG_TWO_SIDED and s[2] == 0 and s[15] == -1     # two-sided, front sector 0, no masked middle
     assert (s[13], s[14]) == (96, 24)                      # opening: back ceil / back floor
     hA, hB = int(tex[s[6]][2]), int(tex[s[9]][2])
     assert (hA, hB) == (128, 24)
