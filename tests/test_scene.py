@@ -67,7 +67,8 @@ def test_view_constants(b2d):
     assert (v.F, v.FY2) == (1413, 1695)     # 2*focal: fovy 65 deg, aspect correction 1.2
 
 
-def _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(24, 96), tex_h=128, yoff=0):
+def _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(24, 96), tex_h=128, yoff=0, mid="-", upper=None,
+                 lower="STEP2"):
     """Two square rooms A (x<0) and B (x>0) sharing the edge x=0; returns seg records of the shared line."""
     from rust_doom_b200 import synthwad as G
     import struct
@@ -79,8 +80,8 @@ def _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(24, 96), tex_h=12
     secs = [G.Sector(front[0], front[1], "FLOOR1", "CEIL1", 160), G.Sector(back[0], back[1], "FLOOR2", "F_SKY1" if back[1] == -1 else "CEIL2", 160)]
     sides = [G.Sidedef(0, 0, "-", "-", "BRICK1", 0) for _ in range(3)] + \
             [G.Sidedef(0, 0, "-", "-", "BRICK1", 1) for _ in range(3)] + \
-            [G.Sidedef(8, yoff, "PANEL72" if tex_h == 72 else "BRICK2", "STEP2", "-", 0),
-             G.Sidedef(8, yoff, "BRICK2", "STEP2", "-", 1)]
+            [G.Sidedef(8, yoff, upper if upper is not None else ("PANEL72" if tex_h == 72 else "BRICK2"), lower, mid, 0),
+             G.Sidedef(8, yoff, "BRICK2", "STEP2", mid, 1)]
     # room A walls: clockwise so the room is on the right
     L = [G.Linedef(0, 3, 1, 0, 0, 0, -1), G.Linedef(3, 2, 1, 0, 0, 1, -1), G.Linedef(1, 0, 1, 0, 0, 2, -1),
          G.Linedef(2, 5, 1, 0, 0, 3, -1), G.Linedef(5, 4, 1, 0, 0, 4, -1), G.Linedef(4, 1, 1, 0, 0, 5, -1),
@@ -181,3 +182,25 @@ def test_wad_layout_quirks(b2d):
     assert ob == pb
     segs = S.section(ob, "segs")
     assert (segs[:, 6] >= 0).sum() > 10                       # lower-case names resolved to textures
+
+
+def test_middle_texture_pegging(b2d):
+    """visitor.rs:808-836 (peg choice), 875-885 (float pegs clamp the quad to the texture height),
+    909-919 (t at `high`); COMBO2 is 64x128."""
+    def mid_of(**kw):
+        data = _micro_level(mid="COMBO2", **kw)
+        oa = W.Archive(data)
+        blob = S.compile_scene(oa, W.TextureDirectory(oa), 0)
+        assert blob == b2d.Scene(b2d.Archive.from_bytes(data), 0).blob
+        s = S.section(blob, "segs")[3]
+        assert s[15] >= 0
+        return [int(v) for v in S.section(blob, "mids")[s[15]][:4]], S.section(blob, "textures")
+    # opening between back floor 24 and back ceiling 96 (height 72)
+    (tex, t_high, low, high), texs = mid_of(two_sided_flags=0x0004)                       # Peg::Top
+    assert (int(texs[tex][1]), int(texs[tex][2])) == (64, 128) and (t_high, low, high) == (0, 24, 96)
+    (_, t_high, low, high), _ = mid_of(two_sided_flags=0x0004 | 0x0010)                   # Peg::Bottom
+    assert (t_high, low, high) == (128 - 72, 24, 96)
+    (_, t_high, low, high), _ = mid_of(two_sided_flags=0x0004 | 0x0010, upper="-", yoff=6)    # Peg::TopFloat
+    assert (t_high, low, high) == (6, 24 + 6, 24 + 128 + 6)
+    (_, t_high, low, high), _ = mid_of(two_sided_flags=0x0004, lower="-", yoff=-5)        # Peg::BottomFloat
+    assert (t_high, low, high) == ((-5) % 128, 96 - 5 - 128, 96 - 5)
