@@ -71,15 +71,17 @@ __device__ __forceinline__ void mark_solid(uint32_t *mask, int lane, int lo, int
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct WalkSmem {
-    size_t off_tx, off_tz, off_segr, off_boxr, off_mask, off_stack, off_list, total;
+    size_t off_tx, off_tz, off_segr, off_boxr, off_node, off_ssec, off_mask, off_stack, off_list, total;
 };
-__host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnodes) {
+__host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnodes, int nss) {
     WalkSmem L;
     size_t o = 0;
     L.off_tx = o; o = align16(o + 4 * (size_t)nverts);
     L.off_tz = o; o = align16(o + 4 * (size_t)nverts);
     L.off_segr = o; o = align16(o + 4 * (size_t)nsegs);
     L.off_boxr = o; o = align16(o + 8 * (size_t)nnodes);
+    L.off_node = o; o = align16(o + 32 * (size_t)nnodes);     // {x,y,dx,dy,rchild,lchild,-,-} per node
+    L.off_ssec = o; o = align16(o + 16 * (size_t)nss);        // SSectorRec copies
     L.off_mask = o; o = align16(o + 4 * kMaskWords);
     L.off_stack = o; o = align16(o + 4 * kStackDepth);
     L.off_list = o; o = align16(o + 2 * (size_t)nsegs);
@@ -98,12 +100,14 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     const int frame = blockIdx.x * (blockDim.x >> 5) + warp;
     if (frame >= n) return;                       // warps are independent: no block barrier below
 
-    const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes);
+    const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss);
     uint8_t *base = smem + (size_t)warp * L.total;
     int32_t *tx = reinterpret_cast<int32_t *>(base + L.off_tx);
     int32_t *tz = reinterpret_cast<int32_t *>(base + L.off_tz);
     uint32_t *segr = reinterpret_cast<uint32_t *>(base + L.off_segr);
     uint32_t *boxr = reinterpret_cast<uint32_t *>(base + L.off_boxr);
+    int4 *node_s = reinterpret_cast<int4 *>(base + L.off_node);       // traversal reads shared memory, not L2
+    int4 *ssec_s = reinterpret_cast<int4 *>(base + L.off_ssec);
     uint32_t *mask = reinterpret_cast<uint32_t *>(base + L.off_mask);
     uint32_t *stack = reinterpret_cast<uint32_t *>(base + L.off_stack);
     uint16_t *list = reinterpret_cast<uint16_t *>(base + L.off_list);
@@ -143,6 +147,12 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         int lo, hi;
         boxr[i] = box_range(fc, vw, b4, lo, hi) ? pack_range(lo, hi, kVisBit) : 0u;
     }
+    for (int i = lane; i < sc.nnodes; i += 32) {
+        const NodeRec &N = sc.nodes[i];
+        node_s[2 * i] = make_int4(N.x, N.y, N.dx, N.dy);
+        node_s[2 * i + 1] = make_int4((int)N.child[0], (int)N.child[1], 0, 0);
+    }
+    for (int i = lane; i < sc.nss; i += 32) ssec_s[i] = *reinterpret_cast<const int4 *>(&sc.ssectors[i]);
     // solid-column mask: columns >= W start out solid
 #pragma unroll
     for (int k = 0; k < kMaskWords / 32; k++) {
@@ -162,7 +172,9 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         if (child & kLeaf) {
             uint32_t id = child & 0x7FFFFFFFu;
             if (id >= (uint32_t)sc.nss) continue;
-            const SSectorRec ss = sc.ssectors[id];
+            const int4 ssv = ssec_s[id];
+            SSectorRec ss;
+            ss.first_seg = ssv.x; ss.num_segs = ssv.y; ss.sector = ssv.z; ss.pad = 0;
             if (ss.sector < 0) continue;
             for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {
                 int k = k0 + lane;
@@ -186,9 +198,9 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
             if (!range_open(mask, lane, 0, vw.W - 1)) break;     // every column is closed
         } else {
             if (child >= (uint32_t)sc.nnodes) continue;
-            const NodeRec &N = sc.nodes[child];
-            int side = node_side(fc.pose, N.x, N.y, N.dx, N.dy);   // 1: left child is near
-            uint32_t near_c = N.child[side], far_c = N.child[side ^ 1];
+            const int4 nl = node_s[2 * child], nc = node_s[2 * child + 1];
+            int side = node_side(fc.pose, nl.x, nl.y, nl.z, nl.w);   // 1: left child is near
+            uint32_t near_c = (uint32_t)(side ? nc.y : nc.x), far_c = (uint32_t)(side ? nc.x : nc.y);
             uint32_t rn = boxr[2 * child + side], rf = boxr[2 * child + (side ^ 1)];
             bool far_vis = (rf & kVisBit) && range_open(mask, lane, range_lo(rf), range_hi(rf));
             bool near_vis = (rn & kVisBit) && range_open(mask, lane, range_lo(rn), range_hi(rn));
@@ -606,7 +618,7 @@ b2d_palette_kernel(const uint32_t *__restrict__ palette, const uint8_t *__restri
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts, sc.nsegs, sc.nnodes).total; }
+size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss).total; }
 
 cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
                         FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream) {
