@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="poses per CPU-baseline step (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--rgba", action="store_true", help="also materialise RGBA8 frames in HBM (5 B/pixel; not the headline config)")
     ap.add_argument("--gather-frames", type=int, default=128, help="frames per rank in the separate all-gather timing (N>1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -197,10 +198,11 @@ def main():
     npix = WIDTH * HEIGHT
     d_poses = torch.from_numpy(poses_np.view(np.int32).reshape(-1, 4).copy()).to(dev)
     d_index = torch.empty((n, HEIGHT, WIDTH), dtype=torch.uint8, device=dev)
+    d_rgba = torch.empty((n, HEIGHT, WIDTH), dtype=torch.int32, device=dev) if args.rgba else None
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():
-        r.render_device(d_poses.data_ptr(), n, d_index.data_ptr(), 0, stream)
+        r.render_device(d_poses.data_ptr(), n, d_index.data_ptr(), d_rgba.data_ptr() if args.rgba else 0, stream)
 
     def barrier():
         if world > 1:
@@ -245,11 +247,11 @@ def main():
 
     # roofline of the dominant kernel (raster): algorithmic bytes = W*H*1 per frame (index FB written once)
     peak, peak_src = measured_peak()
-    alg_bytes = float(n) * npix
+    alg_bytes = float(n) * npix * (5 if args.rgba else 1)
     raster_avg_ms = raster_ms / max(batches, 1)
     achieved = alg_bytes / (raster_avg_ms / 1e3) / 1e9 if raster_avg_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(), "kernel": "b2d_raster_kernel<false>",
+                "traffic": None if args.rgba else ncu_traffic(), "kernel": "b2d_raster_kernel<%s>" % ("rgba" if args.rgba else "index"),
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": raster_avg_ms,
                 "walk_avg_launch_ms": walk_ms / max(batches, 1), "peak_source": peak_src,
                 "note": "index-only output (no RGBA materialised); the kernel is LSU/issue bound, not HBM bound (DESIGN.md)"}
@@ -317,7 +319,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "%s, %d-pose fly-through per GPU, %dx%d, index framebuffer only" % (scene_name, n, WIDTH, HEIGHT),
+            "config": {"workload": "%s, %d-pose fly-through per GPU, %dx%d, %s" % (scene_name, n, WIDTH, HEIGHT, "index + RGBA8 framebuffers" if args.rgba else "index framebuffer only"),
                        "poses_per_step_per_gpu": n, "segs": scene.info.n_segs, "subsectors": scene.info.n_ssectors,
                        "parallelism": "pose-sharded x%d, no data-path collective" % world,
                        "l2": "each step writes %.2f GB of frames per GPU (>> 126 MB L2); the scene (%.0f KB) is legitimately cache-resident"

@@ -41,10 +41,11 @@ __device__ __forceinline__ uint32_t word_bits(int w, int lo, int hi) {
 }
 
 // warp-wide: is any column of [lo, hi] still open?  (lane-striped words + ballot)
-__device__ __forceinline__ bool range_open(const uint32_t *mask, int lane, int lo, int hi) {
+__device__ __forceinline__ bool range_open(const uint32_t *mask, int lane, int lo, int hi, int passes) {
     bool open = false;
 #pragma unroll
     for (int k = 0; k < kMaskWords / 32; k++) {
+        if (k >= passes) break;              // only ceil(W / 1024) lane passes carry columns
         int w = lane + 32 * k;
         uint32_t bits = word_bits(w, lo, hi);
         if (bits & ~mask[w]) open = true;
@@ -59,9 +60,10 @@ __device__ __forceinline__ bool lane_range_open(const uint32_t *mask, int lo, in
     return false;
 }
 
-__device__ __forceinline__ void mark_solid(uint32_t *mask, int lane, int lo, int hi) {
+__device__ __forceinline__ void mark_solid(uint32_t *mask, int lane, int lo, int hi, int passes) {
 #pragma unroll
     for (int k = 0; k < kMaskWords / 32; k++) {
+        if (k >= passes) break;
         int w = lane + 32 * k;
         uint32_t bits = word_bits(w, lo, hi);
         if (bits) mask[w] |= bits;
@@ -163,6 +165,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     __syncwarp();
 
     // 4. front-to-back traversal (control flow is warp-uniform)
+    const int passes = (vw.W + 1023) / 1024;
     int sp = 1, count = 0, status = 0;
     int budget = 2 * (sc.nnodes + sc.nss) + 64;      // a corrupt BSP with a cycle must not hang the GPU
     while (sp > 0) {
@@ -191,19 +194,19 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
                     int j = __ffs(sm) - 1;
                     sm &= sm - 1;
                     uint32_t rj = __shfl_sync(kFull, r, j);
-                    mark_solid(mask, lane, range_lo(rj), range_hi(rj));
+                    mark_solid(mask, lane, range_lo(rj), range_hi(rj), passes);
                 }
                 __syncwarp();
             }
-            if (!range_open(mask, lane, 0, vw.W - 1)) break;     // every column is closed
+            if (!range_open(mask, lane, 0, vw.W - 1, passes)) break;     // every column is closed
         } else {
             if (child >= (uint32_t)sc.nnodes) continue;
             const int4 nl = node_s[2 * child], nc = node_s[2 * child + 1];
             int side = node_side(fc.pose, nl.x, nl.y, nl.z, nl.w);   // 1: left child is near
             uint32_t near_c = (uint32_t)(side ? nc.y : nc.x), far_c = (uint32_t)(side ? nc.x : nc.y);
             uint32_t rn = boxr[2 * child + side], rf = boxr[2 * child + (side ^ 1)];
-            bool far_vis = (rf & kVisBit) && range_open(mask, lane, range_lo(rf), range_hi(rf));
-            bool near_vis = (rn & kVisBit) && range_open(mask, lane, range_lo(rn), range_hi(rn));
+            bool far_vis = (rf & kVisBit) && range_open(mask, lane, range_lo(rf), range_hi(rf), passes);
+            bool near_vis = (rn & kVisBit) && range_open(mask, lane, range_lo(rn), range_hi(rn), passes);
             int need = (far_vis ? 1 : 0) + (near_vis ? 1 : 0);
             if (sp + need > kStackDepth) { status = 1; break; }
             if (lane == 0) {

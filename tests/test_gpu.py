@@ -274,3 +274,21 @@ def test_gpu_masked_middle_textures(b2d):
         ofb, orgba = render.render(sc.blob, render.make_view(w, h), p, rgba=True, threads=8)
         _assert_same(ofb, idx, "masked %dx%d" % (w, h))
         assert np.array_equal(rgba, orgba)
+
+
+def test_gpu_full_benchmark_workload_matches_oracle(b2d, product_scene):
+    """BASELINE.json configs[1] at full size: every one of the 1000 fly-through frames at 1920x1080 is compared
+    with the oracle (the GPU box has enough host cores for the oracle to finish this in seconds)."""
+    import os
+    from rust_doom_b200 import poses as P
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",))), 0)
+    poses = P.flythrough_poses(sc, 1000, 2)
+    r = b2d.Renderer(sc, b2d.make_view(1920, 1080), max_batch=250)
+    gfb = r.render(poses)
+    threads = os.cpu_count() or 8
+    bad = []
+    for c0 in range(0, 1000, 250):
+        ofb = render.render(sc.blob, render.make_view(1920, 1080), poses[c0:c0 + 250], threads=threads)
+        bad += [c0 + i for i in range(250) if not np.array_equal(ofb[i], gfb[c0 + i])]
+    assert not bad, "frames differ: %s" % bad[:10]
