@@ -37,7 +37,7 @@ typedef struct { int32_t W, H, F, FY2; } b2o_view;                  /* F = round
 enum { H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX,
        H_NFLATS, H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX,
        H_OFF_TEXELS, H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX,
-       H_NMIDS = 30, H_OFF_MIDS = 31 };
+       H_NMIDS = 30, H_OFF_MIDS = 31, H_NSPRITES = 32, H_OFF_SPRITES = 33 };
 
 #define LEAF 0x80000000u
 #define SEG_TWO_SIDED 1
@@ -46,16 +46,16 @@ enum { H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_
 
 typedef struct {
     const uint32_t *hdr;
-    const int32_t *verts, *nodes, *ssectors, *segs, *sectors, *mids;
+    const int32_t *verts, *nodes, *ssectors, *segs, *sectors, *mids, *sprites;
     const uint32_t *tex;
     const uint8_t *texels, *flats, *colormap;
     const uint32_t *palette;
-    int nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids;
+    int nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids, nsprites;
 } Scene;
 
 static int scene_bind(Scene *s, const uint8_t *blob) {
     const uint32_t *h = (const uint32_t *)blob;
-    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 2) return -1;
+    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 3) return -1;
     s->hdr = h;
     s->verts = (const int32_t *)(blob + h[H_OFF_VERTS]);
     s->nodes = (const int32_t *)(blob + h[H_OFF_NODES]);
@@ -65,6 +65,8 @@ static int scene_bind(Scene *s, const uint8_t *blob) {
     s->tex = (const uint32_t *)(blob + h[H_OFF_TEX]);
     s->mids = (const int32_t *)(blob + h[H_OFF_MIDS]);
     s->nmids = (int)h[H_NMIDS];
+    s->sprites = (const int32_t *)(blob + h[H_OFF_SPRITES]);
+    s->nsprites = (int)h[H_NSPRITES];
     s->texels = blob + h[H_OFF_TEXELS];
     s->flats = blob + h[H_OFF_FLATS];
     s->colormap = blob + h[H_OFF_COLORMAP];
@@ -138,7 +140,7 @@ static inline int light_row(int b, int32_t z8) {
 /* ---------------------------------------------------------------- per-frame state ------------ */
 /* one screen column of a masked two-sided middle texture, with the clip window that was open behind the
  * seg when the front-to-back pass reached it (Doom's drawseg silhouette, per column) */
-struct Masked { int seg, x, ya, yb, row; int32_t scale, iscale, ucol; };
+struct Masked { int owner, x, ya, yb, row; int32_t tex, tA, hA, iscale, ucol; };
 
 typedef struct {
     const Scene *sc;
@@ -159,7 +161,7 @@ typedef struct {
 
 static inline void put(Frame *f, int x, int y, uint8_t v) {
     f->fb[(size_t)y * f->vw.W + x] = v;
-    if (f->seg_hits) f->seg_hits[f->cur_seg]++;
+    if (f->seg_hits && f->cur_seg >= 0) f->seg_hits[f->cur_seg]++;       /* sprites have no seg */
 }
 
 static void draw_sky(Frame *f, int x, int ya, int yb) {
@@ -329,9 +331,12 @@ static void draw_seg(Frame *f, int si) {
                         f->cap_masked = f->cap_masked ? 2 * f->cap_masked : 1024;
                         f->masked = (struct Masked *)realloc(f->masked, (size_t)f->cap_masked * sizeof *f->masked);
                     }
+                    const int32_t *M = sc->mids + 8 * S[15];
+                    int mya = yrow(f, M[3], (int32_t)scale), myb = yrow(f, M[2], (int32_t)scale);
                     struct Masked *m = &f->masked[f->n_masked++];
-                    m->seg = si; m->x = x; m->ya = y2; m->yb = y3; m->row = row;
-                    m->scale = (int32_t)scale; m->iscale = iscale; m->ucol = ucol;
+                    m->owner = si; m->x = x; m->row = row;
+                    m->ya = mya > y2 ? mya : y2; m->yb = myb < y3 ? myb : y3;
+                    m->tex = M[0]; m->tA = M[1]; m->hA = M[3]; m->iscale = iscale; m->ucol = ucol;
                 }
             }
         }
@@ -344,29 +349,80 @@ static void draw_masked(Frame *f) {
     const Scene *sc = f->sc;
     for (int i = f->n_masked - 1; i >= 0; i--) {
         const struct Masked *m = &f->masked[i];
-        const int32_t *S = sc->segs + 16 * m->seg;
-        const int32_t *M = sc->mids + 8 * S[15];
-        if (M[0] < 0 || M[0] >= sc->ntex) continue;
-        const uint32_t *T = sc->tex + 8 * M[0];
+        if (m->tex < 0 || m->tex >= sc->ntex || m->ya >= m->yb) continue;
+        const uint32_t *T = sc->tex + 8 * m->tex;
         int32_t w = (int32_t)T[1], h = (int32_t)T[2];
         const uint8_t *px = sc->texels + T[0];
         const uint8_t *opaque = T[5] != 0xFFFFFFFFu ? sc->texels + T[5] : NULL;
-        int ya = yrow(f, M[3], m->scale), yb = yrow(f, M[2], m->scale);
-        if (ya < m->ya) ya = m->ya;
-        if (yb > m->yb) yb = m->yb;
-        if (ya >= yb) continue;
-        f->cur_seg = m->seg;
+        f->cur_seg = m->owner;
         int32_t col = floormod32(m->ucol, w);
-        int64_t hrel = clamp64(((int64_t)M[3] << 16) - f->pose.z, -((int64_t)1 << 27), (int64_t)1 << 27);
-        int64_t tbase = ((int64_t)M[1] << 16) + hrel + asr64((int64_t)(1 - f->vw.H) * m->iscale, 5);
+        int64_t hrel = clamp64(((int64_t)m->hA << 16) - f->pose.z, -((int64_t)1 << 27), (int64_t)1 << 27);
+        int64_t tbase = ((int64_t)m->tA << 16) + hrel + asr64((int64_t)(1 - f->vw.H) * m->iscale, 5);
         int32_t tstep = m->iscale >> 4;
         const uint8_t *cm = sc->colormap + 256 * m->row;
-        for (int y = ya; y < yb; y++) {
+        for (int y = m->ya; y < m->yb; y++) {
             int32_t t = (int32_t)(tbase + (int64_t)y * tstep);
             int32_t v = floormod32((int32_t)asr64(t, 16), h);
             if (opaque && !opaque[v * w + col]) continue;
             put(f, m->x, y, cm[px[v * w + col]]);
         }
+    }
+}
+
+/* sprite light (assets/shaders/sprite.frag:15-27): light = min(v, 2v - dist), dist = 1 - 1/(w+1), w = z/100:
+ * row = clamp(max(floor(32(255-b)/255), floor(64(255-b)/255 - 3200/(z+100))), 0, 31) */
+static inline int light_row_sprite(int b, int32_t z8) {
+    int64_t r1 = (32 * (int64_t)(255 - b)) / 255;
+    int64_t Z = (int64_t)z8 + 800;
+    int64_t num = (int64_t)64 * (255 - b) * Z - 6528000;
+    int64_t r2 = num <= 0 ? 0 : num / (255 * Z);
+    int64_t r = r1 > r2 ? r1 : r2;
+    return r > 31 ? 31 : (int)r;
+}
+
+/* A decoration thing (visitor.rs:1062-1137, sprite.vert:40-42): camera-facing billboard of its sprite image's
+ * size, at constant view depth.  Recorded when the front-to-back walk enters the thing's subsector, with the
+ * clip windows open at that moment; drawn with the masked pass. */
+static void record_sprite(Frame *f, int idx) {
+    const Scene *sc = f->sc;
+    const int32_t *SP = sc->sprites + 8 * idx;
+    if (SP[3] < 0 || SP[3] >= sc->ntex) return;
+    const uint32_t *T = sc->tex + 8 * SP[3];
+    const int32_t w = (int32_t)T[1], h = (int32_t)T[2];
+    const int W = f->vw.W;
+    const int64_t F = f->vw.F, FY2 = f->vw.FY2;
+    int64_t px8 = asr64(f->pose.x, 8), py8 = asr64(f->pose.y, 8);
+    int64_t dx = ((int64_t)SP[0] << 8) - px8, dy = ((int64_t)SP[1] << 8) - py8;
+    int64_t cx = asr64(dx * f->sinq - dy * f->cosq, 30), cz = asr64(dx * f->cosq + dy * f->sinq, 30);
+    if (cz < 256) return;                                         /* nearer than 1 map unit / behind */
+    int64_t L = (cx - (int64_t)w * 128) * F, R = (cx + (int64_t)w * 128) * F;
+    int64_t lo = 0, hi = W - 1;
+    constrain(&lo, &hi, cz * (1 - W) - L, 2 * cz, 0);            /* cz*c2 >= L */
+    constrain(&lo, &hi, R - 1 - cz * (1 - W), -2 * cz, 0);       /* cz*c2 <= R-1 */
+    if (lo > hi) return;
+    int64_t scale = (FY2 << 25) / cz;
+    if (scale > (FY2 << 17)) scale = FY2 << 17;
+    if (scale < 1) return;
+    int32_t iscale = (int32_t)clamp64(((int64_t)1 << 38) / scale, 1, 1 << 23);
+    int64_t z8l = ((int64_t)iscale * FY2) >> 18;
+    int32_t z8 = z8l > 65535 ? 65535 : (int32_t)z8l;
+    int row = light_row_sprite(SP[4], z8);
+    int ys_a = yrow(f, SP[2] + h, (int32_t)scale), ys_b = yrow(f, SP[2], (int32_t)scale);
+    for (int x = (int)lo; x <= (int)hi; x++) {
+        int ct = f->ctop[x], cb = f->cbot[x];
+        if (ct >= cb) continue;
+        int ya = ys_a > ct ? ys_a : ct, yb = ys_b < cb ? ys_b : cb;
+        if (ya >= yb) continue;
+        int64_t c2 = 2 * (int64_t)x + 1 - W;
+        int64_t u = floordiv64(cz * c2 - L, 256 * F);
+        if (f->n_masked == f->cap_masked) {
+            f->cap_masked = f->cap_masked ? 2 * f->cap_masked : 1024;
+            f->masked = (struct Masked *)realloc(f->masked, (size_t)f->cap_masked * sizeof *f->masked);
+        }
+        struct Masked *m = &f->masked[f->n_masked++];
+        m->owner = -1; m->x = x; m->ya = ya; m->yb = yb; m->row = row;
+        m->tex = SP[3]; m->tA = 0; m->hA = SP[2] + h; m->iscale = iscale;
+        m->ucol = (int32_t)clamp64(u, 0, w - 1);
     }
 }
 
@@ -378,6 +434,10 @@ static void walk(Frame *f, uint32_t child, int depth) {
         if ((int)id >= sc->nss) return;
         const int32_t *ss = sc->ssectors + 4 * id;
         if (ss[2] < 0) return;
+        {   /* decoration things of this subsector: in front of its far segs, behind everything drawn so far */
+            int first = ss[3] & 0xFFFFFF, cnt = (ss[3] >> 24) & 0xFF;
+            for (int i = 0; i < cnt && first + i < sc->nsprites; i++) record_sprite(f, first + i);
+        }
         for (int i = 0; i < ss[1]; i++) draw_seg(f, ss[0] + i);
         return;
     }

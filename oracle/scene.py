@@ -11,15 +11,18 @@ reference's one-and-only geometry emitter `LevelWalker` and its visitor in `game
                                               game/src/player.rs:72-92 (camera_height)
 * sky texture per level                       wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
 
-The blob layout ("B2DS" v2) is the contract shared with the product's scene compiler
+The blob layout ("B2DS" v3) is the contract shared with the product's scene compiler
 (rust-doom_b200/csrc/b2d_scene.cpp, written independently); tests compare the two byte-for-byte.
 All fields are little-endian int32 unless noted.
 
-header  : 32 x u32 (see H_* indices below)
+header  : 64 x u32 (see H_* indices below)
 verts   : {x, y}                                                   8 B
 nodes   : {x, y, dx, dy, rbox[4], lbox[4], rchild, lchild, 0, 0}   64 B  (box = top,bottom,left,right;
           child bit31 = subsector)
-ssectors: {first_seg, num_segs, sector, 0}                         16 B
+ssectors: {first_seg, num_segs, sector, sprites}                   16 B  (sprites = first | count<<24)
+sprites : {x, y, low, tex, light, 0, 0, 0}                         32 B  decoration things grouped by subsector:
+          billboard of the sprite image's size standing on the floor / hanging from the ceiling
+          (visitor.rs:1062-1137), lit by the sector light without contrast
 segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, light, otop, obot, mid}   64 B
           (mid = index into mids or -1)
 mids    : {tex, t_high, low, high, 0, 0, 0, 0}                     32 B  masked two-sided middle texture:
@@ -44,11 +47,12 @@ import numpy as np
 from . import wad as W
 
 MAGIC = 0x53443242
-VERSION = 2
+VERSION = 3
+HEADER_WORDS = 64
 (H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
  H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
  H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
- H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS) = range(32)
+ H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES) = range(34)
 
 SEG_TWO_SIDED = 1
 SEG_INVALID = 0x80
@@ -82,10 +86,19 @@ def _floormod(a: int, b: int) -> int:
 
 
 def sector_at(level: W.Level, x: float, y: float) -> int:
-    """LevelWalker::sector_at (visitor.rs:1028-1060).  Returns sector id or -1.  Works in WAD
-    coordinates; the reference's `signed_distance` sign is (py-oy)*dx - (px-ox)*dy > 0 => left."""
+    return subsector_at(level, x, y)[1]
+
+
+def subsector_at(level: W.Level, x: float, y: float):
+    """LevelWalker::sector_at (visitor.rs:1028-1060).  Returns (subsector id, sector id) or (-1, -1).  Works
+    in WAD coordinates; the reference's `signed_distance` sign is (py-oy)*dx - (px-ox)*dy > 0 => left."""
+    r = _subsector_at(level, x, y)
+    return r if r[1] >= 0 else (-1, -1)
+
+
+def _subsector_at(level: W.Level, x: float, y: float):
     if len(level.nodes) == 0:
-        return -1
+        return -1, -1
     child = len(level.nodes) - 1
     leaf = False
     for _ in range(4096):
@@ -96,20 +109,20 @@ def sector_at(level: W.Level, x: float, y: float) -> int:
         nxt = int(n["left"]) if sd > 0.0 else int(n["right"])
         child, leaf = nxt & 0x7FFF, bool(nxt & 0x8000)
         if not leaf and child >= len(level.nodes):
-            return -1
+            return -1, -1
     if not leaf or child >= len(level.subsectors):
-        return -1
+        return -1, -1
     ss = level.subsectors[child]
     first, num = int(ss["first_seg"]), int(ss["num_segs"])
     if num == 0 or first + num > len(level.segs):
-        return -1
+        return -1, -1
     segs = level.segs[first:first + num]
     side = level.seg_sidedef_index(segs[0])
     if side < 0:
-        return -1
+        return -1, -1
     sector = int(level.sidedefs[side]["sector"])
     if sector >= len(level.sectors):
-        return -1
+        return -1, -1
     for s in segs:
         if s["v1"] >= len(level.vertices) or s["v2"] >= len(level.vertices):
             continue
@@ -120,8 +133,8 @@ def sector_at(level: W.Level, x: float, y: float) -> int:
             continue
         sd = ((y - float(a["y"])) * dx - (x - float(a["x"])) * dy) / ln
         if sd > 10.0:                       # SEG_TOLERANCE = 0.1 world units = 10 map units
-            return -1
-    return sector
+            return -1, -1
+    return child, sector
 
 
 def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int) -> bytes:
@@ -325,6 +338,44 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
                 mids.append([mtid, _floormod(t_high + yoff, th), low, high, 0, 0, 0, 0])
         segs[i] = rec
 
+    # --- decoration things -> sprites (visitor.rs:1010-1026, 1062-1137; thing table from doom.toml) ------
+    from .thing_table import THINGS
+    sprite_rows = []            # (subsector, thing index, [x, y, low, tex, light, 0, 0, 0])
+    for ti, t in enumerate(level.things):
+        ttype = int(t["type"])
+        if ttype in (1, 2, 3, 4, 11, 14):                     # markers (visitor.rs:1345-1364)
+            continue
+        ssid, sec = subsector_at(level, float(t["x"]), float(t["y"]))
+        if sec < 0 or ttype not in THINGS or ssid >= nss or int(ssectors[ssid, 2]) != sec:
+            continue
+        prefix, frame, hanging = THINGS[ttype]
+        tid = TEX_NONE
+        for rot in (b"0", b"1"):                              # try <sprite><frame>0 then ...1
+            try:
+                nm = W.wad_name(prefix.encode() + frame.encode() + rot)
+            except W.WadError:
+                break
+            if nm in tex.textures:
+                tid = tex_id(nm)
+                break
+        if tid < 0:
+            continue
+        th = int(tex_list[tid].shape[0])
+        sct = level.sectors[sec]
+        low = int(sct["ceil"]) - th if hanging else int(sct["floor"])
+        sprite_rows.append((ssid, ti, [int(t["x"]), int(t["y"]), low, tid, W.light_byte(int(sct["light"]), 0), 0, 0, 0]))
+    sprite_rows.sort(key=lambda r: (r[0], r[1]))
+    sprites = np.array([r[2] for r in sprite_rows], dtype=np.int64).reshape(-1, 8)
+    k = 0
+    while k < len(sprite_rows):
+        ssid = sprite_rows[k][0]
+        j = k
+        while j < len(sprite_rows) and sprite_rows[j][0] == ssid:
+            j += 1
+        cnt = min(j - k, 255)
+        ssectors[ssid, 3] = k | (cnt << 24)
+        k = j
+
     # --- nodes -----------------------------------------------------------------------------------
     nodes = np.zeros((nnodes, 16), dtype=np.int64)
 
@@ -456,15 +507,16 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
              ("ssectors", ssectors.astype("<i4").tobytes()), ("segs", segs.astype("<i4").tobytes()),
              ("sectors", sectors.astype("<i4").tobytes()), ("tex", texrec.astype("<u4").tobytes()),
              ("mids", np.array(mids, dtype="<i4").reshape(-1, 8).tobytes()),
+             ("sprites", (sprites & 0xFFFFFFFF).astype("<u4").tobytes()),
              ("texels", bytes(texels)), ("flats", b"".join(flat_list)), ("colormap", bytes(colormap)),
              ("palette", palette.tobytes())]
-    off = 128
+    off = 4 * HEADER_WORDS
     offs = {}
     for name, data in parts:
         offs[name] = off
         off = _align16(off + len(data))
     total = off
-    hdr = [0] * 32
+    hdr = [0] * HEADER_WORDS
     hdr[H_MAGIC], hdr[H_VERSION], hdr[H_TOTAL] = MAGIC, VERSION, total
     hdr[H_NVERTS], hdr[H_NNODES], hdr[H_NSSECTORS], hdr[H_NSEGS] = nverts, nnodes, nss, nsegs
     hdr[H_NSECTORS], hdr[H_NTEX], hdr[H_NFLATS] = nsect, ntex, len(flat_list)
@@ -481,15 +533,16 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     hdr[H_START_ANGLE], hdr[H_HAS_START] = sang, has_start
     hdr[H_MIN_H], hdr[H_MAX_H] = min_h & 0xFFFFFFFF, max_h & 0xFFFFFFFF
     hdr[H_NMIDS], hdr[H_OFF_MIDS] = len(mids), offs["mids"]
+    hdr[H_NSPRITES], hdr[H_OFF_SPRITES] = len(sprite_rows), offs["sprites"]
     blob = bytearray(total)
-    blob[0:128] = struct.pack("<32I", *hdr)
+    blob[0:4 * HEADER_WORDS] = struct.pack("<%dI" % HEADER_WORDS, *hdr)
     for name, data in parts:
         blob[offs[name]:offs[name] + len(data)] = data
     return bytes(blob)
 
 
 def header(blob: bytes) -> List[int]:
-    return list(struct.unpack_from("<32I", blob, 0))
+    return list(struct.unpack_from("<%dI" % HEADER_WORDS, blob, 0))
 
 
 def section(blob: bytes, which: str) -> np.ndarray:
@@ -511,4 +564,6 @@ def section(blob: bytes, which: str) -> np.ndarray:
         return arr(h[H_OFF_TEX], h[H_NTEX], 8, "<u4")
     if which == "mids":
         return arr(h[H_OFF_MIDS], h[H_NMIDS], 8)
+    if which == "sprites":
+        return arr(h[H_OFF_SPRITES], h[H_NSPRITES], 8)
     raise KeyError(which)

@@ -159,6 +159,7 @@ class Renderer:
         self.max_batch = max_batch
         self.device = device
         self.n_segs = scene.info.n_segs
+        self.worklist_stride = max(1, int(np.frombuffer(scene.blob, dtype='<u4', count=34)[6] + np.frombuffer(scene.blob, dtype='<u4', count=34)[32]))
 
     # -- end to end: host poses in, host frames out -------------------------------------------------
     def render(self, poses: np.ndarray, rgba: bool = False, out_index: Optional[np.ndarray] = None,
@@ -186,7 +187,7 @@ class Renderer:
 
     def worklist(self, n: int):
         counts = np.zeros(n, dtype=np.int32)
-        ids = np.full((n, max(self.n_segs, 1)), -1, dtype=np.int32)
+        ids = np.full((n, self.worklist_stride), -1, dtype=np.int32)
         _check(_lib.load().b2d_debug_worklist(self._h, n, counts.ctypes.data, ids.ctypes.data, ids.shape[1]))
         return counts, ids
 

@@ -30,7 +30,7 @@ struct b2d_renderer {
     int device = 0;
     View view{};
     int max_batch = 0;
-    int stride = 0;                 // worklist entries per frame (= n_segs)
+    int stride = 0;                 // worklist entries per frame (= n_segs + n_sprites)
     uint8_t *d_blob = nullptr;
     uint32_t *d_yslope = nullptr;
     uint16_t *d_skyrow = nullptr;
@@ -263,7 +263,7 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     r->view = View{view->width, view->height, view->F, view->FY2};
     r->max_batch = max_batch;
     const uint32_t *h = reinterpret_cast<const uint32_t *>(s->blob.data());
-    r->stride = (int)h[H_NSEGS] > 0 ? (int)h[H_NSEGS] : 1;
+    r->stride = (int)(h[H_NSEGS] + h[H_NSPRITES]) > 0 ? (int)(h[H_NSEGS] + h[H_NSPRITES]) : 1;   // worklist entries per frame
     auto bail = [&](cudaError_t err, const char *what) { free_renderer(r); return cuda_fail(err, what); };
 #define CUR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return bail(e_, #call); } while (0)
     CUR(cudaMalloc(&r->d_blob, s->blob.size()));
@@ -291,8 +291,10 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.tex = reinterpret_cast<const TexRec *>(r->d_blob + h[H_OFF_TEX]);
     d.mids = reinterpret_cast<const MidRec *>(r->d_blob + h[H_OFF_MIDS]);
     d.nmids = (int32_t)h[H_NMIDS];
+    d.sprites = reinterpret_cast<const SpriteRec *>(r->d_blob + h[H_OFF_SPRITES]);
+    d.nsprites = (int32_t)h[H_NSPRITES];
     d.masked_list = nullptr;
-    if (d.nmids > 0) {   // deferred masked-texture lists: one per raster warp of a full batch
+    if (d.nmids > 0 || d.nsprites > 0) {   // deferred masked-texture lists: one per raster warp of a full batch
         const size_t strips = (size_t)(view->width + 31) / 32;
         CUR(cudaMalloc(&r->d_masked, sizeof(uint32_t) * 33 * kMaskedCap * strips * (size_t)max_batch));
         d.masked_list = r->d_masked;
@@ -311,7 +313,7 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.nflats = (int32_t)h[H_NFLATS]; d.sky_tex = (int32_t)h[H_SKY_TEX];
     d.root = h[H_ROOT];
     d.invF = (uint32_t)(4294967296ULL / (uint64_t)view->F);
-    if (d.nsegs > 65535) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level has more than 65535 segs"); }
+    if (d.nsegs + d.nsprites > 65535) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level has more than 65535 segs + sprites"); }
     if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
     CUR(cudaMalloc(&r->d_poses, sizeof(Pose) * (size_t)max_batch));
     CUR(cudaMalloc(&r->d_frames, sizeof(FrameConst) * (size_t)max_batch));

@@ -73,9 +73,9 @@ __device__ __forceinline__ void mark_solid(uint32_t *mask, int lane, int lo, int
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct WalkSmem {
-    size_t off_tx, off_tz, off_segr, off_boxr, off_node, off_ssec, off_mask, off_stack, off_list, total;
+    size_t off_tx, off_tz, off_segr, off_boxr, off_node, off_ssec, off_sprr, off_mask, off_stack, off_list, total;
 };
-__host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnodes, int nss) {
+__host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnodes, int nss, int nsprites) {
     WalkSmem L;
     size_t o = 0;
     L.off_tx = o; o = align16(o + 4 * (size_t)nverts);
@@ -84,9 +84,10 @@ __host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnode
     L.off_boxr = o; o = align16(o + 8 * (size_t)nnodes);
     L.off_node = o; o = align16(o + 32 * (size_t)nnodes);     // {x,y,dx,dy,rchild,lchild,-,-} per node
     L.off_ssec = o; o = align16(o + 16 * (size_t)nss);        // SSectorRec copies
+    L.off_sprr = o; o = align16(o + 4 * (size_t)nsprites);    // packed column range per sprite
     L.off_mask = o; o = align16(o + 4 * kMaskWords);
     L.off_stack = o; o = align16(o + 4 * kStackDepth);
-    L.off_list = o; o = align16(o + 2 * (size_t)nsegs);
+    L.off_list = o; o = align16(o + 2 * ((size_t)nsegs + (size_t)nsprites));
     L.total = o;
     return L;
 }
@@ -102,7 +103,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     const int frame = blockIdx.x * (blockDim.x >> 5) + warp;
     if (frame >= n) return;                       // warps are independent: no block barrier below
 
-    const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss);
+    const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss, sc.nsprites);
     uint8_t *base = smem + (size_t)warp * L.total;
     int32_t *tx = reinterpret_cast<int32_t *>(base + L.off_tx);
     int32_t *tz = reinterpret_cast<int32_t *>(base + L.off_tz);
@@ -110,6 +111,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     uint32_t *boxr = reinterpret_cast<uint32_t *>(base + L.off_boxr);
     int4 *node_s = reinterpret_cast<int4 *>(base + L.off_node);       // traversal reads shared memory, not L2
     int4 *ssec_s = reinterpret_cast<int4 *>(base + L.off_ssec);
+    uint32_t *sprr = reinterpret_cast<uint32_t *>(base + L.off_sprr);
     uint32_t *mask = reinterpret_cast<uint32_t *>(base + L.off_mask);
     uint32_t *stack = reinterpret_cast<uint32_t *>(base + L.off_stack);
     uint16_t *list = reinterpret_cast<uint16_t *>(base + L.off_list);
@@ -155,6 +157,14 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         node_s[2 * i + 1] = make_int4((int)N.child[0], (int)N.child[1], 0, 0);
     }
     for (int i = lane; i < sc.nss; i += 32) ssec_s[i] = *reinterpret_cast<const int4 *>(&sc.ssectors[i]);
+    for (int i = lane; i < sc.nsprites; i += 32) {          // decoration sprites: exact column interval
+        const SpriteRec &P = sc.sprites[i];
+        SpriteFrame sp;
+        uint32_t packed = 0;
+        if (P.tex >= 0 && P.tex < sc.ntex && sprite_setup(fc, vw, P.x, P.y, (int32_t)sc.tex[P.tex].w, sp))
+            packed = pack_range(sp.lo, sp.hi, kVisBit);
+        sprr[i] = packed;
+    }
     // solid-column mask: columns >= W start out solid
 #pragma unroll
     for (int k = 0; k < kMaskWords / 32; k++) {
@@ -177,8 +187,21 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
             if (id >= (uint32_t)sc.nss) continue;
             const int4 ssv = ssec_s[id];
             SSectorRec ss;
-            ss.first_seg = ssv.x; ss.num_segs = ssv.y; ss.sector = ssv.z; ss.pad = 0;
+            ss.first_seg = ssv.x; ss.num_segs = ssv.y; ss.sector = ssv.z; ss.sprites = ssv.w;
             if (ss.sector < 0) continue;
+            {   // the subsector's decoration sprites come first: they stand in front of its far segs
+                const int sfirst = ss.sprites & 0xFFFFFF, scnt = (ss.sprites >> 24) & 0xFF;
+                for (int k0 = 0; k0 < scnt; k0 += 32) {
+                    int k = k0 + lane, pi = sfirst + k;
+                    uint32_t r = (k < scnt && pi < sc.nsprites) ? sprr[pi] : 0u;
+                    bool vis = (r & kVisBit) && lane_range_open(mask, range_lo(r), range_hi(r));
+                    unsigned m = __ballot_sync(kFull, vis);
+                    int pos = count + __popc(m & ((1u << lane) - 1u));
+                    if (vis && pos < sc.nsegs + sc.nsprites) list[pos] = (uint16_t)(sc.nsegs + pi);
+                    count = min(count + __popc(m), sc.nsegs + sc.nsprites);
+                }
+                __syncwarp();
+            }
             for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {
                 int k = k0 + lane;
                 int si = ss.first_seg + k;
@@ -186,8 +209,8 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
                 bool vis = (r & kVisBit) && lane_range_open(mask, range_lo(r), range_hi(r));
                 unsigned m = __ballot_sync(kFull, vis);
                 int pos = count + __popc(m & ((1u << lane) - 1u));
-                if (vis && pos < sc.nsegs) list[pos] = (uint16_t)si;
-                count = min(count + __popc(m), sc.nsegs);
+                if (vis && pos < sc.nsegs + sc.nsprites) list[pos] = (uint16_t)si;
+                count = min(count + __popc(m), sc.nsegs + sc.nsprites);
                 unsigned sm = __ballot_sync(kFull, vis && (r & kSolidBit));
                 __syncwarp();
                 while (sm) {
@@ -224,8 +247,18 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     // 5. worklist records (lane-parallel): the projection coefficients of each emitted seg
     for (int k = lane; k < count; k += 32) {
         int si = list[k];
-        const SegRec &S = sc.segs[si];
         SegFrame sf;
+        if (si >= sc.nsegs) {                         // sprite entry: seg = -1 - sprite index, (cx, cz) in Nc/Nx
+            const int pi = si - sc.nsegs;
+            const SpriteRec &P = sc.sprites[pi];
+            SpriteFrame sp;
+            sprite_setup(fc, vw, P.x, P.y, (int32_t)sc.tex[P.tex].w, sp);
+            sf.Nc = sp.cx; sf.Nx = sp.cz; sf.Dc = 0; sf.Dx = 0; sf.Dmax = 0; sf.Rm = 0; sf.sh = 0; sf.e = 0;
+            sf.seg = -1 - pi; sf.xlo = (int16_t)sp.lo; sf.xhi = (int16_t)sp.hi; sf.flags = 0; sf.pad = 0;
+            work[(size_t)frame * stride + k] = sf;
+            continue;
+        }
+        const SegRec &S = sc.segs[si];
         seg_frame_setup(vw, tx[S.v1], tz[S.v1], tx[S.v2], tz[S.v2], sf, false);
         sf.seg = si;
         work[(size_t)frame * stride + k] = sf;
@@ -423,30 +456,55 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
         const uint32_t packed = ml[33 * e + 1 + c.lane];
         int ya = (int)(packed & 0xFFFFu), yb = (int)(packed >> 16);
         const SegFrame sf = wl[k];
-        const SegRec S = sc.segs[sf.seg];
-        if (S.mid < 0 || S.mid >= sc.nmids) continue;
-        const MidRec M = sc.mids[S.mid];
-        if (M.tex < 0 || M.tex >= sc.ntex) continue;
-        const TexRec T = sc.tex[M.tex];
-        ColumnEval ce = {0u, 1, 1, 0};
-        if (ya < yb && column_eval(sf, vw, c.x, ce)) {
-            ya = max(ya, yrow(M.high, ce.scale, pose_z, c.H));
-            yb = min(yb, yrow(M.low, ce.scale, pose_z, c.H));
+        int32_t tex, tA, hA, ucol = 0, iscale = 1, row = 0;
+        if (sf.seg < 0) {
+            // decoration sprite (billboard at constant depth): everything but the column is warp-uniform
+            const SpriteRec P = sc.sprites[-1 - sf.seg];
+            if (P.tex < 0 || P.tex >= sc.ntex) continue;
+            const int32_t sw = (int32_t)sc.tex[P.tex].w, sh = (int32_t)sc.tex[P.tex].h;
+            SpriteFrame sp;
+            sp.cx = sf.Nc; sp.cz = sf.Nx;
+            int64_t scale = ((int64_t)vw.FY2 << 25) / sp.cz;
+            const int64_t cap = (int64_t)vw.FY2 << 17;
+            if (scale > cap) scale = cap;
+            iscale = (int32_t)clampv<int64_t>(((int64_t)1 << 38) / scale, 1, 1 << 23);
+            int64_t z8 = ((int64_t)iscale * vw.FY2) >> 18;
+            row = light_row_sprite(P.light, z8 > 65535 ? 65535 : (int32_t)z8);
+            tex = P.tex; tA = 0; hA = P.low + sh;
+            if (ya < yb) {
+                ya = max(ya, yrow(P.low + sh, (int32_t)scale, pose_z, c.H));
+                yb = min(yb, yrow(P.low, (int32_t)scale, pose_z, c.H));
+                ucol = sprite_column(sp, vw, c.x, sw);
+            }
         } else {
-            ya = yb = 0;
+            const SegRec S = sc.segs[sf.seg];
+            if (S.mid < 0 || S.mid >= sc.nmids) continue;
+            const MidRec M = sc.mids[S.mid];
+            tex = M.tex; tA = M.t_high; hA = M.high;
+            ColumnEval ce = {0u, 1, 1, 0};
+            if (ya < yb && column_eval(sf, vw, c.x, ce)) {
+                ya = max(ya, yrow(M.high, ce.scale, pose_z, c.H));
+                yb = min(yb, yrow(M.low, ce.scale, pose_z, c.H));
+                ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+                iscale = ce.iscale;
+                row = light_row(S.light, ce.z8);
+            } else {
+                ya = yb = 0;
+            }
         }
+        if (tex < 0 || tex >= sc.ntex) continue;
+        const TexRec T = sc.tex[tex];
         const bool act = ya < yb;
         int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
         int y1 = __reduce_max_sync(kFull, act ? yb : 0);
         if (y0 >= y1) continue;
-        const int32_t ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
         const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
         const uint8_t *px = sc.texels + T.texel_off + col;
         const bool has_mask = T.mask_off != 0xFFFFFFFFu;
         const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
-        const int32_t tstep = ce.iscale >> 4;
-        const uint32_t cm = c.cmap_s + 256u * (uint32_t)light_row(S.light, ce.z8);
-        uint32_t t = (uint32_t)wall_tbase(M.t_high, M.high, pose_z, c.H, ce.iscale) + (uint32_t)y0 * (uint32_t)tstep;
+        const int32_t tstep = iscale >> 4;
+        const uint32_t cm = c.cmap_s + 256u * (uint32_t)row;
+        uint32_t t = (uint32_t)wall_tbase(tA, hA, pose_z, c.H, iscale) + (uint32_t)y0 * (uint32_t)tstep;
         uint8_t *p8 = c.fb + (size_t)y0 * Wc;
         uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
         for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
@@ -519,6 +577,19 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
             const SegFrame sf = wl[k0 + j];                              // warp-uniform 64 B
             bool in = inside && ct < cb && x >= sf.xlo && x <= sf.xhi;
             if (!__any_sync(kFull, in)) continue;
+            if (sf.seg < 0) {
+                // decoration sprite: remember the windows open right now; it is drawn in the masked pass
+                if (kMasked && ml != nullptr) {
+                    if (mcount < kMaskedCap) {
+                        if (lane == 0) ml[33 * mcount] = (uint32_t)(k0 + j);
+                        ml[33 * mcount + 1 + lane] = in ? ((uint32_t)ct | ((uint32_t)cb << 16)) : 0u;
+                        mcount++;
+                    } else if (lane == 0) {
+                        atomicOr(sc.status_flag, 8);
+                    }
+                }
+                continue;
+            }
             ColumnEval ce = {0u, 1, 1, 0};
             bool ok = in && column_eval(sf, vw, x, ce);
             if (!__any_sync(kFull, ok)) continue;
@@ -621,7 +692,7 @@ b2d_palette_kernel(const uint32_t *__restrict__ palette, const uint8_t *__restri
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss).total; }
+size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss, sc.nsprites).total; }
 
 cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
                         FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream) {
@@ -656,7 +727,7 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
     const bool w1920 = vw.W == 1920 && !getenv("B2D_RASTER_GENERIC_W");
 #define B2D_RASTER_GO(RGBA, KW) do { \
-    if (sc.nmids > 0 && sc.masked_list) \
+    if ((sc.nmids > 0 || sc.nsprites > 0) && sc.masked_list) \
         b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); \
     else \

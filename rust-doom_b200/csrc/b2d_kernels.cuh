@@ -17,13 +17,14 @@ struct DeviceScene {
     const SectorRec *sectors;
     const TexRec *tex;
     const MidRec *mids;          // masked two-sided middle textures (SegRec::mid indexes this)
+    const SpriteRec *sprites;    // decoration things grouped by subsector (SSectorRec::sprites)
     const uint8_t *texels;
     const uint8_t *flats;
     const uint8_t *colormap;     // 34 x 256
     const uint32_t *palette;     // 256 RGBA8
     const uint32_t *yslope;      // per view: H entries
     const uint16_t *skyrow;      // per view: H entries, sky texture row of each screen row
-    int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids;
+    int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids, nsprites;
     uint32_t root;
     uint32_t invF;               // floor(2^32 / F)
     int32_t *status_flag;        // device int: OR of per-frame walk status bits (0 = all frames complete)

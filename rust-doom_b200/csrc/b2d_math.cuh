@@ -328,4 +328,52 @@ B2D_HD bool box_range(const FrameConst &f, const View &vw, const int32_t box[4],
     return true;
 }
 
+// ---- decoration sprites (billboards at constant view depth; visitor.rs:1062-1137, sprite.vert:40-42) ----
+// light (sprite.frag:15-27): light = min(v, 2v - dist), dist = 1 - 1/(w+1), w = z/100
+B2D_HD int light_row_sprite(int b, int32_t z8) {
+    int32_t r1 = (32 * (255 - b)) / 255;
+    uint32_t Z = (uint32_t)z8 + 800u;
+    int32_t num = (int32_t)(64u * (uint32_t)(255 - b) * Z) - 6528000;
+    int32_t r2 = num <= 0 ? 0 : (int32_t)((uint32_t)num / (255u * Z));
+    int32_t r = r1 > r2 ? r1 : r2;
+    return r > 31 ? 31 : r;
+}
+
+struct SpriteFrame {
+    int64_t cx, cz;          // view-space centre, Q8
+    int32_t lo, hi;          // exact covered column interval
+    int32_t scale, iscale, z8;
+};
+
+// Per-frame projection of a sprite of width w (map units) centred at world (x, y).  false = not on screen.
+B2D_HD bool sprite_setup(const FrameConst &f, const View &vw, int32_t x, int32_t y, int32_t w, SpriteFrame &sp) {
+    int32_t tx, tz;
+    to_view(f, x, y, tx, tz);
+    sp.cx = tx; sp.cz = tz;
+    if (tz < 256) return false;                              // nearer than one map unit, or behind
+    const int64_t F = vw.F, W = vw.W;
+    const int64_t L = (sp.cx - (int64_t)w * 128) * F, R = (sp.cx + (int64_t)w * 128) * F;
+    int64_t lo = 0, hi = W - 1;
+    constrain(lo, hi, sp.cz * (1 - W) - L, 2 * sp.cz, 0);            // cz*c2 >= L
+    constrain(lo, hi, R - 1 - sp.cz * (1 - W), -2 * sp.cz, 0);       // cz*c2 <= R-1
+    if (lo > hi) return false;
+    sp.lo = (int32_t)lo; sp.hi = (int32_t)hi;
+    int64_t scale = ((int64_t)vw.FY2 << 25) / sp.cz;
+    const int64_t cap = (int64_t)vw.FY2 << 17;
+    if (scale > cap) scale = cap;
+    if (scale < 1) return false;
+    sp.scale = (int32_t)scale;
+    sp.iscale = (int32_t)clampv<int64_t>(((int64_t)1 << 38) / scale, 1, 1 << 23);
+    int64_t z8 = ((int64_t)sp.iscale * vw.FY2) >> 18;
+    sp.z8 = z8 > 65535 ? 65535 : (int32_t)z8;
+    return true;
+}
+
+// texture column of screen column x (0..w-1)
+B2D_HD int32_t sprite_column(const SpriteFrame &sp, const View &vw, int x, int32_t w) {
+    const int64_t c2 = 2 * (int64_t)x + 1 - vw.W;
+    const int64_t L = (sp.cx - (int64_t)w * 128) * vw.F;
+    return (int32_t)clampv<int64_t>(floordiv64(sp.cz * c2 - L, 256 * (int64_t)vw.F), 0, w - 1);
+}
+
 }  // namespace b2d

@@ -1,8 +1,10 @@
 // See b2d_scene.hpp for the reference citations.
 #include "b2d_scene.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <string>
 
 namespace b2d {
 
@@ -53,9 +55,14 @@ uint64_t isqrt64(uint64_t v) {
     return r;
 }
 
+struct ThingMeta { int type; const char *sprite; char frame; bool hanging; };
+const ThingMeta kThings[] = {
+#include "b2d_thing_table.inc"
+};
+
 struct BlobWriter {
     std::vector<uint8_t> bytes;
-    BlobWriter() : bytes(128, 0) {}
+    BlobWriter() : bytes(4 * H_COUNT, 0) {}
     uint32_t append(const void *p, size_t n) {
         uint32_t off = (uint32_t)bytes.size();
         const uint8_t *b = static_cast<const uint8_t *>(p);
@@ -79,7 +86,7 @@ uint8_t light_byte(int16_t light, int contrast) {
     return (uint8_t)(int)scaled;
 }
 
-int sector_at(const Level &lv, double x, double y) {
+int sector_at(const Level &lv, double x, double y, int *subsector_out) {
     if (lv.nodes.empty()) return -1;
     unsigned child = (unsigned)lv.nodes.size() - 1;
     bool leaf = false;
@@ -108,6 +115,7 @@ int sector_at(const Level &lv, double x, double y) {
         double sd = ((y - (double)a.y) * dx - (x - (double)a.x) * dy) / len;
         if (sd > 10.0) return -1;           // SEG_TOLERANCE 0.1 world units (visitor.rs:1159)
     }
+    if (subsector_out) *subsector_out = (int)child;
     return sector;
 }
 
@@ -273,6 +281,48 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         segs[(size_t)i] = r;
     }
 
+    // decoration things -> sprites, grouped by subsector (visitor.rs:1010-1026, 1062-1137)
+    struct SpriteRow { int ss, thing; SpriteRec rec; };
+    std::vector<SpriteRow> sprite_rows;
+    for (size_t ti = 0; ti < lv.things.size(); ti++) {
+        const Thing &t = lv.things[ti];
+        if (t.type == 1 || t.type == 2 || t.type == 3 || t.type == 4 || t.type == 11 || t.type == 14) continue;
+        int ssid = -1;
+        int sec = sector_at(lv, (double)t.x, (double)t.y, &ssid);
+        if (sec < 0 || ssid < 0 || ssid >= nss || ssectors[(size_t)ssid].sector != sec) continue;
+        const ThingMeta *meta = nullptr;
+        for (const ThingMeta &m : kThings)
+            if (m.type == t.type) { meta = &m; break; }
+        if (!meta) continue;
+        int32_t tid = kTexNone;
+        for (char rot : {'0', '1'}) {                      // <sprite><frame>0, then <sprite><frame>1
+            std::string nm = std::string(meta->sprite) + meta->frame + rot;
+            Name name;
+            try { name = make_name(nm.c_str()); } catch (const WadError &) { break; }
+            if (td.texture(name)) { tid = tex_id(name); break; }
+        }
+        if (tid < 0) continue;
+        const Sector &sct = lv.sectors[(size_t)sec];
+        const int32_t th = tex_list[(size_t)tid]->h;
+        SpriteRow row{ssid, (int)ti, SpriteRec{}};
+        row.rec.x = t.x; row.rec.y = t.y;
+        row.rec.low = meta->hanging ? sct.ceil - th : sct.floor;
+        row.rec.tex = tid;
+        row.rec.light = light_byte(sct.light, 0);
+        sprite_rows.push_back(row);
+    }
+    std::stable_sort(sprite_rows.begin(), sprite_rows.end(),
+                     [](const SpriteRow &a, const SpriteRow &b) { return a.ss != b.ss ? a.ss < b.ss : a.thing < b.thing; });
+    std::vector<SpriteRec> sprites;
+    for (size_t k = 0; k < sprite_rows.size();) {
+        size_t j = k;
+        while (j < sprite_rows.size() && sprite_rows[j].ss == sprite_rows[k].ss) j++;
+        size_t cnt = j - k < 255 ? j - k : 255;
+        ssectors[(size_t)sprite_rows[k].ss].sprites = (int32_t)(k | (cnt << 24));
+        k = j;
+    }
+    for (const SpriteRow &r : sprite_rows) sprites.push_back(r.rec);
+
     std::vector<NodeRec> nodes((size_t)nnodes);
     auto child = [](uint16_t c) -> uint32_t { return (c & 0x8000u) ? ((c & 0x7FFFu) | kLeaf) : (c & 0x7FFFu); };
     // Child bounding boxes are recomputed from the segs each subtree actually holds (never trusted from the
@@ -409,6 +459,8 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     hdr[H_OFF_TEX] = w.append(texrec.data(), texrec.size() * sizeof(TexRec));
     hdr[H_OFF_MIDS] = w.append(mids.data(), mids.size() * sizeof(MidRec));
     hdr[H_NMIDS] = (uint32_t)mids.size();
+    hdr[H_OFF_SPRITES] = w.append(sprites.data(), sprites.size() * sizeof(SpriteRec));
+    hdr[H_NSPRITES] = (uint32_t)sprites.size();
     hdr[H_OFF_TEXELS] = w.append(texels.data(), texels.size());
     hdr[H_TEXEL_BYTES] = (uint32_t)texels.size();
     hdr[H_OFF_FLATS] = w.append(flats.data(), flats.size());

@@ -17,19 +17,23 @@
 namespace b2d {
 
 constexpr uint32_t kSceneMagic = 0x53443242u;   // "B2DS"
-constexpr uint32_t kSceneVersion = 2;
+constexpr uint32_t kSceneVersion = 3;
 constexpr uint32_t kLeaf = 0x80000000u;
 
 enum HeaderField : int {
     H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
     H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
     H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
-    H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_COUNT = 32
+    H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES,
+    H_COUNT = 64
 };
 
 // 64-byte records; all int32.
 struct NodeRec { int32_t x, y, dx, dy, rbox[4], lbox[4]; uint32_t child[2]; int32_t pad[2]; };  // child[0]=right
-struct SSectorRec { int32_t first_seg, num_segs, sector, pad; };
+struct SSectorRec { int32_t first_seg, num_segs, sector, sprites; };   // sprites = first | count << 24
+// decoration thing: billboard of its sprite image's size, centred on (x,y), bottom edge at `low`
+// (floor, or ceiling - height for hanging things; visitor.rs:1062-1137), lit by the sector light
+struct SpriteRec { int32_t x, y, low, tex, light, pad[3]; };
 struct SegRec {
     int32_t v1, v2, front, flags;
     int32_t uoff, len_q12;
@@ -43,7 +47,8 @@ struct MidRec { int32_t tex, t_high, low, high, pad[4]; };
 struct SectorRec { int32_t floor, ceil, floor_flat, ceil_flat, light, pad[3]; };
 struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, mask_off, pad[2]; };   // mask_off = ~0u: opaque
 static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec) == 32 &&
-              sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16 && sizeof(MidRec) == 32, "record layout");
+              sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16 && sizeof(MidRec) == 32 &&
+              sizeof(SpriteRec) == 32, "record layout");
 
 constexpr int32_t kSegTwoSided = 1, kSegInvalid = 0x80;
 constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
@@ -51,7 +56,7 @@ constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
 std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &tex, int level_index);
 
 // LevelWalker::sector_at on the raw level (visitor.rs:1028-1060); -1 if outside.
-int sector_at(const Level &level, double x, double y);
+int sector_at(const Level &level, double x, double y, int *subsector_out = nullptr);
 
 // (light >> 3)/31 (+-2/31, clamped) * 255 truncated to u8, in the reference's float32 arithmetic.
 uint8_t light_byte(int16_t light, int contrast);

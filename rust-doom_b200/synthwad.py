@@ -178,6 +178,17 @@ def _img_grate(rng: SplitMix64, w: int, h: int, hue: int) -> np.ndarray:
     return img.astype(np.int16)
 
 
+def _img_sprite(rng: SplitMix64, w: int, h: int, hue: int) -> np.ndarray:
+    """Elliptic blob with transparent surround (-1), shaded top to bottom."""
+    noise = rng.bytes2d(h, w)
+    ys, xs = np.mgrid[0:h, 0:w]
+    inside = ((2 * xs + 1 - w) * h) ** 2 + ((2 * ys + 1 - h) * w) ** 2 <= (w * h) ** 2
+    shade = np.clip(1 + (ys * 11) // max(h, 1) + (noise % 3).astype(np.int16), 0, 15)
+    img = np.where(inside, (hue * 16 + shade).astype(np.int16), np.int16(-1))
+    stripe = inside & ((ys % 9) == 4)
+    return np.where(stripe, np.int16(7 * 16 + 3), img).astype(np.int16)
+
+
 def _tri(v: np.ndarray, period: int, amp: int) -> np.ndarray:
     """Integer triangle wave in [-amp, amp] (no libm: WAD bytes must not depend on the host)."""
     ph = np.mod(v, period)
@@ -388,6 +399,7 @@ class SynthConfig:
     wall_pct: int = 18
     door_pct: int = 22
     mid_pct: int = 0            # % of two-sided lines that carry a masked middle texture (0 keeps legacy bytes)
+    thing_pct: int = 0          # % of plain room cells that get decoration things + sprite lumps (0 = legacy)
 
 
 # inner convex polygons, CCW, in cell-local coordinates for a 256 cell (scaled by cell/256);
@@ -616,6 +628,17 @@ class LevelBuilder:
         for key in plain[:6]:
             cx, cy = corner(*key)
             self.things.append((cx + cs // 3, cy + cs // 3, 0, 2035, 7))
+        if cfg.thing_pct:
+            # decorations: floor-standing, hanging, a type without metadata (9999) and one whose sprite lump is
+            # missing (2014): the last two are skipped by the loaders (visitor.rs:1063-1094)
+            kinds = [2035, 48, 34, 2028, 63, 46, 9999, 2014]
+            for key in plain:
+                if rng.below(100) >= cfg.thing_pct:
+                    continue
+                cx, cy = corner(*key)
+                for _ in range(1 + rng.below(3)):
+                    self.things.append((cx + cs // 2 + rng.below(129) - 64, cy + cs // 2 + rng.below(129) - 64,
+                                        rng.below(8) * 45, rng.pick(kinds), 7))
         return self
 
     def _connected(self, room) -> bool:
@@ -873,8 +896,13 @@ def build_iwad(seed: int = 1, maps: Sequence[str] = ("E1M1",), cfg: Optional[Syn
         lumps += LevelBuilder(name, ms, cfg).generate().lumps()
     lumps += [("TEXTURE1", texture1), ("PNAMES", pnames)]
     lumps += [("P_START", b"")] + [(n, d) for n, d in patches.items()] + [("P_END", b"")]
-    lumps += [("S_START", b""), ("PLAYA1", encode_picture(_img_gradient(rng, 16, 32, 2), 8, 30)),
-              ("S_END", b"")]
+    sprites = [("PLAYA1", encode_picture(_img_gradient(rng, 16, 32, 2), 8, 30))]
+    if cfg.thing_pct:
+        # <prefix><frame>0 = rotation-less, <prefix><frame>1 = first rotation (visitor.rs:1070-1088 tries 0 then 1)
+        for name, w, h, hue in (("BAR1A0", 24, 32, 6), ("ELECA0", 32, 120, 8), ("CANDA0", 10, 16, 7),
+                                ("COLUA0", 24, 48, 5), ("GOR1A0", 24, 64, 2), ("TREDA1", 26, 80, 12)):
+            sprites.append((name, encode_picture(_img_sprite(rng, w, h, hue), w // 2, h - 4)))
+    lumps += [("S_START", b"")] + sprites + [("S_END", b"")]
     lumps += [("F_START", b"")] + [(n, d) for n, d in flats.items()] + [("F_END", b"")]
     return assemble_wad(lumps)
 

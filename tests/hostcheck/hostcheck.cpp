@@ -23,8 +23,9 @@ struct HostScene {
     const SectorRec *sectors;
     const TexRec *tex;
     const MidRec *mids;
+    const SpriteRec *sprites;
     const uint8_t *texels, *flats, *colormap;
-    int nverts, nnodes, nss, nsegs, ntex, nflats, sky_tex, nmids;
+    int nverts, nnodes, nss, nsegs, ntex, nflats, sky_tex, nmids, nsprites;
     uint32_t root;
 };
 
@@ -40,6 +41,8 @@ HostScene bind(const uint8_t *blob) {
     s.tex = reinterpret_cast<const TexRec *>(blob + h[H_OFF_TEX]);
     s.mids = reinterpret_cast<const MidRec *>(blob + h[H_OFF_MIDS]);
     s.nmids = (int)h[H_NMIDS];
+    s.sprites = reinterpret_cast<const SpriteRec *>(blob + h[H_OFF_SPRITES]);
+    s.nsprites = (int)h[H_NSPRITES];
     s.texels = blob + h[H_OFF_TEXELS];
     s.flats = blob + h[H_OFF_FLATS];
     s.colormap = blob + h[H_OFF_COLORMAP];
@@ -77,6 +80,14 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
         r.vis = box_range(fc, vw, box, lo, hi);
         if (r.vis) { r.lo = lo; r.hi = hi; }
     }
+    std::vector<Range> sprr((size_t)sc.nsprites);
+    for (int i = 0; i < sc.nsprites; i++) {
+        const SpriteRec &P = sc.sprites[i];
+        SpriteFrame sp;
+        if (P.tex >= 0 && P.tex < sc.ntex && sprite_setup(fc, vw, P.x, P.y, (int32_t)sc.tex[P.tex].w, sp)) {
+            sprr[(size_t)i].vis = true; sprr[(size_t)i].lo = sp.lo; sprr[(size_t)i].hi = sp.hi;
+        }
+    }
     std::vector<char> solid((size_t)vw.W, 0);
     auto range_open = [&](int lo, int hi) {
         for (int x = lo; x <= hi; x++) if (!solid[(size_t)x]) return true;
@@ -96,6 +107,13 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
             if (id >= (uint32_t)sc.nss) continue;
             const SSectorRec &ss = sc.ssectors[id];
             if (ss.sector < 0) continue;
+            {
+                const int sfirst = ss.sprites & 0xFFFFFF, scnt = (ss.sprites >> 24) & 0xFF;
+                for (int k = 0; k < scnt && sfirst + k < sc.nsprites; k++) {
+                    const Range &r = sprr[(size_t)(sfirst + k)];
+                    if (r.vis && range_open(r.lo, r.hi)) list.push_back(sc.nsegs + sfirst + k);
+                }
+            }
             for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {
                 std::vector<int> emitted;
                 for (int lane = 0; lane < 32 && k0 + lane < ss.num_segs; lane++) {
@@ -123,8 +141,18 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
     }
     out.clear();
     for (int si : list) {
-        const SegRec &S = sc.segs[si];
         SegFrame sf;
+        if (si >= sc.nsegs) {
+            const int pi = si - sc.nsegs;
+            const SpriteRec &P = sc.sprites[pi];
+            SpriteFrame sp;
+            sprite_setup(fc, vw, P.x, P.y, (int32_t)sc.tex[P.tex].w, sp);
+            std::memset(&sf, 0, sizeof sf);
+            sf.Nc = sp.cx; sf.Nx = sp.cz; sf.seg = -1 - pi; sf.xlo = (int16_t)sp.lo; sf.xhi = (int16_t)sp.hi;
+            out.push_back(sf);
+            continue;
+        }
+        const SegRec &S = sc.segs[si];
         seg_frame_setup(vw, tx[(size_t)S.v1], tz[(size_t)S.v1], tx[(size_t)S.v2], tz[(size_t)S.v2], sf, false);
         sf.seg = si;
         out.push_back(sf);
@@ -198,6 +226,20 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
             bool any_open = false;
             for (int l = 0; l < SW; l++) any_open |= lanes[l].ct < lanes[l].cb;
             if (!any_open) break;
+            if (sf.seg < 0) {        // decoration sprite: defer with the windows open right now
+                Deferred d{k, std::vector<uint32_t>((size_t)SW, 0u)};
+                bool any = false;
+                for (int l = 0; l < SW; l++) {
+                    int x = x0 + l;
+                    const Lane &ln = lanes[(size_t)l];
+                    if (x < W && ln.ct < ln.cb && x >= sf.xlo && x <= sf.xhi) {
+                        d.win[(size_t)l] = (uint32_t)ln.ct | ((uint32_t)ln.cb << 16);
+                        any = true;
+                    }
+                }
+                if (any && deferred.size() < 16) deferred.push_back(d);
+                continue;
+            }
             const SegRec &S = sc.segs[sf.seg];
             const SectorRec &SF = sc.sectors[S.front];
             const int32_t fcl = SF.ceil, ffl = SF.floor;
@@ -252,25 +294,48 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
         // masked middle textures, back to front (mirrors masked_pass in b2d_kernels.cu)
         for (size_t e = deferred.size(); e-- > 0;) {
             const SegFrame &sf = wl[deferred[e].k];
-            const SegRec &S = sc.segs[sf.seg];
-            if (S.mid < 0 || S.mid >= sc.nmids) continue;
-            const MidRec &M = sc.mids[S.mid];
-            if (M.tex < 0 || M.tex >= sc.ntex) continue;
-            const TexRec &T = sc.tex[M.tex];
             for (int l = 0; l < SW; l++) {
                 uint32_t packed = deferred[e].win[(size_t)l];
                 int ya = (int)(packed & 0xFFFFu), yb = (int)(packed >> 16), x = x0 + l;
-                ColumnEval ce;
-                if (!(ya < yb) || !column_eval(sf, vw, x, ce)) continue;
-                ya = std::max(ya, yrow(M.high, ce.scale, fc.pose.z, H));
-                yb = std::min(yb, yrow(M.low, ce.scale, fc.pose.z, H));
-                int32_t ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+                if (!(ya < yb)) continue;
+                int32_t tex, tA, hA, ucol, iscale, row;
+                if (sf.seg < 0) {
+                    const SpriteRec &P = sc.sprites[-1 - sf.seg];
+                    if (P.tex < 0 || P.tex >= sc.ntex) continue;
+                    const int32_t sw = (int32_t)sc.tex[P.tex].w, sh = (int32_t)sc.tex[P.tex].h;
+                    SpriteFrame sp;
+                    sp.cx = sf.Nc; sp.cz = sf.Nx;
+                    int64_t scale = ((int64_t)vw.FY2 << 25) / sp.cz;
+                    const int64_t cap = (int64_t)vw.FY2 << 17;
+                    if (scale > cap) scale = cap;
+                    iscale = (int32_t)clampv<int64_t>(((int64_t)1 << 38) / scale, 1, 1 << 23);
+                    int64_t z8 = ((int64_t)iscale * vw.FY2) >> 18;
+                    row = light_row_sprite(P.light, z8 > 65535 ? 65535 : (int32_t)z8);
+                    tex = P.tex; tA = 0; hA = P.low + sh;
+                    ya = std::max(ya, yrow(P.low + sh, (int32_t)scale, fc.pose.z, H));
+                    yb = std::min(yb, yrow(P.low, (int32_t)scale, fc.pose.z, H));
+                    ucol = sprite_column(sp, vw, x, sw);
+                } else {
+                    const SegRec &S = sc.segs[sf.seg];
+                    if (S.mid < 0 || S.mid >= sc.nmids) continue;
+                    const MidRec &M = sc.mids[S.mid];
+                    ColumnEval ce;
+                    if (!column_eval(sf, vw, x, ce)) continue;
+                    tex = M.tex; tA = M.t_high; hA = M.high;
+                    ya = std::max(ya, yrow(M.high, ce.scale, fc.pose.z, H));
+                    yb = std::min(yb, yrow(M.low, ce.scale, fc.pose.z, H));
+                    ucol = S.uoff + (int32_t)(((uint64_t)ce.s24 * (uint32_t)S.len_q12) >> 36);
+                    iscale = ce.iscale;
+                    row = light_row(S.light, ce.z8);
+                }
+                if (tex < 0 || tex >= sc.ntex) continue;
+                const TexRec &T = sc.tex[tex];
                 uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
                 const uint8_t *px = sc.texels + T.texel_off + col;
                 const bool has_mask = T.mask_off != 0xFFFFFFFFu;
                 const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
-                int32_t tbase = wall_tbase(M.t_high, M.high, fc.pose.z, H, ce.iscale), tstep = ce.iscale >> 4;
-                const uint8_t *cm = sc.colormap + 256 * light_row(S.light, ce.z8);
+                int32_t tbase = wall_tbase(tA, hA, fc.pose.z, H, iscale), tstep = iscale >> 4;
+                const uint8_t *cm = sc.colormap + 256 * row;
                 for (int y = ya; y < yb; y++) {
                     uint32_t idx = wall_row(tbase + y * tstep, T.h, T.hmagic, T.hbias) * T.w;
                     if (has_mask && !mk[idx]) continue;

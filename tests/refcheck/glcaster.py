@@ -11,7 +11,8 @@ colormap row).  Agreement cannot be bit-exact (float vs fixed point at texel/row
 pixels), so tests assert a high identical-pixel fraction instead.
 
 Masked two-sided middle textures are modelled (transparent texels let the ray through, static.frag:21-22).
-Not modelled (same as the oracle): sprites, POLY_BIAS.
+Decoration things are modelled as camera-facing billboards (visitor.rs:1062-1137, sprite.vert:40-42,
+sprite.frag:15-27).  Not modelled: POLY_BIAS.
 """
 from __future__ import annotations
 
@@ -229,6 +230,49 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
             best_t[idx] = t[hit][opaque]
             out[idx] = val[opaque]
             kind[idx] = 1
+
+    # ---- decoration sprites: billboards at constant view depth ---------------------------------------------
+    from oracle.thing_table import THINGS
+    for th in level.things:
+        ttype = int(th["type"])
+        if ttype in (1, 2, 3, 4, 11, 14) or ttype not in THINGS:
+            continue
+        sec = S.sector_at(level, float(th["x"]), float(th["y"]))
+        if sec < 0:
+            continue
+        prefix, frame, hanging = THINGS[ttype]
+        img = None
+        for rot in (b"0", b"1"):
+            img = tex.textures.get(W.wad_name(prefix.encode() + frame.encode() + rot))
+            if img is not None:
+                break
+        if img is None:
+            continue
+        sh, sw = img.shape
+        low = float(secs[sec]["ceil"]) - sh if hanging else float(secs[sec]["floor"])
+        tx0, ty0 = float(th["x"]) - x, float(th["y"]) - y
+        cz = tx0 * fx + ty0 * fy                              # view depth of the thing
+        cx = tx0 * rx + ty0 * ry                              # offset to the right
+        if cz <= 1.0:
+            continue
+        # my rays have unit forward component: the ray reaches depth cz at parameter t = cz
+        hit_x = cz * (ndx.reshape(-1) * tanx)                 # rightward offset of the ray at that depth
+        hz = z + cz * dz
+        u = hit_x - (cx - sw / 2.0)
+        v = (low + sh) - hz
+        hit = (u >= 0) & (u < sw) & (v >= 0) & (v < sh) & (cz < best_t)
+        if not hit.any():
+            continue
+        texel = img[np.floor(v[hit]).astype(np.int64), np.floor(u[hit]).astype(np.int64)]
+        vb = W.light_byte(int(secs[sec]["light"]), 0) / 255.0
+        dist = min(1.0, 1.0 - 1.0 / (cz / 100.0 + 1.0))
+        light = min(vb, vb * 2.0 - dist)                      # sprite.frag:24-26
+        row = int(np.clip(np.floor((1.0 - light) * 32.0), 0, 31))
+        opaque = (texel >> 8) == 0
+        idx = np.nonzero(hit)[0][opaque]
+        best_t[idx] = cz
+        out[idx] = cmaps[row][(texel[opaque] & 0xFF).astype(np.int64)]
+        kind[idx] = 4
 
     # ---- flats: one horizontal plane per distinct height -------------------------------------------------
     floor_h = np.array([min_h if W.is_sky_flat(floor_name[i]) else int(secs[i]["floor"]) for i in range(len(secs))], dtype=np.float64)

@@ -292,3 +292,30 @@ def test_gpu_full_benchmark_workload_matches_oracle(b2d, product_scene):
         ofb = render.render(sc.blob, render.make_view(1920, 1080), poses[c0:c0 + 250], threads=threads)
         bad += [c0 + i for i in range(250) if not np.array_equal(ofb[i], gfb[c0 + i])]
     assert not bad, "frames differ: %s" % bad[:10]
+
+
+def test_gpu_decoration_sprites(b2d, hostcheck):
+    """Thing sprites + masked middles on the GPU: frames vs oracle, worklist (with sprite entries) vs hostcheck."""
+    import torch
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=30, thing_pct=70))), 0)
+    poses = sample_poses(b2d, sc, 48, 81)
+    for (w, h) in ((320, 200), (1920, 1080)):
+        p = poses if w == 320 else poses[:6]
+        r = b2d.Renderer(sc, b2d.make_view(w, h), max_batch=48)
+        idx, rgba = r.render(p, rgba=True)
+        ofb, orgba = render.render(sc.blob, render.make_view(w, h), p, rgba=True, threads=8)
+        _assert_same(ofb, idx, "sprites %dx%d" % (w, h))
+        assert np.array_equal(rgba, orgba)
+    view = b2d.make_view(320, 200)
+    r = b2d.Renderer(sc, view, max_batch=48)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    out = torch.empty((48, 200, 320), dtype=torch.uint8, device="cuda")
+    r.render_device(dp.data_ptr(), 48, out.data_ptr())
+    torch.cuda.synchronize()
+    counts, ids = r.worklist(48)
+    hfb, hcounts, hids = hostcheck(sc.blob, view, poses)
+    assert counts.tolist() == hcounts.tolist()
+    assert any((ids[i, :counts[i]] < 0).any() for i in range(48)), "no sprite entry (negative id) in any worklist"
+    for i in range(48):
+        assert ids[i, :counts[i]].tolist() == hids[i, :hcounts[i]].tolist()

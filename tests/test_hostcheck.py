@@ -100,3 +100,15 @@ def test_hostcheck_masked_middle_textures(b2d, hostcheck):
     assert S.header(sc.blob)[S.H_NMIDS] > 50
     _compare(b2d, hostcheck, sc, 320, 200, 40, 51)
     _compare(b2d, hostcheck, sc, 1920, 1080, 2, 52)
+
+
+def test_hostcheck_decoration_sprites(b2d, hostcheck):
+    """Thing sprites (floor-standing, hanging, rotation-1 fallback, unknown / missing sprites skipped) together
+    with masked middle textures."""
+    from oracle import scene as S
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=30, thing_pct=70))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    assert S.header(sc.blob)[S.H_NSPRITES] > 30
+    _compare(b2d, hostcheck, sc, 320, 200, 48, 71)
+    _compare(b2d, hostcheck, sc, 1920, 1080, 2, 72)

@@ -68,3 +68,25 @@ def test_masked_middle_textures_agree_with_raycaster():
         twice += int(hits.sum()) - 320 * 200          # pixels overdrawn by masked textures
     assert min(fracs) > 0.985 and float(np.mean(fracs)) > 0.992, fracs
     assert twice > 5000, "the poses never looked through a masked texture"
+
+
+def test_decoration_sprites_agree_with_raycaster():
+    """Thing sprites (visitor.rs:1062-1137, sprite.vert/frag): the oracle's per-subsector deferred billboards vs
+    depth-tested billboards in the ray caster."""
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=30, thing_pct=70))
+    a = wad.Archive(data)
+    tex = wad.TextureDirectory(a)
+    blob = scene.compile_scene(a, tex, 0)
+    level = wad.Level(a, 0)
+    assert scene.header(blob)[scene.H_NSPRITES] > 30
+    view = render.make_view(320, 200)
+    fracs, sprite_px, sprite_same = [], 0, 0
+    for (x, y, z, ang) in _poses_in(level, False, 6, 27) + _poses_in(level, True, 4, 28):
+        g, kind = glcaster.render(a, tex, 0, 320, 200, x, y, z, ang, focal2=(view.F, view.FY2))
+        o = render.render(blob, view, render.make_pose(x, y, z, ang))[0]
+        fracs.append(float((g == o).mean()))
+        sprite_px += int((kind == 4).sum())
+        sprite_same += int(((g == o) & (kind == 4)).sum())
+    assert min(fracs) > 0.985 and float(np.mean(fracs)) > 0.992, fracs
+    assert sprite_px > 2000 and sprite_same / sprite_px > 0.97, (sprite_px, sprite_same)
