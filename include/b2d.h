@@ -62,6 +62,7 @@ typedef struct b2d_view {
 
 typedef struct b2d_scene_info {
     int32_t n_verts, n_nodes, n_ssectors, n_segs, n_sectors, n_textures, n_flats;
+    int32_t n_masked_mids, n_sprites;        /* masked middle textures / decoration things compiled in */
     int32_t blob_bytes;
     int32_t has_start;                       /* player-1 start found */
     b2d_pose start;                          /* spawn camera pose (eye = floor + 62) */

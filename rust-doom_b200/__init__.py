@@ -159,7 +159,7 @@ class Renderer:
         self.max_batch = max_batch
         self.device = device
         self.n_segs = scene.info.n_segs
-        self.worklist_stride = max(1, int(np.frombuffer(scene.blob, dtype='<u4', count=34)[6] + np.frombuffer(scene.blob, dtype='<u4', count=34)[32]))
+        self.worklist_stride = max(1, scene.info.n_segs + scene.info.n_sprites)
 
     # -- end to end: host poses in, host frames out -------------------------------------------------
     def render(self, poses: np.ndarray, rgba: bool = False, out_index: Optional[np.ndarray] = None,

@@ -20,7 +20,8 @@ class View(ctypes.Structure):
 class SceneInfo(ctypes.Structure):
     _fields_ = [("n_verts", ctypes.c_int32), ("n_nodes", ctypes.c_int32), ("n_ssectors", ctypes.c_int32),
                 ("n_segs", ctypes.c_int32), ("n_sectors", ctypes.c_int32), ("n_textures", ctypes.c_int32),
-                ("n_flats", ctypes.c_int32), ("blob_bytes", ctypes.c_int32), ("has_start", ctypes.c_int32),
+                ("n_flats", ctypes.c_int32), ("n_masked_mids", ctypes.c_int32), ("n_sprites", ctypes.c_int32),
+                ("blob_bytes", ctypes.c_int32), ("has_start", ctypes.c_int32),
                 ("start", Pose), ("min_height", ctypes.c_int32), ("max_height", ctypes.c_int32)]
 
 

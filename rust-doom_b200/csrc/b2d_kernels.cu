@@ -702,11 +702,9 @@ cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_pos
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     if (per_warp * warps > 227 * 1024) return cudaErrorInvalidValue;
     const size_t smem = per_warp * warps;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024) {   // per device and cheap: set it on every launch that needs the opt-in
         cudaError_t e = cudaFuncSetAttribute(b2d_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
     }
     const int blocks = (n + warps - 1) / warps;
     b2d_walk_kernel<<<blocks, warps * 32, smem, stream>>>(sc, vw, d_poses, n, d_frames, d_work, stride);
@@ -725,7 +723,8 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     constexpr int kWarps = 4;
     const long long total_warps = (long long)n * strips;
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
-    const bool w1920 = vw.W == 1920 && !getenv("B2D_RASTER_GENERIC_W");
+    static const bool generic_w = getenv("B2D_RASTER_GENERIC_W") != nullptr;   // A/B knob for profiles/README.md
+    const bool w1920 = vw.W == 1920 && !generic_w;
 #define B2D_RASTER_GO(RGBA, KW) do { \
     if ((sc.nmids > 0 || sc.nsprites > 0) && sc.masked_list) \
         b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
