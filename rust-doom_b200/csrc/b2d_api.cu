@@ -383,7 +383,7 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
         CU(cudaMemset(r->d_status, 0, sizeof(int32_t)));
         return fail(B2D_ERR_INVALID_ARG, status & 1 ? "BSP traversal stack overflow (tree deeper than 128 pending nodes): frames incomplete"
                                             : (status & 4 ? "BSP traversal did not terminate (cyclic node graph): frames incomplete"
-                                              : (status & 8 ? "more than 16 masked middle textures deferred in one 32-column strip: frames incomplete"
+                                              : (status & 8 ? "more than 32 masked middle textures or sprites deferred in one 32-column strip: frames incomplete"
                                                             : "worklist overflow: frames incomplete")));
     }
     return B2D_OK;

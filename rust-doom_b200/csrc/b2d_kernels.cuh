@@ -32,7 +32,7 @@ struct DeviceScene {
 };
 
 // masked middle textures one 32-column strip can defer per frame (more -> status bit 8, frames incomplete)
-constexpr int kMaskedCap = 16;
+constexpr int kMaskedCap = 32;
 
 // Bytes of dynamic shared memory one BSP-walk warp needs for this scene.
 size_t walk_smem_per_warp(const DeviceScene &sc);

@@ -237,7 +237,7 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                         any = true;
                     }
                 }
-                if (any && deferred.size() < 16) deferred.push_back(d);
+                if (any && deferred.size() < 32) deferred.push_back(d);
                 continue;
             }
             const SegRec &S = sc.segs[sf.seg];
@@ -286,7 +286,7 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 else { ln.ct = y2; ln.cb = y3; }
                 if (two && S.mid >= 0 && y2 < y3) { dfr.win[(size_t)l] = (uint32_t)y2 | ((uint32_t)y3 << 16); any_deferred = true; }
             }
-            if (any_deferred && deferred.size() < 16) deferred.push_back(dfr);
+            if (any_deferred && deferred.size() < 32) deferred.push_back(dfr);
             if (st) for (int d = 0; d < 4; d++) if (hi[d] > lo[d]) st->iters += hi[d] - lo[d];
         }
         for (int l = 0; l < SW; l++)
