@@ -99,6 +99,13 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
                         b2d_renderer **out);
 void b2d_renderer_destroy(b2d_renderer *r);
 
+/* Level time in tics (1/35 s) for every batch rendered afterwards; a new renderer is at tic 0.  Replaces the
+ * reference's u_time uniform (game/src/level.rs:257-260, assets/shaders/static.vert:23-39): animated flats and
+ * wall textures show frame (k + tics/8) mod n of their group, walls of scrolling lines (special 0x30,
+ * wad/src/visitor.rs:922) shift their texture column by one texel per tic.  Synchronises the device, then
+ * re-uploads the time-dependent scene tables (a few KB); a no-op for levels without animated content. */
+int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics);
+
 /* End-to-end: HOST poses in, HOST frames out (pinned staging + copies inside).  index_fb gets
  * n*W*H palette indices, row-major, top row first; rgba_fb (nullable) gets n*W*H RGBA8
  * (R in the low byte).  n may exceed max_batch; it is processed in batches. */

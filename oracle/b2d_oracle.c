@@ -37,25 +37,27 @@ typedef struct { int32_t W, H, F, FY2; } b2o_view;                  /* F = round
 enum { H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX,
        H_NFLATS, H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX,
        H_OFF_TEXELS, H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX,
-       H_NMIDS = 30, H_OFF_MIDS = 31, H_NSPRITES = 32, H_OFF_SPRITES = 33 };
+       H_NMIDS = 30, H_OFF_MIDS = 31, H_NSPRITES = 32, H_OFF_SPRITES = 33, H_NANIM = 34, H_OFF_ANIM = 35,
+       H_OFF_FLAT_ANIM = 36 };
 
 #define LEAF 0x80000000u
 #define SEG_TWO_SIDED 1
+#define SEG_SCROLL 2
 #define SEG_INVALID 0x80
 #define FLAT_SKY (-1)
 
 typedef struct {
     const uint32_t *hdr;
-    const int32_t *verts, *nodes, *ssectors, *segs, *sectors, *mids, *sprites;
+    const int32_t *verts, *nodes, *ssectors, *segs, *sectors, *mids, *sprites, *anim, *flat_anim;
     const uint32_t *tex;
     const uint8_t *texels, *flats, *colormap;
     const uint32_t *palette;
-    int nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids, nsprites;
+    int nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids, nsprites, nanim;
 } Scene;
 
 static int scene_bind(Scene *s, const uint8_t *blob) {
     const uint32_t *h = (const uint32_t *)blob;
-    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 3) return -1;
+    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 4) return -1;
     s->hdr = h;
     s->verts = (const int32_t *)(blob + h[H_OFF_VERTS]);
     s->nodes = (const int32_t *)(blob + h[H_OFF_NODES]);
@@ -67,6 +69,9 @@ static int scene_bind(Scene *s, const uint8_t *blob) {
     s->nmids = (int)h[H_NMIDS];
     s->sprites = (const int32_t *)(blob + h[H_OFF_SPRITES]);
     s->nsprites = (int)h[H_NSPRITES];
+    s->anim = (const int32_t *)(blob + h[H_OFF_ANIM]);
+    s->nanim = (int)h[H_NANIM];
+    s->flat_anim = (const int32_t *)(blob + h[H_OFF_FLAT_ANIM]);
     s->texels = blob + h[H_OFF_TEXELS];
     s->flats = blob + h[H_OFF_FLATS];
     s->colormap = blob + h[H_OFF_COLORMAP];
@@ -146,6 +151,7 @@ typedef struct {
     const Scene *sc;
     b2o_view vw;
     b2o_pose pose;
+    uint32_t tics;            /* level time in 1/35 s */
     int32_t cosq, sinq;       /* Q30 */
     int32_t *tx, *tz;         /* view-space vertices, Q8 */
     int32_t *ctop, *cbot;     /* open window per column: rows [ctop, cbot) */
@@ -162,6 +168,25 @@ typedef struct {
 static inline void put(Frame *f, int x, int y, uint8_t v) {
     f->fb[(size_t)y * f->vw.W + x] = v;
     if (f->seg_hits && f->cur_seg >= 0) f->seg_hits[f->cur_seg]++;       /* sprites have no seg */
+}
+
+/* Animated textures and flats (static.vert:23-39, ANIM_FPS = 8/35 s per frame): an image that is frame k of an
+ * n-frame group shows group frame (k + floor(tics/8)) mod n.  anim_nk = n | k << 16; 0 = not animated. */
+static inline int32_t anim_now(const Scene *sc, int32_t first, uint32_t nk, uint32_t tics, int32_t self) {
+    uint32_t n = nk & 0xFFFF, k = nk >> 16;
+    if (n < 2 || first < 0 || (int64_t)first + n > sc->nanim) return self;
+    return sc->anim[first + (int32_t)(((uint64_t)k + (tics >> 3)) % n)];
+}
+static inline int32_t tex_now(const Frame *f, int32_t tex) {
+    const Scene *sc = f->sc;
+    if (tex < 0 || tex >= sc->ntex) return tex;
+    const uint32_t *T = sc->tex + 8 * tex;
+    return anim_now(sc, (int32_t)T[6], T[7], f->tics, tex);
+}
+static inline int32_t flat_now(const Frame *f, int32_t flat) {
+    const Scene *sc = f->sc;
+    if (flat < 0 || flat >= sc->nflats) return flat;
+    return anim_now(sc, sc->flat_anim[2 * flat], (uint32_t)sc->flat_anim[2 * flat + 1], f->tics, flat);
 }
 
 static void draw_sky(Frame *f, int x, int ya, int yb) {
@@ -186,6 +211,7 @@ static void draw_plane(Frame *f, int x, int ya, int yb, int32_t h, int32_t flat,
     const Scene *sc = f->sc;
     if (ya >= yb) return;
     if (flat == FLAT_SKY) { draw_sky(f, x, ya, yb); return; }
+    flat = flat_now(f, flat);
     if (flat < 0 || flat >= sc->nflats) return;               /* missing flat: pixels stay void */
     const uint8_t *px = sc->flats + 4096 * (size_t)flat;
     int W = f->vw.W;
@@ -214,6 +240,7 @@ static void draw_plane(Frame *f, int x, int ya, int yb, int32_t h, int32_t flat,
 static void draw_wall(Frame *f, int x, int ya, int yb, int32_t tex, int32_t tA, int32_t hA,
                       int32_t ucol, int32_t iscale, int row) {
     const Scene *sc = f->sc;
+    tex = tex_now(f, tex);
     if (ya >= yb || tex < 0 || tex >= sc->ntex) return;       /* untextured: pixels stay void */
     const uint32_t *T = sc->tex + 8 * tex;
     int32_t w = (int32_t)T[1], h = (int32_t)T[2];
@@ -303,7 +330,9 @@ static void draw_seg(Frame *f, int si) {
         int64_t z8l = ((int64_t)iscale * FY2) >> 18;
         int32_t z8 = z8l > 65535 ? 65535 : (int32_t)z8l;
         int row = light_row(S[12], z8);
-        int32_t ucol = S[4] + (int32_t)(((uint64_t)s24 * (uint32_t)S[5]) >> 36);
+        /* scrolling walls (visitor.rs:922, 35 px/s = 1 px per tic): the texture column advances with time */
+        int32_t ucol = S[4] + (int32_t)(((uint64_t)s24 * (uint32_t)S[5]) >> 36)
+                     + ((S[3] & SEG_SCROLL) ? (int32_t)(f->tics & 0xFFFFFF) : 0);
 
         int yfc = yrow(f, fc, (int32_t)scale), yff = yrow(f, ff, (int32_t)scale);
         if (!two) {
@@ -349,8 +378,9 @@ static void draw_masked(Frame *f) {
     const Scene *sc = f->sc;
     for (int i = f->n_masked - 1; i >= 0; i--) {
         const struct Masked *m = &f->masked[i];
-        if (m->tex < 0 || m->tex >= sc->ntex || m->ya >= m->yb) continue;
-        const uint32_t *T = sc->tex + 8 * m->tex;
+        const int32_t mtex = m->owner >= 0 ? tex_now(f, m->tex) : m->tex;
+        if (mtex < 0 || mtex >= sc->ntex || m->ya >= m->yb) continue;
+        const uint32_t *T = sc->tex + 8 * mtex;
         int32_t w = (int32_t)T[1], h = (int32_t)T[2];
         const uint8_t *px = sc->texels + T[0];
         const uint8_t *opaque = T[5] != 0xFFFFFFFFu ? sc->texels + T[5] : NULL;
@@ -451,9 +481,10 @@ static void walk(Frame *f, uint32_t child, int depth) {
     walk(f, (uint32_t)n[12 + (side ^ 1)], depth + 1);
 }
 
-static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *pose, uint8_t *fb,
+static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *pose, uint32_t tics, uint8_t *fb,
                          int32_t *scratch, int32_t *seg_hits) {
     Frame f;
+    f.tics = tics;
     f.sc = sc; f.vw = *vw; f.pose = *pose; f.fb = fb; f.seg_hits = seg_hits; f.cur_seg = 0;
     const int W = vw->W, H = vw->H;
     f.tx = scratch; f.tz = f.tx + sc->nverts;
@@ -491,8 +522,8 @@ void b2o_view_init(b2o_view *v, int W, int H, double tan_half_fovy) {
     v->F = (int32_t)(fx2 + 0.5);
 }
 
-int b2o_render(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *poses, int n,
-               uint8_t *index_fb, uint32_t *rgba_fb, int32_t *seg_hits, int nthreads) {
+int b2o_render_t(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *poses, int n, uint32_t tics,
+                 uint8_t *index_fb, uint32_t *rgba_fb, int32_t *seg_hits, int nthreads) {
     Scene sc;
     if (scene_bind(&sc, scene_blob) != 0) return -1;
     if (vw->W < 1 || vw->H < 1 || vw->W > 4096 || vw->H > 2160 || vw->F < 2 || vw->FY2 < 2) return -2;
@@ -510,7 +541,7 @@ int b2o_render(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *po
 #pragma omp for schedule(dynamic, 1)
             for (int i = 0; i < n; i++) {
                 uint8_t *fb = index_fb + npix * (size_t)i;
-                render_frame(&sc, vw, &poses[i], fb, scratch,
+                render_frame(&sc, vw, &poses[i], tics, fb, scratch,
                              seg_hits ? seg_hits + (size_t)sc.nsegs * i : NULL);
                 if (rgba_fb) {
                     uint32_t *out = rgba_fb + npix * (size_t)i;
@@ -521,6 +552,11 @@ int b2o_render(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *po
         }
     }
     return err;
+}
+
+int b2o_render(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *poses, int n,
+               uint8_t *index_fb, uint32_t *rgba_fb, int32_t *seg_hits, int nthreads) {
+    return b2o_render_t(scene_blob, vw, poses, n, 0, index_fb, rgba_fb, seg_hits, nthreads);
 }
 
 /* CRC-32 (IEEE, reflected) of a byte range: golden-vector digest for frames */

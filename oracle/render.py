@@ -27,9 +27,9 @@ def lib():
         path = _build.build()
         L = ctypes.CDLL(path)
         L.b2o_view_init.argtypes = [ctypes.POINTER(View), ctypes.c_int, ctypes.c_int, ctypes.c_double]
-        L.b2o_render.argtypes = [ctypes.c_void_p, ctypes.POINTER(View), ctypes.c_void_p, ctypes.c_int,
-                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-        L.b2o_render.restype = ctypes.c_int
+        L.b2o_render_t.argtypes = [ctypes.c_void_p, ctypes.POINTER(View), ctypes.c_void_p, ctypes.c_int,
+                                   ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.b2o_render_t.restype = ctypes.c_int
         L.b2o_crc32.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         L.b2o_crc32.restype = ctypes.c_uint32
         L.b2o_sincos_q30.argtypes = [ctypes.c_uint32, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32)]
@@ -53,7 +53,7 @@ def make_pose(x: float, y: float, z: float, angle_deg: float) -> np.ndarray:
 
 
 def render(blob: bytes, view: View, poses: np.ndarray, rgba: bool = False, threads: int = 1,
-           seg_hits: bool = False):
+           seg_hits: bool = False, tics: int = 0):
     poses = np.ascontiguousarray(poses, dtype=POSE)
     n = len(poses)
     W, H = view.W, view.H
@@ -62,7 +62,8 @@ def render(blob: bytes, view: View, poses: np.ndarray, rgba: bool = False, threa
     nsegs = int(np.frombuffer(blob, dtype="<u4", count=32)[6])
     hits = np.zeros((n, nsegs), dtype=np.int32) if seg_hits else None
     buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
-    rc = lib().b2o_render(ctypes.addressof(buf), ctypes.byref(view), poses.ctypes.data, n, fb.ctypes.data,
+    rc = lib().b2o_render_t(ctypes.addressof(buf), ctypes.byref(view), poses.ctypes.data, n,
+                            int(tics) & 0xFFFFFFFF, fb.ctypes.data,
                           out_rgba.ctypes.data if rgba else None,
                           hits.ctypes.data if seg_hits else None, int(threads))
     if rc != 0:

@@ -11,7 +11,7 @@ reference's one-and-only geometry emitter `LevelWalker` and its visitor in `game
                                               game/src/player.rs:72-92 (camera_height)
 * sky texture per level                       wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
 
-The blob layout ("B2DS" v3) is the contract shared with the product's scene compiler
+The blob layout ("B2DS" v4) is the contract shared with the product's scene compiler
 (rust-doom_b200/csrc/b2d_scene.cpp, written independently); tests compare the two byte-for-byte.
 All fields are little-endian int32 unless noted.
 
@@ -28,7 +28,11 @@ segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, ligh
 mids    : {tex, t_high, low, high, 0, 0, 0, 0}                     32 B  masked two-sided middle texture:
           vertical extent [low, high) in map units and the texture row at `high` (visitor.rs:808-836,875-919)
 sectors : {floor, ceil, floor_flat, ceil_flat, light, 0, 0, 0}     32 B  (flat: >=0 id, -1 sky, -2 missing)
-textures: {texel_off, w, h, hmagic, hbias, mask_off, 0, 0}         32 B  (mask_off = 0xFFFFFFFF: fully opaque)
+textures: {texel_off, w, h, hmagic, hbias, mask_off, anim_first, anim_nk}  32 B  (mask_off = 0xFFFFFFFF: opaque;
+          anim_nk = n | k<<16: this texture is frame k of an n-frame animation whose texture ids are
+          anim[anim_first .. +n); n = 0: not animated)
+anim    : i32 ids (texture ids, then flat ids) of animation frames, group by group
+flatanim: {anim_first, anim_nk} per flat                           8 B
 texels  : u8 row-major, textures back to back (transparent texels stored as 0); a texture with holes is
           followed by its opacity plane (1 = opaque), same layout, at mask_off
 flats   : n x 4096 u8
@@ -47,14 +51,15 @@ import numpy as np
 from . import wad as W
 
 MAGIC = 0x53443242
-VERSION = 3
+VERSION = 4
 HEADER_WORDS = 64
 (H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
  H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
  H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
- H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES) = range(34)
+ H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES, H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM) = range(37)
 
 SEG_TWO_SIDED = 1
+SEG_SCROLL = 2            # linedef special 0x30: texture scrolls 35 units/s along s (visitor.rs:922)
 SEG_INVALID = 0x80
 LEAF = 0x80000000
 
@@ -146,7 +151,19 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     tex_ids: Dict[bytes, int] = {}
     tex_list: List[np.ndarray] = []
 
-    def tex_id(name: bytes) -> int:
+    from .anim_table import FLATS as ANIM_FLATS, WALLS as ANIM_WALLS
+    anim_frames: List[int] = []                 # texture ids group by group, then (offset) flat ids
+    tex_anim: Dict[int, Tuple[int, int, int]] = {}      # tex id -> (first, n, k)
+    flat_anim: Dict[int, Tuple[int, int, int]] = {}
+
+    def _group_of(name: bytes, groups):
+        s = name.rstrip(b"\0").decode("ascii")
+        for g in groups:
+            if s in g:
+                return g
+        return None
+
+    def tex_id(name: bytes, _follow=True) -> int:
         if W.is_untextured(name):
             return TEX_NONE
         if name in tex_ids:
@@ -156,14 +173,27 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
             return TEX_NONE                           # visitor.rs:857-860: skip + warn
         tex_ids[name] = len(tex_list)
         tex_list.append(img)
-        return tex_ids[name]
+        tid = tex_ids[name]
+        g = _group_of(name, ANIM_WALLS) if _follow else None
+        if g is not None:
+            # all existing frames of the animation, in group order (tex.rs:421-473, static.vert:23-39)
+            ids = [tex_id(W.wad_name(n.encode()), False) for n in g]
+            ids = [i for i in ids if i >= 0]
+            if len(ids) > 1:
+                first = len(anim_frames)
+                anim_frames.extend(ids)
+                for k, i in enumerate(ids):
+                    tex_anim[i] = (first, len(ids), k)
+        return tid
 
     sky_tex = tex_id(sky_for(level.name))
 
     flat_ids: Dict[bytes, int] = {}
     flat_list: List[bytes] = []
 
-    def flat_id(name: bytes) -> int:
+    flat_groups: List[List[int]] = []
+
+    def flat_id(name: bytes, _follow=True) -> int:
         if W.is_sky_flat(name):
             return FLAT_SKY
         if name in flat_ids:
@@ -173,7 +203,14 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
             return FLAT_MISSING
         flat_ids[name] = len(flat_list)
         flat_list.append(data[:4096])
-        return flat_ids[name]
+        fid = flat_ids[name]
+        g = _group_of(name, ANIM_FLATS) if _follow else None
+        if g is not None:
+            ids = [flat_id(W.wad_name(n.encode()), False) for n in g]
+            ids = [i for i in ids if i >= 0]
+            if len(ids) > 1:
+                flat_groups.append(ids)
+        return fid
 
     def raw_name(arr, i, field) -> bytes:
         dt = arr.dtype
@@ -274,6 +311,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
             return tid, _floormod(t_top_expr(th) + yoff, th)
 
         rec[0], rec[1], rec[2] = v1, v2, front
+        scroll = SEG_SCROLL if int(line["special"]) == 0x30 else 0
         rec[4] = int(sg["offset"]) + xoff                     # s1 (visitor.rs:904)
         rec[5] = math.isqrt((dx * dx + dy * dy) << 24)        # |v2-v1| in Q12 (visitor.rs:905)
         rec[12] = light
@@ -285,14 +323,14 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
                 tid, t = piece(side_name(side, 2), lambda th: th - (fc - ff))
             else:
                 tid, t = piece(side_name(side, 2), lambda th: 0)
-            rec[3] = 0
+            rec[3] = scroll
             rec[6], rec[7], rec[8] = tid, t, fc
             rec[13], rec[14] = fc, ff
         else:
             bsec = level.sectors[back]
             bf, bc = int(bsec["floor"]), int(bsec["ceil"])
             back_sky = W.is_sky_flat(raw_name(level.sectors, back, "ceil_tex"))
-            rec[3] = SEG_TWO_SIDED
+            rec[3] = SEG_TWO_SIDED | scroll
             # upper: exists iff back_ceil < ceil and the back ceiling is not sky (visitor.rs:791-807);
             # Peg::Top if upper-unpegged else Peg::Bottom (t at `high`=ceil: 0 / texh - (ceil-back_ceil)).
             otop = fc
@@ -471,7 +509,8 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
         px = np.where(holes, 0, img & 0xFF).astype(np.uint8)
         hmagic = (1 << 32) // h + 1
         hbias = h * ((16384 + h - 1) // h)
-        texrec[i] = [len(texels), w, h, hmagic & 0xFFFFFFFF, hbias, 0xFFFFFFFF, 0, 0]
+        a_first, a_n, a_k = tex_anim.get(i, (0, 0, 0))
+        texrec[i] = [len(texels), w, h, hmagic & 0xFFFFFFFF, hbias, 0xFFFFFFFF, a_first, a_n | (a_k << 16)]
         texels += px.tobytes()
         while len(texels) % 16:
             texels += b"\0"
@@ -481,6 +520,13 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
             while len(texels) % 16:
                 texels += b"\0"
 
+    # flat animation groups are appended to the frame list after the texture groups
+    flat_anim_rec = np.zeros((len(flat_list), 2), dtype=np.int64)
+    for ids in flat_groups:
+        first = len(anim_frames)
+        anim_frames.extend(ids)
+        for k, i in enumerate(ids):
+            flat_anim_rec[i] = [first, len(ids) | (k << 16)]
     colormap = bytearray(34 * 256)
     for k in range(min(34, len(tex.colormaps))):
         colormap[k * 256:(k + 1) * 256] = tex.colormaps[k]
@@ -508,6 +554,8 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
              ("sectors", sectors.astype("<i4").tobytes()), ("tex", texrec.astype("<u4").tobytes()),
              ("mids", np.array(mids, dtype="<i4").reshape(-1, 8).tobytes()),
              ("sprites", (sprites & 0xFFFFFFFF).astype("<u4").tobytes()),
+             ("anim", np.array(anim_frames, dtype="<i4").tobytes()),
+             ("flatanim", flat_anim_rec.astype("<i4").tobytes()),
              ("texels", bytes(texels)), ("flats", b"".join(flat_list)), ("colormap", bytes(colormap)),
              ("palette", palette.tobytes())]
     off = 4 * HEADER_WORDS
@@ -534,6 +582,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     hdr[H_MIN_H], hdr[H_MAX_H] = min_h & 0xFFFFFFFF, max_h & 0xFFFFFFFF
     hdr[H_NMIDS], hdr[H_OFF_MIDS] = len(mids), offs["mids"]
     hdr[H_NSPRITES], hdr[H_OFF_SPRITES] = len(sprite_rows), offs["sprites"]
+    hdr[H_NANIM], hdr[H_OFF_ANIM], hdr[H_OFF_FLAT_ANIM] = len(anim_frames), offs["anim"], offs["flatanim"]
     blob = bytearray(total)
     blob[0:4 * HEADER_WORDS] = struct.pack("<%dI" % HEADER_WORDS, *hdr)
     for name, data in parts:

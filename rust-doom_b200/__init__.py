@@ -161,6 +161,10 @@ class Renderer:
         self.n_segs = scene.info.n_segs
         self.worklist_stride = max(1, scene.info.n_segs + scene.info.n_sprites)
 
+    def set_time(self, tics: int):
+        """Level time in 1/35 s for the batches rendered afterwards (animated flats / walls, scrolling walls)."""
+        _check(_lib.load().b2d_renderer_set_time(self._h, int(tics) & 0xFFFFFFFF))
+
     # -- end to end: host poses in, host frames out -------------------------------------------------
     def render(self, poses: np.ndarray, rgba: bool = False, out_index: Optional[np.ndarray] = None,
                out_rgba: Optional[np.ndarray] = None):

@@ -46,6 +46,8 @@ struct b2d_renderer {
     Pose *h_poses = nullptr;        // pinned
     cudaStream_t render_stream = nullptr, copy_stream = nullptr;
     cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    std::vector<uint8_t> h_blob;    // host copy of the scene, kept only when it has time-dependent content
+    uint32_t tics = 0;
     int64_t launches = 0;
     int last_n = 0;
     bool profiling = false;
@@ -316,6 +318,7 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.invF = (uint32_t)(4294967296ULL / (uint64_t)view->F);
     if (d.nsegs + d.nsprites > 65535) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level has more than 65535 segs + sprites"); }
     if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
+    if (scene_is_timed(s->blob.data())) r->h_blob = s->blob;
     CUR(cudaMalloc(&r->d_poses, sizeof(Pose) * (size_t)max_batch));
     CUR(cudaMalloc(&r->d_frames, sizeof(FrameConst) * (size_t)max_batch));
     CUR(cudaMalloc(&r->d_work, sizeof(SegFrame) * (size_t)max_batch * (size_t)r->stride));
@@ -325,6 +328,24 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
 }
 
 void b2d_renderer_destroy(b2d_renderer *r) { free_renderer(r); }
+
+int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics) {
+    if (!r) return fail(B2D_ERR_INVALID_ARG, "null renderer");
+    if (r->h_blob.empty() || tics == r->tics) { r->tics = tics; return B2D_OK; }
+    const uint8_t *blob = r->h_blob.data();
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    std::vector<TexRec> tex(h[H_NTEX]);
+    std::vector<SectorRec> sectors(h[H_NSECTORS]);
+    std::vector<SegRec> segs(h[H_NSEGS]);
+    scene_at_time(blob, tics, tex.data(), sectors.data(), segs.data());
+    CU(cudaSetDevice(r->device));
+    CU(cudaDeviceSynchronize());       // batches in flight on any stream still read the old tables
+    CU(cudaMemcpy(r->d_blob + h[H_OFF_TEX], tex.data(), tex.size() * sizeof(TexRec), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r->d_blob + h[H_OFF_SECTORS], sectors.data(), sectors.size() * sizeof(SectorRec), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(r->d_blob + h[H_OFF_SEGS], segs.data(), segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice));
+    r->tics = tics;
+    return B2D_OK;
+}
 
 int b2d_render_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, uint8_t *d_index_fb,
                       uint32_t *d_rgba_fb, void *cuda_stream) {

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <string>
 
 namespace b2d {
@@ -53,6 +54,21 @@ uint64_t isqrt64(uint64_t v) {
     while (r * r > v) r--;
     while ((r + 1) * (r + 1) <= v) r++;
     return r;
+}
+
+struct AnimGroup { bool is_flat; const char *frames[8]; };
+const AnimGroup kAnimGroups[] = {
+#include "b2d_anim_table.inc"
+};
+
+const AnimGroup *anim_group_of(const Name &n, bool is_flat) {
+    const std::string s = name_str(n);
+    for (const AnimGroup &g : kAnimGroups) {
+        if (g.is_flat != is_flat) continue;
+        for (int i = 0; i < 8 && g.frames[i]; i++)
+            if (s == g.frames[i]) return &g;
+    }
+    return nullptr;
 }
 
 struct ThingMeta { int type; const char *sprite; char frame; bool hanging; };
@@ -128,7 +144,13 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     std::unordered_map<Name, int, NameHash> tex_ids, flat_ids;
     std::vector<const Image *> tex_list;
     std::vector<const uint8_t *> flat_list;
-    auto tex_id = [&](const Name &n) -> int32_t {
+    // animation frame lists (static.vert:23-39, tex.rs:421-473): when a texture / flat of an animation group is
+    // used, every existing frame of the group is loaded and the group's ids are appended to `anim_frames`
+    std::vector<int32_t> anim_frames;
+    struct AnimRef { int32_t first, n, k; };
+    std::unordered_map<int, AnimRef> tex_anim;
+    std::vector<std::vector<int32_t>> flat_groups;
+    std::function<int32_t(const Name &, bool)> tex_id_impl = [&](const Name &n, bool follow) -> int32_t {
         if (is_untextured(n)) return kTexNone;
         auto it = tex_ids.find(n);
         if (it != tex_ids.end()) return it->second;
@@ -137,9 +159,25 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         int id = (int)tex_list.size();
         tex_ids[n] = id;
         tex_list.push_back(img);
+        const AnimGroup *g = follow ? anim_group_of(n, false) : nullptr;
+        if (g) {
+            std::vector<int32_t> ids;
+            for (int i = 0; i < 8 && g->frames[i]; i++) {
+                int32_t f = tex_id_impl(make_name(g->frames[i]), false);
+                if (f >= 0) ids.push_back(f);
+            }
+            if (ids.size() > 1) {
+                const int32_t first = (int32_t)anim_frames.size();
+                for (size_t k = 0; k < ids.size(); k++) {
+                    anim_frames.push_back(ids[k]);
+                    tex_anim[ids[k]] = AnimRef{first, (int32_t)ids.size(), (int32_t)k};
+                }
+            }
+        }
         return id;
     };
-    auto flat_id = [&](const Name &n) -> int32_t {
+    auto tex_id = [&](const Name &n) -> int32_t { return tex_id_impl(n, true); };
+    std::function<int32_t(const Name &, bool)> flat_id_impl = [&](const Name &n, bool follow) -> int32_t {
         if (is_sky_flat(n)) return kFlatSky;
         auto it = flat_ids.find(n);
         if (it != flat_ids.end()) return it->second;
@@ -148,8 +186,18 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         int id = (int)flat_list.size();
         flat_ids[n] = id;
         flat_list.push_back(p);
+        const AnimGroup *g = follow ? anim_group_of(n, true) : nullptr;
+        if (g) {
+            std::vector<int32_t> ids;
+            for (int i = 0; i < 8 && g->frames[i]; i++) {
+                int32_t f = flat_id_impl(make_name(g->frames[i]), false);
+                if (f >= 0) ids.push_back(f);
+            }
+            if (ids.size() > 1) flat_groups.push_back(ids);
+        }
         return id;
     };
+    auto flat_id = [&](const Name &n) -> int32_t { return flat_id_impl(n, true); };
 
     const int32_t sky_tex = tex_id(sky_for(lv.name));
 
@@ -229,13 +277,14 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         };
 
         r.v1 = sg.v1; r.v2 = sg.v2; r.front = front; r.mid = -1;
+        const int32_t scroll = line.special == 0x30 ? kSegScroll : 0;          // visitor.rs:922
         r.uoff = (int32_t)sg.offset + sd.xoff;                                   // visitor.rs:904
         r.len_q12 = (int32_t)isqrt64((uint64_t)(dx * dx + dy * dy) << 24);       // visitor.rs:905
         r.light = light_byte(fs.light, contrast);
         if (back < 0) {
             // one-sided: full-height middle (visitor.rs:733-749); Peg::Bottom -> texture bottom at
             // the floor, Peg::Top -> texture top at the ceiling (visitor.rs:909-912)
-            r.flags = 0;
+            r.flags = scroll;
             if (unpeg_lower) piece(sd.middle, r.texA, r.tA, [&](int32_t th) { return th - (fc - ff); });
             else piece(sd.middle, r.texA, r.tA, [&](int32_t) { return 0; });
             r.hA = fc;
@@ -243,7 +292,7 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         } else {
             const Sector &bs = lv.sectors[(size_t)back];
             const int32_t bf = bs.floor, bc = bs.ceil;
-            r.flags = kSegTwoSided;
+            r.flags = kSegTwoSided | scroll;
             r.otop = fc;
             if (bc < fc && !is_sky_flat(bs.ceil_tex)) {                          // visitor.rs:791-807
                 r.otop = bc;
@@ -410,6 +459,10 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         t.hmagic = (uint32_t)((((uint64_t)1 << 32) / (uint64_t)im.h + 1) & 0xFFFFFFFFu);
         t.hbias = (uint32_t)im.h * (uint32_t)((16384 + im.h - 1) / im.h);
         t.mask_off = 0xFFFFFFFFu;
+        {
+            auto an = tex_anim.find((int)i);
+            if (an != tex_anim.end()) { t.anim_first = (uint32_t)an->second.first; t.anim_nk = (uint32_t)an->second.n | ((uint32_t)an->second.k << 16); }
+        }
         bool holes = false;
         for (uint16_t v : im.px) { texels.push_back((v >> 8) ? 0 : (uint8_t)(v & 0xFF)); holes |= (v >> 8) != 0; }
         while (texels.size() % 16) texels.push_back(0);
@@ -422,6 +475,14 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     }
     std::vector<uint8_t> flats(flat_list.size() * 4096);
     for (size_t i = 0; i < flat_list.size(); i++) std::memcpy(&flats[i * 4096], flat_list[i], 4096);
+    std::vector<FlatAnimRec> flat_anim(flat_list.size(), FlatAnimRec{0, 0});
+    for (const auto &ids : flat_groups) {
+        const int32_t first = (int32_t)anim_frames.size();
+        for (size_t k = 0; k < ids.size(); k++) {
+            anim_frames.push_back(ids[k]);
+            flat_anim[(size_t)ids[k]] = FlatAnimRec{first, (int32_t)ids.size() | ((int32_t)k << 16)};
+        }
+    }
     std::vector<uint8_t> colormap(34 * 256, 0);
     for (size_t k = 0; k < td.colormaps.size() && k < 34; k++) std::memcpy(&colormap[k * 256], td.colormaps[k].data(), 256);
     std::vector<uint32_t> palette(256, 0xFF000000u);
@@ -461,6 +522,9 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     hdr[H_NMIDS] = (uint32_t)mids.size();
     hdr[H_OFF_SPRITES] = w.append(sprites.data(), sprites.size() * sizeof(SpriteRec));
     hdr[H_NSPRITES] = (uint32_t)sprites.size();
+    hdr[H_OFF_ANIM] = w.append(anim_frames.data(), anim_frames.size() * 4);
+    hdr[H_NANIM] = (uint32_t)anim_frames.size();
+    hdr[H_OFF_FLAT_ANIM] = w.append(flat_anim.data(), flat_anim.size() * sizeof(FlatAnimRec));
     hdr[H_OFF_TEXELS] = w.append(texels.data(), texels.size());
     hdr[H_TEXEL_BYTES] = (uint32_t)texels.size();
     hdr[H_OFF_FLATS] = w.append(flats.data(), flats.size());

@@ -17,7 +17,7 @@
 namespace b2d {
 
 constexpr uint32_t kSceneMagic = 0x53443242u;   // "B2DS"
-constexpr uint32_t kSceneVersion = 3;
+constexpr uint32_t kSceneVersion = 4;
 constexpr uint32_t kLeaf = 0x80000000u;
 
 enum HeaderField : int {
@@ -25,7 +25,7 @@ enum HeaderField : int {
     H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
     H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
     H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES,
-    H_COUNT = 64
+    H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM, H_COUNT = 64
 };
 
 // 64-byte records; all int32.
@@ -45,13 +45,62 @@ struct SegRec {
 // texture row at `high` (pegging and y offset folded in)
 struct MidRec { int32_t tex, t_high, low, high, pad[4]; };
 struct SectorRec { int32_t floor, ceil, floor_flat, ceil_flat, light, pad[3]; };
-struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, mask_off, pad[2]; };   // mask_off = ~0u: opaque
+// mask_off = ~0u: opaque.  anim_nk = n | k << 16: frame k of an n-frame animation whose ids are anim[anim_first..+n)
+struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, mask_off, anim_first, anim_nk; };
+struct FlatAnimRec { int32_t anim_first, anim_nk; };
 static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec) == 32 &&
               sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16 && sizeof(MidRec) == 32 &&
               sizeof(SpriteRec) == 32, "record layout");
 
-constexpr int32_t kSegTwoSided = 1, kSegInvalid = 0x80;
+constexpr int32_t kSegTwoSided = 1, kSegScroll = 2, kSegInvalid = 0x80;   // scroll: special 0x30 (visitor.rs:922)
 constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
+
+// Level time (static.vert:23-39, visitor.rs:922).  `tics` counts 1/35 s.  An image that is frame k
+// of an n-frame animation group shows group frame (k + tics/8) mod n; walls of a scrolling line (special 0x30)
+// advance their texture column by one texel per tic.  The kernels never see time: the three small tables that
+// depend on it (texture records, sector flats, seg column offsets) are re-derived from the blob here and
+// re-uploaded when the time changes.  Outputs hold H_NTEX / H_NSECTORS / H_NSEGS records.
+inline bool scene_is_timed(const uint8_t *blob) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    if (h[H_NANIM] > 0) return true;
+    const SegRec *segs = reinterpret_cast<const SegRec *>(blob + h[H_OFF_SEGS]);
+    for (uint32_t i = 0; i < h[H_NSEGS]; i++)
+        if (segs[i].flags & kSegScroll) return true;
+    return false;
+}
+
+inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, SectorRec *sectors_out, SegRec *segs_out) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    const TexRec *tex = reinterpret_cast<const TexRec *>(blob + h[H_OFF_TEX]);
+    const SectorRec *sectors = reinterpret_cast<const SectorRec *>(blob + h[H_OFF_SECTORS]);
+    const SegRec *segs = reinterpret_cast<const SegRec *>(blob + h[H_OFF_SEGS]);
+    const int32_t *anim = reinterpret_cast<const int32_t *>(blob + h[H_OFF_ANIM]);
+    const FlatAnimRec *fa = reinterpret_cast<const FlatAnimRec *>(blob + h[H_OFF_FLAT_ANIM]);
+    const uint32_t ntex = h[H_NTEX], nflats = h[H_NFLATS], nanim = h[H_NANIM];
+    auto now = [&](int64_t first, uint32_t nk, int32_t self) -> int32_t {
+        const uint32_t n = nk & 0xFFFFu, k = nk >> 16;
+        if (n < 2 || first < 0 || first + n > nanim) return self;
+        return anim[first + (int64_t)(((uint64_t)k + (tics >> 3)) % n)];
+    };
+    for (uint32_t i = 0; i < ntex; i++) {
+        const int32_t j = now((int32_t)tex[i].anim_first, tex[i].anim_nk, (int32_t)i);
+        tex_out[i] = (j >= 0 && (uint32_t)j < ntex) ? tex[j] : tex[i];
+    }
+    auto flat_now = [&](int32_t f) -> int32_t {
+        if (f < 0 || (uint32_t)f >= nflats) return f;
+        const int32_t j = now(fa[f].anim_first, (uint32_t)fa[f].anim_nk, f);
+        return (j >= 0 && (uint32_t)j < nflats) ? j : f;
+    };
+    for (uint32_t i = 0; i < h[H_NSECTORS]; i++) {
+        sectors_out[i] = sectors[i];
+        sectors_out[i].floor_flat = flat_now(sectors[i].floor_flat);
+        sectors_out[i].ceil_flat = flat_now(sectors[i].ceil_flat);
+    }
+    for (uint32_t i = 0; i < h[H_NSEGS]; i++) {
+        segs_out[i] = segs[i];
+        if (segs[i].flags & kSegScroll) segs_out[i].uoff = segs[i].uoff + (int32_t)(tics & 0xFFFFFFu);
+    }
+}
 
 std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &tex, int level_index);
 

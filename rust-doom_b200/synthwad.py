@@ -246,7 +246,7 @@ class TexDef:
     patches: List[Tuple[int, int, str]]  # (origin_x, origin_y, patch name)
 
 
-def make_graphics(rng: SplitMix64, masked: bool = False):
+def make_graphics(rng: SplitMix64, masked: bool = False, anim: bool = False):
     """Returns (patch lumps {name: bytes} in order, texture defs, flats {name: 4096 bytes})."""
     patches: Dict[str, bytes] = {}
 
@@ -296,6 +296,14 @@ def make_graphics(rng: SplitMix64, masked: bool = False):
         tex += [TexDef("GRATE1", 64, 128, [(0, 0, "WGRATE1")]), TexDef("GRATE2", 32, 64, [(0, 0, "WGRATE2")]),
                 TexDef("FENCE72", 64, 72, [(0, 0, "WFENCE1")])]
 
+    if anim:
+        for k in range(1, 5):
+            add("WSFALL%d" % k, _img_bricks(rng, 64, 128, 4, 8, 4 + 2 * k))
+            tex.append(TexDef("SFALL%d" % k, 64, 128, [(0, 0, "WSFALL%d" % k)]))
+        for k in range(1, 3):
+            add("WFIRE%d" % k, _img_gradient(rng, 128, 128, 2 + 10 * (k - 1)))
+            tex.append(TexDef("FIREBLU%d" % k, 128, 128, [(0, 0, "WFIRE%d" % k)]))
+
     flats: Dict[str, bytes] = {}
 
     def addflat(name, img):
@@ -314,6 +322,9 @@ def make_graphics(rng: SplitMix64, masked: bool = False):
     addflat("CEIL4", _img_panels(rng, 64, 64, 9, 4))
     addflat("NUKAGE1", _img_gradient(rng, 64, 64, 13))
     addflat("F_SKY1", _img_gradient(rng, 64, 64, 4))
+    if anim:
+        addflat("NUKAGE2", _img_gradient(rng, 64, 64, 3))
+        addflat("NUKAGE3", _img_bricks(rng, 64, 64, 13, 8, 8))
     return patches, tex, flats
 
 
@@ -400,6 +411,7 @@ class SynthConfig:
     door_pct: int = 22
     mid_pct: int = 0            # % of two-sided lines that carry a masked middle texture (0 keeps legacy bytes)
     thing_pct: int = 0          # % of plain room cells that get decoration things + sprite lumps (0 = legacy)
+    anim: bool = False          # animated flats/walls (NUKAGE1-3, SFALL1-4, FIREBLU1-2) + scrolling lines (0x30)
 
 
 # inner convex polygons, CCW, in cell-local coordinates for a 256 cell (scaled by cell/256);
@@ -510,6 +522,8 @@ class LevelBuilder:
             cell_segs[cellkey].append(Seg(a, b, line_idx, direction, off))
 
         def wall_tex():
+            if cfg.anim and rng.chance(1, 5):
+                return rng.pick(["SFALL2", "SFALL1", "FIREBLU1", "FIREBLU2", "SFALL4"])
             return rng.pick(WALL_TEX)
 
         def one_sided(cellkey, p, q, sector):
@@ -518,7 +532,7 @@ class LevelBuilder:
             flags = 0x0001 | (0x0010 if rng.chance(1, 4) else 0)
             sd = self.side(sector, middle=wall_tex(), xoff=rng.pick([0, 0, 0, 16, -24, 40]),
                            yoff=rng.pick([0, 0, 0, 8, -16]))
-            li = self.line(a, b, sd, -1, flags=flags)
+            li = self.line(a, b, sd, -1, flags=flags, special=0x30 if (cfg.anim and rng.chance(1, 6)) else 0)
             add_seg(cellkey, li, 0, a, b)
 
         def two_sided(keyA, keyB, p, q):
@@ -888,7 +902,7 @@ def build_iwad(seed: int = 1, maps: Sequence[str] = ("E1M1",), cfg: Optional[Syn
     rng = SplitMix64(seed)
     playpal = make_playpal()
     colormap = make_colormap(playpal)
-    patches, tex, flats = make_graphics(rng, masked=cfg.mid_pct > 0)
+    patches, tex, flats = make_graphics(rng, masked=cfg.mid_pct > 0, anim=cfg.anim)
     pnames, texture1 = make_pnames_texture1(list(patches.keys()), tex)
     lumps: List[Tuple[str, bytes]] = [("PLAYPAL", playpal), ("COLORMAP", colormap)]
     for k, name in enumerate(maps):

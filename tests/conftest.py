@@ -73,7 +73,7 @@ def hostcheck():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOSTCHECK_SO, HOSTCHECK_SRC])
     lib = ctypes.CDLL(HOSTCHECK_SO)
 
-    def run(blob: bytes, view, poses: np.ndarray):
+    def run(blob: bytes, view, poses: np.ndarray, tics: int = 0):
         n = len(poses)
         nsegs = int(np.frombuffer(blob, dtype="<u4", count=32)[6])
         fb = np.empty((n, view.height, view.width), np.uint8)
@@ -81,9 +81,10 @@ def hostcheck():
         ids = np.full((n, max(nsegs, 1)), -1, np.int32)
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         poses = np.ascontiguousarray(poses)
-        lib.hostcheck_render(ctypes.c_void_p(ctypes.addressof(buf)), ctypes.byref(view),
-                             ctypes.c_void_p(poses.ctypes.data), n, ctypes.c_void_p(fb.ctypes.data),
-                             ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(ids.ctypes.data), ids.shape[1])
+        lib.hostcheck_render_t(ctypes.c_void_p(ctypes.addressof(buf)), ctypes.byref(view),
+                               ctypes.c_void_p(poses.ctypes.data), n, ctypes.c_void_p(fb.ctypes.data),
+                               ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(ids.ctypes.data), ids.shape[1],
+                               ctypes.c_uint32(int(tics) & 0xFFFFFFFF))
         return fb, counts, ids
 
     run.lib = lib

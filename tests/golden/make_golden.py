@@ -21,6 +21,9 @@ CASES = [
     dict(name="e1m1_1920x1080", seed=1, maps=["E1M1"], level=0, w=1920, h=1080, n=3),
     dict(name="map12_640x400", seed=21, maps=["MAP01", "MAP12"], level=1, w=640, h=400, n=6),
     dict(name="e1m1_3840x2160", seed=1, maps=["E1M1"], level=0, w=3840, h=2160, n=1),
+    # masked middles + decoration sprites + animated / scrolling walls at level time 100 tics
+    dict(name="e1m1_full_640x400_t100", seed=5, maps=["E1M1"], level=0, w=640, h=400, n=8, tics=100,
+         cfg=dict(mid_pct=30, thing_pct=50, anim=True)),
 ]
 
 
@@ -42,11 +45,11 @@ def golden_poses(blob: bytes, n: int, salt: int) -> np.ndarray:
 def main():
     out = []
     for c in CASES:
-        data = synthwad.build_iwad(c["seed"], c["maps"])
+        data = synthwad.build_iwad(c["seed"], c["maps"], cfg=synthwad.SynthConfig(**c.get("cfg", {})))
         a = wad.Archive(data)
         blob = scene.compile_scene(a, wad.TextureDirectory(a), c["level"])
         poses = golden_poses(blob, c["n"], c["seed"])
-        fb = render.render(blob, render.make_view(c["w"], c["h"]), poses, threads=8)
+        fb = render.render(blob, render.make_view(c["w"], c["h"]), poses, threads=8, tics=c.get("tics", 0))
         out.append(dict(c, wad_crc=render.crc32(np.frombuffer(data, np.uint8)),
                         blob_crc=render.crc32(np.frombuffer(blob, np.uint8)),
                         poses=[[int(v) for v in p] for p in poses.tolist()],

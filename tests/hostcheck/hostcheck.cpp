@@ -348,9 +348,18 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
 
 }  // namespace
 
-extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
-                                int32_t *counts, int32_t *seg_ids, int stride) {
+static int render_impl(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
+                       int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics) {
     HostScene sc = bind(blob);
+    // the product's time handling: the three time-dependent tables are rebuilt by scene_at_time (b2d_scene.hpp)
+    // exactly as b2d_renderer_set_time does before it uploads them
+    std::vector<TexRec> tex_t((size_t)sc.ntex);
+    std::vector<SectorRec> sectors_t((size_t)sc.hdr[H_NSECTORS]);
+    std::vector<SegRec> segs_t((size_t)sc.nsegs);
+    if (tics != 0 && scene_is_timed(blob)) {
+        scene_at_time(blob, tics, tex_t.data(), sectors_t.data(), segs_t.data());
+        sc.tex = tex_t.data(); sc.sectors = sectors_t.data(); sc.segs = segs_t.data();
+    }
     std::vector<uint32_t> yslope((size_t)vw->H);
     for (int y = 0; y < vw->H; y++) yslope[(size_t)y] = yslope_entry(y, *vw);
     uint32_t invF = (uint32_t)(4294967296ULL / (uint64_t)vw->F);
@@ -366,6 +375,16 @@ extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose 
         if (seg_ids) for (int k = 0; k < fc.count && k < stride; k++) seg_ids[(size_t)i * stride + k] = wl[(size_t)k].seg;
     }
     return 0;
+}
+
+extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
+                                int32_t *counts, int32_t *seg_ids, int stride) {
+    return render_impl(blob, vw, poses, n, fb, counts, seg_ids, stride, 0);
+}
+
+extern "C" int hostcheck_render_t(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
+                                  int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics) {
+    return render_impl(blob, vw, poses, n, fb, counts, seg_ids, stride, tics);
 }
 
 extern "C" void hostcheck_sincos(uint32_t angle, int32_t *c, int32_t *s) { sincos_q30(angle, *c, *s); }

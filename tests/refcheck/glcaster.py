@@ -52,8 +52,24 @@ def _sector_at_vec(level: W.Level, px: np.ndarray, py: np.ndarray) -> np.ndarray
 
 
 def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width: int, height: int,
-           x: float, y: float, z: float, angle_deg: float, fov_deg: float = 65.0, focal2=None) -> np.ndarray:
+           x: float, y: float, z: float, angle_deg: float, fov_deg: float = 65.0, focal2=None,
+           tics: int = 0) -> np.ndarray:
     level = W.Level(archive, level_index)
+    from oracle.anim_table import FLATS as ANIM_FLATS, WALLS as ANIM_WALLS
+
+    def anim_name(name, groups, table):
+        """static.vert:23-39 with u_time = tics/35: frame_index = floor(mod(u_time / (8/35), n)); the image that is
+        frame k of its group shows frame k + frame_index (wrapped inside the group: DESIGN.md C14)."""
+        for g in groups:
+            frames = [W.wad_name(f.encode()) for f in g]
+            if name in frames:
+                have = [f for f in frames if table.get(f) is not None]
+                if len(have) < 2 or name not in have:
+                    return name
+                fi = int(math.floor(math.fmod((tics / 35.0) / (8.0 / 35.0) + 1e-9, len(have))))
+                return have[(have.index(name) + fi) % len(have)]
+        return name
+
     W_, H_ = width, height
     tany = math.tan(math.radians(fov_deg) / 2.0)
     tanx = (W_ / H_) * 1.2 * tany                         # perspective(fovy, aspect*1.2), player.rs:84-89
@@ -217,8 +233,10 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
             img = tex.textures.get(name)
             if img is None:
                 continue
+            img = tex.textures.get(anim_name(name, ANIM_WALLS, tex.textures))
             th, tw = img.shape
-            su = float(sg["offset"]) + xoff + s[hit] * length
+            scroll = 35.0 if int(line["special"]) == 0x30 else 0.0      # visitor.rs:922, static.vert:23
+            su = float(sg["offset"]) + xoff + s[hit] * length + (tics / 35.0) * scroll
             tv = t_high + yoff + (high - hz[hit])
             ui = np.floor(su).astype(np.int64) % tw
             vi = np.floor(tv).astype(np.int64) % th
@@ -305,6 +323,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
                 data = tex.flats.get(name)
                 if data is None:
                     continue
+                data = tex.flats.get(anim_name(name, ANIM_FLATS, tex.flats))
                 fl = np.frombuffer(data, np.uint8)
                 u = np.floor(hy[m]).astype(np.int64) % 64            # tile_uv = (wad_y, wad_x), level.rs:537-549
                 v = np.floor(hx[m]).astype(np.int64) % 64

@@ -8,11 +8,11 @@ from oracle import render
 from tests.conftest import sample_poses
 
 
-def _compare(b2d, hostcheck, scene, w, h, n, seed):
+def _compare(b2d, hostcheck, scene, w, h, n, seed, tics=0):
     blob = scene.blob
     poses = sample_poses(b2d, scene, n, seed)
-    ofb, hits = render.render(blob, render.make_view(w, h), poses, threads=4, seg_hits=True)
-    hfb, counts, ids = hostcheck(blob, b2d.make_view(w, h), poses)
+    ofb, hits = render.render(blob, render.make_view(w, h), poses, threads=4, seg_hits=True, tics=tics)
+    hfb, counts, ids = hostcheck(blob, b2d.make_view(w, h), poses, tics=tics)
     bad = [(i, int((ofb[i] != hfb[i]).sum())) for i in range(len(poses)) if not np.array_equal(ofb[i], hfb[i])]
     assert not bad, "frames differ (index, pixels): %s" % bad[:5]
     for i in range(len(poses)):
@@ -112,3 +112,22 @@ def test_hostcheck_decoration_sprites(b2d, hostcheck):
     assert S.header(sc.blob)[S.H_NSPRITES] > 30
     _compare(b2d, hostcheck, sc, 320, 200, 48, 71)
     _compare(b2d, hostcheck, sc, 1920, 1080, 2, 72)
+
+
+def test_hostcheck_animated_and_scrolling(b2d, hostcheck):
+    """Level time (C14): animated flats / wall textures and scrolling walls.  The oracle resolves the frame and
+    the scroll per drawn column; the product rebuilds three scene tables per time step (scene_at_time)."""
+    from oracle import scene as S
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=20, thing_pct=30, anim=True))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    hdr = S.header(sc.blob)
+    assert hdr[S.H_NANIM] >= 6
+    poses = sample_poses(b2d, sc, 16, 91)
+    base = render.render(sc.blob, render.make_view(320, 200), poses, threads=4)
+    changed = 0
+    for tics in (0, 1, 7, 8, 9, 23, 24, 100, 12345, (1 << 24) - 1, (1 << 24) + 5, 0xFFFFFFFF):
+        _compare(b2d, hostcheck, sc, 320, 200, 16, 91, tics=tics)
+        changed += int((render.render(sc.blob, render.make_view(320, 200), poses, threads=4, tics=tics) != base).sum())
+    assert changed > 20000, "time never changed a pixel"
+    _compare(b2d, hostcheck, sc, 1920, 1080, 2, 92, tics=77)

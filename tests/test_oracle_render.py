@@ -19,7 +19,7 @@ def _cases():
 
 def _case_inputs(c):
     from rust_doom_b200 import synthwad
-    data = synthwad.build_iwad(c["seed"], c["maps"])
+    data = synthwad.build_iwad(c["seed"], c["maps"], cfg=synthwad.SynthConfig(**c.get("cfg", {})))
     a = wad.Archive(data)
     blob = scene.compile_scene(a, wad.TextureDirectory(a), c["level"])
     poses = np.array([tuple(p) for p in c["poses"]], dtype=render.POSE)
@@ -31,7 +31,7 @@ def test_golden_frames(c):
     data, blob, poses = _case_inputs(c)
     assert render.crc32(np.frombuffer(data, np.uint8)) == c["wad_crc"], "synthetic IWAD bytes changed"
     assert render.crc32(np.frombuffer(blob, np.uint8)) == c["blob_crc"], "compiled scene changed"
-    fb = render.render(blob, render.make_view(c["w"], c["h"]), poses, threads=4)
+    fb = render.render(blob, render.make_view(c["w"], c["h"]), poses, threads=4, tics=c.get("tics", 0))
     assert [render.crc32(fb[i]) for i in range(len(poses))] == c["frame_crc"]
 
 

@@ -90,3 +90,25 @@ def test_decoration_sprites_agree_with_raycaster():
         sprite_same += int(((g == o) & (kind == 4)).sum())
     assert min(fracs) > 0.985 and float(np.mean(fracs)) > 0.992, fracs
     assert sprite_px > 2000 and sprite_same / sprite_px > 0.97, (sprite_px, sprite_same)
+
+
+def test_animation_and_scrolling_agree_with_raycaster():
+    """u_time semantics (static.vert:23-39, visitor.rs:922): frame = floor(tics/8) mod n, scroll = 1 texel per tic."""
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(anim=True))
+    a = wad.Archive(data)
+    tex = wad.TextureDirectory(a)
+    blob = scene.compile_scene(a, tex, 0)
+    level = wad.Level(a, 0)
+    view = render.make_view(320, 200)
+    fracs, moved = [], 0
+    poses = _poses_in(level, False, 4, 37) + _poses_in(level, True, 2, 38)
+    for tics in (0, 5, 8, 19, 1000):
+        for (x, y, z, ang) in poses:
+            g, _ = glcaster.render(a, tex, 0, 320, 200, x, y, z, ang, focal2=(view.F, view.FY2), tics=tics)
+            o = render.render(blob, view, render.make_pose(x, y, z, ang), tics=tics)[0]
+            o0 = render.render(blob, view, render.make_pose(x, y, z, ang))[0]
+            fracs.append(float((g == o).mean()))
+            moved += int((o != o0).sum())
+    assert min(fracs) > 0.985 and float(np.mean(fracs)) > 0.992, fracs
+    assert moved > 20000, "time never changed a pixel"
