@@ -57,7 +57,7 @@ typedef struct {
 
 static int scene_bind(Scene *s, const uint8_t *blob) {
     const uint32_t *h = (const uint32_t *)blob;
-    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 4) return -1;
+    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 5) return -1;
     s->hdr = h;
     s->verts = (const int32_t *)(blob + h[H_OFF_VERTS]);
     s->nodes = (const int32_t *)(blob + h[H_OFF_NODES]);
@@ -152,6 +152,7 @@ typedef struct {
     b2o_view vw;
     b2o_pose pose;
     uint32_t tics;            /* level time in 1/35 s */
+    const int16_t *light_ov;  /* per sector: light byte at `tics` of a sector with a light effect, -1 = static (C15) */
     int32_t cosq, sinq;       /* Q30 */
     int32_t *tx, *tz;         /* view-space vertices, Q8 */
     int32_t *ctop, *cbot;     /* open window per column: rows [ctop, cbot) */
@@ -187,6 +188,12 @@ static inline int32_t flat_now(const Frame *f, int32_t flat) {
     const Scene *sc = f->sc;
     if (flat < 0 || flat >= sc->nflats) return flat;
     return anim_now(sc, sc->flat_anim[2 * flat], (uint32_t)sc->flat_anim[2 * flat + 1], f->tics, flat);
+}
+
+/* light byte of something lit by `sector`: the effect's value at the frame's time, else the static byte */
+static inline int lit(const Frame *f, int32_t sector, int32_t static_byte) {
+    if (f->light_ov && sector >= 0 && sector < f->sc->nsectors && f->light_ov[sector] >= 0) return f->light_ov[sector];
+    return static_byte;
 }
 
 static void draw_sky(Frame *f, int x, int ya, int yb) {
@@ -329,7 +336,7 @@ static void draw_seg(Frame *f, int si) {
         int32_t iscale = (int32_t)clamp64(isc, 1, 1 << 23);
         int64_t z8l = ((int64_t)iscale * FY2) >> 18;
         int32_t z8 = z8l > 65535 ? 65535 : (int32_t)z8l;
-        int row = light_row(S[12], z8);
+        int row = light_row(lit(f, S[2], S[12]), z8);
         /* scrolling walls (visitor.rs:922, 35 px/s = 1 px per tic): the texture column advances with time */
         int32_t ucol = S[4] + (int32_t)(((uint64_t)s24 * (uint32_t)S[5]) >> 36)
                      + ((S[3] & SEG_SCROLL) ? (int32_t)(f->tics & 0xFFFFFF) : 0);
@@ -338,9 +345,9 @@ static void draw_seg(Frame *f, int si) {
         if (!two) {
             int y1 = clamp32(yfc, ct, cb);
             int y2 = clamp32(yff, y1, cb);
-            if (ceil_vis) draw_plane(f, x, ct, y1, fc, SF[3], SF[4]);
+            if (ceil_vis) draw_plane(f, x, ct, y1, fc, SF[3], lit(f, S[2], SF[4]));
             draw_wall(f, x, y1, y2, S[6], S[7], S[8], ucol, iscale, row);
-            if (floor_vis) draw_plane(f, x, y2, cb, ff, SF[2], SF[4]);
+            if (floor_vis) draw_plane(f, x, y2, cb, ff, SF[2], lit(f, S[2], SF[4]));
             f->ctop[x] = H; f->cbot[x] = 0; f->open_cols--;
         } else {
             int yot = yrow(f, otop, (int32_t)scale), yob = yrow(f, obot, (int32_t)scale);
@@ -348,10 +355,10 @@ static void draw_seg(Frame *f, int si) {
             int y2 = clamp32(yot, y1, cb);
             int y3 = clamp32(yob, y2, cb);
             int y4 = clamp32(yff, y3, cb);
-            if (ceil_vis) draw_plane(f, x, ct, y1, fc, SF[3], SF[4]);
+            if (ceil_vis) draw_plane(f, x, ct, y1, fc, SF[3], lit(f, S[2], SF[4]));
             if (otop < fc) draw_wall(f, x, y1, y2, S[6], S[7], S[8], ucol, iscale, row);
             if (obot > ff) draw_wall(f, x, y3, y4, S[9], S[10], S[11], ucol, iscale, row);
-            if (floor_vis) draw_plane(f, x, y4, cb, ff, SF[2], SF[4]);
+            if (floor_vis) draw_plane(f, x, y4, cb, ff, SF[2], lit(f, S[2], SF[4]));
             if (y2 >= y3) { f->ctop[x] = H; f->cbot[x] = 0; f->open_cols--; }
             else {
                 f->ctop[x] = y2; f->cbot[x] = y3;
@@ -436,7 +443,7 @@ static void record_sprite(Frame *f, int idx) {
     int32_t iscale = (int32_t)clamp64(((int64_t)1 << 38) / scale, 1, 1 << 23);
     int64_t z8l = ((int64_t)iscale * FY2) >> 18;
     int32_t z8 = z8l > 65535 ? 65535 : (int32_t)z8l;
-    int row = light_row_sprite(SP[4], z8);
+    int row = light_row_sprite(lit(f, SP[5], SP[4]), z8);
     int ys_a = yrow(f, SP[2] + h, (int32_t)scale), ys_b = yrow(f, SP[2], (int32_t)scale);
     for (int x = (int)lo; x <= (int)hi; x++) {
         int ct = f->ctop[x], cb = f->cbot[x];
@@ -481,10 +488,10 @@ static void walk(Frame *f, uint32_t child, int depth) {
     walk(f, (uint32_t)n[12 + (side ^ 1)], depth + 1);
 }
 
-static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *pose, uint32_t tics, uint8_t *fb,
-                         int32_t *scratch, int32_t *seg_hits) {
+static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *pose, uint32_t tics,
+                         const int16_t *light_ov, uint8_t *fb, int32_t *scratch, int32_t *seg_hits) {
     Frame f;
-    f.tics = tics;
+    f.tics = tics; f.light_ov = light_ov;
     f.sc = sc; f.vw = *vw; f.pose = *pose; f.fb = fb; f.seg_hits = seg_hits; f.cur_seg = 0;
     const int W = vw->W, H = vw->H;
     f.tx = scratch; f.tz = f.tx + sc->nverts;
@@ -522,8 +529,9 @@ void b2o_view_init(b2o_view *v, int W, int H, double tan_half_fovy) {
     v->F = (int32_t)(fx2 + 0.5);
 }
 
+/* light_ov: NULL, or one int16 per sector (oracle/scene.py sector_lights_at(blob, tics)) */
 int b2o_render_t(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *poses, int n, uint32_t tics,
-                 uint8_t *index_fb, uint32_t *rgba_fb, int32_t *seg_hits, int nthreads) {
+                 const int16_t *light_ov, uint8_t *index_fb, uint32_t *rgba_fb, int32_t *seg_hits, int nthreads) {
     Scene sc;
     if (scene_bind(&sc, scene_blob) != 0) return -1;
     if (vw->W < 1 || vw->H < 1 || vw->W > 4096 || vw->H > 2160 || vw->F < 2 || vw->FY2 < 2) return -2;
@@ -541,7 +549,7 @@ int b2o_render_t(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *
 #pragma omp for schedule(dynamic, 1)
             for (int i = 0; i < n; i++) {
                 uint8_t *fb = index_fb + npix * (size_t)i;
-                render_frame(&sc, vw, &poses[i], tics, fb, scratch,
+                render_frame(&sc, vw, &poses[i], tics, light_ov, fb, scratch,
                              seg_hits ? seg_hits + (size_t)sc.nsegs * i : NULL);
                 if (rgba_fb) {
                     uint32_t *out = rgba_fb + npix * (size_t)i;
@@ -556,7 +564,7 @@ int b2o_render_t(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *
 
 int b2o_render(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *poses, int n,
                uint8_t *index_fb, uint32_t *rgba_fb, int32_t *seg_hits, int nthreads) {
-    return b2o_render_t(scene_blob, vw, poses, n, 0, index_fb, rgba_fb, seg_hits, nthreads);
+    return b2o_render_t(scene_blob, vw, poses, n, 0, NULL, index_fb, rgba_fb, seg_hits, nthreads);
 }
 
 /* CRC-32 (IEEE, reflected) of a byte range: golden-vector digest for frames */

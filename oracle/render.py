@@ -28,7 +28,8 @@ def lib():
         L = ctypes.CDLL(path)
         L.b2o_view_init.argtypes = [ctypes.POINTER(View), ctypes.c_int, ctypes.c_int, ctypes.c_double]
         L.b2o_render_t.argtypes = [ctypes.c_void_p, ctypes.POINTER(View), ctypes.c_void_p, ctypes.c_int,
-                                   ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+                                   ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                   ctypes.c_int]
         L.b2o_render_t.restype = ctypes.c_int
         L.b2o_crc32.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
         L.b2o_crc32.restype = ctypes.c_uint32
@@ -62,8 +63,10 @@ def render(blob: bytes, view: View, poses: np.ndarray, rgba: bool = False, threa
     nsegs = int(np.frombuffer(blob, dtype="<u4", count=32)[6])
     hits = np.zeros((n, nsegs), dtype=np.int32) if seg_hits else None
     buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+    from . import scene as _scene
+    lights = np.ascontiguousarray(_scene.sector_lights_at(blob, tics), dtype=np.int16)   # light effects at `tics`
     rc = lib().b2o_render_t(ctypes.addressof(buf), ctypes.byref(view), poses.ctypes.data, n,
-                            int(tics) & 0xFFFFFFFF, fb.ctypes.data,
+                            int(tics) & 0xFFFFFFFF, lights.ctypes.data if len(lights) else None, fb.ctypes.data,
                           out_rgba.ctypes.data if rgba else None,
                           hits.ctypes.data if seg_hits else None, int(threads))
     if rc != 0:

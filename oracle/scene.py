@@ -11,7 +11,7 @@ reference's one-and-only geometry emitter `LevelWalker` and its visitor in `game
                                               game/src/player.rs:72-92 (camera_height)
 * sky texture per level                       wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
 
-The blob layout ("B2DS" v4) is the contract shared with the product's scene compiler
+The blob layout ("B2DS" v5) is the contract shared with the product's scene compiler
 (rust-doom_b200/csrc/b2d_scene.cpp, written independently); tests compare the two byte-for-byte.
 All fields are little-endian int32 unless noted.
 
@@ -20,7 +20,7 @@ verts   : {x, y}                                                   8 B
 nodes   : {x, y, dx, dy, rbox[4], lbox[4], rchild, lchild, 0, 0}   64 B  (box = top,bottom,left,right;
           child bit31 = subsector)
 ssectors: {first_seg, num_segs, sector, sprites}                   16 B  (sprites = first | count<<24)
-sprites : {x, y, low, tex, light, 0, 0, 0}                         32 B  decoration things grouped by subsector:
+sprites : {x, y, low, tex, light, sector, 0, 0}                       32 B  decoration things grouped by subsector:
           billboard of the sprite image's size standing on the floor / hanging from the ceiling
           (visitor.rs:1062-1137), lit by the sector light without contrast
 segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, light, otop, obot, mid}   64 B
@@ -33,6 +33,8 @@ textures: {texel_off, w, h, hmagic, hbias, mask_off, anim_first, anim_nk}  32 B 
           anim[anim_first .. +n); n = 0: not animated)
 anim    : i32 ids (texture ids, then flat ids) of animation frames, group by group
 flatanim: {anim_first, anim_nk} per flat                           8 B
+lights  : {kind, level, alt, speed, duration, sync, 0, 0} per sector  32 B  (kind u32: 0 none, 1 glow, 2 random,
+          3 alternate; the rest float32: light.rs:27-80); the `light` fields above hold the value at tic 0
 texels  : u8 row-major, textures back to back (transparent texels stored as 0); a texture with holes is
           followed by its opacity plane (1 = opaque), same layout, at mask_off
 flats   : n x 4096 u8
@@ -51,17 +53,20 @@ import numpy as np
 from . import wad as W
 
 MAGIC = 0x53443242
-VERSION = 4
+VERSION = 5
 HEADER_WORDS = 64
 (H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
  H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
  H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
- H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES, H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM) = range(37)
+ H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES, H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM,
+ H_OFF_LIGHTS) = range(38)
 
 SEG_TWO_SIDED = 1
 SEG_SCROLL = 2            # linedef special 0x30: texture scrolls 35 units/s along s (visitor.rs:922)
 SEG_INVALID = 0x80
 LEAF = 0x80000000
+
+LIGHT_NONE, LIGHT_GLOW, LIGHT_RANDOM, LIGHT_ALTERNATE = 0, 1, 2, 3
 
 FLAT_SKY = -1
 FLAT_MISSING = -2
@@ -140,6 +145,86 @@ def _subsector_at(level: W.Level, x: float, y: float):
         if sd > 10.0:                       # SEG_TOLERANCE = 0.1 world units = 10 map units
             return -1, -1
     return child, sector
+
+
+_f = np.float32
+
+
+def _f32bits(v) -> int:
+    return int(np.array([v], dtype="<f4").view("<u4")[0])
+
+
+def light_info(level: "W.Level", i: int) -> Tuple[int, np.float32, np.float32, np.float32, np.float32, np.float32]:
+    """wad/src/light.rs:27-115 new_light: (kind, level, alt_level, speed, duration, sync), all float32."""
+    s = level.sectors[i]
+    base = _f(np.int16(s["light"]) >> 3) / _f(31.0)
+    stype = int(s["type"])
+    none = (LIGHT_NONE, base, _f(0), _f(0), _f(0), _f(0))
+    if stype not in W.EFFECT_TYPES:
+        return none
+    alt = _f(np.int16(level.sector_min_light(i)) >> 3) / _f(31.0)
+    if abs(alt - base) < _f(1.1920929e-07):                         # f32::EPSILON
+        return none
+    if stype in (12, 13, 8):                                         # SLOW_STROBE_SYNC, FAST_STROBE_SYNC, GLOW
+        sync = _f(0.0)
+    else:                                                            # id_to_sync, light.rs:109-111
+        sync = _f(((i * 1664525 + 1013904223) & 0xFFFF)) / _f(15.0)
+    kind, speed, duration = {
+        1: (LIGHT_RANDOM, 20.0, 0.06), 17: (LIGHT_RANDOM, 8.0, 0.5),
+        3: (LIGHT_ALTERNATE, 1.0, 0.85), 12: (LIGHT_ALTERNATE, 1.0, 0.85),
+        2: (LIGHT_ALTERNATE, 2.0, 0.7), 4: (LIGHT_ALTERNATE, 2.0, 0.7), 13: (LIGHT_ALTERNATE, 2.0, 0.7),
+        8: (LIGHT_GLOW, 0.5, 0.0)}[stype]
+    return (kind, base, alt, _f(speed), _f(duration), sync)
+
+
+def _fract(x: np.float32) -> np.float32:
+    return _f(x - np.floor(x))
+
+
+def _sin_f32(x: np.float32) -> np.float32:
+    """The correctly rounded float32 sine (double-precision sine, rounded once): DESIGN.md C15."""
+    return _f(math.sin(float(x)))
+
+
+def light_level_at(info, time: np.float32) -> np.float32:
+    """game/src/lights.rs:33-66, float32 operation by operation."""
+    kind, level, alt, speed, duration, sync = info
+    if kind == LIGHT_NONE:
+        return level
+    if kind == LIGHT_GLOW:
+        scale = _f(level - alt)
+        phase = _f(_f(time * speed) / scale)
+        return _f(_f(_f(abs(_f(_f(0.5) - _fract(phase))) * _f(2.0)) * scale) + alt)
+    if kind == LIGHT_RANDOM:
+        t = np.floor(_f(time * speed))
+        arg = _f(_f(_f(sync + _f(t / _f(1000.0))) * _f(12.9898)) + _f(sync * _f(78.233)))
+        noise = _fract(_f(_f(1.0) + _f(_sin_f32(arg) * _f(43758.547))))
+        return alt if noise < duration else level
+    ph = _fract(_f(_f(time * speed) + _f(sync * _f(3.5435))))
+    return alt if ph < duration else level
+
+
+def light_byte_at(info, tics: int) -> int:
+    """lights.rs:26-30: (clamp(level_at(time)) * 255.0) as u8 with time = tics / 35 seconds."""
+    with np.errstate(all="ignore"):
+        time = _f(_f(int(tics) & 0xFFFFFFFF) / _f(35.0))
+        v = light_level_at(info, time)
+        v = _f(0.0) if v < _f(0.0) else (_f(1.0) if v > _f(1.0) else v)
+        r = float(_f(v * _f(255.0)))
+    return int(r) & 0xFF if r >= 0 else 0
+
+
+def sector_lights_at(blob: bytes, tics: int) -> np.ndarray:
+    """int16 per sector: the light byte at `tics` for sectors with a light effect, -1 for the others."""
+    h = header(blob)
+    n = h[H_NSECTORS]
+    rec = np.frombuffer(blob, dtype="<u4", count=8 * n, offset=h[H_OFF_LIGHTS]).reshape(n, 8)
+    out = np.full(n, -1, dtype=np.int16)
+    for i in range(n):
+        if rec[i, 0] != LIGHT_NONE:
+            fl = rec[i, 1:6].copy().view("<f4")
+            out[i] = light_byte_at((int(rec[i, 0]), fl[0], fl[1], fl[2], fl[3], fl[4]), tics)
+    return out
 
 
 def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int) -> bytes:
@@ -222,16 +307,19 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     sectors = np.zeros((nsect, 8), dtype=np.int32)
     sec_bytes = level.sectors.tobytes()
     has_effect = []
+    lights = np.zeros((nsect, 8), dtype="<u4")     # {kind, level, alt, speed, duration, sync (f32 bits), 0, 0}
+    sector_light0 = []                             # light byte at tic 0 (effects evaluated, lights.rs:26-30)
     for i in range(nsect):
         s = level.sectors[i]
         fname = W.wad_name(sec_bytes[i * 26 + 4:i * 26 + 12])
         cname = W.wad_name(sec_bytes[i * 26 + 12:i * 26 + 20])
-        eff = False
-        if int(s["type"]) in W.EFFECT_TYPES:
-            eff = (level.sector_min_light(i) >> 3) != (int(s["light"]) >> 3)
-        has_effect.append(eff)
+        info = light_info(level, i)
+        has_effect.append(info[0] != LIGHT_NONE)
+        lights[i, 0] = info[0]
+        lights[i, 1:6] = [_f32bits(v) for v in info[1:]]
+        sector_light0.append(light_byte_at(info, 0) if has_effect[i] else W.light_byte(int(s["light"]), 0))
         sectors[i] = [int(s["floor"]), int(s["ceil"]), flat_id(fname), flat_id(cname),
-                      W.light_byte(int(s["light"]), 0), 0, 0, 0]
+                      sector_light0[i], 0, 0, 0]
     if nsect:
         min_h = int(level.sectors["floor"].min()) - 512      # visitor.rs:1173-1182
         max_h = int(level.sectors["ceil"].max()) + 512
@@ -295,7 +383,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
                 contrast = 1
             elif dx == 0:
                 contrast = -1
-        light = W.light_byte(int(fsec["light"]), contrast)
+        light = sector_light0[front] if has_effect[front] else W.light_byte(int(fsec["light"]), contrast)
 
         back_side = level.seg_back_sidedef_index(sg)
         back = -1
@@ -401,7 +489,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
         th = int(tex_list[tid].shape[0])
         sct = level.sectors[sec]
         low = int(sct["ceil"]) - th if hanging else int(sct["floor"])
-        sprite_rows.append((ssid, ti, [int(t["x"]), int(t["y"]), low, tid, W.light_byte(int(sct["light"]), 0), 0, 0, 0]))
+        sprite_rows.append((ssid, ti, [int(t["x"]), int(t["y"]), low, tid, sector_light0[sec], sec, 0, 0]))
     sprite_rows.sort(key=lambda r: (r[0], r[1]))
     sprites = np.array([r[2] for r in sprite_rows], dtype=np.int64).reshape(-1, 8)
     k = 0
@@ -555,7 +643,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
              ("mids", np.array(mids, dtype="<i4").reshape(-1, 8).tobytes()),
              ("sprites", (sprites & 0xFFFFFFFF).astype("<u4").tobytes()),
              ("anim", np.array(anim_frames, dtype="<i4").tobytes()),
-             ("flatanim", flat_anim_rec.astype("<i4").tobytes()),
+             ("flatanim", flat_anim_rec.astype("<i4").tobytes()), ("lights", lights.tobytes()),
              ("texels", bytes(texels)), ("flats", b"".join(flat_list)), ("colormap", bytes(colormap)),
              ("palette", palette.tobytes())]
     off = 4 * HEADER_WORDS
@@ -583,6 +671,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     hdr[H_NMIDS], hdr[H_OFF_MIDS] = len(mids), offs["mids"]
     hdr[H_NSPRITES], hdr[H_OFF_SPRITES] = len(sprite_rows), offs["sprites"]
     hdr[H_NANIM], hdr[H_OFF_ANIM], hdr[H_OFF_FLAT_ANIM] = len(anim_frames), offs["anim"], offs["flatanim"]
+    hdr[H_OFF_LIGHTS] = offs["lights"]
     blob = bytearray(total)
     blob[0:4 * HEADER_WORDS] = struct.pack("<%dI" % HEADER_WORDS, *hdr)
     for name, data in parts:

@@ -337,12 +337,15 @@ int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics) {
     std::vector<TexRec> tex(h[H_NTEX]);
     std::vector<SectorRec> sectors(h[H_NSECTORS]);
     std::vector<SegRec> segs(h[H_NSEGS]);
-    scene_at_time(blob, tics, tex.data(), sectors.data(), segs.data());
+    std::vector<SpriteRec> sprites(h[H_NSPRITES]);
+    scene_at_time(blob, tics, tex.data(), sectors.data(), segs.data(), sprites.data());
     CU(cudaSetDevice(r->device));
     CU(cudaDeviceSynchronize());       // batches in flight on any stream still read the old tables
     CU(cudaMemcpy(r->d_blob + h[H_OFF_TEX], tex.data(), tex.size() * sizeof(TexRec), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(r->d_blob + h[H_OFF_SECTORS], sectors.data(), sectors.size() * sizeof(SectorRec), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(r->d_blob + h[H_OFF_SEGS], segs.data(), segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice));
+    if (!sprites.empty())
+        CU(cudaMemcpy(r->d_blob + h[H_OFF_SPRITES], sprites.data(), sprites.size() * sizeof(SpriteRec), cudaMemcpyHostToDevice));
     r->tics = tics;
     return B2D_OK;
 }

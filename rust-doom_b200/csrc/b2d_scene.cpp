@@ -204,6 +204,7 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     static const int kEffectTypes[] = {1, 2, 4, 13, 3, 12, 8, 17};    // light.rs:127-134
     std::vector<SectorRec> sectors((size_t)nsect);
     std::vector<char> has_effect((size_t)nsect, 0);
+    std::vector<LightRec> lights((size_t)nsect, LightRec{});
     int32_t min_h = 32767, max_h = -32768;
     for (int i = 0; i < nsect; i++) {
         const Sector &s = lv.sectors[(size_t)i];
@@ -211,11 +212,25 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         for (int t : kEffectTypes)
             if (s.type == t) eff = (lv.sector_min_light(i) >> 3) != (s.light >> 3);
         has_effect[(size_t)i] = eff;
+        LightRec &L = lights[(size_t)i];                                // light.rs:27-80 new_light
+        L.level = (float)(int16_t)(s.light >> 3) / 31.0f;
+        if (eff) {
+            L.alt = (float)(int16_t)(lv.sector_min_light(i) >> 3) / 31.0f;
+            const bool synced = s.type == 12 || s.type == 13 || s.type == 8;
+            L.sync = synced ? 0.0f : (float)(((uint64_t)i * 1664525u + 1013904223u) & 0xFFFFu) / 15.0f;
+            switch (s.type) {
+                case 1: L.kind = kLightRandom; L.speed = 20.0f; L.duration = 0.06f; break;          // FLASH
+                case 17: L.kind = kLightRandom; L.speed = 8.0f; L.duration = 0.5f; break;           // FLICKER
+                case 3: case 12: L.kind = kLightAlternate; L.speed = 1.0f; L.duration = 0.85f; break;   // slow strobe
+                case 2: case 4: case 13: L.kind = kLightAlternate; L.speed = 2.0f; L.duration = 0.7f; break;
+                default: L.kind = kLightGlow; L.speed = 0.5f; L.duration = 0.0f; break;             // GLOW (8)
+            }
+        }
         SectorRec r{};
         r.floor = s.floor; r.ceil = s.ceil;
         r.floor_flat = flat_id(s.floor_tex);
         r.ceil_flat = flat_id(s.ceil_tex);
-        r.light = light_byte(s.light, 0);
+        r.light = eff ? light_byte_at(L, 0) : light_byte(s.light, 0);     // effects evaluated at tic 0
         sectors[(size_t)i] = r;
         if (s.floor < min_h) min_h = s.floor;
         if (s.ceil > max_h) max_h = s.ceil;
@@ -280,7 +295,7 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         const int32_t scroll = line.special == 0x30 ? kSegScroll : 0;          // visitor.rs:922
         r.uoff = (int32_t)sg.offset + sd.xoff;                                   // visitor.rs:904
         r.len_q12 = (int32_t)isqrt64((uint64_t)(dx * dx + dy * dy) << 24);       // visitor.rs:905
-        r.light = light_byte(fs.light, contrast);
+        r.light = has_effect[(size_t)front] ? sectors[(size_t)front].light : light_byte(fs.light, contrast);
         if (back < 0) {
             // one-sided: full-height middle (visitor.rs:733-749); Peg::Bottom -> texture bottom at
             // the floor, Peg::Top -> texture top at the ceiling (visitor.rs:909-912)
@@ -357,7 +372,8 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
         row.rec.x = t.x; row.rec.y = t.y;
         row.rec.low = meta->hanging ? sct.ceil - th : sct.floor;
         row.rec.tex = tid;
-        row.rec.light = light_byte(sct.light, 0);
+        row.rec.light = sectors[(size_t)sec].light;
+        row.rec.sector = sec;
         sprite_rows.push_back(row);
     }
     std::stable_sort(sprite_rows.begin(), sprite_rows.end(),
@@ -525,6 +541,7 @@ std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &t
     hdr[H_OFF_ANIM] = w.append(anim_frames.data(), anim_frames.size() * 4);
     hdr[H_NANIM] = (uint32_t)anim_frames.size();
     hdr[H_OFF_FLAT_ANIM] = w.append(flat_anim.data(), flat_anim.size() * sizeof(FlatAnimRec));
+    hdr[H_OFF_LIGHTS] = w.append(lights.data(), lights.size() * sizeof(LightRec));
     hdr[H_OFF_TEXELS] = w.append(texels.data(), texels.size());
     hdr[H_TEXEL_BYTES] = (uint32_t)texels.size();
     hdr[H_OFF_FLATS] = w.append(flats.data(), flats.size());

@@ -9,6 +9,7 @@
 //   sky texture of the level                   wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
 //   player-1 start                             visitor.rs:1010-1060, game/src/level.rs:757-762
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <vector>
 
@@ -17,7 +18,7 @@
 namespace b2d {
 
 constexpr uint32_t kSceneMagic = 0x53443242u;   // "B2DS"
-constexpr uint32_t kSceneVersion = 4;
+constexpr uint32_t kSceneVersion = 5;
 constexpr uint32_t kLeaf = 0x80000000u;
 
 enum HeaderField : int {
@@ -25,7 +26,7 @@ enum HeaderField : int {
     H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
     H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
     H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES,
-    H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM, H_COUNT = 64
+    H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM, H_OFF_LIGHTS, H_COUNT = 64
 };
 
 // 64-byte records; all int32.
@@ -33,7 +34,7 @@ struct NodeRec { int32_t x, y, dx, dy, rbox[4], lbox[4]; uint32_t child[2]; int3
 struct SSectorRec { int32_t first_seg, num_segs, sector, sprites; };   // sprites = first | count << 24
 // decoration thing: billboard of its sprite image's size, centred on (x,y), bottom edge at `low`
 // (floor, or ceiling - height for hanging things; visitor.rs:1062-1137), lit by the sector light
-struct SpriteRec { int32_t x, y, low, tex, light, pad[3]; };
+struct SpriteRec { int32_t x, y, low, tex, light, sector, pad[2]; };
 struct SegRec {
     int32_t v1, v2, front, flags;
     int32_t uoff, len_q12;
@@ -48,9 +49,12 @@ struct SectorRec { int32_t floor, ceil, floor_flat, ceil_flat, light, pad[3]; };
 // mask_off = ~0u: opaque.  anim_nk = n | k << 16: frame k of an n-frame animation whose ids are anim[anim_first..+n)
 struct TexRec { uint32_t texel_off, w, h, hmagic, hbias, mask_off, anim_first, anim_nk; };
 struct FlatAnimRec { int32_t anim_first, anim_nk; };
+// sector light effect (wad/src/light.rs:5-25): kind 0 none, 1 glow, 2 random, 3 alternate
+struct LightRec { uint32_t kind; float level, alt, speed, duration, sync; uint32_t pad[2]; };
+constexpr uint32_t kLightNone = 0, kLightGlow = 1, kLightRandom = 2, kLightAlternate = 3;
 static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec) == 32 &&
               sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16 && sizeof(MidRec) == 32 &&
-              sizeof(SpriteRec) == 32, "record layout");
+              sizeof(SpriteRec) == 32 && sizeof(LightRec) == 32, "record layout");
 
 constexpr int32_t kSegTwoSided = 1, kSegScroll = 2, kSegInvalid = 0x80;   // scroll: special 0x30 (visitor.rs:922)
 constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
@@ -59,17 +63,62 @@ constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
 // of an n-frame animation group shows group frame (k + tics/8) mod n; walls of a scrolling line (special 0x30)
 // advance their texture column by one texel per tic.  The kernels never see time: the three small tables that
 // depend on it (texture records, sector flats, seg column offsets) are re-derived from the blob here and
-// re-uploaded when the time changes.  Outputs hold H_NTEX / H_NSECTORS / H_NSEGS records.
+// re-uploaded when the time changes.  Sector light effects (C15) ride on the same mechanism: the light bytes of
+// effect sectors, their segs and their sprites are re-evaluated.  Outputs hold H_NTEX / H_NSECTORS / H_NSEGS /
+// H_NSPRITES records.
+// Light level of a sector at `tics` (game/src/lights.rs:26-66), float32 operation by operation (volatile keeps
+// every intermediate a rounded float32: no x87 excess precision, no fused multiply-add).  The sine of the random
+// effect's hash is the correctly rounded float32 sine: double-precision sine, rounded once.
+inline uint8_t light_byte_at(const LightRec &L, uint32_t tics) {
+    volatile float time = (float)tics / 35.0f;
+    volatile float v = L.level;
+    auto fract = [](float x) -> float { volatile float f = std::floor(x); volatile float r = x - f; return r; };
+    if (L.kind == kLightGlow) {
+        volatile float scale = L.level - L.alt;
+        volatile float ts = time * L.speed;
+        volatile float phase = ts / scale;
+        volatile float d = 0.5f - fract(phase);
+        volatile float a = std::fabs(d);
+        volatile float a2 = a * 2.0f;
+        volatile float a3 = a2 * scale;
+        v = a3 + L.alt;
+    } else if (L.kind == kLightRandom) {
+        volatile float ts = time * L.speed;
+        volatile float t = std::floor(ts);
+        volatile float t1 = t / 1000.0f;
+        volatile float s1 = L.sync + t1;
+        volatile float s2 = s1 * 12.9898f;
+        volatile float s3 = L.sync * 78.233f;
+        volatile float arg = s2 + s3;
+        volatile float sn = (float)std::sin((double)arg);
+        volatile float n1 = sn * 43758.547f;
+        volatile float n2 = 1.0f + n1;
+        v = fract(n2) < L.duration ? L.alt : L.level;
+    } else if (L.kind == kLightAlternate) {
+        volatile float ts = time * L.speed;
+        volatile float s3 = L.sync * 3.5435f;
+        volatile float ph = ts + s3;
+        v = fract(ph) < L.duration ? L.alt : L.level;
+    }
+    if (v < 0.0f) v = 0.0f; else if (v > 1.0f) v = 1.0f;
+    volatile float scaled = v * 255.0f;
+    return scaled >= 0.0f ? (uint8_t)(int)scaled : 0;
+}
+
 inline bool scene_is_timed(const uint8_t *blob) {
     const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
     if (h[H_NANIM] > 0) return true;
+    const LightRec *lights = reinterpret_cast<const LightRec *>(blob + h[H_OFF_LIGHTS]);
+    for (uint32_t i = 0; i < h[H_NSECTORS]; i++)
+        if (lights[i].kind != kLightNone) return true;
     const SegRec *segs = reinterpret_cast<const SegRec *>(blob + h[H_OFF_SEGS]);
     for (uint32_t i = 0; i < h[H_NSEGS]; i++)
         if (segs[i].flags & kSegScroll) return true;
     return false;
 }
 
-inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, SectorRec *sectors_out, SegRec *segs_out) {
+inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, SectorRec *sectors_out, SegRec *segs_out,
+                          SpriteRec *sprites_out) {
     const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
     const TexRec *tex = reinterpret_cast<const TexRec *>(blob + h[H_OFF_TEX]);
     const SectorRec *sectors = reinterpret_cast<const SectorRec *>(blob + h[H_OFF_SECTORS]);
@@ -91,14 +140,27 @@ inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, S
         const int32_t j = now(fa[f].anim_first, (uint32_t)fa[f].anim_nk, f);
         return (j >= 0 && (uint32_t)j < nflats) ? j : f;
     };
-    for (uint32_t i = 0; i < h[H_NSECTORS]; i++) {
+    const LightRec *lights = reinterpret_cast<const LightRec *>(blob + h[H_OFF_LIGHTS]);
+    const SpriteRec *sprites = reinterpret_cast<const SpriteRec *>(blob + h[H_OFF_SPRITES]);
+    const uint32_t nsect = h[H_NSECTORS];
+    for (uint32_t i = 0; i < nsect; i++) {
         sectors_out[i] = sectors[i];
         sectors_out[i].floor_flat = flat_now(sectors[i].floor_flat);
         sectors_out[i].ceil_flat = flat_now(sectors[i].ceil_flat);
+        if (lights[i].kind != kLightNone) sectors_out[i].light = light_byte_at(lights[i], tics);
     }
+    // walls and sprites of a sector with a light effect carry the sector's light (no fake contrast, visitor.rs:889)
     for (uint32_t i = 0; i < h[H_NSEGS]; i++) {
         segs_out[i] = segs[i];
+        if (segs[i].flags & kSegInvalid) continue;
         if (segs[i].flags & kSegScroll) segs_out[i].uoff = segs[i].uoff + (int32_t)(tics & 0xFFFFFFu);
+        const uint32_t f = (uint32_t)segs[i].front;
+        if (f < nsect && lights[f].kind != kLightNone) segs_out[i].light = sectors_out[f].light;
+    }
+    for (uint32_t i = 0; i < h[H_NSPRITES]; i++) {
+        sprites_out[i] = sprites[i];
+        const uint32_t f = (uint32_t)sprites[i].sector;
+        if (f < nsect && lights[f].kind != kLightNone) sprites_out[i].light = sectors_out[f].light;
     }
 }
 

@@ -501,6 +501,8 @@ class LevelBuilder:
                     height += 128
                 light = rng.pick([96, 112, 128, 144, 160, 176, 192, 208, 224, 255, 255, 80])
                 stype = rng.pick([0] * 14 + [1, 8])
+                if self.cfg.anim and rng.chance(1, 3):          # every light effect kind (light.rs:127-134)
+                    stype = rng.pick([1, 2, 3, 4, 8, 12, 13, 17])
                 self.sectors.append(Sector(
                     fl, fl + height, rng.pick(FLOOR_FLATS),
                     "F_SKY1" if is_sky else rng.pick(CEIL_FLATS), light, stype))

@@ -356,9 +356,10 @@ static int render_impl(const uint8_t *blob, const View *vw, const Pose *poses, i
     std::vector<TexRec> tex_t((size_t)sc.ntex);
     std::vector<SectorRec> sectors_t((size_t)sc.hdr[H_NSECTORS]);
     std::vector<SegRec> segs_t((size_t)sc.nsegs);
+    std::vector<SpriteRec> sprites_t((size_t)sc.nsprites);
     if (tics != 0 && scene_is_timed(blob)) {
-        scene_at_time(blob, tics, tex_t.data(), sectors_t.data(), segs_t.data());
-        sc.tex = tex_t.data(); sc.sectors = sectors_t.data(); sc.segs = segs_t.data();
+        scene_at_time(blob, tics, tex_t.data(), sectors_t.data(), segs_t.data(), sprites_t.data());
+        sc.tex = tex_t.data(); sc.sectors = sectors_t.data(); sc.segs = segs_t.data(); sc.sprites = sprites_t.data();
     }
     std::vector<uint32_t> yslope((size_t)vw->H);
     for (int y = 0; y < vw->H; y++) yslope[(size_t)y] = yslope_entry(y, *vw);
@@ -385,6 +386,18 @@ extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose 
 extern "C" int hostcheck_render_t(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
                                   int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics) {
     return render_impl(blob, vw, poses, n, fb, counts, seg_ids, stride, tics);
+}
+
+// the product's light-effect evaluation (scene_at_time): light byte per sector at `tics`, -1 without effect
+extern "C" void hostcheck_lights(const uint8_t *blob, uint32_t tics, int16_t *out) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    std::vector<TexRec> tex(h[H_NTEX]);
+    std::vector<SectorRec> sectors(h[H_NSECTORS]);
+    std::vector<SegRec> segs(h[H_NSEGS]);
+    std::vector<SpriteRec> sprites(h[H_NSPRITES]);
+    scene_at_time(blob, tics, tex.data(), sectors.data(), segs.data(), sprites.data());
+    const LightRec *lights = reinterpret_cast<const LightRec *>(blob + h[H_OFF_LIGHTS]);
+    for (uint32_t i = 0; i < h[H_NSECTORS]; i++) out[i] = lights[i].kind != kLightNone ? (int16_t)sectors[i].light : (int16_t)-1;
 }
 
 extern "C" void hostcheck_sincos(uint32_t angle, int32_t *c, int32_t *s) { sincos_q30(angle, *c, *s); }

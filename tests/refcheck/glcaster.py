@@ -131,6 +131,35 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
     for i in range(len(secs)):
         eff = int(secs[i]["type"]) in W.EFFECT_TYPES and (level.sector_min_light(i) >> 3) != (int(secs[i]["light"]) >> 3)
         has_effect.append(eff)
+
+    def effect_light_byte(i):
+        """Light of an effect sector at u_time = tics/35 (wad/src/light.rs:27-80 parameters, game/src/lights.rs:26-66
+        evaluation), in the reference's float32 arithmetic."""
+        f = np.float32
+        stype = int(secs[i]["type"])
+        level_f = f(np.int16(secs[i]["light"]) >> 3) / f(31.0)
+        alt = f(np.int16(level.sector_min_light(i)) >> 3) / f(31.0)
+        sync = f(0.0) if stype in (12, 13, 8) else f((i * 1664525 + 1013904223) & 0xFFFF) / f(15.0)
+        time = f(tics & 0xFFFFFFFF) / f(35.0)
+        fract = lambda x: f(x - np.floor(x))                 # noqa: E731
+        if stype == 8:                                       # glow
+            scale = f(level_f - alt)
+            phase = f(f(time * f(0.5)) / scale)
+            val = f(f(f(abs(f(f(0.5) - fract(phase))) * f(2.0)) * scale) + alt)
+        elif stype in (1, 17):                               # flash / flicker: hash noise per time slot
+            speed, duration = (f(20.0), f(0.06)) if stype == 1 else (f(8.0), f(0.5))
+            slot = np.floor(f(time * speed))
+            arg = f(f(f(sync + f(slot / f(1000.0))) * f(12.9898)) + f(sync * f(78.233)))
+            noise = fract(f(f(1.0) + f(f(math.sin(float(arg))) * f(43758.547))))
+            val = alt if noise < duration else level_f
+        else:                                                # strobes
+            speed, duration = (f(1.0), f(0.85)) if stype in (3, 12) else (f(2.0), f(0.7))
+            val = alt if fract(f(f(time * speed) + f(sync * f(3.5435)))) < duration else level_f
+        val = min(max(float(val), 0.0), 1.0)
+        return int(float(f(f(val) * f(255.0))))
+
+    sector_byte = [effect_light_byte(i) if has_effect[i] else W.light_byte(int(secs[i]["light"]), 0)
+                   for i in range(len(secs))]
     ss_sector = {}
     for ssi in range(len(level.subsectors)):
         first, num = int(level.subsectors[ssi]["first_seg"]), int(level.subsectors[ssi]["num_segs"])
@@ -172,7 +201,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         contrast = 0
         if not has_effect[front]:
             contrast = 1 if ey == 0 else (-1 if ex == 0 else 0)
-        lb = W.light_byte(int(fsec["light"]), contrast)
+        lb = sector_byte[front] if has_effect[front] else W.light_byte(int(fsec["light"]), contrast)
         back_side = level.seg_back_sidedef_index(sg)
         back = int(level.sidedefs[back_side]["sector"]) if back_side >= 0 else -1
         pieces = []                                         # (low, high, texture name or 'SKY', t at high)
@@ -282,7 +311,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         if not hit.any():
             continue
         texel = img[np.floor(v[hit]).astype(np.int64), np.floor(u[hit]).astype(np.int64)]
-        vb = W.light_byte(int(secs[sec]["light"]), 0) / 255.0
+        vb = sector_byte[sec] / 255.0
         dist = min(1.0, 1.0 - 1.0 / (cz / 100.0 + 1.0))
         light = min(vb, vb * 2.0 - dist)                      # sprite.frag:24-26
         row = int(np.clip(np.floor((1.0 - light) * 32.0), 0, 31))
@@ -295,7 +324,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
     # ---- flats: one horizontal plane per distinct height -------------------------------------------------
     floor_h = np.array([min_h if W.is_sky_flat(floor_name[i]) else int(secs[i]["floor"]) for i in range(len(secs))], dtype=np.float64)
     ceil_h = np.array([max_h if W.is_sky_flat(ceil_name[i]) else int(secs[i]["ceil"]) for i in range(len(secs))], dtype=np.float64)
-    sec_light = np.array([W.light_byte(int(secs[i]["light"]), 0) for i in range(len(secs))], dtype=np.float64)
+    sec_light = np.array(sector_byte, dtype=np.float64)
     for is_ceiling, heights in ((False, floor_h), (True, ceil_h)):
         for h in np.unique(heights):
             with np.errstate(divide="ignore", invalid="ignore"):

@@ -131,3 +131,31 @@ def test_hostcheck_animated_and_scrolling(b2d, hostcheck):
         changed += int((render.render(sc.blob, render.make_view(320, 200), poses, threads=4, tics=tics) != base).sum())
     assert changed > 20000, "time never changed a pixel"
     _compare(b2d, hostcheck, sc, 1920, 1080, 2, 92, tics=77)
+
+
+def test_light_effects_product_equals_oracle_over_time(b2d, hostcheck):
+    """C15: glow / flash / flicker / strobe light levels in float32 (lights.rs:26-66) — the product's C++ evaluation
+    and the oracle's numpy evaluation give the same byte for every effect sector at every sampled tic."""
+    import ctypes
+    from oracle import scene as S
+    from rust_doom_b200 import synthwad
+    kinds = set()
+    for seed in (1, 2):
+        data = synthwad.build_iwad(seed, ("E1M1",), cfg=synthwad.SynthConfig(anim=True))
+        blob = b2d.Scene(b2d.Archive.from_bytes(data), 0).blob
+        h = S.header(blob)
+        n = h[S.H_NSECTORS]
+        rec = np.frombuffer(blob, dtype="<u4", count=8 * n, offset=h[S.H_OFF_LIGHTS]).reshape(n, 8)
+        kinds |= set(rec[:, 0].tolist())
+        buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
+        rng = np.random.default_rng(seed)
+        tics = list(range(0, 300)) + rng.integers(0, 1 << 32, 300, dtype=np.uint64).tolist() + [(1 << 32) - 1, 1 << 24]
+        seen = set()
+        for t in tics:
+            out = np.empty(n, np.int16)
+            hostcheck.lib.hostcheck_lights(ctypes.c_void_p(ctypes.addressof(buf)), ctypes.c_uint32(t), ctypes.c_void_p(out.ctypes.data))
+            want = S.sector_lights_at(blob, t)
+            assert np.array_equal(out, want), (seed, t, out.tolist(), want.tolist())
+            seen |= set(map(tuple, np.stack([np.arange(n), out], 1)[out >= 0].tolist()))
+        assert len(seen) > 3 * int((rec[:, 0] != 0).sum()), "lights never changed over time"
+    assert kinds == {0, 1, 2, 3}, kinds

@@ -204,3 +204,22 @@ def test_middle_texture_pegging(b2d):
     assert (t_high, low, high) == (6, 24 + 6, 24 + 128 + 6)
     (_, t_high, low, high), _ = mid_of(two_sided_flags=0x0004, lower="-", yoff=-5)        # Peg::BottomFloat
     assert (t_high, low, high) == ((-5) % 128, 96 - 5 - 128, 96 - 5)
+
+
+def test_light_effect_parameters_and_hand_values():
+    """new_light (light.rs:27-80) restated; hand-computed values of light_level_at (lights.rs:33-66)."""
+    f = np.float32
+    # glow: level 1.0, alt 0.5, speed 0.5: triangle wave of period scale/speed = 1 s between level and alt
+    info = (S.LIGHT_GLOW, f(1.0), f(0.5), f(0.5), f(0.0), f(0.0))
+    assert S.light_byte_at(info, 0) == 255                      # phase 0 -> level
+    assert 126 <= S.light_byte_at(info, 17) <= 131              # ~half a period -> ~alt (0.5*255 = 127.5)
+    assert S.light_byte_at(info, 35) == 255                     # one full period (time = 1.0 exactly)
+    # strobe, sync 0: alt during the first `duration` of each 1/speed period
+    info = (S.LIGHT_ALTERNATE, f(1.0), f(0.0), f(2.0), f(0.7), f(0.0))
+    assert [S.light_byte_at(info, t) for t in (0, 5, 12, 13, 17, 18, 30)] == [0, 0, 0, 255, 255, 0, 255]
+    # flash: alt with probability ~duration
+    info = (S.LIGHT_RANDOM, f(1.0), f(0.0), f(20.0), f(0.06), f(123.4))
+    vals = [S.light_byte_at(info, t) for t in range(0, 7000, 7)]
+    assert set(vals) == {0, 255} and 0.02 < vals.count(0) / len(vals) < 0.12
+    # static sector: clamped, truncated
+    assert S.light_byte_at((S.LIGHT_NONE, f(144 >> 3) / f(31.0), f(0), f(0), f(0), f(0)), 99) == W.light_byte(144, 0)
