@@ -36,6 +36,7 @@ struct b2d_renderer {
     uint16_t *d_skyrow = nullptr;
     int32_t *d_status = nullptr;
     uint32_t *d_masked = nullptr;
+    uint8_t *d_lit = nullptr;       // colormap-applied copies of the texels and flats (32 light rows each)
     DeviceScene ds{};
     Pose *d_poses = nullptr;
     FrameConst *d_frames = nullptr;
@@ -106,6 +107,7 @@ void free_renderer(b2d_renderer *r) {
     if (r->d_skyrow) cudaFree(r->d_skyrow);
     if (r->d_status) cudaFree(r->d_status);
     if (r->d_masked) cudaFree(r->d_masked);
+    if (r->d_lit) cudaFree(r->d_lit);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
 }
@@ -306,6 +308,16 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.flats = r->d_blob + h[H_OFF_FLATS];
     d.colormap = r->d_blob + h[H_OFF_COLORMAP];
     d.palette = reinterpret_cast<const uint32_t *>(r->d_blob + h[H_OFF_PALETTE]);
+    {   // pre-lit texel and flat planes: 32 x (texel bytes + flat bytes)
+        const size_t tstride = (h[H_TEXEL_BYTES] + 255u) & ~(size_t)255, fstride = (size_t)h[H_NFLATS] * 4096u;
+        if (tstride * 32 > 0xFFFFFFFFull || fstride * 32 > 0xFFFFFFFFull) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level textures too large"); }
+        CUR(cudaMalloc(&r->d_lit, 32 * (tstride + fstride) + 256));
+        CUR(launch_prelight(d.colormap, d.texels, r->d_lit, h[H_TEXEL_BYTES], tstride, nullptr));
+        CUR(launch_prelight(d.colormap, d.flats, r->d_lit + 32 * tstride, fstride, fstride, nullptr));
+        CUR(cudaDeviceSynchronize());
+        d.lit_texels = r->d_lit; d.lit_flats = r->d_lit + 32 * tstride;
+        d.lit_texel_stride = (uint32_t)tstride; d.lit_flat_stride = (uint32_t)fstride;
+    }
     d.yslope = r->d_yslope;
     d.skyrow = r->d_skyrow;
     CUR(cudaMalloc(&r->d_status, sizeof(int32_t)));

@@ -320,6 +320,27 @@ __device__ __forceinline__ void put_px(const RasterCtx &c, uint8_t *p8, uint32_t
     }
 }
 
+// Rows are produced in batches of kBatch: all texel loads first, then all colormap lookups, then the stores.
+// Issuing the independent loads back to back keeps kBatch of them in flight per warp (the one-row-at-a-time
+// form serialises load -> lookup -> store and leaves the LSU idle while each warp waits).  `full` (warp-uniform)
+// says every lane owns all rows of the batch, so the stores need no predicate.
+constexpr int kBatch = 8;
+
+template <bool kRgba, int kW>
+__device__ __forceinline__ void store_batch(const RasterCtx &c, uint8_t *p8, uint32_t *p32, const uint32_t (&v)[kBatch],
+                                            int y, int ya, int yb, bool full) {
+    const int Wc = kW ? kW : c.W;
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, true, v[k]);
+    } else {
+        const uint32_t len = (uint32_t)(yb - ya), d = (uint32_t)(y - ya);
+#pragma unroll
+        for (int k = 0; k < kBatch; k++)
+            put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, d + (uint32_t)k < len, v[k]);
+    }
+}
+
 // rows [ya, yb) of this lane's column := void (index 0); lanes with ya >= yb idle
 template <bool kRgba, int kW, int kUnroll>
 __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int yb) {
@@ -338,7 +359,7 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     const DeviceScene &sc = *c.sc;
     if (sc.sky_tex < 0) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const TexRec T = sc.tex[sc.sky_tex];
-    const uint8_t *px = sc.texels + T.texel_off + c.skycol;
+    const uint8_t *px = sc.lit_texels + T.texel_off + c.skycol;          // light row 0
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
@@ -346,11 +367,17 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
-#pragma unroll(kUnroll)
-    for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) {
-        uint32_t v = sc.skyrow[y];                                        // warp-uniform table entry
-        uint32_t texel = px[v * T.w];
-        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(c.cmap_s + texel));
+    const int full_lo = __reduce_max_sync(kFull, act ? ya : 0x7FFFFFFF);
+    const int full_hi = __reduce_min_sync(kFull, act ? yb : 0);
+    int y = y0;
+    for (; y + kBatch <= y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
+        uint32_t v[kBatch];
+#pragma unroll
+        for (int k = 0; k < kBatch; k++) v[k] = __ldg(px + (uint32_t)sc.skyrow[y + k] * T.w);   // warp-uniform table entry
+        store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
+    }
+    for (; y < y1; y++, p8 += Wc, p32 += Wc) {
+        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + (uint32_t)sc.skyrow[y] * T.w));
     }
 }
 
@@ -363,11 +390,13 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
     if (!visible) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     if (flat == kFlatSky) { draw_sky_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
-    const uint8_t *px = sc.flats + 4096u * (uint32_t)flat;
+    const uint8_t *px = sc.lit_flats + 4096u * (uint32_t)flat;
     const uint32_t habs = plane_habs(h, fc.pose.z);
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+    const int full_lo = __reduce_max_sync(kFull, act ? ya : 0x7FFFFFFF);
+    const int full_hi = __reduce_min_sync(kFull, act ? yb : 0);
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
@@ -378,19 +407,27 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         if (yy < y1) {
             PlaneRow pr = plane_row(habs, sc.yslope[yy], fc, vw, sc.invF);
             c.row4[c.lane] = make_uint4(pr.baseU, pr.stepU, pr.baseV, pr.stepV);
-            c.row1[c.lane] = c.cmap_s + 256u * (uint32_t)light_row(lightb, pr.z8);
+            c.row1[c.lane] = sc.lit_flat_stride * (uint32_t)light_row(lightb, pr.z8);
         }
         __syncwarp();
         const int rows = min(32, y1 - yc);
-#pragma unroll(kUnroll)
-        for (int j = 0; j < rows; j++, p8 += Wc, p32 += Wc) {
-            const uint4 r4 = lds_v4_volatile(c.row4_s + 16u * (uint32_t)j);   // shared-memory broadcast
-            const uint32_t cm = lds_u32_volatile(c.row1_s + 4u * (uint32_t)j);
+        int j = 0;
+        for (; j + kBatch <= rows; j += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
+            uint32_t v[kBatch], cm[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) {
+                const uint4 r4 = c.row4[j + k];                               // shared-memory broadcast
+                cm[k] = c.row1[j + k];
+                v[k] = __ldg(px + (cm[k] + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w)));   // always in bounds
+            }
             const int y = yc + j;
-            uint32_t U = r4.x + xx * r4.y;
-            uint32_t V = r4.z + xx * r4.w;
-            uint32_t texel = px[flat_index(U, V)];                         // always in bounds: unconditional
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
+            store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
+        }
+        for (; j < rows; j++, p8 += Wc, p32 += Wc) {
+            const uint4 r4 = c.row4[j];
+            const uint32_t cm = c.row1[j];
+            const int y = yc + j;
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + (cm + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w))));
         }
         __syncwarp();
     }
@@ -405,11 +442,12 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
     if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const TexRec T = sc.tex[tex];
     bool act = ya < yb;
-    const uint8_t *px = sc.texels + T.texel_off + (uint32_t)floormod32(ucol, (int32_t)T.w);
+    const uint8_t *px = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off + (uint32_t)floormod32(ucol, (int32_t)T.w);
     const int32_t tstep = iscale >> 4;
-    const uint32_t cm = c.cmap_s + 256u * (uint32_t)row;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
+    const int full_lo = __reduce_max_sync(kFull, act ? ya : 0x7FFFFFFF);
+    const int full_hi = __reduce_min_sync(kFull, act ? yb : 0);
     uint32_t t = (uint32_t)wall_tbase(tA, hA, fc.pose.z, c.H, iscale) + (uint32_t)y0 * (uint32_t)tstep;
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
@@ -421,17 +459,27 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
         const int lw = 31 - __clz((int)T.w);
         const uint32_t mask = (T.h - 1u) << lw;
         const int sh = 16 - lw;            // w <= 4096 -> sh >= 4
-#pragma unroll(kUnroll)
-        for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
-            uint32_t texel = px[(t >> sh) & mask];
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
+        int y = y0;
+        for (; y + kBatch <= y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * (uint32_t)tstep) {
+            uint32_t v[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++) v[k] = __ldg(px + (((t + (uint32_t)k * (uint32_t)tstep) >> sh) & mask));
+            store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
+        }
+        for (; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + ((t >> sh) & mask)));
         }
     } else {
-#pragma unroll(kUnroll)
-        for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
-            uint32_t v = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
-            uint32_t texel = px[v * T.w];
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, lds_u8(cm + texel));
+        int y = y0;
+        for (; y + kBatch <= y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * (uint32_t)tstep) {
+            uint32_t v[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; k++)
+                v[k] = __ldg(px + wall_row((int32_t)(t + (uint32_t)k * (uint32_t)tstep), T.h, T.hmagic, T.hbias) * T.w);
+            store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
+        }
+        for (; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w));
         }
     }
 }
@@ -735,6 +783,30 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
     else { if (w1920) B2D_RASTER_GO(false, 1920); else B2D_RASTER_GO(false, 0); }
 #undef B2D_RASTER_GO
+    return cudaGetLastError();
+}
+
+namespace {
+__global__ void __launch_bounds__(256)
+b2d_prelight_kernel(const uint8_t *__restrict__ colormap, const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                    size_t n, size_t stride) {
+    __shared__ uint8_t cm[32 * 256];
+    for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) cm[i] = colormap[i];
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t t = src[i];
+#pragma unroll 4
+        for (int r = 0; r < 32; r++) dst[(size_t)r * stride + i] = cm[r * 256 + t];
+    }
+}
+}  // namespace
+
+cudaError_t launch_prelight(const uint8_t *d_colormap, const uint8_t *d_src, uint8_t *d_dst, size_t n, size_t stride,
+                            cudaStream_t stream) {
+    if (n == 0) return cudaSuccess;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    b2d_prelight_kernel<<<blocks, 256, 0, stream>>>(d_colormap, d_src, d_dst, n, stride);
     return cudaGetLastError();
 }
 

@@ -21,6 +21,11 @@ struct DeviceScene {
     const uint8_t *texels;
     const uint8_t *flats;
     const uint8_t *colormap;     // 34 x 256
+    // colormap applied ahead of time: lit_texels[r * lit_texel_stride + i] = colormap[r][texels[i]] for the 32 light
+    // rows r, likewise lit_flats; the solid pass fetches the final palette index with one load per pixel
+    const uint8_t *lit_texels;
+    const uint8_t *lit_flats;
+    uint32_t lit_texel_stride, lit_flat_stride;
     const uint32_t *palette;     // 256 RGBA8
     const uint32_t *yslope;      // per view: H entries
     const uint16_t *skyrow;      // per view: H entries, sky texture row of each screen row
@@ -49,6 +54,10 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
                           uint32_t *d_rgba, cudaStream_t stream);
 
 // Kernel 3: palette LUT on its own (index -> RGBA8), 16 pixels per thread.
+// dst[r * stride + i] = colormap[r][src[i]] for r < 32, i < n
+cudaError_t launch_prelight(const uint8_t *d_colormap, const uint8_t *d_src, uint8_t *d_dst, size_t n, size_t stride,
+                            cudaStream_t stream);
+
 cudaError_t launch_palette(const uint32_t *d_palette, const uint8_t *d_index, uint32_t *d_rgba,
                            size_t n_pixels, cudaStream_t stream);
 
