@@ -95,16 +95,22 @@ __host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnode
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: BSP walk -> worklist
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 7)     // 7 CTAs/SM (72 registers): 1036 frames resident on 148 SMs
 b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const Pose *__restrict__ poses, int n,
                 FrameConst *__restrict__ frames, SegFrame *__restrict__ work, int stride) {
+    // One CTA per frame.  The per-frame setup (steps 1-3) and the worklist records (step 5) are data-parallel and
+    // use all 128 threads; the traversal itself (step 4) is sequential and runs in warp 0 with the lanes working
+    // on the segs of a subsector / the words of the column mask.  The kernel is latency-bound (one frame = one
+    // dependent chain), so spreading the parallel phases over four warps shortens the chain directly.
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int frame = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (frame >= n) return;                       // warps are independent: no block barrier below
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int frame = blockIdx.x;
+    if (frame >= n) return;                       // whole CTA
 
     const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss, sc.nsprites);
-    uint8_t *base = smem + (size_t)warp * L.total;
+    uint8_t *base = smem;
+    __shared__ int s_count, s_status;
     int32_t *tx = reinterpret_cast<int32_t *>(base + L.off_tx);
     int32_t *tz = reinterpret_cast<int32_t *>(base + L.off_tz);
     uint32_t *segr = reinterpret_cast<uint32_t *>(base + L.off_segr);
@@ -120,16 +126,16 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     frame_setup(poses[frame], fc);
 
     // 1. all vertices into view space (lane-parallel)
-    for (int i = lane; i < sc.nverts; i += 32) {
+    for (int i = tid; i < sc.nverts; i += nthr) {
         int32_t vx = sc.verts[2 * i], vy = sc.verts[2 * i + 1];
         int32_t a, b;
         to_view(fc, vx, vy, a, b);
         tx[i] = a; tz[i] = b;
     }
-    __syncwarp();
+    __syncthreads();
 
     // 2. per-seg exact column interval + static/solid flags (lane-parallel, 64-bit setup)
-    for (int i = lane; i < sc.nsegs; i += 32) {
+    for (int i = tid; i < sc.nsegs; i += nthr) {
         const SegRec &S = sc.segs[i];
         uint32_t packed = 0;
         int32_t flags = S.flags;
@@ -144,20 +150,20 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         segr[i] = packed;
     }
     // 3. conservative column range of both child boxes of every node
-    for (int i = lane; i < 2 * sc.nnodes; i += 32) {
+    for (int i = tid; i < 2 * sc.nnodes; i += nthr) {
         const NodeRec &N = sc.nodes[i >> 1];
         const int32_t *box = (i & 1) ? N.lbox : N.rbox;
         int32_t b4[4] = {box[0], box[1], box[2], box[3]};
         int lo, hi;
         boxr[i] = box_range(fc, vw, b4, lo, hi) ? pack_range(lo, hi, kVisBit) : 0u;
     }
-    for (int i = lane; i < sc.nnodes; i += 32) {
+    for (int i = tid; i < sc.nnodes; i += nthr) {
         const NodeRec &N = sc.nodes[i];
         node_s[2 * i] = make_int4(N.x, N.y, N.dx, N.dy);
         node_s[2 * i + 1] = make_int4((int)N.child[0], (int)N.child[1], 0, 0);
     }
-    for (int i = lane; i < sc.nss; i += 32) ssec_s[i] = *reinterpret_cast<const int4 *>(&sc.ssectors[i]);
-    for (int i = lane; i < sc.nsprites; i += 32) {          // decoration sprites: exact column interval
+    for (int i = tid; i < sc.nss; i += nthr) ssec_s[i] = *reinterpret_cast<const int4 *>(&sc.ssectors[i]);
+    for (int i = tid; i < sc.nsprites; i += nthr) {          // decoration sprites: exact column interval
         const SpriteRec &P = sc.sprites[i];
         SpriteFrame sp;
         uint32_t packed = 0;
@@ -166,17 +172,13 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         sprr[i] = packed;
     }
     // solid-column mask: columns >= W start out solid
-#pragma unroll
-    for (int k = 0; k < kMaskWords / 32; k++) {
-        int w = lane + 32 * k;
-        mask[w] = ~word_bits(w, 0, vw.W - 1);
-    }
-    if (lane == 0) stack[0] = sc.root;
-    __syncwarp();
+    for (int w = tid; w < kMaskWords; w += nthr) mask[w] = ~word_bits(w, 0, vw.W - 1);
+    if (tid == 0) stack[0] = sc.root;
+    __syncthreads();
 
-    // 4. front-to-back traversal (control flow is warp-uniform)
+    // 4. front-to-back traversal in warp 0 (control flow is warp-uniform)
     const int passes = (vw.W + 1023) / 1024;
-    int sp = 1, count = 0, status = 0;
+    int sp = warp == 0 ? 1 : 0, count = 0, status = 0;
     int budget = 2 * (sc.nnodes + sc.nss) + 64;      // a corrupt BSP with a cycle must not hang the GPU
     while (sp > 0) {
         if (--budget < 0) { status |= 4; break; }
@@ -242,10 +244,15 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         }
     }
     __syncwarp();
-    if (count > stride) { count = stride; status |= 2; }
+    if (warp == 0 && lane == 0) {
+        if (count > stride) { count = stride; status |= 2; }
+        s_count = count; s_status = status;
+    }
+    __syncthreads();
+    count = s_count; status = s_status;
 
-    // 5. worklist records (lane-parallel): the projection coefficients of each emitted seg
-    for (int k = lane; k < count; k += 32) {
+    // 5. worklist records (thread-parallel): the projection coefficients of each emitted seg
+    for (int k = tid; k < count; k += nthr) {
         int si = list[k];
         SegFrame sf;
         if (si >= sc.nsegs) {                         // sprite entry: seg = -1 - sprite index, (cx, cz) in Nc/Nx
@@ -263,7 +270,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         sf.seg = si;
         work[(size_t)frame * stride + k] = sf;
     }
-    if (lane == 0) {
+    if (tid == 0) {
         if (status) atomicOr(sc.status_flag, status);
         fc.count = count;
         fc.status = status;
@@ -745,16 +752,13 @@ size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts,
 cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
                         FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
-    const size_t per_warp = walk_smem_per_warp(sc);
-    int warps = 4;
-    while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
-    if (per_warp * warps > 227 * 1024) return cudaErrorInvalidValue;
-    const size_t smem = per_warp * warps;
+    const size_t smem = walk_smem_per_warp(sc);          // one frame per CTA
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
     if (smem > 48 * 1024) {   // per device and cheap: set it on every launch that needs the opt-in
         cudaError_t e = cudaFuncSetAttribute(b2d_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int blocks = (n + warps - 1) / warps;
+    const int blocks = n, warps = 4;
     b2d_walk_kernel<<<blocks, warps * 32, smem, stream>>>(sc, vw, d_poses, n, d_frames, d_work, stride);
     return cudaGetLastError();
 }
