@@ -1,17 +1,18 @@
 // sm_100a kernels of the Doom-WAD software renderer.
 //
-//   b2d_walk_kernel    : one warp per frame.  Lane-parallel view transform of all vertices, per-seg
+//   b2d_walk_kernel    : one CTA per frame.  Thread-parallel view transform of all vertices, per-seg
 //                        projection setup and per-node-child bounding-box ranges into shared memory,
-//                        then a front-to-back BSP walk with a warp-wide solid-column bitmask
+//                        then (warp 0) a front-to-back BSP walk with a warp-wide solid-column bitmask
 //                        (ballot / lane-striped words) that emits the compact seg worklist.
 //   b2d_raster_kernel  : one warp per (frame, 32-column strip); lane = screen column.  Consumes the
 //                        worklist front to back, keeps the per-column clip window in registers,
-//                        draws wall columns, floor/ceiling spans and sky with the light->colormap
-//                        lookup from shared memory; every pixel is written exactly once.
+//                        draws wall columns, floor/ceiling spans and sky from texel planes that already
+//                        carry the light->colormap lookup; every pixel is written exactly once.
+//   b2d_prelight_*     : build those planes once per renderer (32 light rows x texels / flats).
 //   b2d_palette_kernel : index -> RGBA8 with the 256-entry palette in shared memory, 128-bit I/O.
 //
 // There is no dense contraction anywhere on this path, so no tensor-core (tcgen05) work: the
-// kernels are integer/LSU bound and are tuned against the HBM write roofline.
+// kernels are integer/LSU/latency bound and are tuned against the HBM write roofline.
 #include "b2d_kernels.cuh"
 
 #include <cstdlib>
@@ -285,30 +286,14 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // shared-memory accesses by 32-bit shared-window address: keeps the per-pixel address arithmetic to one
 // add (the generic-pointer form re-derives the window base for every access)
-__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
-    uint32_t v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
-    return v;
-}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     uint32_t v;
     asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
-__device__ __forceinline__ uint32_t lds_u32_volatile(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint4 lds_v4_volatile(uint32_t a) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
-    return v;
-}
 
 struct RasterCtx {
     const DeviceScene *sc;
-    uint32_t cmap_s;           // shared-window address of the colormap (32 x 256)
     uint32_t pal_s;            // ... of the palette (rgba only)
     uint32_t row4_s, row1_s;   // ... of this warp's 32-entry staging of per-row plane constants
     uint4 *row4;               // generic pointers to the same staging (for the lane-parallel writes)
@@ -325,6 +310,15 @@ __device__ __forceinline__ void put_px(const RasterCtx &c, uint8_t *p8, uint32_t
         *p8 = (uint8_t)v;
         if (kRgba) *p32 = lds_u32(c.pal_s + 4u * v);
     }
+}
+
+// Layout of a texture inside the pre-lit planes.  Heights that are a multiple of 4 (every stock wall texture) are
+// stored **4 rows interleaved**: texel (row, col) lives at ((row >> 2) * w + col) * 4 + (row & 3), so one aligned
+// 32-bit word holds four vertically adjacent texels of a column and the 32 lanes of a warp (adjacent columns) read
+// one 128-byte line.  A wall column that is magnified on screen -- the common case at 1080p -- then needs two word
+// loads for eight rows instead of eight byte loads.  Other heights keep the blob's row-major layout.
+__host__ __device__ __forceinline__ bool tex_interleaved(const TexRec &T) {
+    return (T.h & 3u) == 0u && (T.texel_off & 3u) == 0u && T.h <= 4096u;
 }
 
 // Rows are produced in batches of kBatch: all texel loads first, then all colormap lookups, then the stores.
@@ -358,6 +352,7 @@ __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int y
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
+#pragma unroll 1
     for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) put_px<kRgba>(c, p8, p32, y >= ya && y < yb, 0u);
 }
 
@@ -366,7 +361,9 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     const DeviceScene &sc = *c.sc;
     if (sc.sky_tex < 0) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const TexRec T = sc.tex[sc.sky_tex];
-    const uint8_t *px = sc.lit_texels + T.texel_off + c.skycol;          // light row 0
+    const bool inter = tex_interleaved(T);
+    const uint8_t *px = sc.lit_texels + T.texel_off + (inter ? 4u * c.skycol : c.skycol);   // light row 0
+    const uint32_t w4 = 4u * T.w;
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
@@ -374,17 +371,10 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
-    const int full_lo = __reduce_max_sync(kFull, act ? ya : 0x7FFFFFFF);
-    const int full_hi = __reduce_min_sync(kFull, act ? yb : 0);
-    int y = y0;
-    for (; y + kBatch <= y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
-        uint32_t v[kBatch];
-#pragma unroll
-        for (int k = 0; k < kBatch; k++) v[k] = __ldg(px + (uint32_t)sc.skyrow[y + k] * T.w);   // warp-uniform table entry
-        store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
-    }
-    for (; y < y1; y++, p8 += Wc, p32 += Wc) {
-        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + (uint32_t)sc.skyrow[y] * T.w));
+#pragma unroll 2
+    for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) {
+        const uint32_t r = sc.skyrow[y];                                   // warp-uniform table entry
+        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + (inter ? (r >> 2) * w4 + (r & 3u) : r * T.w)));
     }
 }
 
@@ -449,45 +439,56 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
     if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     const TexRec T = sc.tex[tex];
     bool act = ya < yb;
-    const uint8_t *px = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off + (uint32_t)floormod32(ucol, (int32_t)T.w);
-    const int32_t tstep = iscale >> 4;
+    const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
+    const uint8_t *pl = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off;   // this lane's light plane
+    const uint32_t tstep = (uint32_t)(iscale >> 4);
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
     int y1 = __reduce_max_sync(kFull, act ? yb : 0);
     const int full_lo = __reduce_max_sync(kFull, act ? ya : 0x7FFFFFFF);
     const int full_hi = __reduce_min_sync(kFull, act ? yb : 0);
-    uint32_t t = (uint32_t)wall_tbase(tA, hA, fc.pose.z, c.H, iscale) + (uint32_t)y0 * (uint32_t)tstep;
+    uint32_t t = (uint32_t)wall_tbase(tA, hA, fc.pose.z, c.H, iscale) + (uint32_t)y0 * tstep;
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
     // Texel loads are unconditional (t is a bounded linear function of y for every lane, so the row index
-    // is always inside the texture); only the store is predicated.  That keeps the loop branch-free.
-    if (((T.h & (T.h - 1u)) | (T.w & (T.w - 1u))) == 0u) {
-        // power-of-two texture: row*w = ((t >> 16) & (h-1)) << log2(w) as one shift + one mask
-        const int lw = 31 - __clz((int)T.w);
-        const uint32_t mask = (T.h - 1u) << lw;
-        const int sh = 16 - lw;            // w <= 4096 -> sh >= 4
-        int y = y0;
-        for (; y + kBatch <= y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * (uint32_t)tstep) {
+    // is always inside the texture); only the store is predicated.  That keeps the loops branch-free.
+    if (tex_interleaved(T)) {
+        // 4-row interleaved plane.  Rows of a batch: u_k = asr(t + k*tstep, 16), texture row = floormod(u_k, h).
+        // With r0 the row of the first pixel, pixel k reads byte (r0 & 3) + u_k - u_0 of the 8 bytes made of row
+        // quad r0 >> 2 and the next one (wrapping at h, a multiple of 4).  If that byte index stays below 8 for
+        // every lane -- the column is magnified -- two aligned word loads serve the whole batch.
+        const uint32_t colb = 4u * col, w4 = 4u * T.w, nq = T.h >> 2;
+        for (int y = y0; y < y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * tstep) {
+            const uint32_t r0 = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
+            const uint32_t b0 = (r0 & 3u) - (uint32_t)((int32_t)t >> 16);
+            const uint32_t b7 = b0 + (uint32_t)((int32_t)(t + 7u * tstep) >> 16);
             uint32_t v[kBatch];
+            if (__all_sync(kFull, b7 < 8u)) {
+                const uint32_t q0 = r0 >> 2, q1 = (q0 + 1u == nq) ? 0u : q0 + 1u;
+                const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
+                const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q1 * w4 + colb)));
 #pragma unroll
-            for (int k = 0; k < kBatch; k++) v[k] = __ldg(px + (((t + (uint32_t)k * (uint32_t)tstep) >> sh) & mask));
+                for (int k = 0; k < kBatch; k++) {
+                    const uint32_t bk = b0 + (uint32_t)((int32_t)(t + (uint32_t)k * tstep) >> 16);
+                    v[k] = __byte_perm(w0, w1, bk);
+                    if (kRgba) v[k] &= 0xFFu;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kBatch; k++) {
+                    const uint32_t rk = wall_row((int32_t)(t + (uint32_t)k * tstep), T.h, T.hmagic, T.hbias);
+                    v[k] = __ldg(pl + ((rk >> 2) * w4 + colb + (rk & 3u)));
+                }
+            }
+            // rows past y1 belong to no lane: the predicated form drops them, so there is no tail loop
             store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
-        }
-        for (; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + ((t >> sh) & mask)));
         }
     } else {
-        int y = y0;
-        for (; y + kBatch <= y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * (uint32_t)tstep) {
-            uint32_t v[kBatch];
-#pragma unroll
-            for (int k = 0; k < kBatch; k++)
-                v[k] = __ldg(px + wall_row((int32_t)(t + (uint32_t)k * (uint32_t)tstep), T.h, T.hmagic, T.hbias) * T.w);
-            store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
-        }
-        for (; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
+        // heights that are not a multiple of 4 (patches used as textures, odd PWAD content): rare, kept small
+        const uint8_t *px = pl + col;
+#pragma unroll 1
+        for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += tstep)
             put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w));
-        }
     }
 }
 
@@ -498,12 +499,12 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
 // register allocation of the solid pass is not affected.
 template <bool kRgba, int kW>
 __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, int32_t pose_z, uint8_t *fb,
-                                         uint32_t *rgba, uint32_t cmap_s, uint32_t pal_s, int x, int lane,
+                                         uint32_t *rgba, uint32_t pal_s, int x, int lane,
                                          const SegFrame *wl, const uint32_t *ml, int count) {
     // everything arrives by value (or points at kernel parameters): taking the address of the solid pass's
     // register-resident context would force it into local memory
     RasterCtx c;
-    c.sc = &sc; c.cmap_s = cmap_s; c.pal_s = pal_s; c.fb = fb; c.rgba = rgba;
+    c.sc = &sc; c.pal_s = pal_s; c.fb = fb; c.rgba = rgba;
     c.W = vw.W; c.H = vw.H; c.x = x; c.lane = lane;
     const int Wc = kW ? kW : c.W;
     for (int e = count - 1; e >= 0; e--) {
@@ -554,18 +555,21 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
         int y1 = __reduce_max_sync(kFull, act ? yb : 0);
         if (y0 >= y1) continue;
         const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
-        const uint8_t *px = sc.texels + T.texel_off + col;
+        // colour from this lane's pre-lit plane (layout: tex_interleaved), opacity from the blob's row-major plane
+        const bool inter = tex_interleaved(T);
+        const uint8_t *px = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off + (inter ? 4u * col : col);
+        const uint32_t w4 = 4u * T.w;
         const bool has_mask = T.mask_off != 0xFFFFFFFFu;
         const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
         const int32_t tstep = iscale >> 4;
-        const uint32_t cm = c.cmap_s + 256u * (uint32_t)row;
         uint32_t t = (uint32_t)wall_tbase(tA, hA, pose_z, c.H, iscale) + (uint32_t)y0 * (uint32_t)tstep;
         uint8_t *p8 = c.fb + (size_t)y0 * Wc;
         uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
+#pragma unroll 2
         for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
-            uint32_t idx = wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w;
-            bool on = y >= ya && y < yb && (!has_mask || mk[idx] != 0);
-            put_px<kRgba>(c, p8, p32, on, lds_u8(cm + px[idx]));
+            const uint32_t r = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
+            bool on = y >= ya && y < yb && (!has_mask || mk[r * T.w] != 0);
+            put_px<kRgba>(c, p8, p32, on, __ldg(px + (inter ? (r >> 2) * w4 + (r & 3u) : r * T.w)));
         }
     }
 }
@@ -575,18 +579,13 @@ __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
                   const SegFrame *__restrict__ work, int stride, int n, int strips,
                   uint8_t *__restrict__ index_fb, uint32_t *__restrict__ rgba_fb) {
-    __shared__ __align__(16) uint8_t s_cmap[32 * 256];
     __shared__ uint32_t s_pal[kRgba ? 256 : 1];
     __shared__ uint4 s_row4[kWarps][32];
     __shared__ uint32_t s_row1[kWarps][32];
-    {   // colormap rows 0..31 (and the palette) into shared memory, 128-bit loads
-        const uint4 *src = reinterpret_cast<const uint4 *>(sc.colormap);
-        uint4 *dst = reinterpret_cast<uint4 *>(s_cmap);
-        for (int i = threadIdx.x; i < 32 * 256 / 16; i += blockDim.x) dst[i] = src[i];
-        if (kRgba)
-            for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pal[i] = sc.palette[i];
+    if (kRgba) {   // the palette into shared memory (colours come pre-lit from global memory: no colormap here)
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pal[i] = sc.palette[i];
+        __syncthreads();
     }
-    __syncthreads();
 
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -599,7 +598,6 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     const FrameConst fc = frames[frame];
     RasterCtx c;
     c.sc = &sc;
-    c.cmap_s = (uint32_t)__cvta_generic_to_shared(s_cmap);
     c.pal_s = (uint32_t)__cvta_generic_to_shared(s_pal);
     c.row4 = s_row4[threadIdx.x >> 5]; c.row1 = s_row1[threadIdx.x >> 5];
     c.row4_s = (uint32_t)__cvta_generic_to_shared(c.row4);
@@ -675,18 +673,24 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 }
                 yend = cb;
             }
-            // ceiling region [ct, y1)
-            draw_plane_warp<kRgba, kW, kUnroll>(c, fc, vw, ok ? ct : 0, ok ? y1 : 0, fcl, SF.ceil_flat, SF.light, ceil_vis);
-            if (!two) {
-                draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
-            } else {
-                if (S.otop < fcl)
-                    draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? y1 : 0, ok ? y2 : 0, S.texA, S.tA, S.hA, ucol, ce.iscale, row);
-                if (S.obot > ffl)
-                    draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? y3 : 0, ok ? y4 : 0, S.texB, S.tB, S.hB, ucol, ce.iscale, row);
+            // The two flat spans (ceiling [ct, y1), floor [y4, cb)) and the two wall pieces go through ONE inlined
+            // copy of each span routine (loops kept rolled): the routines are large, and the kernel's speed depends
+            // on its hot code staying resident in the instruction cache.
+#pragma unroll 1
+            for (int pz = 0; pz < 2; pz++) {
+                const bool top = pz == 0;
+                draw_plane_warp<kRgba, kW, kUnroll>(c, fc, vw, ok ? (top ? ct : y4) : 0, ok ? (top ? y1 : yend) : 0,
+                                                    top ? fcl : ffl, top ? SF.ceil_flat : SF.floor_flat, SF.light,
+                                                    top ? ceil_vis : floor_vis);
             }
-            // floor region [y4, cb)
-            draw_plane_warp<kRgba, kW, kUnroll>(c, fc, vw, ok ? y4 : 0, ok ? yend : 0, ffl, SF.floor_flat, SF.light, floor_vis);
+#pragma unroll 1
+            for (int pw = 0; pw < 2; pw++) {
+                const bool upper = pw == 0;            // A: upper (two-sided) or the one-sided middle; B: lower
+                if (upper ? (two && !(S.otop < fcl)) : !(two && S.obot > ffl)) continue;
+                draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? (upper ? y1 : y3) : 0, ok ? (upper ? y2 : y4) : 0,
+                                                   upper ? S.texA : S.texB, upper ? S.tA : S.tB, upper ? S.hA : S.hB,
+                                                   ucol, ce.iscale, row);
+            }
             if (ok) {
                 if (!two || y2 >= y3) { ct = H; cb = 0; }
                 else { ct = y2; cb = y3; }
@@ -710,7 +714,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     fill_void_warp<kRgba, kW, kUnroll>(c, inside ? ct : 0, inside ? cb : 0);
     if (kMasked && mcount > 0) {
         __syncwarp();
-        masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.cmap_s, c.pal_s, x, lane, wl, ml, mcount);
+        masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.pal_s, x, lane, wl, ml, mcount);
     }
 }
 
@@ -768,11 +772,11 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
                           uint32_t *d_rgba, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     const int strips = (vw.W + 31) / 32;
-    // Launch shape (tuned on B200, profiles/README.md): 4 warps per CTA and 64 registers/thread, i.e. 8 CTAs =
-    // 32 warps resident per SM (the kernel is latency bound below that; 8- and 16-warp CTAs lose 5-15 % to
-    // intra-CTA imbalance); row loops unrolled x8; the frame width is a compile-time constant for the
-    // benchmark resolution so that the unrolled row stores use immediate offsets.
-    constexpr int kWarps = 4;
+    // Launch shape (tuned on B200, profiles/README.md): ONE warp per CTA and 64 registers/thread, i.e. 32 CTAs =
+    // 32 warps resident per SM.  Strips differ a lot in cost; with several warps per CTA the finished warps' slots
+    // stay empty until the slowest warp of the CTA is done (1-warp CTAs: +10 % over 2 or 4, 8 and 16 lose more).
+    // The frame width is a compile-time constant for the benchmark resolution (immediate store offsets).
+    constexpr int kWarps = 1;
     const long long total_warps = (long long)n * strips;
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
     static const bool generic_w = getenv("B2D_RASTER_GENERIC_W") != nullptr;   // A/B knob for profiles/README.md
@@ -804,6 +808,35 @@ b2d_prelight_kernel(const uint8_t *__restrict__ colormap, const uint8_t *__restr
     }
 }
 }  // namespace
+
+namespace {
+// one CTA per texture: pre-lit copies in the layout tex_interleaved() selects
+__global__ void __launch_bounds__(256)
+b2d_prelight_tex_kernel(const uint8_t *__restrict__ colormap, const uint8_t *__restrict__ texels,
+                        const TexRec *__restrict__ tex, int ntex, uint8_t *__restrict__ dst, size_t stride) {
+    __shared__ uint8_t cm[32 * 256];
+    for (int i = threadIdx.x; i < 32 * 256; i += blockDim.x) cm[i] = colormap[i];
+    __syncthreads();
+    for (int ti = blockIdx.x; ti < ntex; ti += gridDim.x) {
+        const TexRec T = tex[ti];
+        const bool inter = tex_interleaved(T);
+        const uint32_t n = T.w * T.h;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t row = i / T.w, col = i - row * T.w;
+            const uint32_t o = inter ? ((row >> 2) * T.w + col) * 4u + (row & 3u) : i;
+            const uint32_t t = texels[T.texel_off + i];
+            for (int r = 0; r < 32; r++) dst[(size_t)r * stride + T.texel_off + o] = cm[r * 256 + t];
+        }
+    }
+}
+}  // namespace
+
+cudaError_t launch_prelight_textures(const uint8_t *d_colormap, const uint8_t *d_texels, const TexRec *d_tex, int ntex,
+                                     uint8_t *d_dst, size_t stride, cudaStream_t stream) {
+    if (ntex <= 0) return cudaSuccess;
+    b2d_prelight_tex_kernel<<<ntex < 148 * 8 ? ntex : 148 * 8, 256, 0, stream>>>(d_colormap, d_texels, d_tex, ntex, d_dst, stride);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_prelight(const uint8_t *d_colormap, const uint8_t *d_src, uint8_t *d_dst, size_t n, size_t stride,
                             cudaStream_t stream) {

@@ -58,6 +58,10 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
 cudaError_t launch_prelight(const uint8_t *d_colormap, const uint8_t *d_src, uint8_t *d_dst, size_t n, size_t stride,
                             cudaStream_t stream);
 
+// pre-lit copy of every texture of the table, in the per-texture layout the raster kernel expects
+cudaError_t launch_prelight_textures(const uint8_t *d_colormap, const uint8_t *d_texels, const TexRec *d_tex, int ntex,
+                                     uint8_t *d_dst, size_t stride, cudaStream_t stream);
+
 cudaError_t launch_palette(const uint32_t *d_palette, const uint8_t *d_index, uint32_t *d_rgba,
                            size_t n_pixels, cudaStream_t stream);
 
