@@ -387,7 +387,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
     if (!visible) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     if (flat == kFlatSky) { draw_sky_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
     if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
-    const uint8_t *px = sc.lit_flats + 4096u * (uint32_t)flat;
+    const uint8_t *px = sc.lit_flats;                   // + per-row plane offset + flat offset (row1) + texel
     const uint32_t habs = plane_habs(h, fc.pose.z);
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
@@ -404,7 +404,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         if (yy < y1) {
             PlaneRow pr = plane_row(habs, sc.yslope[yy], fc, vw, sc.invF);
             c.row4[c.lane] = make_uint4(pr.baseU, pr.stepU, pr.baseV, pr.stepV);
-            c.row1[c.lane] = sc.lit_flat_stride * (uint32_t)light_row(lightb, pr.z8);
+            c.row1[c.lane] = sc.lit_flat_stride * (uint32_t)light_row(lightb, pr.z8) + 4096u * (uint32_t)flat;
         }
         __syncwarp();
         const int rows = min(32, y1 - yc);
@@ -460,8 +460,9 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
         const uint32_t colb = 4u * col, w4 = 4u * T.w, nq = T.h >> 2;
         for (int y = y0; y < y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * tstep) {
             const uint32_t r0 = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
-            const uint32_t b0 = (r0 & 3u) - (uint32_t)((int32_t)t >> 16);
-            const uint32_t b7 = b0 + (uint32_t)((int32_t)(t + 7u * tstep) >> 16);
+            // acc = t with its integer part replaced by r0 & 3: byte index of pixel k = (acc + k*tstep) >> 16
+            const uint32_t acc = (t & 0xFFFFu) | ((r0 & 3u) << 16);
+            const uint32_t b7 = (acc + 7u * tstep) >> 16;
             uint32_t v[kBatch];
             if (__all_sync(kFull, b7 < 8u)) {
                 const uint32_t q0 = r0 >> 2, q1 = (q0 + 1u == nq) ? 0u : q0 + 1u;
@@ -469,8 +470,7 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
                 const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q1 * w4 + colb)));
 #pragma unroll
                 for (int k = 0; k < kBatch; k++) {
-                    const uint32_t bk = b0 + (uint32_t)((int32_t)(t + (uint32_t)k * tstep) >> 16);
-                    v[k] = __byte_perm(w0, w1, bk);
+                    v[k] = __byte_perm(w0, w1, (acc + (uint32_t)k * tstep) >> 16);
                     if (kRgba) v[k] &= 0xFFu;
                 }
             } else {
