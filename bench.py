@@ -254,7 +254,7 @@ def main():
                 "traffic": None if args.rgba else ncu_traffic(), "kernel": "b2d_raster_kernel<%s>" % ("rgba" if args.rgba else "index"),
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": raster_avg_ms,
                 "walk_avg_launch_ms": walk_ms / max(batches, 1), "peak_source": peak_src,
-                "note": "index-only output (no RGBA materialised); the kernel is L1/LSU-wavefront bound, not HBM bound (DESIGN.md 5/6, profiles/README.md)"}
+                "note": "index-only output (no RGBA materialised); the kernel is issue/latency bound at 32 warps/SM, not HBM bound (DESIGN.md 5/6, profiles/README.md)"}
 
     # ------------------------------------------------------------------ end to end (host buffers)
     e2e = None
