@@ -312,14 +312,7 @@ __device__ __forceinline__ void put_px(const RasterCtx &c, uint8_t *p8, uint32_t
     }
 }
 
-// Layout of a texture inside the pre-lit planes.  Heights that are a multiple of 4 (every stock wall texture) are
-// stored **4 rows interleaved**: texel (row, col) lives at ((row >> 2) * w + col) * 4 + (row & 3), so one aligned
-// 32-bit word holds four vertically adjacent texels of a column and the 32 lanes of a warp (adjacent columns) read
-// one 128-byte line.  A wall column that is magnified on screen -- the common case at 1080p -- then needs two word
-// loads for eight rows instead of eight byte loads.  Other heights keep the blob's row-major layout.
-__host__ __device__ __forceinline__ bool tex_interleaved(const TexRec &T) {
-    return (T.h & 3u) == 0u && (T.texel_off & 3u) == 0u && T.h <= 4096u;
-}
+__host__ __device__ __forceinline__ bool tex_interleaved(const TexRec &T) { return b2d::tex_interleaved(T.h, T.texel_off); }
 
 // Rows are produced in batches of kBatch: all texel loads first, then all colormap lookups, then the stores.
 // Issuing the independent loads back to back keeps kBatch of them in flight per warp (the one-row-at-a-time
@@ -457,20 +450,20 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
         // With r0 the row of the first pixel, pixel k reads byte (r0 & 3) + u_k - u_0 of the 8 bytes made of row
         // quad r0 >> 2 and the next one (wrapping at h, a multiple of 4).  If that byte index stays below 8 for
         // every lane -- the column is magnified -- two aligned word loads serve the whole batch.
-        const uint32_t colb = 4u * col, w4 = 4u * T.w, nq = T.h >> 2;
+        const uint32_t colb = 4u * col, w4 = 4u * T.w;
         for (int y = y0; y < y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * tstep) {
             const uint32_t r0 = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
             // acc = t with its integer part replaced by r0 & 3: byte index of pixel k = (acc + k*tstep) >> 16
-            const uint32_t acc = (t & 0xFFFFu) | ((r0 & 3u) << 16);
+            const uint32_t acc = wall_acc(t, r0);
             const uint32_t b7 = (acc + 7u * tstep) >> 16;
             uint32_t v[kBatch];
             if (__all_sync(kFull, b7 < 8u)) {
-                const uint32_t q0 = r0 >> 2, q1 = (q0 + 1u == nq) ? 0u : q0 + 1u;
+                const uint32_t q0 = r0 >> 2, q1 = next_quad(q0, T.h);
                 const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
                 const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q1 * w4 + colb)));
 #pragma unroll
                 for (int k = 0; k < kBatch; k++) {
-                    v[k] = __byte_perm(w0, w1, (acc + (uint32_t)k * tstep) >> 16);
+                    v[k] = pick_byte(w0, w1, (acc + (uint32_t)k * tstep) >> 16);
                     if (kRgba) v[k] &= 0xFFu;
                 }
             } else {
@@ -823,7 +816,7 @@ b2d_prelight_tex_kernel(const uint8_t *__restrict__ colormap, const uint8_t *__r
         const uint32_t n = T.w * T.h;
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
             const uint32_t row = i / T.w, col = i - row * T.w;
-            const uint32_t o = inter ? ((row >> 2) * T.w + col) * 4u + (row & 3u) : i;
+            const uint32_t o = lit_index(inter, T.w, row, col);
             const uint32_t t = texels[T.texel_off + i];
             for (int r = 0; r < 32; r++) dst[(size_t)r * stride + T.texel_off + o] = cm[r * 256 + t];
         }

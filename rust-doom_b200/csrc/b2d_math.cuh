@@ -290,6 +290,29 @@ B2D_HD uint32_t wall_row(int32_t t, uint32_t h, uint32_t hmagic, uint32_t hbias)
     return n - q * h;
 }
 
+// ---- pre-lit texel planes (product-side data layout; results are the same bytes as colormap[row][texel]) -------
+// Layout of a texture inside a pre-lit plane.  Heights that are a multiple of 4 (every stock wall texture) are
+// stored **4 rows interleaved**: texel (row, col) lives at ((row >> 2) * w + col) * 4 + (row & 3), so one aligned
+// 32-bit word holds four vertically adjacent texels of a column and the 32 lanes of a warp (adjacent columns) read
+// one 128-byte line.  A wall column that is magnified on screen -- the common case at 1080p -- then needs two word
+// loads for eight rows instead of eight byte loads.  Other heights keep the blob's row-major layout.
+B2D_HD bool tex_interleaved(uint32_t h, uint32_t texel_off) { return (h & 3u) == 0u && (texel_off & 3u) == 0u && h <= 4096u; }
+B2D_HD uint32_t lit_index(bool inter, uint32_t w, uint32_t row, uint32_t col) {
+    return inter ? ((row >> 2) * w + col) * 4u + (row & 3u) : row * w + col;
+}
+// Word path of a batch of rows t, t + tstep, ...: `acc` is t with its integer part replaced by (first row & 3);
+// pixel k of the batch reads byte (acc + k * tstep) >> 16 of the 8 bytes {row quad r0 >> 2, next row quad}.
+B2D_HD uint32_t wall_acc(uint32_t t, uint32_t r0) { return (t & 0xFFFFu) | ((r0 & 3u) << 16); }
+B2D_HD uint32_t next_quad(uint32_t q0, uint32_t h) { return q0 + 1u == (h >> 2) ? 0u : q0 + 1u; }
+// the byte PRMT selects for a selector below 8 (bytes 0-3 from lo, 4-7 from hi)
+B2D_HD uint32_t pick_byte(uint32_t lo, uint32_t hi, uint32_t sel) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(lo, hi, sel);
+#else
+    return ((sel & 4u) ? hi : lo) >> (8u * (sel & 3u)) & 0xFFu;
+#endif
+}
+
 // sky: column from yaw + screen x (one texture width per NDC unit, 8 widths per turn); row mirrored
 // below the horizon.
 B2D_HD uint32_t sky_u32(int x, const View &vw, uint32_t angle) {

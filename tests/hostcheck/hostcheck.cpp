@@ -25,6 +25,8 @@ struct HostScene {
     const MidRec *mids;
     const SpriteRec *sprites;
     const uint8_t *texels, *flats, *colormap;
+    const uint8_t *lit_texels, *lit_flats;      // host restatement of the b2d_prelight kernels (see build_lit)
+    uint32_t lit_texel_stride, lit_flat_stride;
     int nverts, nnodes, nss, nsegs, ntex, nflats, sky_tex, nmids, nsprites;
     uint32_t root;
 };
@@ -51,6 +53,30 @@ HostScene bind(const uint8_t *blob) {
     s.sky_tex = (int32_t)h[H_SKY_TEX];
     s.root = h[H_ROOT];
     return s;
+}
+
+// The pre-lit planes the raster kernel reads (b2d_prelight_tex_kernel / b2d_prelight_kernel), built on the host with
+// the same layout helpers (b2d_math.cuh): lit[r * stride + off + lit_index(...)] = colormap[r][texel].
+struct LitPlanes { std::vector<uint8_t> texels, flats; };
+void build_lit(HostScene &sc, LitPlanes &lp) {
+    const uint32_t *h = sc.hdr;
+    const size_t tstride = (h[H_TEXEL_BYTES] + 255u) & ~(size_t)255, fstride = (size_t)sc.nflats * 4096u;
+    lp.texels.assign(32 * tstride + 256, 0);
+    lp.flats.assign(32 * fstride + 256, 0);
+    for (int ti = 0; ti < sc.ntex; ti++) {
+        const TexRec &T = sc.tex[ti];
+        const bool inter = tex_interleaved(T.h, T.texel_off);
+        for (uint32_t row = 0; row < T.h; row++)
+            for (uint32_t col = 0; col < T.w; col++) {
+                const uint32_t t = sc.texels[T.texel_off + row * T.w + col];
+                for (int r = 0; r < 32; r++)
+                    lp.texels[(size_t)r * tstride + T.texel_off + lit_index(inter, T.w, row, col)] = sc.colormap[256 * r + t];
+            }
+    }
+    for (size_t i = 0; i < fstride; i++)
+        for (int r = 0; r < 32; r++) lp.flats[(size_t)r * fstride + i] = sc.colormap[256 * r + sc.flats[i]];
+    sc.lit_texels = lp.texels.data(); sc.lit_flats = lp.flats.data();
+    sc.lit_texel_stride = (uint32_t)tstride; sc.lit_flat_stride = (uint32_t)fstride;
 }
 
 struct Range { int lo = 0, hi = -1; bool vis = false, solid = false; };
@@ -174,10 +200,11 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
     auto draw_sky = [&](int x, const Lane &ln, int ya, int yb) {
         if (sc.sky_tex < 0) { fill_void(x, ya, yb); return; }
         const TexRec &T = sc.tex[sc.sky_tex];
-        const uint8_t *px = sc.texels + T.texel_off;
+        const bool inter = tex_interleaved(T.h, T.texel_off);
+        const uint8_t *px = sc.lit_texels + T.texel_off;                       // light row 0
         for (int y = ya; y < yb; y++) {
             int v = sky_row(y, H, (int32_t)T.h);
-            put(x, y, sc.colormap[px[(uint32_t)v * T.w + ln.skycol]]);
+            put(x, y, px[lit_index(inter, T.w, (uint32_t)v, ln.skycol)]);
         }
     };
     auto draw_plane = [&](int x, const Lane &ln, int ya, int yb, int32_t h, int32_t flat, int lightb, bool visible) {
@@ -185,27 +212,48 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
         if (!visible) { fill_void(x, ya, yb); return; }
         if (flat == kFlatSky) { draw_sky(x, ln, ya, yb); return; }
         if (flat < 0 || flat >= sc.nflats) { fill_void(x, ya, yb); return; }
-        const uint8_t *px = sc.flats + 4096u * (uint32_t)flat;
+        const uint8_t *px = sc.lit_flats;
         uint32_t habs = plane_habs(h, fc.pose.z);
         for (int y = ya; y < yb; y++) {
             PlaneRow pr = plane_row(habs, yslope[(size_t)y], fc, vw, invF);
-            const uint8_t *cm = sc.colormap + 256 * light_row(lightb, pr.z8);
+            const uint32_t rowoff = sc.lit_flat_stride * (uint32_t)light_row(lightb, pr.z8) + 4096u * (uint32_t)flat;
             uint32_t U = pr.baseU + (uint32_t)x * pr.stepU, V = pr.baseV + (uint32_t)x * pr.stepV;
-            put(x, y, cm[px[flat_index(U, V)]]);
+            put(x, y, px[rowoff + flat_index(U, V)]);
         }
     };
     auto draw_wall = [&](int x, int ya, int yb, int32_t tex, int32_t tA, int32_t hA, int32_t ucol, int32_t iscale, int row) {
         if (ya >= yb) return;
         if (tex < 0 || tex >= sc.ntex) { fill_void(x, ya, yb); return; }
         const TexRec &T = sc.tex[tex];
-        const uint8_t *px = sc.texels + T.texel_off;
-        int32_t col = floormod32(ucol, (int32_t)T.w);
-        int32_t tbase = wall_tbase(tA, hA, fc.pose.z, H, iscale), tstep = iscale >> 4;
-        const uint8_t *cm = sc.colormap + 256 * row;
-        for (int y = ya; y < yb; y++) {
-            int32_t t = tbase + y * tstep;
-            uint32_t v = wall_row(t, T.h, T.hmagic, T.hbias);
-            put(x, y, cm[px[v * T.w + (uint32_t)col]]);
+        const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
+        const uint8_t *pl = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off;
+        const uint32_t tstep = (uint32_t)(iscale >> 4);
+        uint32_t t = (uint32_t)wall_tbase(tA, hA, fc.pose.z, H, iscale) + (uint32_t)ya * tstep;
+        if (!tex_interleaved(T.h, T.texel_off)) {
+            for (int y = ya; y < yb; y++, t += tstep) put(x, y, pl[wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w + col]);
+            return;
+        }
+        // batches of 8 rows as in draw_wall_warp: two aligned words + byte pick when the 8 rows stay inside two
+        // consecutive row quads, eight byte fetches otherwise (the kernel decides per warp, here per lane: both
+        // forms must give the same bytes, which is what the comparison with the oracle checks)
+        const uint32_t colb = 4u * col, w4 = 4u * T.w;
+        for (int y = ya; y < yb; y += 8, t += 8u * tstep) {
+            const uint32_t r0 = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
+            const uint32_t acc = wall_acc(t, r0);
+            uint32_t v[8];
+            if (((acc + 7u * tstep) >> 16) < 8u) {
+                const uint32_t q0 = r0 >> 2, q1 = next_quad(q0, T.h);
+                uint32_t w0, w1;
+                std::memcpy(&w0, pl + (q0 * w4 + colb), 4);
+                std::memcpy(&w1, pl + (q1 * w4 + colb), 4);
+                for (uint32_t k = 0; k < 8; k++) v[k] = pick_byte(w0, w1, (acc + k * tstep) >> 16) & 0xFFu;
+            } else {
+                for (uint32_t k = 0; k < 8; k++) {
+                    const uint32_t rk = wall_row((int32_t)(t + k * tstep), T.h, T.hmagic, T.hbias);
+                    v[k] = pl[(rk >> 2) * w4 + colb + (rk & 3u)];
+                }
+            }
+            for (int k = 0; k < 8 && y + k < yb; k++) put(x, y + k, (uint8_t)v[k]);
         }
     };
 
@@ -331,15 +379,15 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 if (tex < 0 || tex >= sc.ntex) continue;
                 const TexRec &T = sc.tex[tex];
                 uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
-                const uint8_t *px = sc.texels + T.texel_off + col;
+                const bool inter = tex_interleaved(T.h, T.texel_off);
+                const uint8_t *px = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off;
                 const bool has_mask = T.mask_off != 0xFFFFFFFFu;
                 const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
                 int32_t tbase = wall_tbase(tA, hA, fc.pose.z, H, iscale), tstep = iscale >> 4;
-                const uint8_t *cm = sc.colormap + 256 * row;
                 for (int y = ya; y < yb; y++) {
-                    uint32_t idx = wall_row(tbase + y * tstep, T.h, T.hmagic, T.hbias) * T.w;
-                    if (has_mask && !mk[idx]) continue;
-                    put(x, y, cm[px[idx]]);
+                    const uint32_t r = wall_row(tbase + y * tstep, T.h, T.hmagic, T.hbias);
+                    if (has_mask && !mk[r * T.w]) continue;
+                    put(x, y, px[lit_index(inter, T.w, r, col)]);
                 }
             }
         }
@@ -351,6 +399,8 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
 static int render_impl(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
                        int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics) {
     HostScene sc = bind(blob);
+    LitPlanes lit;
+    build_lit(sc, lit);                // from the blob's own table: set_time only re-points records
     // the product's time handling: the three time-dependent tables are rebuilt by scene_at_time (b2d_scene.hpp)
     // exactly as b2d_renderer_set_time does before it uploads them
     std::vector<TexRec> tex_t((size_t)sc.ntex);
@@ -406,6 +456,8 @@ extern "C" void hostcheck_sincos(uint32_t angle, int32_t *c, int32_t *s) { sinco
 extern "C" int hostcheck_stats(const uint8_t *blob, const View *vw, const Pose *poses, int n, int strip_width,
                                long long *out4) {
     HostScene sc = bind(blob);
+    LitPlanes lit;
+    build_lit(sc, lit);
     std::vector<uint32_t> yslope((size_t)vw->H);
     for (int y = 0; y < vw->H; y++) yslope[(size_t)y] = yslope_entry(y, *vw);
     uint32_t invF = (uint32_t)(4294967296ULL / (uint64_t)vw->F);
