@@ -18,6 +18,32 @@ import time
 import numpy as np
 
 
+def encode_ppm(rgb: np.ndarray) -> bytes:
+    """Binary PPM (P6) of an (H, W, 3) uint8 image."""
+    h, w, _ = rgb.shape
+    return b"P6\n%d %d\n255\n" % (w, h) + np.ascontiguousarray(rgb).tobytes()
+
+
+def encode_png(rgb: np.ndarray) -> bytes:
+    """Minimal PNG (8-bit RGB, one IDAT, filter 0) of an (H, W, 3) uint8 image."""
+    import struct
+    import zlib
+    h, w, _ = rgb.shape
+    raw = np.zeros((h, 1 + 3 * w), dtype=np.uint8)
+    raw[:, 1:] = np.ascontiguousarray(rgb).reshape(h, 3 * w)
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0))
+            + chunk(b"IDAT", zlib.compress(raw.tobytes(), 6)) + chunk(b"IEND", b""))
+
+
+def rgba_to_rgb(rgba_frame: np.ndarray) -> np.ndarray:
+    """(H, W) uint32 R | G<<8 | B<<16 | A<<24 (the library's RGBA8) -> (H, W, 3) uint8."""
+    h, w = rgba_frame.shape
+    return rgba_frame.view(np.uint8).reshape(h, w, 4)[:, :, :3]
+
+
 def main(argv=None) -> int:
     import rust_doom_b200 as b2d
     from rust_doom_b200 import poses as P
@@ -30,7 +56,12 @@ def main(argv=None) -> int:
     ap.add_argument("-l", "--level", type=int, default=0)
     ap.add_argument("-f", "--fov", type=float, default=65.0)
     ap.add_argument("--poses", type=int, default=1, help="1 = spawn pose, N>1 = N-pose fly-through")
-    ap.add_argument("--dump", default=None, help="write the first frame as a binary PPM")
+    ap.add_argument("--dump", default=None, help="write the first frame (.png, otherwise binary PPM)")
+    ap.add_argument("--stream", default=None,
+                    help="write every frame, in order, as concatenated binary PPMs (e.g. ffmpeg -f image2pipe -i FILE)")
+    ap.add_argument("--tics-per-frame", type=int, default=0,
+                    help="advance the level time by this many tics (1/35 s) per frame: animated flats / walls, "
+                         "scrolling walls, light effects")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("command", nargs="?", choices=["check", "list-levels"], default=None)
     args = ap.parse_args(argv)
@@ -60,14 +91,23 @@ def main(argv=None) -> int:
             poses = P.flythrough_poses(scene, args.poses, 2)
         r = b2d.Renderer(scene, view, device=args.device, max_batch=min(len(poses), 256))
         t0 = time.perf_counter()
-        idx, rgba = r.render(poses, rgba=True)
+        if args.tics_per_frame > 0:          # time is a per-batch input: one batch per frame
+            rgba = np.empty((len(poses), h, w), dtype=np.uint32)
+            for i in range(len(poses)):
+                r.set_time(i * args.tics_per_frame)
+                rgba[i] = r.render(poses[i:i + 1], rgba=True)[1][0]
+        else:
+            rgba = r.render(poses, rgba=True)[1]
         dt = time.perf_counter() - t0
         print("rendered %d frame(s) %dx%d in %.2f ms (%.0f frames/s end to end)" % (len(poses), w, h, dt * 1e3, len(poses) / dt))
         if args.dump:
-            rgb = rgba[0].view(np.uint8).reshape(h, w, 4)[:, :, :3]
+            rgb = rgba_to_rgb(rgba[0])
             with open(args.dump, "wb") as f:
-                f.write(b"P6\n%d %d\n255\n" % (w, h))
-                f.write(np.ascontiguousarray(rgb).tobytes())
+                f.write(encode_png(rgb) if args.dump.lower().endswith(".png") else encode_ppm(rgb))
+        if args.stream:
+            with open(args.stream, "wb") as f:
+                for i in range(len(rgba)):
+                    f.write(encode_ppm(rgba_to_rgb(rgba[i])))
         return 0
     except b2d.B2dError as e:
         print("Fatal error: %s" % e, file=sys.stderr)

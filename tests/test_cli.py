@@ -1,0 +1,59 @@
+"""Host-side CLI pieces (src/main.rs:17-124 mirror): flag parsing, level listing, image writers."""
+import struct
+import zlib
+
+import numpy as np
+import pytest
+
+from rust_doom_b200 import cli
+
+
+def test_list_levels_and_check_on_synthetic_iwad(capsys):
+    assert cli.main(["list-levels"]) == 0
+    out = capsys.readouterr().out.split()
+    assert out[:2] == ["0", "E1M1"]
+    assert cli.main(["check"]) == 0
+    assert "Level 0 (E1M1)" in capsys.readouterr().out
+
+
+def test_bad_resolution_is_an_argument_error(capsys):
+    assert cli.main(["--resolution", "1920by1080", "list-levels"]) == 2
+    assert "WIDTHxHEIGHT" in capsys.readouterr().err
+
+
+def test_missing_iwad_reports_fatal_error(capsys):
+    assert cli.main(["--iwad", "/nonexistent/doom1.wad", "list-levels"]) == 1
+    assert "Fatal error" in capsys.readouterr().err
+
+
+def test_ppm_and_png_writers_roundtrip():
+    rng = np.random.default_rng(3)
+    rgb = rng.integers(0, 256, (5, 7, 3), dtype=np.uint8)
+    rgba = (rgb[:, :, 0].astype(np.uint32) | (rgb[:, :, 1].astype(np.uint32) << 8)
+            | (rgb[:, :, 2].astype(np.uint32) << 16) | np.uint32(0xFF000000))
+    assert np.array_equal(cli.rgba_to_rgb(rgba), rgb)
+    ppm = cli.encode_ppm(rgb)
+    assert ppm.startswith(b"P6\n7 5\n255\n") and ppm[-105:] == rgb.tobytes()
+    png = cli.encode_png(rgb)
+    assert png[:8] == b"\x89PNG\r\n\x1a\n"
+    # parse the chunks back
+    pos, chunks = 8, {}
+    while pos < len(png):
+        n, tag = struct.unpack(">I4s", png[pos:pos + 8])
+        data = png[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", png[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + data) & 0xFFFFFFFF
+        chunks[tag] = data
+        pos += 12 + n
+    assert struct.unpack(">IIBBBBB", chunks[b"IHDR"]) == (7, 5, 8, 2, 0, 0, 0)
+    raw = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), np.uint8).reshape(5, 1 + 21)
+    assert (raw[:, 0] == 0).all() and np.array_equal(raw[:, 1:].reshape(5, 7, 3), rgb)
+
+
+@pytest.mark.gpu
+def test_cli_renders_dump_and_stream(tmp_path, capsys):
+    png, stream = tmp_path / "f.png", tmp_path / "s.ppm"
+    assert cli.main(["--resolution", "320x200", "--poses", "3", "--tics-per-frame", "8",
+                     "--dump", str(png), "--stream", str(stream)]) == 0
+    assert "rendered 3 frame(s) 320x200" in capsys.readouterr().out
+    assert png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
+    assert len(stream.read_bytes()) == 3 * (len(b"P6\n320 200\n255\n") + 320 * 200 * 3)
