@@ -336,7 +336,7 @@ __device__ __forceinline__ void store_batch(const RasterCtx &c, uint8_t *p8, uin
 }
 
 // rows [ya, yb) of this lane's column := void (index 0); lanes with ya >= yb idle
-template <bool kRgba, int kW, int kUnroll>
+template <bool kRgba, int kW>
 __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int yb) {
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
@@ -349,10 +349,10 @@ __device__ __forceinline__ void fill_void_warp(const RasterCtx &c, int ya, int y
     for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) put_px<kRgba>(c, p8, p32, y >= ya && y < yb, 0u);
 }
 
-template <bool kRgba, int kW, int kUnroll>
+template <bool kRgba, int kW>
 __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb) {
     const DeviceScene &sc = *c.sc;
-    if (sc.sky_tex < 0) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
+    if (sc.sky_tex < 0) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
     const TexRec T = sc.tex[sc.sky_tex];
     const bool inter = tex_interleaved(T);
     const uint8_t *px = sc.lit_texels + T.texel_off + (inter ? 4u * c.skycol : c.skycol);   // light row 0
@@ -371,15 +371,15 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
     }
 }
 
-template <bool kRgba, int kW, int kUnroll>
+template <bool kRgba, int kW>
 __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameConst &fc, const View &vw,
                                                 int ya, int yb, int32_t h, int32_t flat, int lightb,
                                                 bool visible) {
     const DeviceScene &sc = *c.sc;
     if (!__any_sync(kFull, ya < yb)) return;
-    if (!visible) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
-    if (flat == kFlatSky) { draw_sky_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
-    if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
+    if (!visible) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
+    if (flat == kFlatSky) { draw_sky_warp<kRgba, kW>(c, ya, yb); return; }
+    if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
     const uint8_t *px = sc.lit_flats;                   // + per-row plane offset + flat offset (row1) + texel
     const uint32_t habs = plane_habs(h, fc.pose.z);
     bool act = ya < yb;
@@ -423,13 +423,13 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
     }
 }
 
-template <bool kRgba, int kW, int kUnroll>
+template <bool kRgba, int kW>
 __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameConst &fc, int ya, int yb,
                                                int32_t tex, int32_t tA, int32_t hA, int32_t ucol,
                                                int32_t iscale, int row) {
     const DeviceScene &sc = *c.sc;
     if (!__any_sync(kFull, ya < yb)) return;
-    if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba, kW, kUnroll>(c, ya, yb); return; }
+    if (tex < 0 || tex >= sc.ntex) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
     const TexRec T = sc.tex[tex];
     bool act = ya < yb;
     const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
@@ -567,7 +567,7 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
     }
 }
 
-template <bool kRgba, int kMinBlocks, int kW, int kUnroll, int kWarps, bool kMasked>
+template <bool kRgba, int kMinBlocks, int kW, int kWarps, bool kMasked>
 __global__ void __launch_bounds__(kWarps * 32, kMinBlocks)
 b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ View vw, const FrameConst *__restrict__ frames,
                   const SegFrame *__restrict__ work, int stride, int n, int strips,
@@ -672,7 +672,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
 #pragma unroll 1
             for (int pz = 0; pz < 2; pz++) {
                 const bool top = pz == 0;
-                draw_plane_warp<kRgba, kW, kUnroll>(c, fc, vw, ok ? (top ? ct : y4) : 0, ok ? (top ? y1 : yend) : 0,
+                draw_plane_warp<kRgba, kW>(c, fc, vw, ok ? (top ? ct : y4) : 0, ok ? (top ? y1 : yend) : 0,
                                                     top ? fcl : ffl, top ? SF.ceil_flat : SF.floor_flat, SF.light,
                                                     top ? ceil_vis : floor_vis);
             }
@@ -680,7 +680,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
             for (int pw = 0; pw < 2; pw++) {
                 const bool upper = pw == 0;            // A: upper (two-sided) or the one-sided middle; B: lower
                 if (upper ? (two && !(S.otop < fcl)) : !(two && S.obot > ffl)) continue;
-                draw_wall_warp<kRgba, kW, kUnroll>(c, fc, ok ? (upper ? y1 : y3) : 0, ok ? (upper ? y2 : y4) : 0,
+                draw_wall_warp<kRgba, kW>(c, fc, ok ? (upper ? y1 : y3) : 0, ok ? (upper ? y2 : y4) : 0,
                                                    upper ? S.texA : S.texB, upper ? S.tA : S.tB, upper ? S.hA : S.hB,
                                                    ucol, ce.iscale, row);
             }
@@ -704,7 +704,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
         }
     }
     // whatever is still open is void
-    fill_void_warp<kRgba, kW, kUnroll>(c, inside ? ct : 0, inside ? cb : 0);
+    fill_void_warp<kRgba, kW>(c, inside ? ct : 0, inside ? cb : 0);
     if (kMasked && mcount > 0) {
         __syncwarp();
         masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.pal_s, x, lane, wl, ml, mcount);
@@ -776,10 +776,10 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     const bool w1920 = vw.W == 1920 && !generic_w;
 #define B2D_RASTER_GO(RGBA, KW) do { \
     if ((sc.nmids > 0 || sc.nsprites > 0) && sc.masked_list) \
-        b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
+        b2d_raster_kernel<RGBA, 32 / kWarps, KW, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); \
     else \
-        b2d_raster_kernel<RGBA, 32 / kWarps, KW, 8, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
+        b2d_raster_kernel<RGBA, 32 / kWarps, KW, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); } while (0)
     if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
     else { if (w1920) B2D_RASTER_GO(false, 1920); else B2D_RASTER_GO(false, 0); }
