@@ -467,10 +467,29 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
                     if (kRgba) v[k] &= 0xFFu;
                 }
             } else {
+                // less magnified: re-anchor after 4 rows -- two word pairs serve the batch as long as each half
+                // stays inside two row quads (up to ~1.3 texture rows per screen row); byte loads otherwise
+                const uint32_t t4 = t + 4u * tstep;
+                const uint32_t r4 = wall_row((int32_t)t4, T.h, T.hmagic, T.hbias);
+                const uint32_t acc4 = wall_acc(t4, r4);
+                if (__all_sync(kFull, ((acc + 3u * tstep) >> 16) < 8u && ((acc4 + 3u * tstep) >> 16) < 8u)) {
+                    const uint32_t q0 = r0 >> 2, q4 = r4 >> 2;
+                    const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
+                    const uint32_t a1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (next_quad(q0, T.h) * w4 + colb)));
+                    const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q4 * w4 + colb)));
+                    const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (next_quad(q4, T.h) * w4 + colb)));
 #pragma unroll
-                for (int k = 0; k < kBatch; k++) {
-                    const uint32_t rk = wall_row((int32_t)(t + (uint32_t)k * tstep), T.h, T.hmagic, T.hbias);
-                    v[k] = __ldg(pl + ((rk >> 2) * w4 + colb + (rk & 3u)));
+                    for (int k = 0; k < 4; k++) {
+                        v[k] = pick_byte(a0, a1, (acc + (uint32_t)k * tstep) >> 16);
+                        v[k + 4] = pick_byte(b0, b1, (acc4 + (uint32_t)k * tstep) >> 16);
+                        if (kRgba) { v[k] &= 0xFFu; v[k + 4] &= 0xFFu; }
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kBatch; k++) {
+                        const uint32_t rk = wall_row((int32_t)(t + (uint32_t)k * tstep), T.h, T.hmagic, T.hbias);
+                        v[k] = __ldg(pl + ((rk >> 2) * w4 + colb + (rk & 3u)));
+                    }
                 }
             }
             // rows past y1 belong to no lane: the predicated form drops them, so there is no tail loop

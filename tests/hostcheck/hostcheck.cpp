@@ -248,9 +248,25 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 std::memcpy(&w1, pl + (q1 * w4 + colb), 4);
                 for (uint32_t k = 0; k < 8; k++) v[k] = pick_byte(w0, w1, (acc + k * tstep) >> 16) & 0xFFu;
             } else {
-                for (uint32_t k = 0; k < 8; k++) {
-                    const uint32_t rk = wall_row((int32_t)(t + k * tstep), T.h, T.hmagic, T.hbias);
-                    v[k] = pl[(rk >> 2) * w4 + colb + (rk & 3u)];
+                const uint32_t t4 = t + 4u * tstep;
+                const uint32_t r4 = wall_row((int32_t)t4, T.h, T.hmagic, T.hbias);
+                const uint32_t acc4 = wall_acc(t4, r4);
+                if (((acc + 3u * tstep) >> 16) < 8u && ((acc4 + 3u * tstep) >> 16) < 8u) {   // two 4-row halves
+                    const uint32_t q0 = r0 >> 2, q4 = r4 >> 2;
+                    uint32_t a0, a1, b0, b1;
+                    std::memcpy(&a0, pl + (q0 * w4 + colb), 4);
+                    std::memcpy(&a1, pl + (next_quad(q0, T.h) * w4 + colb), 4);
+                    std::memcpy(&b0, pl + (q4 * w4 + colb), 4);
+                    std::memcpy(&b1, pl + (next_quad(q4, T.h) * w4 + colb), 4);
+                    for (uint32_t k = 0; k < 4; k++) {
+                        v[k] = pick_byte(a0, a1, (acc + k * tstep) >> 16) & 0xFFu;
+                        v[k + 4] = pick_byte(b0, b1, (acc4 + k * tstep) >> 16) & 0xFFu;
+                    }
+                } else {
+                    for (uint32_t k = 0; k < 8; k++) {
+                        const uint32_t rk = wall_row((int32_t)(t + k * tstep), T.h, T.hmagic, T.hbias);
+                        v[k] = pl[(rk >> 2) * w4 + colb + (rk & 3u)];
+                    }
                 }
             }
             for (int k = 0; k < 8 && y + k < yb; k++) put(x, y + k, (uint8_t)v[k]);
