@@ -246,7 +246,7 @@ class TexDef:
     patches: List[Tuple[int, int, str]]  # (origin_x, origin_y, patch name)
 
 
-def make_graphics(rng: SplitMix64, masked: bool = False, anim: bool = False):
+def make_graphics(rng: SplitMix64, masked: bool = False, anim: bool = False, odd: bool = False):
     """Returns (patch lumps {name: bytes} in order, texture defs, flats {name: 4096 bytes})."""
     patches: Dict[str, bytes] = {}
 
@@ -303,6 +303,14 @@ def make_graphics(rng: SplitMix64, masked: bool = False, anim: bool = False):
         for k in range(1, 3):
             add("WFIRE%d" % k, _img_gradient(rng, 128, 128, 2 + 10 * (k - 1)))
             tex.append(TexDef("FIREBLU%d" % k, 128, 128, [(0, 0, "WFIRE%d" % k)]))
+
+    if odd:
+        # sizes no stock texture has: heights that are not a multiple of 4, widths that are not a power of two
+        add("WODD1", _img_bricks(rng, 64, 70, 3, 10, 7))
+        add("WODD2", _img_gradient(rng, 48, 33, 11))
+        add("WODD3", _img_panels(rng, 100, 126, 7, 5))
+        tex += [TexDef("ODD70", 64, 70, [(0, 0, "WODD1")]), TexDef("ODD33", 48, 33, [(0, 0, "WODD2")]),
+                TexDef("ODD126", 100, 126, [(0, 0, "WODD3")])]
 
     flats: Dict[str, bytes] = {}
 
@@ -412,6 +420,7 @@ class SynthConfig:
     mid_pct: int = 0            # % of two-sided lines that carry a masked middle texture (0 keeps legacy bytes)
     thing_pct: int = 0          # % of plain room cells that get decoration things + sprite lumps (0 = legacy)
     anim: bool = False          # animated flats/walls (NUKAGE1-3, SFALL1-4, FIREBLU1-2) + scrolling lines (0x30)
+    odd_tex: bool = False       # wall textures with odd heights / non power-of-two widths (ODD70, ODD33, ODD126)
 
 
 # inner convex polygons, CCW, in cell-local coordinates for a 256 cell (scaled by cell/256);
@@ -526,6 +535,8 @@ class LevelBuilder:
         def wall_tex():
             if cfg.anim and rng.chance(1, 5):
                 return rng.pick(["SFALL2", "SFALL1", "FIREBLU1", "FIREBLU2", "SFALL4"])
+            if cfg.odd_tex and rng.chance(1, 3):
+                return rng.pick(["ODD70", "ODD33", "ODD126"])
             return rng.pick(WALL_TEX)
 
         def one_sided(cellkey, p, q, sector):
@@ -904,7 +915,7 @@ def build_iwad(seed: int = 1, maps: Sequence[str] = ("E1M1",), cfg: Optional[Syn
     rng = SplitMix64(seed)
     playpal = make_playpal()
     colormap = make_colormap(playpal)
-    patches, tex, flats = make_graphics(rng, masked=cfg.mid_pct > 0, anim=cfg.anim)
+    patches, tex, flats = make_graphics(rng, masked=cfg.mid_pct > 0, anim=cfg.anim, odd=cfg.odd_tex)
     pnames, texture1 = make_pnames_texture1(list(patches.keys()), tex)
     lumps: List[Tuple[str, bytes]] = [("PLAYPAL", playpal), ("COLORMAP", colormap)]
     for k, name in enumerate(maps):

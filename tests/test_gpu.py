@@ -348,3 +348,14 @@ def test_gpu_animated_and_scrolling(b2d):
     r2 = b2d.Renderer(sc, b2d.make_view(1920, 1080), max_batch=4)
     r2.set_time(1001)
     _assert_same(render.render(sc.blob, render.make_view(1920, 1080), poses[:4], threads=8, tics=1001), r2.render(poses[:4]), "1080p")
+
+
+def test_gpu_odd_texture_sizes(b2d):
+    """Wall textures whose height is not a multiple of 4 / whose width is not a power of two (row-major pre-lit
+    layout, magic floor-mod) mixed with 4-row interleaved ones."""
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(4, ("E1M1",), cfg=synthwad.SynthConfig(odd_tex=True, mid_pct=20))), 0)
+    poses = sample_poses(b2d, sc, 32, 61)
+    for (w, h, n) in ((320, 200, 32), (1920, 1080, 6), (1000, 700, 6)):
+        r = b2d.Renderer(sc, b2d.make_view(w, h), max_batch=32)
+        _assert_same(render.render(sc.blob, render.make_view(w, h), poses[:n], threads=8), r.render(poses[:n]), "odd %dx%d" % (w, h))

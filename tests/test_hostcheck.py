@@ -159,3 +159,17 @@ def test_light_effects_product_equals_oracle_over_time(b2d, hostcheck):
             seen |= set(map(tuple, np.stack([np.arange(n), out], 1)[out >= 0].tolist()))
         assert len(seen) > 3 * int((rec[:, 0] != 0).sum()), "lights never changed over time"
     assert kinds == {0, 1, 2, 3}, kinds
+
+
+def test_hostcheck_odd_texture_sizes(b2d, hostcheck):
+    """Heights that are not a multiple of 4 and widths that are not a power of two: the row-major layout of the
+    pre-lit planes and the magic-reciprocal floor-mod, next to the 4-row interleaved textures of the same level."""
+    from oracle import scene as S
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(4, ("E1M1",), cfg=synthwad.SynthConfig(odd_tex=True, mid_pct=20))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    h = S.header(sc.blob)
+    tex = np.frombuffer(sc.blob, dtype="<u4", count=8 * h[S.H_NTEX], offset=h[S.H_OFF_TEX]).reshape(-1, 8)
+    assert {70, 33, 126} <= set(tex[:, 2].tolist())
+    _compare(b2d, hostcheck, sc, 320, 200, 32, 61)
+    _compare(b2d, hostcheck, sc, 1920, 1080, 2, 62)
