@@ -310,12 +310,12 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.palette = reinterpret_cast<const uint32_t *>(r->d_blob + h[H_OFF_PALETTE]);
     {   // pre-lit texel and flat planes: 32 x (texel bytes + flat bytes)
         const size_t tstride = (h[H_TEXEL_BYTES] + 255u) & ~(size_t)255, fstride = (size_t)h[H_NFLATS] * 4096u;
-        if (tstride * 32 > 0xFFFFFFFFull || fstride * 32 > 0xFFFFFFFFull) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level textures too large"); }
-        CUR(cudaMalloc(&r->d_lit, 32 * (tstride + fstride) + 256));
+        if (tstride * 33 > 0xFFFFFFFFull || fstride * 32 > 0xFFFFFFFFull) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level textures too large"); }
+        CUR(cudaMalloc(&r->d_lit, 33 * tstride + 32 * fstride + 256));    // plane 32 of the texels: opacity
         CUR(launch_prelight_textures(d.colormap, d.texels, d.tex, (int)h[H_NTEX], r->d_lit, tstride, nullptr));
-        CUR(launch_prelight(d.colormap, d.flats, r->d_lit + 32 * tstride, fstride, fstride, nullptr));
+        CUR(launch_prelight(d.colormap, d.flats, r->d_lit + 33 * tstride, fstride, fstride, nullptr));
         CUR(cudaDeviceSynchronize());
-        d.lit_texels = r->d_lit; d.lit_flats = r->d_lit + 32 * tstride;
+        d.lit_texels = r->d_lit; d.lit_flats = r->d_lit + 33 * tstride;
         d.lit_texel_stride = (uint32_t)tstride; d.lit_flat_stride = (uint32_t)fstride;
     }
     d.yslope = r->d_yslope;

@@ -567,21 +567,62 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
         int y1 = __reduce_max_sync(kFull, act ? yb : 0);
         if (y0 >= y1) continue;
         const uint32_t col = (uint32_t)floormod32(ucol, (int32_t)T.w);
-        // colour from this lane's pre-lit plane (layout: tex_interleaved), opacity from the blob's row-major plane
+        // colour from this lane's pre-lit plane, opacity from plane 32 (same layout, written by the pre-light kernel
+        // for textures with holes)
         const bool inter = tex_interleaved(T);
-        const uint8_t *px = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off + (inter ? 4u * col : col);
-        const uint32_t w4 = 4u * T.w;
         const bool has_mask = T.mask_off != 0xFFFFFFFFu;
-        const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
-        const int32_t tstep = iscale >> 4;
-        uint32_t t = (uint32_t)wall_tbase(tA, hA, pose_z, c.H, iscale) + (uint32_t)y0 * (uint32_t)tstep;
+        const uint8_t *pl = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off;
+        const uint8_t *pm = sc.lit_texels + (size_t)32 * sc.lit_texel_stride + T.texel_off;
+        const uint32_t tstep = (uint32_t)(iscale >> 4);
+        uint32_t t = (uint32_t)wall_tbase(tA, hA, pose_z, c.H, iscale) + (uint32_t)y0 * tstep;
         uint8_t *p8 = c.fb + (size_t)y0 * Wc;
         uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
-#pragma unroll 2
-        for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += (uint32_t)tstep) {
-            const uint32_t r = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
-            bool on = y >= ya && y < yb && (!has_mask || mk[r * T.w] != 0);
-            put_px<kRgba>(c, p8, p32, on, __ldg(px + (inter ? (r >> 2) * w4 + (r & 3u) : r * T.w)));
+        const uint32_t len = (uint32_t)(yb - ya);
+        if (inter) {
+            // batches of 8 rows as in draw_wall_warp: magnified columns (sprites nearly always are) read two colour
+            // words and two opacity words per batch
+            const uint32_t colb = 4u * col, w4 = 4u * T.w;
+#pragma unroll 1
+            for (int y = y0; y < y1; y += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc, t += (uint32_t)kBatch * tstep) {
+                const uint32_t r0 = wall_row((int32_t)t, T.h, T.hmagic, T.hbias);
+                const uint32_t acc = wall_acc(t, r0);
+                const uint32_t d = (uint32_t)(y - ya);
+                uint32_t v[kBatch], o[kBatch];
+                if (__all_sync(kFull, ((acc + 7u * tstep) >> 16) < 8u)) {
+                    const uint32_t o0 = (r0 >> 2) * w4 + colb, o1 = next_quad(r0 >> 2, T.h) * w4 + colb;
+                    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(pl + o0));
+                    const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(pl + o1));
+                    uint32_t m0 = 0x01010101u, m1 = 0x01010101u;
+                    if (has_mask) {
+                        m0 = __ldg(reinterpret_cast<const uint32_t *>(pm + o0));
+                        m1 = __ldg(reinterpret_cast<const uint32_t *>(pm + o1));
+                    }
+#pragma unroll
+                    for (int k = 0; k < kBatch; k++) {
+                        const uint32_t bk = (acc + (uint32_t)k * tstep) >> 16;
+                        v[k] = pick_byte(w0, w1, bk) & 0xFFu;
+                        o[k] = pick_byte(m0, m1, bk) & 0xFFu;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kBatch; k++) {
+                        const uint32_t rk = wall_row((int32_t)(t + (uint32_t)k * tstep), T.h, T.hmagic, T.hbias);
+                        const uint32_t off = (rk >> 2) * w4 + colb + (rk & 3u);
+                        v[k] = __ldg(pl + off);
+                        o[k] = has_mask ? (uint32_t)__ldg(pm + off) : 1u;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < kBatch; k++)
+                    put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, d + (uint32_t)k < len && o[k] != 0u, v[k]);
+            }
+        } else {
+#pragma unroll 1
+            for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += tstep) {
+                const uint32_t off = wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w + col;
+                const bool on = (uint32_t)(y - ya) < len && (!has_mask || __ldg(pm + off) != 0);
+                put_px<kRgba>(c, p8, p32, on, __ldg(pl + off));
+            }
         }
     }
 }
@@ -838,6 +879,7 @@ b2d_prelight_tex_kernel(const uint8_t *__restrict__ colormap, const uint8_t *__r
             const uint32_t o = lit_index(inter, T.w, row, col);
             const uint32_t t = texels[T.texel_off + i];
             for (int r = 0; r < 32; r++) dst[(size_t)r * stride + T.texel_off + o] = cm[r * 256 + t];
+            if (T.mask_off != 0xFFFFFFFFu) dst[(size_t)32 * stride + T.texel_off + o] = texels[T.mask_off + i];   // opacity
         }
     }
 }

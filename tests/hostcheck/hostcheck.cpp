@@ -61,7 +61,7 @@ struct LitPlanes { std::vector<uint8_t> texels, flats; };
 void build_lit(HostScene &sc, LitPlanes &lp) {
     const uint32_t *h = sc.hdr;
     const size_t tstride = (h[H_TEXEL_BYTES] + 255u) & ~(size_t)255, fstride = (size_t)sc.nflats * 4096u;
-    lp.texels.assign(32 * tstride + 256, 0);
+    lp.texels.assign(33 * tstride + 256, 0);          // plane 32: opacity of textures with holes
     lp.flats.assign(32 * fstride + 256, 0);
     for (int ti = 0; ti < sc.ntex; ti++) {
         const TexRec &T = sc.tex[ti];
@@ -71,6 +71,8 @@ void build_lit(HostScene &sc, LitPlanes &lp) {
                 const uint32_t t = sc.texels[T.texel_off + row * T.w + col];
                 for (int r = 0; r < 32; r++)
                     lp.texels[(size_t)r * tstride + T.texel_off + lit_index(inter, T.w, row, col)] = sc.colormap[256 * r + t];
+                if (T.mask_off != 0xFFFFFFFFu)
+                    lp.texels[(size_t)32 * tstride + T.texel_off + lit_index(inter, T.w, row, col)] = sc.texels[T.mask_off + row * T.w + col];
             }
     }
     for (size_t i = 0; i < fstride; i++)
@@ -398,11 +400,11 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 const bool inter = tex_interleaved(T.h, T.texel_off);
                 const uint8_t *px = sc.lit_texels + (size_t)row * sc.lit_texel_stride + T.texel_off;
                 const bool has_mask = T.mask_off != 0xFFFFFFFFu;
-                const uint8_t *mk = sc.texels + (has_mask ? T.mask_off : T.texel_off) + col;
+                const uint8_t *pm = sc.lit_texels + (size_t)32 * sc.lit_texel_stride + T.texel_off;   // opacity plane
                 int32_t tbase = wall_tbase(tA, hA, fc.pose.z, H, iscale), tstep = iscale >> 4;
                 for (int y = ya; y < yb; y++) {
                     const uint32_t r = wall_row(tbase + y * tstep, T.h, T.hmagic, T.hbias);
-                    if (has_mask && !mk[r * T.w]) continue;
+                    if (has_mask && !pm[lit_index(inter, T.w, r, col)]) continue;
                     put(x, y, px[lit_index(inter, T.w, r, col)]);
                 }
             }

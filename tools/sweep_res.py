@@ -25,11 +25,13 @@ def main():
                  ("masked middles only", 1, ("E1M1",), synthwad.SynthConfig(mid_pct=30)),
                  ("sprites only", 1, ("E1M1",), synthwad.SynthConfig(thing_pct=50)),
                  ("animation / light effects only", 1, ("E1M1",), synthwad.SynthConfig(anim=True))]
+    if os.environ.get("B2D_SWEEP_FULL"):       # the content-rich level alone (for ncu captures)
+        cases = cases[1:]
     for name, seed, maps, cfg in cases:
         sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, maps, cfg=cfg)), 0)
         poses = P.flythrough_poses(sc, n, 2)
         dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
-        for (w, h) in (((1920, 1080),) if os.environ.get("B2D_SWEEP_PARTS") else ((320, 200), (1280, 720), (1920, 1080), (3840, 2160))):
+        for (w, h) in (((1920, 1080),) if (os.environ.get("B2D_SWEEP_PARTS") or os.environ.get("B2D_SWEEP_FULL")) else ((320, 200), (1280, 720), (1920, 1080), (3840, 2160))):
             m = n if w < 3000 else n // 4
             r = b2d.Renderer(sc, b2d.make_view(w, h), max_batch=m)
             out = torch.empty((m, h, w), dtype=torch.uint8, device="cuda")
