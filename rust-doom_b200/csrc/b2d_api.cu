@@ -301,7 +301,10 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.masked_list = nullptr;
     if (d.nmids > 0 || d.nsprites > 0) {   // deferred masked-texture lists: one per raster warp of a full batch
         const size_t strips = (size_t)(view->width + 31) / 32;
-        CUR(cudaMalloc(&r->d_masked, sizeof(uint32_t) * 33 * kMaskedCap * strips * (size_t)max_batch));
+        int cap = d.nmids + d.nsprites;
+        cap = cap < 8 ? 8 : (cap > kMaskedCapMax ? kMaskedCapMax : cap);
+        d.masked_cap = cap;
+        CUR(cudaMalloc(&r->d_masked, sizeof(uint32_t) * 33 * (size_t)cap * strips * (size_t)max_batch));
         d.masked_list = r->d_masked;
     }
     d.texels = r->d_blob + h[H_OFF_TEXELS];
@@ -419,7 +422,7 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
         CU(cudaMemset(r->d_status, 0, sizeof(int32_t)));
         return fail(B2D_ERR_INVALID_ARG, status & 1 ? "BSP traversal stack overflow (tree deeper than 128 pending nodes): frames incomplete"
                                             : (status & 4 ? "BSP traversal did not terminate (cyclic node graph): frames incomplete"
-                                              : (status & 8 ? "more than 32 masked middle textures or sprites deferred in one 32-column strip: frames incomplete"
+                                              : (status & 8 ? "more masked middle textures / sprites deferred in one 32-column strip than the renderer holds (min(level total, 128)): frames incomplete"
                                                             : "worklist overflow: frames incomplete")));
     }
     return B2D_OK;

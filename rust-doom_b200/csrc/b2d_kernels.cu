@@ -662,7 +662,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     if (sc.sky_tex >= 0 && inside) c.skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
 
     int ct = 0, cb = inside ? H : 0;              // open window [ct, cb) of this lane's column
-    uint32_t *ml = (kMasked && sc.masked_list) ? sc.masked_list + (size_t)gw * (33 * kMaskedCap) : nullptr;
+    uint32_t *ml = (kMasked && sc.masked_list) ? sc.masked_list + (size_t)gw * (33 * (size_t)sc.masked_cap) : nullptr;
     int mcount = 0;
     const SegFrame *wl = work + (size_t)frame * stride;
     const int count = fc.count;
@@ -686,7 +686,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
             if (sf.seg < 0) {
                 // decoration sprite: remember the windows open right now; it is drawn in the masked pass
                 if (kMasked && ml != nullptr) {
-                    if (mcount < kMaskedCap) {
+                    if (mcount < sc.masked_cap) {
                         if (lane == 0) ml[33 * mcount] = (uint32_t)(k0 + j);
                         ml[33 * mcount + 1 + lane] = in ? ((uint32_t)ct | ((uint32_t)cb << 16)) : 0u;
                         mcount++;
@@ -752,7 +752,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 // defer the masked middle texture: remember the window that is open behind this seg
                 const bool keep = ok && y2 < y3;
                 if (__any_sync(kFull, keep)) {
-                    if (mcount < kMaskedCap) {
+                    if (mcount < sc.masked_cap) {
                         if (lane == 0) ml[33 * mcount] = (uint32_t)(k0 + j);
                         ml[33 * mcount + 1 + lane] = keep ? ((uint32_t)y2 | ((uint32_t)y3 << 16)) : 0u;
                         mcount++;

@@ -33,11 +33,13 @@ struct DeviceScene {
     uint32_t root;
     uint32_t invF;               // floor(2^32 / F)
     int32_t *status_flag;        // device int: OR of per-frame walk status bits (0 = all frames complete)
-    uint32_t *masked_list;       // per raster warp: kMaskedCap x 33 words (worklist index + 32 packed windows)
+    uint32_t *masked_list;       // per raster warp: masked_cap x 33 words (worklist index + 32 packed windows)
+    int32_t masked_cap;          // entries one 32-column strip can defer per frame (more -> status bit 8)
 };
 
-// masked middle textures one 32-column strip can defer per frame (more -> status bit 8, frames incomplete)
-constexpr int kMaskedCap = 32;
+// masked middle textures + sprites one 32-column strip can defer per frame: min(masked mids + sprites of the level,
+// kMaskedCapMax), at least 8 (more deferred in one strip -> status bit 8, frames incomplete)
+constexpr int kMaskedCapMax = 128;
 
 // Bytes of dynamic shared memory one BSP-walk warp needs for this scene.
 size_t walk_smem_per_warp(const DeviceScene &sc);

@@ -285,6 +285,8 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
             if (sc.sky_tex >= 0 && x < W) lanes[l].skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
         }
         struct Deferred { size_t k; std::vector<uint32_t> win; };
+        int masked_cap = sc.nmids + sc.nsprites;          // as b2d_renderer_create sizes the deferred lists
+        masked_cap = masked_cap < 8 ? 8 : (masked_cap > 128 ? 128 : masked_cap);
         std::vector<Deferred> deferred;
         for (size_t k = 0; k < wl.size(); k++) {
             const SegFrame &sf = wl[k];
@@ -303,7 +305,7 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                         any = true;
                     }
                 }
-                if (any && deferred.size() < 32) deferred.push_back(d);
+                if (any && deferred.size() < (size_t)masked_cap) deferred.push_back(d);
                 continue;
             }
             const SegRec &S = sc.segs[sf.seg];
@@ -352,7 +354,7 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
                 else { ln.ct = y2; ln.cb = y3; }
                 if (two && S.mid >= 0 && y2 < y3) { dfr.win[(size_t)l] = (uint32_t)y2 | ((uint32_t)y3 << 16); any_deferred = true; }
             }
-            if (any_deferred && deferred.size() < 32) deferred.push_back(dfr);
+            if (any_deferred && deferred.size() < (size_t)masked_cap) deferred.push_back(dfr);
             if (st) for (int d = 0; d < 4; d++) if (hi[d] > lo[d]) st->iters += hi[d] - lo[d];
         }
         for (int l = 0; l < SW; l++)
