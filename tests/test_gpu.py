@@ -359,3 +359,20 @@ def test_gpu_odd_texture_sizes(b2d):
     for (w, h, n) in ((320, 200, 32), (1920, 1080, 6), (1000, 700, 6)):
         r = b2d.Renderer(sc, b2d.make_view(w, h), max_batch=32)
         _assert_same(render.render(sc.blob, render.make_view(w, h), poses[:n], threads=8), r.render(poses[:n]), "odd %dx%d" % (w, h))
+
+
+def test_gpu_campaign_mixed_content(b2d):
+    """Six more generated levels with every kind of content switched on (masked middles, sprites, animation,
+    scrolling, light effects, odd texture sizes), odd resolutions, non-zero level times."""
+    from rust_doom_b200 import synthwad
+    sizes = ((640, 400), (1000, 700), (333, 777))
+    for i, seed in enumerate(range(31, 37)):
+        cfg = synthwad.SynthConfig(mid_pct=10 * (i % 4), thing_pct=15 * (i % 3), anim=bool(i & 1), odd_tex=bool(i & 2))
+        sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, ("MAP07",), cfg=cfg)), 0)
+        poses = sample_poses(b2d, sc, 12, 300 + seed)
+        w, h = sizes[i % 3]
+        tics = (0, 9, 123456)[i % 3]
+        r = b2d.Renderer(sc, b2d.make_view(w, h), max_batch=12)
+        r.set_time(tics)
+        _assert_same(render.render(sc.blob, render.make_view(w, h), poses, threads=8, tics=tics), r.render(poses),
+                     "seed %d %dx%d tics %d" % (seed, w, h, tics))

@@ -173,3 +173,14 @@ def test_hostcheck_odd_texture_sizes(b2d, hostcheck):
     assert {70, 33, 126} <= set(tex[:, 2].tolist())
     _compare(b2d, hostcheck, sc, 320, 200, 32, 61)
     _compare(b2d, hostcheck, sc, 1920, 1080, 2, 62)
+
+
+def test_hostcheck_campaign_mixed_content(b2d, hostcheck):
+    """The GPU campaign's levels (all content kinds, odd sizes, level times) through the CPU execution of the product maths."""
+    from rust_doom_b200 import synthwad
+    sizes = ((640, 400), (500, 350), (333, 777))
+    for i, seed in enumerate(range(31, 37)):
+        cfg = synthwad.SynthConfig(mid_pct=10 * (i % 4), thing_pct=15 * (i % 3), anim=bool(i & 1), odd_tex=bool(i & 2))
+        sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, ("MAP07",), cfg=cfg)), 0)
+        w, h = sizes[i % 3]
+        _compare(b2d, hostcheck, sc, w, h, 6, 300 + seed, tics=(0, 9, 123456)[i % 3])
