@@ -21,8 +21,9 @@ struct DeviceScene {
     const uint8_t *texels;
     const uint8_t *flats;
     const uint8_t *colormap;     // 34 x 256
-    // colormap applied ahead of time: lit_texels[r * lit_texel_stride + i] = colormap[r][texels[i]] for the 32 light
-    // rows r, likewise lit_flats; the solid pass fetches the final palette index with one load per pixel
+    // colormap applied ahead of time (per renderer, next to the blob): plane r < 32 of a texture holds
+    // colormap[r][texel] in the layout b2d_math.cuh:tex_interleaved()/lit_index() select, plane 32 the opacity of
+    // textures with holes; lit_flats likewise (row-major).  A pixel is one load: no colormap lookup at run time.
     const uint8_t *lit_texels;
     const uint8_t *lit_flats;
     uint32_t lit_texel_stride, lit_flat_stride;
@@ -41,10 +42,10 @@ struct DeviceScene {
 // kMaskedCapMax), at least 8 (more deferred in one strip -> status bit 8, frames incomplete)
 constexpr int kMaskedCapMax = 128;
 
-// Bytes of dynamic shared memory one BSP-walk warp needs for this scene.
+// Bytes of dynamic shared memory the BSP-walk kernel needs per frame (= per CTA) for this scene.
 size_t walk_smem_per_warp(const DeviceScene &sc);
 
-// Kernel 1: front-to-back BSP walk, one warp per frame.  Writes frames[i] and up to `stride`
+// Kernel 1: front-to-back BSP walk, one CTA per frame.  Writes frames[i] and up to `stride`
 // worklist entries per frame at work[i*stride ...].
 cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
                         FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream);
@@ -55,15 +56,15 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
                           const SegFrame *d_work, int stride, int n, uint8_t *d_index_fb,
                           uint32_t *d_rgba, cudaStream_t stream);
 
-// Kernel 3: palette LUT on its own (index -> RGBA8), 16 pixels per thread.
-// dst[r * stride + i] = colormap[r][src[i]] for r < 32, i < n
+// Pre-light kernels (once per renderer).  Flats: dst[r * stride + i] = colormap[r][src[i]] for r < 32, i < n.
 cudaError_t launch_prelight(const uint8_t *d_colormap, const uint8_t *d_src, uint8_t *d_dst, size_t n, size_t stride,
                             cudaStream_t stream);
 
-// pre-lit copy of every texture of the table, in the per-texture layout the raster kernel expects
+// Textures: 32 pre-lit planes (+ opacity plane 32) of every texture of the table, in its per-texture layout.
 cudaError_t launch_prelight_textures(const uint8_t *d_colormap, const uint8_t *d_texels, const TexRec *d_tex, int ntex,
                                      uint8_t *d_dst, size_t stride, cudaStream_t stream);
 
+// Kernel 3: palette LUT on its own (index -> RGBA8), 16 pixels per thread.
 cudaError_t launch_palette(const uint32_t *d_palette, const uint8_t *d_index, uint32_t *d_rgba,
                            size_t n_pixels, cudaStream_t stream);
 
