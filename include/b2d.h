@@ -121,6 +121,16 @@ int b2d_render_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, uint8_
 int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_rgba, size_t n_pixels,
                            void *cuda_stream);
 
+/* The same work as b2d_render_device in two calls, for pipelines that have the next batch's poses early (a recorded
+ * camera path, an encoder that renders ahead).  b2d_walk_device enqueues the BSP walk of a batch on `cuda_stream` into
+ * one of the renderer's two worklist slots and returns a ticket; b2d_raster_device enqueues the raster of that ticket on
+ * its own `cuda_stream`.  The two calls are ordered through events, not by the streams: with two streams the walk of
+ * batch k+1 overlaps the raster of batch k (the walk is a latency-bound ~0.1 ms, the raster fills the machine).  At
+ * most two batches can be walked and not yet rastered; tickets are rastered once.  d_poses is read by the walk
+ * only.  Replaces nothing in the reference (its render loop is synchronous, engine/src/renderer.rs:62-175). */
+int b2d_walk_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, void *cuda_stream, int64_t *ticket_out);
+int b2d_raster_device(b2d_renderer *r, int64_t ticket, uint8_t *d_index_fb, uint32_t *d_rgba_fb, void *cuda_stream);
+
 /* Introspection for tests/profiling: copies the BSP-walk worklist of the LAST b2d_render_device
  * batch to the host.  counts_out[n], and for frame i seg ids seg_ids_out[i*stride .. +counts[i]). */
 int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *seg_ids_out, size_t stride);

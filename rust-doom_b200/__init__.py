@@ -186,6 +186,15 @@ class Renderer:
     def render_device(self, poses_ptr: int, n: int, index_ptr: int, rgba_ptr: int = 0, stream: int = 0):
         _check(_lib.load().b2d_render_device(self._h, poses_ptr, n, index_ptr, rgba_ptr or None, stream or None))
 
+    def walk_device(self, poses_ptr: int, n: int, stream: int = 0) -> int:
+        """BSP walk of a batch on `stream`; returns the ticket to hand to raster_device (possibly on another stream)."""
+        t = ctypes.c_int64(-1)
+        _check(_lib.load().b2d_walk_device(self._h, poses_ptr, n, stream or None, ctypes.byref(t)))
+        return int(t.value)
+
+    def raster_device(self, ticket: int, index_ptr: int, rgba_ptr: int = 0, stream: int = 0):
+        _check(_lib.load().b2d_raster_device(self._h, ticket, index_ptr, rgba_ptr or None, stream or None))
+
     def palette_lut_device(self, index_ptr: int, rgba_ptr: int, n_pixels: int, stream: int = 0):
         _check(_lib.load().b2d_palette_lut_device(self._h, index_ptr, rgba_ptr, n_pixels, stream or None))
 

@@ -39,8 +39,15 @@ struct b2d_renderer {
     uint8_t *d_lit = nullptr;       // colormap-applied copies of the texels and flats (32 light rows each)
     DeviceScene ds{};
     Pose *d_poses = nullptr;
-    FrameConst *d_frames = nullptr;
-    SegFrame *d_work = nullptr;
+    // two worklist slots: the BSP walk of batch k+1 may run (b2d_walk_device, another stream) while batch k is rastered
+    FrameConst *d_frames[2] = {nullptr, nullptr};
+    SegFrame *d_work[2] = {nullptr, nullptr};
+    cudaEvent_t walk_done[2] = {nullptr, nullptr}, raster_done[2] = {nullptr, nullptr};
+    int slot_n[2] = {0, 0};          // frames walked into the slot
+    int64_t slot_ticket[2] = {-1, -1};
+    bool slot_rastered[2] = {true, true};
+    int64_t next_ticket = 0;
+    int last_slot = 0;
     // host-path staging (allocated on first b2d_render): double-buffered frame outputs
     uint8_t *d_index[2] = {nullptr, nullptr};
     uint32_t *d_rgba[2] = {nullptr, nullptr};
@@ -52,7 +59,8 @@ struct b2d_renderer {
     int64_t launches = 0;
     int last_n = 0;
     bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;   // triples: before walk, between, after raster
+    std::vector<cudaEvent_t> prof_events;   // pairs: before / after one kernel launch
+    std::vector<int> prof_kinds;            // per pair: 0 = walk, 1 = raster
 };
 
 namespace {
@@ -100,8 +108,12 @@ void free_renderer(b2d_renderer *r) {
     if (r->h_poses) cudaFreeHost(r->h_poses);
     if (r->render_stream) cudaStreamDestroy(r->render_stream);
     if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
-    if (r->d_work) cudaFree(r->d_work);
-    if (r->d_frames) cudaFree(r->d_frames);
+    for (int i = 0; i < 2; i++) {
+        if (r->d_work[i]) cudaFree(r->d_work[i]);
+        if (r->d_frames[i]) cudaFree(r->d_frames[i]);
+        if (r->walk_done[i]) cudaEventDestroy(r->walk_done[i]);
+        if (r->raster_done[i]) cudaEventDestroy(r->raster_done[i]);
+    }
     if (r->d_poses) cudaFree(r->d_poses);
     if (r->d_yslope) cudaFree(r->d_yslope);
     if (r->d_skyrow) cudaFree(r->d_skyrow);
@@ -112,27 +124,73 @@ void free_renderer(b2d_renderer *r) {
     delete r;
 }
 
-int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
-                   cudaStream_t stream) {
-    // walk -> raster on the caller's stream.  (Measured on B200: splitting a batch so that the second
-    // half's BSP walk runs on an auxiliary stream under the first half's raster is *slower* -- the walk is
-    // a single latency-bound wave of ~0.15 ms whatever the batch size, and two raster launches pay two
-    // tails: 456 k vs 488 k frames/s at 1000 frames per batch.  See profiles/README.md.)
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+// BSP walk of a batch into the next worklist slot, on `stream`.  The slot's previous raster (if any, on whatever
+// stream) is awaited through an event, so a caller may run walks and rasters on two streams and have the walk of
+// batch k+1 overlap the raster of batch k.
+int walk_into_slot(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t stream, int64_t *ticket_out) {
+    const int slot = (int)(r->next_ticket & 1);
+    if (!r->slot_rastered[slot]) return fail(B2D_ERR_INVALID_ARG, "both worklist slots hold batches that were walked but not rastered yet");
+    if (!r->d_frames[slot]) {
+        CU(cudaMalloc(&r->d_frames[slot], sizeof(FrameConst) * (size_t)r->max_batch));
+        CU(cudaMalloc(&r->d_work[slot], sizeof(SegFrame) * (size_t)r->max_batch * (size_t)r->stride));
+    }
+    if (!r->walk_done[slot]) {
+        CU(cudaEventCreateWithFlags(&r->walk_done[slot], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r->raster_done[slot], cudaEventDisableTiming));
+    } else {
+        CU(cudaStreamWaitEvent(stream, r->raster_done[slot], 0));      // the raster that last read this slot
+    }
+    cudaEvent_t ev[2] = {nullptr, nullptr};
     if (r->profiling) {
         for (auto &e : ev) CU(cudaEventCreate(&e));
         CU(cudaEventRecord(ev[0], stream));
     }
-    CU(launch_walk(r->ds, r->view, d_poses, n, r->d_frames, r->d_work, r->stride, stream));
-    if (r->profiling) CU(cudaEventRecord(ev[1], stream));
-    CU(launch_raster(r->ds, r->view, r->d_frames, r->d_work, r->stride, n, d_index, d_rgba, stream));
+    CU(launch_walk(r->ds, r->view, d_poses, n, r->d_frames[slot], r->d_work[slot], r->stride, stream));
     if (r->profiling) {
-        CU(cudaEventRecord(ev[2], stream));
+        CU(cudaEventRecord(ev[1], stream));
         for (auto e : ev) r->prof_events.push_back(e);
+        r->prof_kinds.push_back(0);
     }
-    r->launches += 2;
+    CU(cudaEventRecord(r->walk_done[slot], stream));
+    r->slot_n[slot] = n;
+    r->slot_ticket[slot] = r->next_ticket;
+    r->slot_rastered[slot] = false;
+    r->last_slot = slot;
     r->last_n = n;
+    r->launches += 1;
+    *ticket_out = r->next_ticket++;
     return B2D_OK;
+}
+
+int raster_from_slot(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t *d_rgba, cudaStream_t stream) {
+    const int slot = (int)(ticket & 1);
+    if (ticket < 0 || r->slot_ticket[slot] != ticket || r->slot_rastered[slot])
+        return fail(B2D_ERR_INVALID_ARG, "unknown or already rastered walk ticket");
+    CU(cudaStreamWaitEvent(stream, r->walk_done[slot], 0));
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (r->profiling) {
+        for (auto &e : ev) CU(cudaEventCreate(&e));
+        CU(cudaEventRecord(ev[0], stream));
+    }
+    CU(launch_raster(r->ds, r->view, r->d_frames[slot], r->d_work[slot], r->stride, r->slot_n[slot], d_index, d_rgba, stream));
+    if (r->profiling) {
+        CU(cudaEventRecord(ev[1], stream));
+        for (auto e : ev) r->prof_events.push_back(e);
+        r->prof_kinds.push_back(1);
+    }
+    CU(cudaEventRecord(r->raster_done[slot], stream));
+    r->slot_rastered[slot] = true;
+    r->launches += 1;
+    return B2D_OK;
+}
+
+// walk -> raster on the caller's stream
+int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
+                   cudaStream_t stream) {
+    int64_t ticket = -1;
+    int rc = walk_into_slot(r, d_poses, n, stream, &ticket);
+    if (rc != B2D_OK) return rc;
+    return raster_from_slot(r, ticket, d_index, d_rgba, stream);
 }
 
 }  // namespace
@@ -335,8 +393,8 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
     if (scene_is_timed(s->blob.data())) r->h_blob = s->blob;
     CUR(cudaMalloc(&r->d_poses, sizeof(Pose) * (size_t)max_batch));
-    CUR(cudaMalloc(&r->d_frames, sizeof(FrameConst) * (size_t)max_batch));
-    CUR(cudaMalloc(&r->d_work, sizeof(SegFrame) * (size_t)max_batch * (size_t)r->stride));
+    CUR(cudaMalloc(&r->d_frames[0], sizeof(FrameConst) * (size_t)max_batch));
+    CUR(cudaMalloc(&r->d_work[0], sizeof(SegFrame) * (size_t)max_batch * (size_t)r->stride));
 #undef CUR
     *out = r;
     return B2D_OK;
@@ -373,6 +431,19 @@ int b2d_render_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, uint8_
     CU(cudaSetDevice(r->device));
     return enqueue_frames(r, reinterpret_cast<const Pose *>(d_poses), (int)n, d_index_fb, d_rgba_fb,
                           static_cast<cudaStream_t>(cuda_stream));
+}
+
+int b2d_walk_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, void *cuda_stream, int64_t *ticket_out) {
+    if (!r || !d_poses || !ticket_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    if (n == 0 || n > (size_t)r->max_batch) return fail(B2D_ERR_INVALID_ARG, "n must be in 1..max_batch");
+    CU(cudaSetDevice(r->device));
+    return walk_into_slot(r, reinterpret_cast<const Pose *>(d_poses), (int)n, static_cast<cudaStream_t>(cuda_stream), ticket_out);
+}
+
+int b2d_raster_device(b2d_renderer *r, int64_t ticket, uint8_t *d_index_fb, uint32_t *d_rgba_fb, void *cuda_stream) {
+    if (!r || !d_index_fb) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(r->device));
+    return raster_from_slot(r, ticket, d_index_fb, d_rgba_fb, static_cast<cudaStream_t>(cuda_stream));
 }
 
 int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_fb, uint32_t *rgba_fb) {
@@ -442,14 +513,15 @@ int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *
     CU(cudaSetDevice(r->device));
     CU(cudaDeviceSynchronize());
     std::vector<FrameConst> frames(n);
-    CU(cudaMemcpy(frames.data(), r->d_frames, sizeof(FrameConst) * n, cudaMemcpyDeviceToHost));
+    const int slot = r->last_slot;
+    CU(cudaMemcpy(frames.data(), r->d_frames[slot], sizeof(FrameConst) * n, cudaMemcpyDeviceToHost));
     std::vector<SegFrame> work;
     for (size_t i = 0; i < n; i++) {
         counts_out[i] = frames[i].status ? -frames[i].status : frames[i].count;
         if (!seg_ids_out) continue;
         size_t c = (size_t)frames[i].count;
         work.resize(c);
-        if (c) CU(cudaMemcpy(work.data(), r->d_work + i * (size_t)r->stride, sizeof(SegFrame) * c, cudaMemcpyDeviceToHost));
+        if (c) CU(cudaMemcpy(work.data(), r->d_work[slot] + i * (size_t)r->stride, sizeof(SegFrame) * c, cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < c && k < stride; k++) seg_ids_out[i * stride + k] = work[k].seg;
     }
     return B2D_OK;
@@ -465,16 +537,18 @@ int b2d_profile_read(b2d_renderer *r, double *walk_ms, double *raster_ms, int64_
     if (!r) return fail(B2D_ERR_INVALID_ARG, "null renderer");
     CU(cudaSetDevice(r->device));
     CU(cudaDeviceSynchronize());
+    // events arrive as pairs (before, after one kernel launch); prof_kinds says which kernel: 0 = walk, 1 = raster
     double w = 0.0, ra = 0.0;
-    for (size_t i = 0; i + 2 < r->prof_events.size(); i += 3) {
-        float a = 0.f, b = 0.f;
+    int64_t nb = 0;
+    for (size_t i = 0; i + 1 < r->prof_events.size(); i += 2) {
+        float a = 0.f;
         CU(cudaEventElapsedTime(&a, r->prof_events[i], r->prof_events[i + 1]));
-        CU(cudaEventElapsedTime(&b, r->prof_events[i + 1], r->prof_events[i + 2]));
-        w += a; ra += b;
+        if (r->prof_kinds[i / 2] == 0) w += a; else { ra += a; nb++; }
     }
     if (walk_ms) *walk_ms = w;
     if (raster_ms) *raster_ms = ra;
-    if (batches) *batches = (int64_t)(r->prof_events.size() / 3);
+    if (batches) *batches = nb;
+    r->prof_kinds.clear();
     for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
     r->prof_events.clear();
     return B2D_OK;

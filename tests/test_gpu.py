@@ -376,3 +376,35 @@ def test_gpu_campaign_mixed_content(b2d):
         r.set_time(tics)
         _assert_same(render.render(sc.blob, render.make_view(w, h), poses, threads=8, tics=tics), r.render(poses),
                      "seed %d %dx%d tics %d" % (seed, w, h, tics))
+
+
+def test_gpu_split_walk_raster_api_overlapped(b2d, product_scene):
+    """b2d_walk_device / b2d_raster_device on two streams: batch k+1 is walked while batch k is rastered; frames
+    equal the one-call path; ticket misuse is an error, not a crash."""
+    import torch
+    view = b2d.make_view(640, 400)
+    r = b2d.Renderer(product_scene, view, max_batch=32)
+    batches = [sample_poses(b2d, product_scene, 32, 500 + k) for k in range(5)]
+    dps = [torch.from_numpy(p.view(np.int32).reshape(-1, 4).copy()).cuda() for p in batches]
+    outs = [torch.empty((32, 400, 640), dtype=torch.uint8, device="cuda") for _ in batches]
+    s_walk, s_raster = torch.cuda.Stream(priority=-1), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    ticket = r.walk_device(dps[0].data_ptr(), 32, s_walk.cuda_stream)
+    for k in range(5):
+        r.raster_device(ticket, outs[k].data_ptr(), 0, s_raster.cuda_stream)
+        if k + 1 < 5:
+            ticket = r.walk_device(dps[k + 1].data_ptr(), 32, s_walk.cuda_stream)
+    torch.cuda.synchronize()
+    oview = render.make_view(640, 400)
+    for k in range(5):
+        _assert_same(render.render(product_scene.blob, oview, batches[k], threads=8), outs[k].cpu().numpy(), "batch %d" % k)
+    with pytest.raises(b2d.B2dError):
+        r.raster_device(ticket, outs[0].data_ptr())            # already rastered
+    t1 = r.walk_device(dps[0].data_ptr(), 32)
+    t2 = r.walk_device(dps[1].data_ptr(), 32)
+    with pytest.raises(b2d.B2dError):
+        r.walk_device(dps[2].data_ptr(), 32)                    # both slots pending
+    r.raster_device(t1, outs[0].data_ptr())
+    r.raster_device(t2, outs[1].data_ptr())
+    torch.cuda.synchronize()
+    _assert_same(render.render(product_scene.blob, oview, batches[1], threads=8), outs[1].cpu().numpy(), "after misuse")
