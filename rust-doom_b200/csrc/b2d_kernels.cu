@@ -828,7 +828,7 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     // Launch shape (tuned on B200, profiles/README.md): ONE warp per CTA and 64 registers/thread, i.e. 32 CTAs =
     // 32 warps resident per SM.  Strips differ a lot in cost; with several warps per CTA the finished warps' slots
     // stay empty until the slowest warp of the CTA is done (1-warp CTAs: +10 % over 2 or 4, 8 and 16 lose more).
-    // The frame width is a compile-time constant for the benchmark resolution (immediate store offsets).
+    // The frame width is a compile-time constant for the benchmark resolutions (immediate store offsets).
     constexpr int kWarps = 1;
     const long long total_warps = (long long)n * strips;
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
@@ -842,7 +842,10 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
         b2d_raster_kernel<RGBA, 32 / kWarps, KW, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); } while (0)
     if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
-    else { if (w1920) B2D_RASTER_GO(false, 1920); else B2D_RASTER_GO(false, 0); }
+    else {
+        const bool w3840 = vw.W == 3840 && !generic_w;      // BASELINE.json's 4K configuration (index frames only)
+        if (w1920) B2D_RASTER_GO(false, 1920); else if (w3840) B2D_RASTER_GO(false, 3840); else B2D_RASTER_GO(false, 0);
+    }
 #undef B2D_RASTER_GO
     return cudaGetLastError();
 }
