@@ -1,0 +1,48 @@
+#!/usr/bin/env python3
+"""Random parity campaign on the GPU: libb2d.so (CUDA kernels through the C ABI) against the oracle on random
+generated levels (all content kinds), random resolutions, fields of view and level times.  Same generator as
+tools/campaign.py.  usage: python tools/campaign_gpu.py [cases]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+import rust_doom_b200 as b2d  # noqa: E402
+from oracle import render  # noqa: E402
+from rust_doom_b200 import synthwad  # noqa: E402
+from tests.conftest import sample_poses  # noqa: E402
+
+
+def main():
+    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    rng = np.random.default_rng(12345)
+    bad, t0, pixels = 0, time.time(), 0
+    for it in range(cases):
+        seed = int(rng.integers(100, 100000))
+        cfg = synthwad.SynthConfig(mid_pct=int(rng.integers(0, 50)), thing_pct=int(rng.integers(0, 60)),
+                                   anim=bool(rng.integers(0, 2)), odd_tex=bool(rng.integers(0, 2)),
+                                   rock_pct=int(rng.integers(5, 30)), sky_pct=int(rng.integers(0, 40)),
+                                   door_pct=int(rng.integers(5, 40)))
+        name = ["E1M1", "E2M3", "MAP05", "MAP15", "MAP25"][int(rng.integers(0, 5))]
+        sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, (name,), cfg=cfg)), 0)
+        w, h = int(rng.integers(40, 1300)), int(rng.integers(30, 900))
+        tics = int(rng.integers(0, 1 << 32)) if rng.integers(0, 2) else 0
+        fov = float(rng.uniform(40, 110))
+        poses = sample_poses(b2d, sc, 4, seed)
+        o = render.render(sc.blob, render.make_view(w, h, fov), poses, threads=8, tics=tics)
+        r = b2d.Renderer(sc, b2d.make_view(w, h, fov), max_batch=4)
+        r.set_time(tics)
+        g = r.render(poses)
+        pixels += o.size
+        if not np.array_equal(o, g):
+            bad += 1
+            print("MISMATCH", seed, cfg, name, w, h, tics, fov, int((o != g).sum()))
+    print("gpu campaign: %d cases, %d mismatching, %.1f Mpixel compared, %.1f s" % (cases, bad, pixels / 1e6, time.time() - t0))
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
