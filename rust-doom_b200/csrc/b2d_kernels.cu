@@ -328,7 +328,7 @@ __device__ __forceinline__ void store_batch(const RasterCtx &c, uint8_t *p8, uin
 #pragma unroll
         for (int k = 0; k < kBatch; k++) put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, true, v[k]);
     } else {
-        const uint32_t len = (uint32_t)(yb - ya), d = (uint32_t)(y - ya);
+        const uint32_t len = yb > ya ? (uint32_t)(yb - ya) : 0u, d = (uint32_t)(y - ya);
 #pragma unroll
         for (int k = 0; k < kBatch; k++)
             put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, d + (uint32_t)k < len, v[k]);
@@ -577,7 +577,7 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
         uint32_t t = (uint32_t)wall_tbase(tA, hA, pose_z, c.H, iscale) + (uint32_t)y0 * tstep;
         uint8_t *p8 = c.fb + (size_t)y0 * Wc;
         uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
-        const uint32_t len = (uint32_t)(yb - ya);
+        const uint32_t len = act ? (uint32_t)(yb - ya) : 0u;   // the clipped window can be inverted (ya > yb): no rows then
         if (inter) {
             // batches of 8 rows as in draw_wall_warp: magnified columns (sprites nearly always are) read two colour
             // words and two opacity words per batch

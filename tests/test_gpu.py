@@ -408,3 +408,17 @@ def test_gpu_split_walk_raster_api_overlapped(b2d, product_scene):
     r.raster_device(t2, outs[1].data_ptr())
     torch.cuda.synchronize()
     _assert_same(render.render(product_scene.blob, oview, batches[1], threads=8), outs[1].cpu().numpy(), "after misuse")
+
+
+def test_gpu_masked_windows_clipped_to_nothing(b2d):
+    """Regression (found by tools/campaign_gpu.py): a deferred sprite / masked middle whose rows, after clipping to
+    the window that was open behind it, are empty or inverted (first row below the last) must draw nothing."""
+    from rust_doom_b200 import synthwad
+    for seed, name, cfg, w, h, tics, fov in (
+            (8802, "MAP05", synthwad.SynthConfig(rock_pct=17, sky_pct=36, door_pct=5, mid_pct=35, thing_pct=37, anim=True, odd_tex=True), 123, 746, 769541036, 77.81427875224603),
+            (40250, "MAP05", synthwad.SynthConfig(rock_pct=27, sky_pct=31, door_pct=9, mid_pct=16, thing_pct=55, odd_tex=True), 701, 554, 110894393, 98.25319284638539)):
+        sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, (name,), cfg=cfg)), 0)
+        poses = sample_poses(b2d, sc, 4, seed)
+        r = b2d.Renderer(sc, b2d.make_view(w, h, fov), max_batch=4)
+        r.set_time(tics)
+        _assert_same(render.render(sc.blob, render.make_view(w, h, fov), poses, threads=8, tics=tics), r.render(poses), "seed %d" % seed)
