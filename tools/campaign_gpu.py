@@ -32,10 +32,16 @@ def main():
         tics = int(rng.integers(0, 1 << 32)) if rng.integers(0, 2) else 0
         fov = float(rng.uniform(40, 110))
         poses = sample_poses(b2d, sc, 4, seed)
-        o = render.render(sc.blob, render.make_view(w, h, fov), poses, threads=8, tics=tics)
-        r = b2d.Renderer(sc, b2d.make_view(w, h, fov), max_batch=4)
+        want_rgba = it % 4 == 3                         # every fourth case also materialises RGBA8 frames
+        o = render.render(sc.blob, render.make_view(w, h, fov), poses, threads=8, tics=tics, rgba=want_rgba)
+        r = b2d.Renderer(sc, b2d.make_view(w, h, fov), max_batch=int(rng.integers(1, 5)))
         r.set_time(tics)
-        g = r.render(poses)
+        g = r.render(poses, rgba=want_rgba)
+        if want_rgba:
+            if not np.array_equal(o[1], g[1]):
+                bad += 1
+                print("RGBA MISMATCH", seed, cfg, name, w, h, tics, fov)
+            o, g = o[0], g[0]
         pixels += o.size
         if not np.array_equal(o, g):
             bad += 1
