@@ -123,6 +123,13 @@ class Scene:
         p["x"], p["y"], p["z"], p["angle"] = s.x, s.y, s.z, s.angle
         return p
 
+    def palette_rgb(self) -> np.ndarray:
+        """(256, 3) uint8 RGB of PLAYPAL[0] as stored in the scene blob (header word 20 = palette offset)."""
+        blob = self.blob
+        off = int(np.frombuffer(blob, dtype="<u4", count=21)[20])
+        rgba = np.frombuffer(blob, dtype="<u4", count=256, offset=off)
+        return np.stack([rgba & 0xFF, (rgba >> 8) & 0xFF, (rgba >> 16) & 0xFF], axis=1).astype(np.uint8)
+
     def sector_at(self, x: float, y: float) -> Tuple[int, int, int]:
         """(sector id or -1, floor, ceiling) -- LevelWalker::sector_at."""
         f, c = ctypes.c_int32(), ctypes.c_int32()

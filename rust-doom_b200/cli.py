@@ -12,6 +12,7 @@ honoured (its value is parsed but never read there: main.rs:131 vs game/src/game
 from __future__ import annotations
 
 import argparse
+import os
 import sys
 import time
 
@@ -42,6 +43,52 @@ def rgba_to_rgb(rgba_frame: np.ndarray) -> np.ndarray:
     """(H, W) uint32 R | G<<8 | B<<16 | A<<24 (the library's RGBA8) -> (H, W, 3) uint8."""
     h, w = rgba_frame.shape
     return rgba_frame.view(np.uint8).reshape(h, w, 4)[:, :, :3]
+
+
+def _main_sharded(b2d, scene, view, poses, args, w, h, world) -> int:
+    """Under torchrun: every rank renders its contiguous block of the poses on its own GPU (no data-path
+    collective); with --stream the finished index frames travel to rank 0 in pose order (parallel.
+    write_frames_in_order), which applies the palette and writes the PPM stream."""
+    import torch
+    import torch.distributed as dist
+    from rust_doom_b200 import parallel
+
+    rank, local_rank = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        s, e, per = parallel.shard_bounds(len(poses), rank, world)
+        mine = poses[s:e]
+        r = b2d.Renderer(scene, view, device=local_rank, max_batch=max(1, min(per, 256)))
+        local = torch.empty((len(mine), h, w), dtype=torch.uint8, device="cuda")
+        t0 = time.perf_counter()
+        for c0 in range(0, len(mine), r.max_batch):
+            c1 = min(len(mine), c0 + r.max_batch)
+            dp = torch.from_numpy(mine[c0:c1].view(np.int32).reshape(-1, 4).copy()).cuda()
+            r.render_device(dp.data_ptr(), c1 - c0, local[c0:c1].data_ptr())
+        torch.cuda.synchronize()
+        dist.barrier()
+        if rank == 0:
+            dt = time.perf_counter() - t0
+            print("rendered %d frame(s) %dx%d on %d GPUs in %.2f ms" % (len(poses), w, h, world, dt * 1e3))
+        if args.stream or args.dump:
+            pal = scene.palette_rgb()
+            out = open(args.stream, "wb") if (args.stream and rank == 0) else None
+
+            def sink(frames, first):
+                if out is not None:
+                    for f in frames:
+                        out.write(encode_ppm(pal[f]))
+                if args.dump and first == 0:
+                    with open(args.dump, "wb") as fh:
+                        fh.write(encode_png(pal[frames[0]]) if args.dump.lower().endswith(".png") else encode_ppm(pal[frames[0]]))
+
+            parallel.write_frames_in_order(local, len(poses), sink, chunk_frames=32)
+            if out is not None:
+                out.close()
+        return 0
+    finally:
+        dist.destroy_process_group()
 
 
 def main(argv=None) -> int:
@@ -89,6 +136,9 @@ def main(argv=None) -> int:
             poses = scene.start_pose if scene.start_pose is not None else P.random_poses(scene, 1, 1)
         else:
             poses = P.flythrough_poses(scene, args.poses, 2)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world > 1:
+            return _main_sharded(b2d, scene, view, poses, args, w, h, world)
         r = b2d.Renderer(scene, view, device=args.device, max_batch=min(len(poses), 256))
         t0 = time.perf_counter()
         if args.tics_per_frame > 0:          # time is a per-batch input: one batch per frame

@@ -69,3 +69,38 @@ def all_gather_frames(local, n_total: int, chunk_frames: int = 256, group=None, 
             if g1 > g0:
                 out[g0:g1] = parts[r, :g1 - g0]
     return out
+
+
+def write_frames_in_order(local, n_total: int, write_fn, chunk_frames: int = 64, group=None) -> int:
+    """Frame sink on the gather rank: streams every rank's finished frames to rank 0 in global
+    pose order, `chunk_frames` at a time, and hands them to `write_fn(frames_uint8_cpu_numpy, first_index)` there.
+
+    `local` is this rank's contiguous block [valid, H, W] (torch uint8, any device).  Only a chunk is ever in
+    flight, so the job size is not bounded by rank 0's memory.  Point-to-point transfers (NCCL on GPUs, gloo in the
+    CPU tests); ranks other than 0 and the current sender just advance.  Returns the number of frames written
+    (on rank 0; 0 elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    per = (n_total + world - 1) // world
+    H, W = int(local.shape[1]), int(local.shape[2])
+    written = 0
+    for r in range(world):
+        g0, g1 = min(n_total, r * per), min(n_total, (r + 1) * per)
+        for c0 in range(g0, g1, chunk_frames):
+            c1 = min(g1, c0 + chunk_frames)
+            if rank == r:
+                chunk = local[c0 - g0:c1 - g0].contiguous()
+                if rank == 0:
+                    write_fn(chunk.cpu().numpy(), c0)
+                    written += c1 - c0
+                else:
+                    dist.send(chunk, dst=0, group=group)
+            elif rank == 0:
+                buf = torch.empty((c1 - c0, H, W), dtype=local.dtype, device=local.device)
+                dist.recv(buf, src=r, group=group)
+                write_fn(buf.cpu().numpy(), c0)
+                written += c1 - c0
+    return written

@@ -57,3 +57,12 @@ def test_cli_renders_dump_and_stream(tmp_path, capsys):
     assert "rendered 3 frame(s) 320x200" in capsys.readouterr().out
     assert png.read_bytes()[:8] == b"\x89PNG\r\n\x1a\n"
     assert len(stream.read_bytes()) == 3 * (len(b"P6\n320 200\n255\n") + 320 * 200 * 3)
+
+
+def test_scene_palette_matches_oracle_blob(b2d, product_scene, oracle_scene):
+    from oracle import scene as S
+    pal = product_scene.palette_rgb()
+    h = S.header(oracle_scene)
+    want = np.frombuffer(oracle_scene, dtype="<u4", count=256, offset=h[S.H_OFF_PALETTE])
+    assert pal.shape == (256, 3) and pal.dtype == np.uint8
+    assert np.array_equal(pal[:, 0], want & 0xFF) and np.array_equal(pal[:, 2], (want >> 16) & 0xFF)
