@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2d.so")
 SOURCES = ["b2d_api.cu", "b2d_kernels.cu", "b2d_wad.cpp", "b2d_scene.cpp"]
-HEADERS = ["b2d_math.cuh", "b2d_kernels.cuh", "b2d_scene.hpp", "b2d_wad.hpp", "../../include/b2d.h"]
+HEADERS = ["b2d_cli.cpp", "b2d_math.cuh", "b2d_kernels.cuh", "b2d_scene.hpp", "b2d_wad.hpp", "../../include/b2d.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter", "-shared",
@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 
 def needs_build() -> bool:
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(os.path.join(HERE, "b2d")):
         return True
     t = os.path.getmtime(OUT)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
@@ -32,7 +32,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
+    build_cli(verbose)
     return OUT
+
+
+CLI_OUT = os.path.join(HERE, "b2d")
+
+
+def build_cli(verbose: bool = False) -> str:
+    """The compiled front end on the C ABI (csrc/b2d_cli.cpp): plain g++, links libb2d.so, rpath = its directory."""
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-o", CLI_OUT,
+           os.path.join(CSRC, "b2d_cli.cpp"), "-L" + HERE, "-lb2d", "-Wl,-rpath,$ORIGIN"]
+    if verbose:
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return CLI_OUT
 
 
 if __name__ == "__main__":

@@ -66,3 +66,53 @@ def test_scene_palette_matches_oracle_blob(b2d, product_scene, oracle_scene):
     want = np.frombuffer(oracle_scene, dtype="<u4", count=256, offset=h[S.H_OFF_PALETTE])
     assert pal.shape == (256, 3) and pal.dtype == np.uint8
     assert np.array_equal(pal[:, 0], want & 0xFF) and np.array_equal(pal[:, 2], (want >> 16) & 0xFF)
+
+
+def _b2d_binary():
+    import os
+    from rust_doom_b200 import build as B
+    B.build()
+    return os.path.join(os.path.dirname(B.OUT), "b2d")
+
+
+def test_compiled_cli_on_the_c_abi(tmp_path):
+    """rust-doom_b200/csrc/b2d_cli.cpp (C++ on include/b2d.h only): list-levels / check / error behaviour of
+    src/main.rs:89-124, and no CPU rendering path."""
+    import subprocess
+    from rust_doom_b200 import synthwad
+    wad = tmp_path / "syn.wad"
+    wad.write_bytes(synthwad.build_iwad(1, ("E1M1", "E1M2")))
+    exe = _b2d_binary()
+    out = subprocess.run([exe, "--iwad", str(wad), "list-levels"], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.split() == ["0", "E1M1", "1", "E1M2"]
+    out = subprocess.run([exe, "-i", str(wad), "check"], capture_output=True, text=True)
+    assert out.returncode == 0 and "Level 1 (E1M2)" in out.stdout and out.stdout.count(": ok") == 2
+    out = subprocess.run([exe, "-i", str(tmp_path / "missing.wad"), "list-levels"], capture_output=True, text=True)
+    assert out.returncode == 1 and "Fatal error" in out.stderr
+    bad = tmp_path / "bad.wad"
+    bad.write_bytes(b"PWAD" + bytes(8))
+    out = subprocess.run([exe, "-i", str(bad), "check"], capture_output=True, text=True)
+    assert out.returncode == 1 and "Fatal error" in out.stderr
+    out = subprocess.run([exe, "-i", str(wad), "-r", "320by200"], capture_output=True, text=True)
+    assert out.returncode == 2
+
+
+@pytest.mark.gpu
+def test_compiled_cli_renders_the_same_frames_as_the_python_mirror(tmp_path, b2d):
+    import subprocess
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=20, thing_pct=30, anim=True))
+    wad = tmp_path / "syn.wad"
+    wad.write_bytes(data)
+    stream = tmp_path / "s.ppm"
+    out = subprocess.run([_b2d_binary(), "-i", str(wad), "-r", "320x200", "--poses", "4", "--tics", "40",
+                          "--stream", str(stream)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    poses = np.repeat(sc.start_pose, 4)
+    poses["angle"] = (poses["angle"].astype(np.uint64) + (np.arange(4, dtype=np.uint64) << np.uint64(32)) // np.uint64(4)).astype(np.uint32)
+    r = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=4)
+    r.set_time(40)
+    rgba = r.render(poses, rgba=True)[1]
+    want = b"".join(cli.encode_ppm(cli.rgba_to_rgb(rgba[i])) for i in range(4))
+    assert stream.read_bytes() == want
