@@ -21,6 +21,8 @@
  *                                                assets/shaders/sky.vert:9-16, sky.frag:12-26
  *   - projection fovy 65deg, aspect*1.2, near .01 (= 1 map unit)
  *                                                game/src/player.rs:84-89, engine/src/projections.rs:93-101
+ *   - masked two-sided middles, decoration sprites (billboards), level time (animated flats / walls, scrolling
+ *     walls, sector light effects): DESIGN.md C12-C15 with their reference citations
  * The visibility algorithm itself (front-to-back BSP walk with per-column clip windows, Doom
  * style) is new; it is written here in the most literal per-column / per-pixel form.  All
  * arithmetic is integer (DESIGN.md "pixel contract"); the CUDA path must reproduce every bit.
