@@ -21,7 +21,7 @@ def host(blob, view, poses, tics):
     buf=(ctypes.c_char*len(blob)).from_buffer_copy(blob); poses=np.ascontiguousarray(poses)
     lib.hostcheck_render_t(ctypes.c_void_p(ctypes.addressof(buf)), ctypes.byref(view), ctypes.c_void_p(poses.ctypes.data), n, ctypes.c_void_p(fb.ctypes.data), ctypes.c_void_p(counts.ctypes.data), None, 0, ctypes.c_uint32(tics))
     return fb
-rng=np.random.default_rng(12345)
+rng=np.random.default_rng(int(os.environ.get("B2D_CAMPAIGN_SEED", "12345")))
 bad=0; t0=time.time()
 for it in range(int(sys.argv[1]) if len(sys.argv) > 1 else 200):
     seed=int(rng.integers(100,100000))
