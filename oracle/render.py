@@ -3,8 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import math
-import os
-from typing import Optional, Tuple
+from typing import Tuple
 
 import numpy as np
 

@@ -46,7 +46,7 @@ from __future__ import annotations
 import math
 import re
 import struct
-from typing import Dict, List, Optional, Tuple
+from typing import Dict, List, Tuple
 
 import numpy as np
 

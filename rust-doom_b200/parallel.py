@@ -9,7 +9,7 @@ torch.distributed (NCCL on GPUs, gloo in the CPU tests), chunked so that the gat
 """
 from __future__ import annotations
 
-from typing import Iterator, Optional, Tuple
+from typing import Iterator, Tuple
 
 import numpy as np
 
