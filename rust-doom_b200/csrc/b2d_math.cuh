@@ -307,7 +307,9 @@ B2D_HD uint32_t next_quad(uint32_t q0, uint32_t h) { return q0 + 1u == (h >> 2) 
 // the byte PRMT selects for a selector below 8 (bytes 0-3 from lo, 4-7 from hi)
 B2D_HD uint32_t pick_byte(uint32_t lo, uint32_t hi, uint32_t sel) {
 #if defined(__CUDA_ARCH__)
-    return __byte_perm(lo, hi, sel);
+    uint32_t d;                      // raw PRMT: sel < 8, so no sign-replicate bit and no need for __byte_perm's mask
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(lo), "r"(hi), "r"(sel));
+    return d;
 #else
     return ((sel & 4u) ? hi : lo) >> (8u * (sel & 3u)) & 0xFFu;
 #endif
