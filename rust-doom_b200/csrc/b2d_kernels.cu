@@ -408,7 +408,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
             for (int k = 0; k < kBatch; k++) {
                 const uint4 r4 = c.row4[j + k];                               // shared-memory broadcast
                 cm[k] = c.row1[j + k];
-                v[k] = __ldg(px + (cm[k] + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w)));   // always in bounds
+                v[k] = __ldg(px + cm[k] + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w));   // 3-input 64-bit add; always in bounds
             }
             const int y = yc + j;
             store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
@@ -417,7 +417,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
             const uint4 r4 = c.row4[j];
             const uint32_t cm = c.row1[j];
             const int y = yc + j;
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + (cm + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w))));
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + cm + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w)));
         }
         __syncwarp();
     }
