@@ -422,3 +422,14 @@ def test_gpu_masked_windows_clipped_to_nothing(b2d):
         r = b2d.Renderer(sc, b2d.make_view(w, h, fov), max_batch=4)
         r.set_time(tics)
         _assert_same(render.render(sc.blob, render.make_view(w, h, fov), poses, threads=8, tics=tics), r.render(poses), "seed %d" % seed)
+
+
+def test_gpu_random_campaign_short():
+    """A short run of tools/campaign_gpu.py (random levels with all content kinds, random resolution / field of view /
+    level time / batch size, RGBA every fourth case) so that every GPU test tier draws fresh-ish coverage."""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "campaign_gpu.py")
+    spec = importlib.util.spec_from_file_location("campaign_gpu", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(cases=40, seed=2024) == 0

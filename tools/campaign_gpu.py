@@ -16,9 +16,10 @@ from rust_doom_b200 import synthwad  # noqa: E402
 from tests.conftest import sample_poses  # noqa: E402
 
 
-def main():
-    cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
-    rng = np.random.default_rng(12345)
+def main(cases=None, seed=12345):
+    if cases is None:
+        cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
+    rng = np.random.default_rng(seed)
     bad, t0, pixels = 0, time.time(), 0
     for it in range(cases):
         seed = int(rng.integers(100, 100000))
