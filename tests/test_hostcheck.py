@@ -184,3 +184,14 @@ def test_hostcheck_campaign_mixed_content(b2d, hostcheck):
         sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(seed, ("MAP07",), cfg=cfg)), 0)
         w, h = sizes[i % 3]
         _compare(b2d, hostcheck, sc, w, h, 6, 300 + seed, tics=(0, 9, 123456)[i % 3])
+
+
+def test_campaign_tool_smoke(hostcheck):
+    """tools/campaign.py (random CPU parity campaign) keeps running: 6 cases, no mismatch."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "campaign.py"), "6"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert "bad 0" in out.stdout, out.stdout[-500:]
