@@ -421,6 +421,7 @@ class SynthConfig:
     thing_pct: int = 0          # % of plain room cells that get decoration things + sprite lumps (0 = legacy)
     anim: bool = False          # animated flats/walls (NUKAGE1-3, SFALL1-4, FIREBLU1-2) + scrolling lines (0x30)
     odd_tex: bool = False       # wall textures with odd heights / non power-of-two widths (ODD70, ODD33, ODD126)
+    light_fx: bool = True       # sector light specials (flash, glow, strobes); False = every sector static
 
 
 # inner convex polygons, CCW, in cell-local coordinates for a 256 cell (scaled by cell/256);
@@ -512,6 +513,8 @@ class LevelBuilder:
                 stype = rng.pick([0] * 14 + [1, 8])
                 if self.cfg.anim and rng.chance(1, 3):          # every light effect kind (light.rs:127-134)
                     stype = rng.pick([1, 2, 3, 4, 8, 12, 13, 17])
+                if not self.cfg.light_fx:
+                    stype = 0
                 self.sectors.append(Sector(
                     fl, fl + height, rng.pick(FLOOR_FLATS),
                     "F_SKY1" if is_sky else rng.pick(CEIL_FLATS), light, stype))

@@ -195,3 +195,24 @@ def test_campaign_tool_smoke(hostcheck):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "campaign.py"), "6"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-500:]
     assert "bad 0" in out.stdout, out.stdout[-500:]
+
+
+def test_level_time_is_periodic_without_light_effects(b2d, hostcheck):
+    """Size-independent property of C14: with static lights, a frame depends on time only through the animation
+    frame (period 8 tics x lcm(2, 3, 4) frames = 96) and the scroll offset (mod the texture widths, all dividing 256),
+    so it repeats every lcm(96, 256) = 768 tics -- and does change within the period."""
+    from oracle import scene as S
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(7, ("E1M1",), cfg=synthwad.SynthConfig(anim=True, light_fx=False, mid_pct=15))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    assert (S.sector_lights_at(sc.blob, 0) < 0).all() and S.header(sc.blob)[S.H_NANIM] >= 6
+    poses = sample_poses(b2d, sc, 10, 77)
+    ov, pv = render.make_view(480, 270), b2d.make_view(480, 270)
+    for t in (0, 5, 1234567):
+        a = render.render(sc.blob, ov, poses, threads=4, tics=t)
+        b = render.render(sc.blob, ov, poses, threads=4, tics=t + 768)
+        c = render.render(sc.blob, ov, poses, threads=4, tics=t + 8)
+        assert np.array_equal(a, b), "oracle not periodic at t=%d" % t
+        assert not np.array_equal(a, c), "time had no effect"
+        ha, hb = hostcheck(sc.blob, pv, poses, tics=t)[0], hostcheck(sc.blob, pv, poses, tics=t + 768)[0]
+        assert np.array_equal(ha, a) and np.array_equal(hb, a)
