@@ -2,6 +2,7 @@
 // side (WAD loader, scene compiler) and the CUDA kernels.  There is deliberately no CPU rendering
 // path here: every render entry point launches the sm_100a kernels or fails with B2D_ERR_CUDA.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -389,6 +390,10 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.nflats = (int32_t)h[H_NFLATS]; d.sky_tex = (int32_t)h[H_SKY_TEX];
     d.root = h[H_ROOT];
     d.invF = (uint32_t)(4294967296ULL / (uint64_t)view->F);
+    {
+        const char *tune = getenv("B2D_TUNE");
+        d.tune = tune ? (uint32_t)strtoul(tune, nullptr, 0) : 0u;
+    }
     if (d.nsegs + d.nsprites > 65535) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level has more than 65535 segs + sprites"); }
     if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
     if (scene_is_timed(s->blob.data())) r->h_blob = s->blob;

@@ -328,10 +328,10 @@ __device__ __forceinline__ void store_batch(const RasterCtx &c, uint8_t *p8, uin
 #pragma unroll
         for (int k = 0; k < kBatch; k++) put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, true, v[k]);
     } else {
-        const uint32_t len = yb > ya ? (uint32_t)(yb - ya) : 0u, d = (uint32_t)(y - ya);
+        const uint32_t m = row_mask(y, ya, yb, kBatch);      // one bit test per row instead of two compares
 #pragma unroll
         for (int k = 0; k < kBatch; k++)
-            put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, d + (uint32_t)k < len, v[k]);
+            put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, (m >> k) & 1u, v[k]);
     }
 }
 
@@ -397,7 +397,9 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         if (yy < y1) {
             PlaneRow pr = plane_row(habs, sc.yslope[yy], fc, vw, sc.invF);
             c.row4[c.lane] = make_uint4(pr.baseU, pr.stepU, pr.baseV, pr.stepV);
-            c.row1[c.lane] = sc.lit_flat_stride * (uint32_t)light_row(lightb, pr.z8) + 4096u * (uint32_t)flat;
+            // plane + flat offset / 64: the texel offset is then two instructions, LEA.HI (cm6 + (U >> 26)) and a funnel
+            // shift ((.) << 6 | V >> 26)
+            c.row1[c.lane] = (sc.lit_flat_stride >> 6) * (uint32_t)light_row(lightb, pr.z8) + 64u * (uint32_t)flat;
         }
         __syncwarp();
         const int rows = min(32, y1 - yc);
@@ -408,7 +410,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
             for (int k = 0; k < kBatch; k++) {
                 const uint4 r4 = c.row4[j + k];                               // shared-memory broadcast
                 cm[k] = c.row1[j + k];
-                v[k] = __ldg(px + cm[k] + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w));   // 3-input 64-bit add; always in bounds
+                v[k] = __ldg(px + flat_offset(cm[k], r4.x + xx * r4.y, r4.z + xx * r4.w));   // always in bounds
             }
             const int y = yc + j;
             store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
@@ -417,9 +419,44 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
             const uint4 r4 = c.row4[j];
             const uint32_t cm = c.row1[j];
             const int y = yc + j;
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + cm + flat_index(r4.x + xx * r4.y, r4.z + xx * r4.w)));
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + flat_offset(cm, r4.x + xx * r4.y, r4.z + xx * r4.w)));
         }
         __syncwarp();
+    }
+}
+
+// Magnified wall columns (every lane's texture step <= kWallFast8 / kWallFast16, b2d_math.cuh): R rows per batch from
+// two aligned word loads, the row quad tracked incrementally -- per pixel one IMAD + one shift (byte index), one PRMT, one store.
+template <bool kRgba, int kW, int R>
+__device__ __forceinline__ void wall_fast_loop(const RasterCtx &c, const uint8_t *plq, uint32_t w4, uint32_t nq, uint32_t q,
+                                               uint32_t acc, uint32_t ts29, int y0, int y1, int ya, int yb,
+                                               int full_lo, int full_hi) {
+    const int Wc = kW ? kW : c.W;
+    uint8_t *p8 = c.fb + (size_t)y0 * Wc;
+    uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
+    asm("" : "+l"(plq));       // keep the column's plane pointer whole: one IMAD.WIDE per load instead of re-adding the base
+#pragma unroll 1
+    for (int y = y0; y < y1; y += R, p8 += (size_t)R * Wc, p32 += (size_t)R * Wc) {
+        const uint32_t q1 = q + 1u == nq ? 0u : q + 1u;
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q * w4));
+        const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q1 * w4));
+        if (y >= full_lo && y + R <= full_hi) {
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                uint32_t v = pick_byte(w0, w1, wall_sel(acc, ts29, (uint32_t)k));
+                if (kRgba) v &= 0xFFu;
+                put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, true, v);
+            }
+        } else {
+            const uint32_t m = row_mask(y, ya, yb, R);
+#pragma unroll
+            for (int k = 0; k < R; k++) {
+                uint32_t v = pick_byte(w0, w1, wall_sel(acc, ts29, (uint32_t)k));
+                if (kRgba) v &= 0xFFu;
+                put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, (m >> k) & 1u, v);
+            }
+        }
+        wall_advance(acc, q, ts29, (uint32_t)R, nq);
     }
 }
 
@@ -445,6 +482,19 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
     // Texel loads are unconditional (t is a bounded linear function of y for every lane, so the row index
     // is always inside the texture); only the store is predicated.  That keeps the loops branch-free.
+    if (tex_interleaved(T) && T.h >= 8u && !(sc.tune & 1u)) {
+        // magnified columns: the whole piece runs on the incremental path when every lane qualifies (inactive lanes step 0)
+        const uint32_t ts = act ? tstep : 0u;
+        const bool f16 = !(sc.tune & 2u) && __all_sync(kFull, ts <= kWallFast16);
+        if (f16 || __all_sync(kFull, ts <= kWallFast8)) {
+            const uint32_t tt = act ? t : 0u;
+            const uint32_t r0 = wall_row((int32_t)tt, T.h, T.hmagic, T.hbias);
+            const uint8_t *plq = pl + 4u * col;
+            if (f16) wall_fast_loop<kRgba, kW, 16>(c, plq, 4u * T.w, T.h >> 2, r0 >> 2, wall_acc29(tt, r0), ts << 13, y0, y1, ya, yb, full_lo, full_hi);
+            else wall_fast_loop<kRgba, kW, 8>(c, plq, 4u * T.w, T.h >> 2, r0 >> 2, wall_acc29(tt, r0), ts << 13, y0, y1, ya, yb, full_lo, full_hi);
+            return;
+        }
+    }
     if (tex_interleaved(T)) {
         // 4-row interleaved plane.  Rows of a batch: u_k = asr(t + k*tstep, 16), texture row = floormod(u_k, h).
         // With r0 the row of the first pixel, pixel k reads byte (r0 & 3) + u_k - u_0 of the 8 bytes made of row

@@ -36,6 +36,8 @@ struct DeviceScene {
     int32_t *status_flag;        // device int: OR of per-frame walk status bits (0 = all frames complete)
     uint32_t *masked_list;       // per raster warp: masked_cap x 33 words (worklist index + 32 packed windows)
     int32_t masked_cap;          // entries one 32-column strip can defer per frame (more -> status bit 8)
+    uint32_t tune;               // A/B switches for profiles/ (env B2D_TUNE, default 0): 1 no incremental wall path,
+                                 // 2 no 16-row batches
 };
 
 // masked middle textures + sprites one 32-column strip can defer per frame: min(masked mids + sprites of the level,

@@ -277,6 +277,14 @@ B2D_HD PlaneRow plane_row(uint32_t habs, uint32_t yslope, const FrameConst &f, c
     return pr;
 }
 B2D_HD uint32_t flat_index(uint32_t U, uint32_t V) { return ((U >> 26) << 6) | (V >> 26); }
+// the same index on top of a plane/flat offset given in units of 64 bytes: ((cm6 + (U >> 26)) << 6) | (V >> 26)
+B2D_HD uint32_t flat_offset(uint32_t cm6, uint32_t U, uint32_t V) {
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(V, cm6 + (U >> 26), 6);
+#else
+    return ((cm6 + (U >> 26)) << 6) | (V >> 26);
+#endif
+}
 
 // wall texture row: t(y) = tbase + y*tstep (Q16); row index = floor-mod of t>>16 by the height,
 // evaluated with the per-texture magic reciprocal (exact for |t>>16| < 2^14, h <= 4096).
@@ -313,6 +321,34 @@ B2D_HD uint32_t pick_byte(uint32_t lo, uint32_t hi, uint32_t sel) {
 #else
     return ((sel & 4u) ? hi : lo) >> (8u * (sel & 3u)) & 0xFFu;
 #endif
+}
+
+// ---- magnified wall columns: incremental row tracking -----------------------------------------------------------
+// A column whose texture step is small enough that R consecutive screen rows (and the step to the next batch),
+// starting anywhere inside a row quad, stay inside that quad and the next one (R * tstep <= 4 texture rows) needs no
+// per-batch floor-mod: the state is the row quad q (0 .. h/4-1) and a Q29 accumulator whose top three bits are the
+// byte index inside the 8-byte window {quad q, quad q+1} and whose low 29 bits are the fraction of the texture row.
+// Row k of a batch reads byte (acc + k * (tstep << 13)) >> 29 of that window: one IMAD, one shift.  Same rows as
+// wall_row(t0 + k*tstep) by construction: (t0 + k*tstep) >> 16 == (t0 >> 16) + (((t0 & 0xFFFF) + k*tstep) >> 16)
+// while nothing wraps, and the byte index never exceeds 3 + 4 = 7.
+constexpr uint32_t kWallFast8 = 32768u;    // 8 * tstep <= 4 * 65536
+constexpr uint32_t kWallFast16 = 16384u;   // 16 * tstep <= 4 * 65536
+B2D_HD uint32_t wall_acc29(uint32_t t, uint32_t r0) { return ((r0 & 3u) << 29) | ((t & 0xFFFFu) << 13); }
+B2D_HD uint32_t wall_sel(uint32_t acc, uint32_t ts29, uint32_t k) { return (acc + k * ts29) >> 29; }
+// after R rows: move the window by whole quads (at most one: the index is <= 7; nq >= 2), keep (row & 3 | fraction)
+B2D_HD void wall_advance(uint32_t &acc, uint32_t &q, uint32_t ts29, uint32_t R, uint32_t nq) {
+    acc += R * ts29;
+    q += acc >> 31;
+    if (q >= nq) q -= nq;
+    acc &= 0x7FFFFFFFu;
+}
+// bit k set <=> row y + k lies in [ya, yb), k < R <= 16
+B2D_HD uint32_t row_mask(int y, int ya, int yb, int R) {
+    int lo = ya - y, hi = yb - y;
+    if (lo < 0) lo = 0;
+    if (hi > R) hi = R;
+    if (hi <= lo) return 0u;
+    return ((1u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
 // sky: column from yaw + screen x (one texture width per NDC unit, 8 widths per turn); row mirrored

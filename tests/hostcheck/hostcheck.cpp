@@ -218,9 +218,9 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
         uint32_t habs = plane_habs(h, fc.pose.z);
         for (int y = ya; y < yb; y++) {
             PlaneRow pr = plane_row(habs, yslope[(size_t)y], fc, vw, invF);
-            const uint32_t rowoff = sc.lit_flat_stride * (uint32_t)light_row(lightb, pr.z8) + 4096u * (uint32_t)flat;
+            const uint32_t cm6 = (sc.lit_flat_stride >> 6) * (uint32_t)light_row(lightb, pr.z8) + 64u * (uint32_t)flat;
             uint32_t U = pr.baseU + (uint32_t)x * pr.stepU, V = pr.baseV + (uint32_t)x * pr.stepV;
-            put(x, y, px[rowoff + flat_index(U, V)]);
+            put(x, y, px[flat_offset(cm6, U, V)]);
         }
     };
     auto draw_wall = [&](int x, int ya, int yb, int32_t tex, int32_t tA, int32_t hA, int32_t ucol, int32_t iscale, int row) {
@@ -233,6 +233,28 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
         uint32_t t = (uint32_t)wall_tbase(tA, hA, fc.pose.z, H, iscale) + (uint32_t)ya * tstep;
         if (!tex_interleaved(T.h, T.texel_off)) {
             for (int y = ya; y < yb; y++, t += tstep) put(x, y, pl[wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w + col]);
+            return;
+        }
+        if (T.h >= 8u && tstep <= kWallFast8) {
+            // the incremental path of wall_fast_loop (the kernel takes it when every lane of the warp qualifies; here per
+            // lane, alternating between the 16- and the 8-row form, and starting a few rows above ya the way a lane whose
+            // neighbours start higher does)
+            const int R = (tstep <= kWallFast16 && (x & 1) == 0) ? 16 : 8;
+            const int y0 = std::max(0, ya - (x % 5) * 3);
+            const uint32_t t0 = (uint32_t)wall_tbase(tA, hA, fc.pose.z, H, iscale) + (uint32_t)y0 * tstep;
+            const uint32_t r0 = wall_row((int32_t)t0, T.h, T.hmagic, T.hbias);
+            uint32_t q = r0 >> 2, acc = wall_acc29(t0, r0);
+            const uint32_t ts29 = tstep << 13, nq = T.h >> 2, w4f = 4u * T.w;
+            for (int y = y0; y < yb; y += R) {
+                const uint32_t q1 = q + 1u == nq ? 0u : q + 1u;
+                uint32_t w0, w1;
+                std::memcpy(&w0, pl + 4u * col + (size_t)q * w4f, 4);
+                std::memcpy(&w1, pl + 4u * col + (size_t)q1 * w4f, 4);
+                const uint32_t m = row_mask(y, ya, yb, R);
+                for (int k = 0; k < R; k++)
+                    if ((m >> k) & 1u) put(x, y + k, (uint8_t)(pick_byte(w0, w1, wall_sel(acc, ts29, (uint32_t)k)) & 0xFFu));
+                wall_advance(acc, q, ts29, (uint32_t)R, nq);
+            }
             return;
         }
         // batches of 8 rows as in draw_wall_warp: two aligned words + byte pick when the 8 rows stay inside two
