@@ -101,10 +101,24 @@ void b2d_renderer_destroy(b2d_renderer *r);
 
 /* Level time in tics (1/35 s) for every batch rendered afterwards; a new renderer is at tic 0.  Replaces the
  * reference's u_time uniform (game/src/level.rs:257-260, assets/shaders/static.vert:23-39): animated flats and
- * wall textures show frame (k + tics/8) mod n of their group, walls of scrolling lines (special 0x30,
- * wad/src/visitor.rs:922) shift their texture column by one texel per tic.  Synchronises the device, then
- * re-uploads the time-dependent scene tables (a few KB); a no-op for levels without animated content. */
+ * wall textures show frame (tics/8) mod n of their group -- whichever frame name the map uses, because the
+ * reference binds every frame name to the group's first frame (wad/src/tex.rs:260, 302-306) -- and walls of
+ * scrolling lines (special 0x30, wad/src/visitor.rs:922) shift their texture column by one texel per tic; sector
+ * light effects (wad/src/light.rs:27-80) are re-evaluated.  A no-op for levels without time-dependent content.
+ *
+ * _async: the time-dependent scene tables (a few KB ... ~200 KB) are rebuilt on the host and copied in stream order
+ * on `cuda_stream`; everything this renderer enqueued before -- on any stream -- is awaited by that stream first and
+ * later launches on other streams wait for the upload, so the host never blocks on the device (this is the call for
+ * a per-frame System::update loop).  b2d_renderer_set_time additionally waits until the upload has completed. */
+int b2d_renderer_set_time_async(b2d_renderer *r, uint32_t tics, void *cuda_stream);
 int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics);
+
+/* Sticky completeness status of everything rendered since the last call (device-resident entry points do not
+ * synchronise, so they cannot report it themselves): synchronises the device, returns the OR of
+ *   1 BSP traversal stack overflow   2 worklist overflow   4 BSP traversal did not terminate (cyclic node graph)
+ *   8 more masked middles / sprites deferred than the renderer holds (per 32-column strip, or arena exhausted)
+ * in *bits_out (0 = every frame complete) and clears it.  b2d_render reports the same bits as an error. */
+int b2d_renderer_status(b2d_renderer *r, int32_t *bits_out);
 
 /* End-to-end: HOST poses in, HOST frames out (pinned staging + copies inside).  index_fb gets
  * n*W*H palette indices, row-major, top row first; rgba_fb (nullable) gets n*W*H RGBA8
@@ -127,7 +141,8 @@ int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_
  * its own `cuda_stream`.  The two calls are ordered through events, not by the streams: with two streams the walk of
  * batch k+1 overlaps the raster of batch k (the walk is a latency-bound ~0.1 ms, the raster fills the machine).  At
  * most two batches can be walked and not yet rastered; tickets are rastered once.  d_poses is read by the walk
- * only.  Replaces nothing in the reference (its render loop is synchronous, engine/src/renderer.rs:62-175). */
+ * only.  Levels with masked middle textures or sprites share one arena of deferred entries per renderer: their rasters are
+ * ordered one after the other through an event, whatever streams they are enqueued on.  Replaces nothing in the reference (its render loop is synchronous, engine/src/renderer.rs:62-175). */
 int b2d_walk_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, void *cuda_stream, int64_t *ticket_out);
 int b2d_raster_device(b2d_renderer *r, int64_t ticket, uint8_t *d_index_fb, uint32_t *d_rgba_fb, void *cuda_stream);
 

@@ -173,12 +173,14 @@ static inline void put(Frame *f, int x, int y, uint8_t v) {
     if (f->seg_hits && f->cur_seg >= 0) f->seg_hits[f->cur_seg]++;       /* sprites have no seg */
 }
 
-/* Animated textures and flats (static.vert:23-39, ANIM_FPS = 8/35 s per frame): an image that is frame k of an
- * n-frame group shows group frame (k + floor(tics/8)) mod n.  anim_nk = n | k << 16; 0 = not animated. */
+/* Animated textures and flats (static.vert:23-39, ANIM_FPS = 8/35 s per frame): every frame name of an n-frame group
+ * is bound to the atlas position of the group's FIRST frame (wad/src/tex.rs:260 `positions[i - entry.frame_offset]`,
+ * tex.rs:302-306 `anim_start_pos`), so whichever frame name a wall or flat uses, it shows group frame
+ * floor(tics/8) mod n -- frame 0 at tic 0.  anim_nk = n | k << 16 (k is informational); 0 = not animated. */
 static inline int32_t anim_now(const Scene *sc, int32_t first, uint32_t nk, uint32_t tics, int32_t self) {
-    uint32_t n = nk & 0xFFFF, k = nk >> 16;
+    uint32_t n = nk & 0xFFFF;
     if (n < 2 || first < 0 || (int64_t)first + n > sc->nanim) return self;
-    return sc->anim[first + (int32_t)(((uint64_t)k + (tics >> 3)) % n)];
+    return sc->anim[first + (int32_t)((tics >> 3) % n)];
 }
 static inline int32_t tex_now(const Frame *f, int32_t tex) {
     const Scene *sc = f->sc;

@@ -172,6 +172,17 @@ class Renderer:
         """Level time in 1/35 s for the batches rendered afterwards (animated flats / walls, scrolling walls)."""
         _check(_lib.load().b2d_renderer_set_time(self._h, int(tics) & 0xFFFFFFFF))
 
+    def set_time_async(self, tics: int, stream: int = 0):
+        """Same, without blocking the host: the table upload is ordered on `stream` (a cudaStream_t as int)."""
+        _check(_lib.load().b2d_renderer_set_time_async(self._h, int(tics) & 0xFFFFFFFF, ctypes.c_void_p(stream)))
+
+    def status(self) -> int:
+        """Sticky completeness bits of everything rendered since the last call (0 = every frame complete); synchronises
+        the device and clears them.  1 stack overflow, 2 worklist overflow, 4 cyclic BSP, 8 masked-entry overflow."""
+        bits = ctypes.c_int32(0)
+        _check(_lib.load().b2d_renderer_status(self._h, ctypes.byref(bits)))
+        return int(bits.value)
+
     # -- end to end: host poses in, host frames out -------------------------------------------------
     def render(self, poses: np.ndarray, rgba: bool = False, out_index: Optional[np.ndarray] = None,
                out_rgba: Optional[np.ndarray] = None):

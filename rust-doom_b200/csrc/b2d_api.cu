@@ -57,6 +57,16 @@ struct b2d_renderer {
     cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     std::vector<uint8_t> h_blob;    // host copy of the scene, kept only when it has time-dependent content
     uint32_t tics = 0;
+    // time-dependent tables (texture records, sectors, segs, sprites): rebuilt on the host into one of two pinned
+    // staging buffers and copied over their sections of the device blob in stream order (b2d_renderer_set_time_async)
+    uint8_t *h_timed[2] = {nullptr, nullptr};
+    cudaEvent_t timed_copied[2] = {nullptr, nullptr};     // staging buffer i has been read by its copy
+    cudaEvent_t tables_ready = nullptr;                   // last table upload; launches on other streams wait for it
+    bool tables_pending = false;
+    int timed_next = 0;
+    size_t timed_bytes = 0;
+    cudaEvent_t masked_done = nullptr;                    // last raster that used the masked-entry arena
+    uint32_t *d_masked_counter = nullptr;
     int64_t launches = 0;
     int last_n = 0;
     bool profiling = false;
@@ -120,6 +130,13 @@ void free_renderer(b2d_renderer *r) {
     if (r->d_skyrow) cudaFree(r->d_skyrow);
     if (r->d_status) cudaFree(r->d_status);
     if (r->d_masked) cudaFree(r->d_masked);
+    if (r->d_masked_counter) cudaFree(r->d_masked_counter);
+    if (r->masked_done) cudaEventDestroy(r->masked_done);
+    if (r->tables_ready) cudaEventDestroy(r->tables_ready);
+    for (int i = 0; i < 2; i++) {
+        if (r->h_timed[i]) cudaFreeHost(r->h_timed[i]);
+        if (r->timed_copied[i]) cudaEventDestroy(r->timed_copied[i]);
+    }
     if (r->d_lit) cudaFree(r->d_lit);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
@@ -141,6 +158,7 @@ int walk_into_slot(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t str
     } else {
         CU(cudaStreamWaitEvent(stream, r->raster_done[slot], 0));      // the raster that last read this slot
     }
+    if (r->tables_pending) CU(cudaStreamWaitEvent(stream, r->tables_ready, 0));   // a table upload on another stream
     cudaEvent_t ev[2] = {nullptr, nullptr};
     if (r->profiling) {
         for (auto &e : ev) CU(cudaEventCreate(&e));
@@ -168,6 +186,13 @@ int raster_from_slot(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t
     if (ticket < 0 || r->slot_ticket[slot] != ticket || r->slot_rastered[slot])
         return fail(B2D_ERR_INVALID_ARG, "unknown or already rastered walk ticket");
     CU(cudaStreamWaitEvent(stream, r->walk_done[slot], 0));
+    if (r->tables_pending) CU(cudaStreamWaitEvent(stream, r->tables_ready, 0));
+    if (r->ds.masked_list) {
+        // one arena of deferred masked entries per renderer: rasters that use it run one after the other (each fills the
+        // machine on its own, so nothing is lost), whatever streams they were enqueued on
+        CU(cudaStreamWaitEvent(stream, r->masked_done, 0));
+        CU(cudaMemsetAsync(r->d_masked_counter, 0, sizeof(uint32_t), stream));
+    }
     cudaEvent_t ev[2] = {nullptr, nullptr};
     if (r->profiling) {
         for (auto &e : ev) CU(cudaEventCreate(&e));
@@ -180,8 +205,40 @@ int raster_from_slot(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t
         r->prof_kinds.push_back(1);
     }
     CU(cudaEventRecord(r->raster_done[slot], stream));
+    if (r->ds.masked_list) CU(cudaEventRecord(r->masked_done, stream));
     r->slot_rastered[slot] = true;
     r->launches += 1;
+    return B2D_OK;
+}
+
+// Rebuild the time-dependent tables for `tics` on the host (scene_at_time) and copy them over their sections of the
+// device blob in stream order.  Everything this renderer has enqueued so far -- on any stream -- is awaited by `stream`
+// first (the walk/raster events of both worklist slots), and later launches on other streams wait for the upload, so the
+// host never blocks on the device: no cudaDeviceSynchronize in the System::update loop this stands in for.
+int upload_timed_tables(b2d_renderer *r, uint32_t tics, cudaStream_t stream) {
+    const uint8_t *blob = r->h_blob.data();
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    const int buf = r->timed_next;
+    r->timed_next ^= 1;
+    CU(cudaEventSynchronize(r->timed_copied[buf]));          // the copy issued two uploads ago has read this buffer
+    uint8_t *p = r->h_timed[buf];
+    TexRec *tex = reinterpret_cast<TexRec *>(p);
+    SectorRec *sectors = reinterpret_cast<SectorRec *>(tex + h[H_NTEX]);
+    SegRec *segs = reinterpret_cast<SegRec *>(sectors + h[H_NSECTORS]);
+    SpriteRec *sprites = reinterpret_cast<SpriteRec *>(segs + h[H_NSEGS]);
+    scene_at_time(blob, tics, tex, sectors, segs, sprites);
+    for (int i = 0; i < 2; i++) {
+        if (r->walk_done[i]) CU(cudaStreamWaitEvent(stream, r->walk_done[i], 0));
+        if (r->raster_done[i]) CU(cudaStreamWaitEvent(stream, r->raster_done[i], 0));
+    }
+    CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_TEX], tex, h[H_NTEX] * sizeof(TexRec), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_SECTORS], sectors, h[H_NSECTORS] * sizeof(SectorRec), cudaMemcpyHostToDevice, stream));
+    CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_SEGS], segs, h[H_NSEGS] * sizeof(SegRec), cudaMemcpyHostToDevice, stream));
+    if (h[H_NSPRITES])
+        CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_SPRITES], sprites, h[H_NSPRITES] * sizeof(SpriteRec), cudaMemcpyHostToDevice, stream));
+    CU(cudaEventRecord(r->timed_copied[buf], stream));
+    CU(cudaEventRecord(r->tables_ready, stream));
+    r->tables_pending = true;
     return B2D_OK;
 }
 
@@ -357,14 +414,30 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.nmids = (int32_t)h[H_NMIDS];
     d.sprites = reinterpret_cast<const SpriteRec *>(r->d_blob + h[H_OFF_SPRITES]);
     d.nsprites = (int32_t)h[H_NSPRITES];
-    d.masked_list = nullptr;
-    if (d.nmids > 0 || d.nsprites > 0) {   // deferred masked-texture lists: one per raster warp of a full batch
+    d.masked_list = nullptr; d.masked_counter = nullptr; d.masked_chunks = 0; d.masked_cap = 0;
+    if (d.nmids > 0 || d.nsprites > 0) {
+        // arena of deferred masked entries: chunks of kMaskedChunk entries handed out on demand.  Sized for two chunks per
+        // (frame, 32-column strip) of a full batch -- frames defer a handful of entries per strip -- and never more than the
+        // worst case (every strip at its cap).  1000 x 1080p: 63 MB instead of the 1 GB a fixed per-strip list takes.
         const size_t strips = (size_t)(view->width + 31) / 32;
         int cap = d.nmids + d.nsprites;
         cap = cap < 8 ? 8 : (cap > kMaskedCapMax ? kMaskedCapMax : cap);
         d.masked_cap = cap;
-        CUR(cudaMalloc(&r->d_masked, sizeof(uint32_t) * 33 * (size_t)cap * strips * (size_t)max_batch));
+        const size_t per_strip = ((size_t)cap + kMaskedChunk - 1) / kMaskedChunk;
+        size_t chunks = strips * (size_t)max_batch * (per_strip < 2 ? per_strip : 2);
+        if (chunks < 4096) chunks = 4096;
+        const size_t worst = strips * (size_t)max_batch * per_strip;
+        if (chunks > worst) chunks = worst;
+        if (const char *env = getenv("B2D_MASKED_CHUNKS")) chunks = (size_t)strtoull(env, nullptr, 0);   // tests: force exhaustion
+        if (chunks < 1) chunks = 1;
+        d.masked_chunks = (uint32_t)chunks;
+        CUR(cudaMalloc(&r->d_masked, sizeof(uint32_t) * 33 * kMaskedChunk * chunks));
+        CUR(cudaMalloc(&r->d_masked_counter, sizeof(uint32_t)));
+        CUR(cudaMemset(r->d_masked_counter, 0, sizeof(uint32_t)));
+        CUR(cudaEventCreateWithFlags(&r->masked_done, cudaEventDisableTiming));
+        CUR(cudaEventRecord(r->masked_done, nullptr));
         d.masked_list = r->d_masked;
+        d.masked_counter = r->d_masked_counter;
     }
     d.texels = r->d_blob + h[H_OFF_TEXELS];
     d.flats = r->d_blob + h[H_OFF_FLATS];
@@ -396,7 +469,22 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     }
     if (d.nsegs + d.nsprites > 65535) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level has more than 65535 segs + sprites"); }
     if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
-    if (scene_is_timed(s->blob.data())) r->h_blob = s->blob;
+    if (scene_is_timed(s->blob.data())) {
+        r->h_blob = s->blob;
+        r->timed_bytes = h[H_NTEX] * sizeof(TexRec) + h[H_NSECTORS] * sizeof(SectorRec) + h[H_NSEGS] * sizeof(SegRec) +
+                         h[H_NSPRITES] * sizeof(SpriteRec);
+        for (int i = 0; i < 2; i++) {
+            CUR(cudaMallocHost(&r->h_timed[i], r->timed_bytes ? r->timed_bytes : 1));
+            CUR(cudaEventCreateWithFlags(&r->timed_copied[i], cudaEventDisableTiming));
+        }
+        CUR(cudaEventCreateWithFlags(&r->tables_ready, cudaEventDisableTiming));
+        // tic 0 is a time like any other: a frame name with k > 0 shows its group's frame 0 (tex.rs:260, 302-306).  The
+        // pre-lit planes above were built from the blob's own (per-image) records; from here on the records are re-pointed.
+        int rc = upload_timed_tables(r, 0, nullptr);
+        if (rc != B2D_OK) { free_renderer(r); return rc; }
+        CUR(cudaStreamSynchronize(nullptr));
+        r->tables_pending = false;
+    }
     CUR(cudaMalloc(&r->d_poses, sizeof(Pose) * (size_t)max_batch));
     CUR(cudaMalloc(&r->d_frames[0], sizeof(FrameConst) * (size_t)max_batch));
     CUR(cudaMalloc(&r->d_work[0], sizeof(SegFrame) * (size_t)max_batch * (size_t)r->stride));
@@ -407,24 +495,33 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
 
 void b2d_renderer_destroy(b2d_renderer *r) { free_renderer(r); }
 
-int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics) {
+int b2d_renderer_set_time_async(b2d_renderer *r, uint32_t tics, void *cuda_stream) {
     if (!r) return fail(B2D_ERR_INVALID_ARG, "null renderer");
     if (r->h_blob.empty() || tics == r->tics) { r->tics = tics; return B2D_OK; }
-    const uint8_t *blob = r->h_blob.data();
-    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
-    std::vector<TexRec> tex(h[H_NTEX]);
-    std::vector<SectorRec> sectors(h[H_NSECTORS]);
-    std::vector<SegRec> segs(h[H_NSEGS]);
-    std::vector<SpriteRec> sprites(h[H_NSPRITES]);
-    scene_at_time(blob, tics, tex.data(), sectors.data(), segs.data(), sprites.data());
     CU(cudaSetDevice(r->device));
-    CU(cudaDeviceSynchronize());       // batches in flight on any stream still read the old tables
-    CU(cudaMemcpy(r->d_blob + h[H_OFF_TEX], tex.data(), tex.size() * sizeof(TexRec), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(r->d_blob + h[H_OFF_SECTORS], sectors.data(), sectors.size() * sizeof(SectorRec), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(r->d_blob + h[H_OFF_SEGS], segs.data(), segs.size() * sizeof(SegRec), cudaMemcpyHostToDevice));
-    if (!sprites.empty())
-        CU(cudaMemcpy(r->d_blob + h[H_OFF_SPRITES], sprites.data(), sprites.size() * sizeof(SpriteRec), cudaMemcpyHostToDevice));
-    r->tics = tics;
+    int rc = upload_timed_tables(r, tics, static_cast<cudaStream_t>(cuda_stream));
+    if (rc == B2D_OK) r->tics = tics;
+    return rc;
+}
+
+int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics) {
+    int rc = b2d_renderer_set_time_async(r, tics, nullptr);
+    if (rc != B2D_OK) return rc;
+    if (r->tables_pending) {
+        CU(cudaEventSynchronize(r->tables_ready));
+        r->tables_pending = false;
+    }
+    return B2D_OK;
+}
+
+int b2d_renderer_status(b2d_renderer *r, int32_t *bits_out) {
+    if (!r || !bits_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(r->device));
+    CU(cudaDeviceSynchronize());
+    int32_t status = 0;
+    CU(cudaMemcpy(&status, r->d_status, sizeof status, cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemset(r->d_status, 0, sizeof(int32_t)));
+    *bits_out = status;
     return B2D_OK;
 }
 

@@ -554,6 +554,30 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
     }
 }
 
+// Deferred masked entries (33 words: worklist index + one packed window per lane) live in a per-launch arena of
+// kMaskedChunk-entry chunks handed out by an atomic counter; a warp keeps the ids of its chunks in shared memory.  Memory
+// follows what frames actually defer (a few entries per strip) instead of strips x cap x batch.
+__device__ __forceinline__ uint32_t *masked_entry(const DeviceScene &sc, const uint32_t *chunks, int e) {
+    return sc.masked_list + ((size_t)chunks[e / kMaskedChunk] * kMaskedChunk + (size_t)(e % kMaskedChunk)) * 33u;
+}
+// next entry of this warp, or nullptr when the strip's cap or the arena is exhausted (status bit 8: frames incomplete)
+__device__ __forceinline__ uint32_t *masked_push(const DeviceScene &sc, uint32_t *chunks, int &mcount, int lane) {
+    bool ok = mcount < sc.masked_cap;
+    if (ok && mcount % kMaskedChunk == 0) {
+        uint32_t id = 0;
+        if (lane == 0) id = atomicAdd(sc.masked_counter, 1u);
+        id = __shfl_sync(kFull, id, 0);
+        ok = id < sc.masked_chunks;
+        if (ok && lane == 0) chunks[mcount / kMaskedChunk] = id;
+        __syncwarp();
+    }
+    if (!ok) {
+        if (lane == 0) atomicOr(sc.status_flag, 8);
+        return nullptr;
+    }
+    return masked_entry(sc, chunks, mcount++);
+}
+
 // Back-to-front pass over the masked middle textures this strip deferred during the solid pass.  Each entry
 // holds the worklist index and, per lane, the clip window [ya, yb) that was open behind the seg when the
 // front-to-back walk reached it (the per-column silhouette of everything nearer).  Texels whose opacity plane
@@ -562,7 +586,7 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
 template <bool kRgba, int kW>
 __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, int32_t pose_z, uint8_t *fb,
                                          uint32_t *rgba, uint32_t pal_s, int x, int lane,
-                                         const SegFrame *wl, const uint32_t *ml, int count) {
+                                         const SegFrame *wl, const uint32_t *chunks, int count) {
     // everything arrives by value (or points at kernel parameters): taking the address of the solid pass's
     // register-resident context would force it into local memory
     RasterCtx c;
@@ -570,8 +594,9 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
     c.W = vw.W; c.H = vw.H; c.x = x; c.lane = lane;
     const int Wc = kW ? kW : c.W;
     for (int e = count - 1; e >= 0; e--) {
-        const uint32_t k = ml[33 * e];
-        const uint32_t packed = ml[33 * e + 1 + c.lane];
+        const uint32_t *ml = masked_entry(sc, chunks, e);
+        const uint32_t k = ml[0];
+        const uint32_t packed = ml[1 + c.lane];
         int ya = (int)(packed & 0xFFFFu), yb = (int)(packed >> 16);
         const SegFrame sf = wl[k];
         int32_t tex, tA, hA, ucol = 0, iscale = 1, row = 0;
@@ -685,6 +710,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     __shared__ uint32_t s_pal[kRgba ? 256 : 1];
     __shared__ uint4 s_row4[kWarps][32];
     __shared__ uint32_t s_row1[kWarps][32];
+    __shared__ uint32_t s_chunks[kMasked ? kWarps : 1][kMasked ? kMaskedCapMax / kMaskedChunk : 1];
     if (kRgba) {   // the palette into shared memory (colours come pre-lit from global memory: no colormap here)
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pal[i] = sc.palette[i];
         __syncthreads();
@@ -712,7 +738,8 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     if (sc.sky_tex >= 0 && inside) c.skycol = umulhi32(sky_u32(x, vw, fc.pose.angle), sc.tex[sc.sky_tex].w);
 
     int ct = 0, cb = inside ? H : 0;              // open window [ct, cb) of this lane's column
-    uint32_t *ml = (kMasked && sc.masked_list) ? sc.masked_list + (size_t)gw * (33 * (size_t)sc.masked_cap) : nullptr;
+    uint32_t *chunks = s_chunks[kMasked ? (threadIdx.x >> 5) : 0];
+    const bool defer = kMasked && sc.masked_list != nullptr;
     int mcount = 0;
     const SegFrame *wl = work + (size_t)frame * stride;
     const int count = fc.count;
@@ -735,13 +762,11 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
             if (!__any_sync(kFull, in)) continue;
             if (sf.seg < 0) {
                 // decoration sprite: remember the windows open right now; it is drawn in the masked pass
-                if (kMasked && ml != nullptr) {
-                    if (mcount < sc.masked_cap) {
-                        if (lane == 0) ml[33 * mcount] = (uint32_t)(k0 + j);
-                        ml[33 * mcount + 1 + lane] = in ? ((uint32_t)ct | ((uint32_t)cb << 16)) : 0u;
-                        mcount++;
-                    } else if (lane == 0) {
-                        atomicOr(sc.status_flag, 8);
+                if (defer) {
+                    uint32_t *ml = masked_push(sc, chunks, mcount, lane);
+                    if (ml) {
+                        if (lane == 0) ml[0] = (uint32_t)(k0 + j);
+                        ml[1 + lane] = in ? ((uint32_t)ct | ((uint32_t)cb << 16)) : 0u;
                     }
                 }
                 continue;
@@ -798,16 +823,14 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                 if (!two || y2 >= y3) { ct = H; cb = 0; }
                 else { ct = y2; cb = y3; }
             }
-            if (kMasked && two && S.mid >= 0 && ml != nullptr) {
+            if (defer && two && S.mid >= 0) {
                 // defer the masked middle texture: remember the window that is open behind this seg
                 const bool keep = ok && y2 < y3;
                 if (__any_sync(kFull, keep)) {
-                    if (mcount < sc.masked_cap) {
-                        if (lane == 0) ml[33 * mcount] = (uint32_t)(k0 + j);
-                        ml[33 * mcount + 1 + lane] = keep ? ((uint32_t)y2 | ((uint32_t)y3 << 16)) : 0u;
-                        mcount++;
-                    } else if (lane == 0) {
-                        atomicOr(sc.status_flag, 8);
+                    uint32_t *ml = masked_push(sc, chunks, mcount, lane);
+                    if (ml) {
+                        if (lane == 0) ml[0] = (uint32_t)(k0 + j);
+                        ml[1 + lane] = keep ? ((uint32_t)y2 | ((uint32_t)y3 << 16)) : 0u;
                     }
                 }
             }
@@ -817,7 +840,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     fill_void_warp<kRgba, kW>(c, inside ? ct : 0, inside ? cb : 0);
     if (kMasked && mcount > 0) {
         __syncwarp();
-        masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.pal_s, x, lane, wl, ml, mcount);
+        masked_pass<kRgba, kW>(sc, vw, fc.pose.z, c.fb, c.rgba, c.pal_s, x, lane, wl, chunks, mcount);
     }
 }
 

@@ -59,9 +59,10 @@ static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec)
 constexpr int32_t kSegTwoSided = 1, kSegScroll = 2, kSegInvalid = 0x80;   // scroll: special 0x30 (visitor.rs:922)
 constexpr int32_t kFlatSky = -1, kFlatMissing = -2, kTexNone = -1;
 
-// Level time (static.vert:23-39, visitor.rs:922).  `tics` counts 1/35 s.  An image that is frame k
-// of an n-frame animation group shows group frame (k + tics/8) mod n; walls of a scrolling line (special 0x30)
-// advance their texture column by one texel per tic.  The kernels never see time: the three small tables that
+// Level time (static.vert:23-39, visitor.rs:922).  `tics` counts 1/35 s.  Every frame name of an
+// n-frame animation group is bound to the group's first frame (tex.rs:260, 302-306), so an animated image shows
+// group frame (tics/8) mod n whichever frame name the map uses (frame 0 at tic 0: the tables are resolved at
+// renderer creation too); walls of a scrolling line (special 0x30) advance their texture column by one texel per tic.  The kernels never see time: the three small tables that
 // depend on it (texture records, sector flats, seg column offsets) are re-derived from the blob here and
 // re-uploaded when the time changes.  Sector light effects (C15) ride on the same mechanism: the light bytes of
 // effect sectors, their segs and their sprites are re-evaluated.  Outputs hold H_NTEX / H_NSECTORS / H_NSEGS /
@@ -127,9 +128,9 @@ inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, S
     const FlatAnimRec *fa = reinterpret_cast<const FlatAnimRec *>(blob + h[H_OFF_FLAT_ANIM]);
     const uint32_t ntex = h[H_NTEX], nflats = h[H_NFLATS], nanim = h[H_NANIM];
     auto now = [&](int64_t first, uint32_t nk, int32_t self) -> int32_t {
-        const uint32_t n = nk & 0xFFFFu, k = nk >> 16;
+        const uint32_t n = nk & 0xFFFFu;
         if (n < 2 || first < 0 || first + n > nanim) return self;
-        return anim[first + (int64_t)(((uint64_t)k + (tics >> 3)) % n)];
+        return anim[first + (int64_t)((tics >> 3) % n)];
     };
     for (uint32_t i = 0; i < ntex; i++) {
         const int32_t j = now((int32_t)tex[i].anim_first, tex[i].anim_nk, (int32_t)i);

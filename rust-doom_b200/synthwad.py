@@ -464,6 +464,13 @@ class LevelBuilder:
         self.sidedefs.append(Sidedef(xoff, yoff, upper, lower, middle, sector))
         return len(self.sidedefs) - 1
 
+    def _nukage(self, flat: str) -> str:
+        """With animation on, a NUKAGE floor uses any frame name of its group (k > 0 too: the reference shows the same
+        image for all of them, tex.rs:302-306); chosen by sector index so that no random draw is consumed."""
+        if self.cfg.anim and flat == "NUKAGE1":
+            return ("NUKAGE1", "NUKAGE3", "NUKAGE2")[len(self.sectors) % 3]
+        return flat
+
     def line(self, v1, v2, right, left=-1, flags=None, special=0) -> int:
         if flags is None:
             flags = 0x0001 if left < 0 else 0x0004
@@ -516,7 +523,7 @@ class LevelBuilder:
                 if not self.cfg.light_fx:
                     stype = 0
                 self.sectors.append(Sector(
-                    fl, fl + height, rng.pick(FLOOR_FLATS),
+                    fl, fl + height, self._nukage(rng.pick(FLOOR_FLATS)),
                     "F_SKY1" if is_sky else rng.pick(CEIL_FLATS), light, stype))
                 cell_sector[i][j] = len(self.sectors) - 1
                 heights[i][j] = fl
@@ -719,7 +726,7 @@ class LevelBuilder:
             dc = rng.pick([0, 0, -16, -32, 24])
             fl = so.floor + df
             ce = max(fl + 56, so.ceil + dc) if so.ceil_flat != "F_SKY1" else so.ceil
-            self.sectors.append(Sector(fl, ce, rng.pick(FLOOR_FLATS), so.ceil_flat if so.ceil_flat == "F_SKY1"
+            self.sectors.append(Sector(fl, ce, self._nukage(rng.pick(FLOOR_FLATS)), so.ceil_flat if so.ceil_flat == "F_SKY1"
                                        else rng.pick(CEIL_FLATS), rng.pick([128, 160, 192, 255, 96])))
             inner_sector = len(self.sectors) - 1
         n = len(pts)

@@ -449,7 +449,7 @@ static int render_impl(const uint8_t *blob, const View *vw, const Pose *poses, i
     std::vector<SectorRec> sectors_t((size_t)sc.hdr[H_NSECTORS]);
     std::vector<SegRec> segs_t((size_t)sc.nsegs);
     std::vector<SpriteRec> sprites_t((size_t)sc.nsprites);
-    if (tics != 0 && scene_is_timed(blob)) {
+    if (scene_is_timed(blob)) {          // tic 0 included: a frame name with k > 0 shows the group's frame 0
         scene_at_time(blob, tics, tex_t.data(), sectors_t.data(), segs_t.data(), sprites_t.data());
         sc.tex = tex_t.data(); sc.sectors = sectors_t.data(); sc.segs = segs_t.data(); sc.sprites = sprites_t.data();
     }

@@ -58,8 +58,9 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
     from oracle.anim_table import FLATS as ANIM_FLATS, WALLS as ANIM_WALLS
 
     def anim_name(name, groups, table):
-        """static.vert:23-39 with u_time = tics/35: frame_index = floor(mod(u_time / (8/35), n)); the image that is
-        frame k of its group shows frame k + frame_index (wrapped inside the group: DESIGN.md C14)."""
+        """static.vert:23-39 with u_time = tics/35: frame_index = floor(mod(u_time / (8/35), n)), added to the atlas
+        position of the group's FIRST frame (tex.rs:260, 302-306 bind every frame name to it): the image shown is group
+        frame frame_index whichever frame name the map uses."""
         for g in groups:
             frames = [W.wad_name(f.encode()) for f in g]
             if name in frames:
@@ -67,7 +68,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
                 if len(have) < 2 or name not in have:
                     return name
                 fi = int(math.floor(math.fmod((tics / 35.0) / (8.0 / 35.0) + 1e-9, len(have))))
-                return have[(have.index(name) + fi) % len(have)]
+                return have[fi % len(have)]
         return name
 
     W_, H_ = width, height

@@ -216,3 +216,38 @@ def test_level_time_is_periodic_without_light_effects(b2d, hostcheck):
         assert not np.array_equal(a, c), "time had no effect"
         ha, hb = hostcheck(sc.blob, pv, poses, tics=t)[0], hostcheck(sc.blob, pv, poses, tics=t + 768)[0]
         assert np.array_equal(ha, a) and np.array_equal(hb, a)
+
+
+def test_every_frame_name_of_a_group_shows_the_same_image(b2d, hostcheck):
+    """tex.rs:260 / 302-306: every frame name of an animation group is bound to the atlas position of the group's first
+    frame, so NUKAGE3 / NUKAGE2 floors and SFALL2 / SFALL4 / FIREBLU2 walls render exactly like NUKAGE1 / SFALL1 /
+    FIREBLU1 at every tic (frame floor(tics/8) mod n of the group; frame 0 at tic 0).  Rewriting the k > 0 names of a
+    generated level to the k = 0 name must not change a pixel, for the oracle and for the product's tables."""
+    from oracle import scene as S, wad as W
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(3, ("E1M1",), cfg=synthwad.SynthConfig(anim=True, light_fx=False))
+    same = bytearray(data)
+    renames = {b"NUKAGE3\0": b"NUKAGE1\0", b"NUKAGE2\0": b"NUKAGE1\0", b"SFALL2\0\0": b"SFALL1\0\0", b"SFALL4\0\0": b"SFALL1\0\0",
+               b"FIREBLU2": b"FIREBLU1"}
+    arch = W.Archive(data)
+    hits = 0
+    marker = arch.levels[0]
+    for lump in (3, 8):                             # SIDEDEFS, SECTORS of level 0 (wad/src/level.rs:13-20): only the
+        _, off, size = arch.lumps[marker + lump]     # level's references, not the texture / flat definitions
+        body = bytes(same[off:off + size])
+        for old, new in renames.items():
+            hits += body.count(old)
+            body = body.replace(old, new)
+        same[off:off + size] = body
+    assert hits >= 4, "the generated level uses no k > 0 frame names"
+    sc_k = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    sc_0 = b2d.Scene(b2d.Archive.from_bytes(bytes(same)), 0)
+    poses = sample_poses(b2d, sc_k, 12, 5)
+    v = render.make_view(320, 200)
+    pv = b2d.make_view(320, 200)
+    for tics in (0, 7, 8, 16, 31, 1000):
+        a = render.render(sc_k.blob, v, poses, threads=4, tics=tics)
+        b = render.render(sc_0.blob, v, poses, threads=4, tics=tics)
+        assert np.array_equal(a, b), "oracle: a k > 0 frame name rendered differently at tic %d" % tics
+        ha, _, _ = hostcheck(sc_k.blob, pv, poses, tics=tics)
+        assert np.array_equal(ha, a), "product tables differ from the oracle at tic %d" % tics
