@@ -40,10 +40,12 @@ extern "C" {
 #define B2D_ERR_CUDA (-3)
 #define B2D_ERR_INVALID_ARG (-4)
 #define B2D_ERR_NO_MEMORY (-5)
+#define B2D_ERR_NCCL (-6)
 
 typedef struct b2d_archive b2d_archive;     /* wad::Archive */
 typedef struct b2d_scene b2d_scene;         /* WadSystem's current level, compiled for the GPU */
 typedef struct b2d_renderer b2d_renderer;   /* engine::Renderer replacement, bound to one device */
+typedef struct b2d_comm b2d_comm;           /* one rank of a multi-GPU job (NCCL communicator + gather buffers + streams) */
 
 /* Camera pose.  Position in 16.16 fixed-point WAD map units (z = eye height, absolute);
  * angle in BAM (2^32 = 360 deg, 0 = east / +x, counter-clockwise).  Pitch and roll are 0
@@ -145,6 +147,51 @@ int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_
  * ordered one after the other through an event, whatever streams they are enqueued on.  Replaces nothing in the reference (its render loop is synchronous, engine/src/renderer.rs:62-175). */
 int b2d_walk_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, void *cuda_stream, int64_t *ticket_out);
 int b2d_raster_device(b2d_renderer *r, int64_t ticket, uint8_t *d_index_fb, uint32_t *d_rgba_fb, void *cuda_stream);
+
+/* ---- multi-GPU: pose-sharded render with a chunked, overlapped all-gather of finished frames ------------------
+ * The reference has no collective and no multi-device path; the hand-off this replaces is the
+ * per-frame `frame.finish()` of engine/src/renderer.rs:160-167.  One process per GPU.  NCCL (libnccl.so.2) is bound
+ * at run time; without it these calls fail with B2D_ERR_NCCL and the rest of the library works.
+ *
+ * b2d_comm_unique_id: on one rank; the caller distributes the 128 bytes (MPI, torch.distributed, a file).
+ * b2d_comm_create:    collective over `world` ranks (ncclCommInitRank); binds the rank to `device`. */
+#define B2D_COMM_ID_BYTES 128
+int b2d_comm_unique_id(uint8_t id_out[B2D_COMM_ID_BYTES]);
+int b2d_comm_create(const uint8_t id[B2D_COMM_ID_BYTES], int rank, int world, int device, b2d_comm **out);
+void b2d_comm_destroy(b2d_comm *c);
+int b2d_comm_info(const b2d_comm *c, int *rank_out, int *world_out, int *nccl_version_out);
+
+#define B2D_SHARD_RENDER_ONLY 0     /* render this rank's block, no exchange */
+#define B2D_SHARD_RENDER_GATHER 1   /* render + all-gather of every chunk, overlapped */
+#define B2D_SHARD_GATHER_ONLY 2     /* the same gathers without rendering (to time the exchange alone) */
+
+typedef struct b2d_sharded_stats {
+    double total_ms;                /* device time, first launch -> last consumer, this rank */
+    double render_ms, gather_ms;    /* sums of the per-chunk kernel / ncclAllGather times (they overlap each other) */
+    int64_t frames_local, frames_gathered, chunks, chunk_frames;
+    int64_t bytes_received;         /* (world-1)/world of the gathered bytes */
+    char registration[64];          /* how the gather buffers were registered with NCCL */
+} b2d_sharded_stats;
+
+/* Called on the host once per chunk, right after the chunk's work has been ENQUEUED: d_frames holds `ranks` x
+ * frames_per_rank finished index frames (rank-major; frame j of rank q is pose q*per + first_local_pose + j, with
+ * per = ceil(n_total/world)), valid for work enqueued on `cuda_stream`, which is ordered after the gather.  The
+ * buffer is reused two chunks later, after everything the callback enqueued on that stream. */
+typedef void (*b2d_chunk_fn)(void *user, int chunk_index, size_t first_local_pose, size_t frames_per_rank,
+                             const uint8_t *d_frames, int ranks, void *cuda_stream);
+
+/* Collective.  `poses` (HOST, n_total entries, identical on every rank) is split into contiguous blocks of
+ * per = ceil(n_total/world); rank q renders block q (a short last block is padded by repeating the last pose) in
+ * chunks of min(chunk_frames, max_batch) frames, each chunk rastered straight into this rank's slice of the
+ * all-gather buffer (no staging copy) and gathered in place on a second stream while the next chunk renders; the
+ * consumer callback (nullable) runs on a third.  Synchronous: returns when this rank's part is complete. */
+int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size_t n_total, size_t chunk_frames,
+                       int mode, b2d_chunk_fn fn, void *user, b2d_sharded_stats *stats_out);
+
+/* One 32-bit checksum per frame on the device: sum_i (p[i] + 1) * (i * 0x9E3779B1 + 0x7F4A7C15) mod 2^32
+ * (position sensitive, order independent).  Used to validate gathered frames without moving them to the host. */
+int b2d_frame_checksums_device(const uint8_t *d_frames, size_t n_frames, size_t frame_bytes, uint32_t *d_out,
+                               void *cuda_stream);
 
 /* Introspection for tests/profiling: copies the BSP-walk worklist of the LAST b2d_render_device
  * batch to the host.  counts_out[n], and for frame i seg ids seg_ids_out[i*stride .. +counts[i]). */

@@ -148,6 +148,54 @@ class Scene:
             pass
 
 
+class Comm:
+    """One rank of a multi-GPU job: NCCL communicator + registered all-gather buffers + streams (b2d_comm)."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        assert len(unique_id) == _lib.COMM_ID_BYTES
+        h = ctypes.c_void_p()
+        buf = (ctypes.c_char * _lib.COMM_ID_BYTES).from_buffer_copy(unique_id)
+        _check(_lib.load().b2d_comm_create(ctypes.addressof(buf), rank, world, device, ctypes.byref(h)))
+        self._h = h
+        self.rank, self.world, self.device = rank, world, device
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (ctypes.c_char * _lib.COMM_ID_BYTES)()
+        _check(_lib.load().b2d_comm_unique_id(ctypes.addressof(buf)))
+        return bytes(buf)
+
+    @property
+    def nccl_version(self) -> int:
+        v = ctypes.c_int(0)
+        _check(_lib.load().b2d_comm_info(self._h, None, None, ctypes.byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if self._h:
+            _lib.load().b2d_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def frame_checksums_device(frames_ptr: int, n_frames: int, frame_bytes: int, out_ptr: int, stream: int = 0):
+    """b2d_frame_checksums_device: one uint32 per frame into device memory at out_ptr (see frame_checksum)."""
+    _check(_lib.load().b2d_frame_checksums_device(frames_ptr, n_frames, frame_bytes, out_ptr, stream or None))
+
+
+def frame_checksum(frame: np.ndarray) -> int:
+    """Host restatement of the device checksum: sum_i (p[i] + 1) * (i * 0x9E3779B1 + 0x7F4A7C15) mod 2^32."""
+    p = np.ascontiguousarray(frame, dtype=np.uint8).reshape(-1).astype(np.uint64)
+    i = np.arange(p.size, dtype=np.uint64)
+    w = (i * np.uint64(0x9E3779B1) + np.uint64(0x7F4A7C15)) & np.uint64(0xFFFFFFFF)
+    return int(((p + np.uint64(1)) * w).sum(dtype=np.uint64) & np.uint64(0xFFFFFFFF))
+
+
 def make_view(width: int, height: int, fov_deg: float = DEFAULT_FOV_DEG) -> "_lib.View":
     v = _lib.View()
     _check(_lib.load().b2d_view_init(ctypes.byref(v), width, height, float(fov_deg)))
@@ -234,6 +282,27 @@ class Renderer:
     @property
     def launch_count(self) -> int:
         return int(_lib.load().b2d_launch_count(self._h))
+
+    # -- multi-GPU ------------------------------------------------------------------------------------
+    def render_sharded(self, comm: "Comm", poses: np.ndarray, chunk_frames: int = 256, mode: int = _lib.SHARD_RENDER_GATHER,
+                       on_chunk=None) -> dict:
+        """b2d_render_sharded: collective over the communicator.  `poses` is the whole job's pose list (identical on
+        every rank); on_chunk(chunk_index, first_local_pose, frames_per_rank, device_ptr, ranks, stream) is called on
+        the host after each chunk has been enqueued (work it enqueues on `stream` sees the gathered frames)."""
+        poses = np.ascontiguousarray(poses, dtype=POSE_DTYPE)
+        st = _lib.ShardedStats()
+
+        def tramp(_user, k, first, cnt, ptr, ranks, stream):
+            if on_chunk is not None:
+                on_chunk(int(k), int(first), int(cnt), int(ptr or 0), int(ranks), int(stream or 0))
+
+        cb = _lib.CHUNK_FN(tramp)
+        _check(_lib.load().b2d_render_sharded(self._h, comm._h, poses.ctypes.data, len(poses), int(chunk_frames), int(mode),
+                                              cb, None, ctypes.byref(st)))
+        return {"total_ms": st.total_ms, "render_ms": st.render_ms, "gather_ms": st.gather_ms,
+                "frames_local": int(st.frames_local), "frames_gathered": int(st.frames_gathered),
+                "chunks": int(st.chunks), "chunk_frames": int(st.chunk_frames), "bytes_received": int(st.bytes_received),
+                "registration": st.registration.decode("ascii", "replace")}
 
     def close(self):
         if self._h:

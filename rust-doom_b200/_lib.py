@@ -32,7 +32,24 @@ EXPORTS = [
     "b2d_renderer_destroy", "b2d_renderer_set_time", "b2d_renderer_set_time_async", "b2d_renderer_status", "b2d_render", "b2d_render_device", "b2d_walk_device",
     "b2d_raster_device", "b2d_palette_lut_device",
     "b2d_debug_worklist", "b2d_launch_count", "b2d_profile_enable", "b2d_profile_read",
+    "b2d_comm_unique_id", "b2d_comm_create", "b2d_comm_destroy", "b2d_comm_info", "b2d_render_sharded",
+    "b2d_frame_checksums_device",
 ]
+
+COMM_ID_BYTES = 128
+SHARD_RENDER_ONLY, SHARD_RENDER_GATHER, SHARD_GATHER_ONLY = 0, 1, 2
+
+
+class ShardedStats(ctypes.Structure):
+    _fields_ = [("total_ms", ctypes.c_double), ("render_ms", ctypes.c_double), ("gather_ms", ctypes.c_double),
+                ("frames_local", ctypes.c_int64), ("frames_gathered", ctypes.c_int64), ("chunks", ctypes.c_int64),
+                ("chunk_frames", ctypes.c_int64), ("bytes_received", ctypes.c_int64),
+                ("registration", ctypes.c_char * 64)]
+
+
+# void fn(void *user, int chunk, size_t first_local_pose, size_t frames_per_rank, const uint8_t *d_frames, int ranks, void *stream)
+CHUNK_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
+                            ctypes.c_int, ctypes.c_void_p)
 
 _lib = None
 
@@ -90,5 +107,12 @@ def load() -> ctypes.CDLL:
     L.b2d_raster_device.restype = ctypes.c_int
     L.b2d_launch_count.argtypes = [vp]
     L.b2d_launch_count.restype = ctypes.c_int64
+    L.b2d_comm_unique_id.argtypes = [vp]
+    L.b2d_comm_create.argtypes = [vp, ci, ci, ci, ctypes.POINTER(vp)]
+    L.b2d_comm_destroy.argtypes = [vp]
+    L.b2d_comm_destroy.restype = None
+    L.b2d_comm_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    L.b2d_render_sharded.argtypes = [vp, vp, vp, cs, cs, ci, CHUNK_FN, vp, ctypes.POINTER(ShardedStats)]
+    L.b2d_frame_checksums_device.argtypes = [vp, cs, cs, vp, vp]
     _lib = L
     return L

@@ -9,12 +9,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb2d.so")
-SOURCES = ["b2d_api.cu", "b2d_kernels.cu", "b2d_wad.cpp", "b2d_scene.cpp"]
-HEADERS = ["b2d_cli.cpp", "b2d_math.cuh", "b2d_kernels.cuh", "b2d_scene.hpp", "b2d_wad.hpp", "../../include/b2d.h"]
+SOURCES = ["b2d_api.cu", "b2d_kernels.cu", "b2d_sharded.cu", "b2d_wad.cpp", "b2d_scene.cpp"]
+HEADERS = ["b2d_cli.cpp", "b2d_math.cuh", "b2d_kernels.cuh", "b2d_internal.hpp", "b2d_scene.hpp", "b2d_wad.hpp", "../../include/b2d.h"]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter", "-shared",
-              "-Xptxas", "-v" if os.environ.get("B2D_PTXAS_V") else "-warn-spills"]
+              "-Xptxas", "-v" if os.environ.get("B2D_PTXAS_V") else "-warn-spills", "-ldl"]
 
 
 def needs_build() -> bool:

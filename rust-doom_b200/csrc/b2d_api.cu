@@ -8,76 +8,15 @@
 #include <string>
 #include <vector>
 
-#include "../../include/b2d.h"
-#include "b2d_kernels.cuh"
-#include "b2d_scene.hpp"
-#include "b2d_wad.hpp"
-
-using namespace b2d;
+#include "b2d_internal.hpp"
 
 static_assert(sizeof(b2d_pose) == sizeof(Pose) && sizeof(b2d_view) == sizeof(View), "ABI structs");
 
-struct b2d_archive {
-    std::unique_ptr<Archive> wad;
-};
-
-struct b2d_scene {
-    std::vector<uint8_t> blob;
-    Level level;
-    b2d_scene_info info;
-};
-
-struct b2d_renderer {
-    int device = 0;
-    View view{};
-    int max_batch = 0;
-    int stride = 0;                 // worklist entries per frame (= n_segs + n_sprites)
-    uint8_t *d_blob = nullptr;
-    uint32_t *d_yslope = nullptr;
-    uint16_t *d_skyrow = nullptr;
-    int32_t *d_status = nullptr;
-    uint32_t *d_masked = nullptr;
-    uint8_t *d_lit = nullptr;       // colormap-applied copies of the texels and flats (32 light rows each)
-    DeviceScene ds{};
-    Pose *d_poses = nullptr;
-    // two worklist slots: the BSP walk of batch k+1 may run (b2d_walk_device, another stream) while batch k is rastered
-    FrameConst *d_frames[2] = {nullptr, nullptr};
-    SegFrame *d_work[2] = {nullptr, nullptr};
-    cudaEvent_t walk_done[2] = {nullptr, nullptr}, raster_done[2] = {nullptr, nullptr};
-    int slot_n[2] = {0, 0};          // frames walked into the slot
-    int64_t slot_ticket[2] = {-1, -1};
-    bool slot_rastered[2] = {true, true};
-    int64_t next_ticket = 0;
-    int last_slot = 0;
-    // host-path staging (allocated on first b2d_render): double-buffered frame outputs
-    uint8_t *d_index[2] = {nullptr, nullptr};
-    uint32_t *d_rgba[2] = {nullptr, nullptr};
-    Pose *h_poses = nullptr;        // pinned
-    cudaStream_t render_stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
-    std::vector<uint8_t> h_blob;    // host copy of the scene, kept only when it has time-dependent content
-    uint32_t tics = 0;
-    // time-dependent tables (texture records, sectors, segs, sprites): rebuilt on the host into one of two pinned
-    // staging buffers and copied over their sections of the device blob in stream order (b2d_renderer_set_time_async)
-    uint8_t *h_timed[2] = {nullptr, nullptr};
-    cudaEvent_t timed_copied[2] = {nullptr, nullptr};     // staging buffer i has been read by its copy
-    cudaEvent_t tables_ready = nullptr;                   // last table upload; launches on other streams wait for it
-    bool tables_pending = false;
-    int timed_next = 0;
-    size_t timed_bytes = 0;
-    cudaEvent_t masked_done = nullptr;                    // last raster that used the masked-entry arena
-    uint32_t *d_masked_counter = nullptr;
-    int64_t launches = 0;
-    int last_n = 0;
-    bool profiling = false;
-    std::vector<cudaEvent_t> prof_events;   // pairs: before / after one kernel launch
-    std::vector<int> prof_kinds;            // per pair: 0 = walk, 1 = raster
-};
-
 namespace {
-
 thread_local std::string g_error;
+}
 
+namespace b2d {
 int fail(int code, const std::string &msg) {
     g_error = msg;
     return code;
@@ -86,6 +25,9 @@ int fail(int code, const std::string &msg) {
 int cuda_fail(cudaError_t e, const char *what) {
     return fail(B2D_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
+}  // namespace b2d
+
+namespace {
 
 #define CU(call)                                         \
     do {                                                 \
@@ -242,16 +184,16 @@ int upload_timed_tables(b2d_renderer *r, uint32_t tics, cudaStream_t stream) {
     return B2D_OK;
 }
 
+}  // namespace
+
 // walk -> raster on the caller's stream
-int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
-                   cudaStream_t stream) {
+int b2d::enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
+                        cudaStream_t stream) {
     int64_t ticket = -1;
     int rc = walk_into_slot(r, d_poses, n, stream, &ticket);
     if (rc != B2D_OK) return rc;
     return raster_from_slot(r, ticket, d_index, d_rgba, stream);
 }
-
-}  // namespace
 
 extern "C" {
 
