@@ -24,10 +24,12 @@
  *   - masked two-sided middles, decoration sprites (billboards), level time (animated flats / walls, scrolling
  *     walls, sector light effects): DESIGN.md C12-C15 with their reference citations
  * The visibility algorithm itself (front-to-back BSP walk with per-column clip windows, Doom
- * style) is new; it is written here in the most literal per-column / per-pixel form.  All
- * arithmetic is integer (DESIGN.md "pixel contract"); the CUDA path must reproduce every bit.
+ * style) is new; it is written here column by column, the way a CPU Doom renderer draws (per-column
+ * set-up once, a tight row loop per wall piece; the plane constants of a screen row memoised per plane).
+ * All arithmetic is integer (DESIGN.md "pixel contract"); the CUDA path must reproduce every bit.
+ * It doubles as bench.py's CPU baseline, so it is compiled for the host it runs on.
  *
- * Build: gcc -O2 -fopenmp -shared -fPIC (see oracle/build.py).
+ * Build: gcc -O3 -march=native -fopenmp -shared -fPIC (see oracle/build.py).
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -166,6 +168,11 @@ typedef struct {
     int cur_seg;
     struct Masked *masked;    /* masked middle-texture columns met during the solid pass, front to back */
     int n_masked, cap_masked;
+    /* per screen row: the plane constants of the last (height, light) drawn on that row.  Columns of one seg are drawn
+     * one after the other and share their floor / ceiling plane, so the 64-bit set-up runs once per row per plane, not
+     * once per pixel (same values: this is a memo, not a different formula). */
+    int64_t *prow_key;        /* (h << 9 | lightb) + 1, 0 = empty */
+    uint32_t *prow;           /* 5 words per row: baseU, stepU, baseV, stepV, 256 * light row */
 } Frame;
 
 static inline void put(Frame *f, int x, int y, uint8_t v) {
@@ -228,23 +235,31 @@ static void draw_plane(Frame *f, int x, int ya, int yb, int32_t h, int32_t flat,
     int W = f->vw.W;
     int64_t hrel = clamp64(((int64_t)h << 16) - f->pose.z, -((int64_t)1 << 27), (int64_t)1 << 27);
     uint64_t a = (uint64_t)(hrel < 0 ? -hrel : hrel);
+    const int64_t key = (((int64_t)h << 9) | (int64_t)(lightb & 0x1FF)) + 1;
     for (int y = ya; y < yb; y++) {
-        uint64_t zz = (a * f->yslope[y]) >> 16;
-        int32_t z16 = zz > 0x7FFFFFFFull ? 0x7FFFFFFF : (int32_t)zz;
-        int32_t fxw = (int32_t)asr64((int64_t)z16 * f->cosq, 30);
-        int32_t fyw = (int32_t)asr64((int64_t)z16 * f->sinq, 30);
-        int64_t Rx = fyw, Ry = -(int64_t)fxw;                 /* right = (sin, -cos) scaled by z */
-        uint32_t stepU = (uint32_t)(uint64_t)asr64(Rx * (int64_t)f->invF, 21);
-        uint32_t halfU = (uint32_t)(uint64_t)asr64(Rx * (int64_t)f->invF, 22);
-        uint32_t stepV = (uint32_t)(uint64_t)asr64(Ry * (int64_t)f->invF, 21);
-        uint32_t halfV = (uint32_t)(uint64_t)asr64(Ry * (int64_t)f->invF, 22);
-        uint32_t baseU = ((uint32_t)(f->pose.x + fxw) << 10) + (uint32_t)(1 - W) * halfU;
-        uint32_t baseV = ((uint32_t)(f->pose.y + fyw) << 10) + (uint32_t)(1 - W) * halfV;
-        uint32_t U = baseU + (uint32_t)x * stepU;             /* wad x, Q26 mod 64 */
-        uint32_t V = baseV + (uint32_t)x * stepV;             /* wad y */
+        uint32_t *pr = f->prow + 5 * (size_t)y;
+        if (f->prow_key[y] != key) {
+            uint64_t zz = (a * f->yslope[y]) >> 16;
+            int32_t z16 = zz > 0x7FFFFFFFull ? 0x7FFFFFFF : (int32_t)zz;
+            int32_t fxw = (int32_t)asr64((int64_t)z16 * f->cosq, 30);
+            int32_t fyw = (int32_t)asr64((int64_t)z16 * f->sinq, 30);
+            int64_t Rx = fyw, Ry = -(int64_t)fxw;                 /* right = (sin, -cos) scaled by z */
+            uint32_t stepU = (uint32_t)(uint64_t)asr64(Rx * (int64_t)f->invF, 21);
+            uint32_t halfU = (uint32_t)(uint64_t)asr64(Rx * (int64_t)f->invF, 22);
+            uint32_t stepV = (uint32_t)(uint64_t)asr64(Ry * (int64_t)f->invF, 21);
+            uint32_t halfV = (uint32_t)(uint64_t)asr64(Ry * (int64_t)f->invF, 22);
+            pr[0] = ((uint32_t)(f->pose.x + fxw) << 10) + (uint32_t)(1 - W) * halfU;
+            pr[1] = stepU;
+            pr[2] = ((uint32_t)(f->pose.y + fyw) << 10) + (uint32_t)(1 - W) * halfV;
+            pr[3] = stepV;
+            int32_t z8 = z16 >> 13; if (z8 > 65535) z8 = 65535;
+            pr[4] = 256u * (uint32_t)light_row(lightb, z8);
+            f->prow_key[y] = key;
+        }
+        uint32_t U = pr[0] + (uint32_t)x * pr[1];             /* wad x, Q26 mod 64 */
+        uint32_t V = pr[2] + (uint32_t)x * pr[3];             /* wad y */
         uint8_t texel = px[((U >> 26) << 6) | (V >> 26)];
-        int32_t z8 = z16 >> 13; if (z8 > 65535) z8 = 65535;
-        put(f, x, y, sc->colormap[256 * light_row(lightb, z8) + texel]);
+        put(f, x, y, sc->colormap[pr[4] + texel]);
     }
 }
 
@@ -261,10 +276,19 @@ static void draw_wall(Frame *f, int x, int ya, int yb, int32_t tex, int32_t tA, 
     int64_t tbase = ((int64_t)tA << 16) + hrel + asr64((int64_t)(1 - f->vw.H) * iscale, 5);
     int32_t tstep = iscale >> 4;
     const uint8_t *cm = sc->colormap + 256 * row;
-    for (int y = ya; y < yb; y++) {
-        int32_t t = (int32_t)(tbase + (int64_t)y * tstep);
-        int32_t v = floormod32((int32_t)asr64(t, 16), h);
-        put(f, x, y, cm[px[v * w + col]]);
+    px += col;
+    if ((h & (h - 1)) == 0) {                                 /* power-of-two height: floor-mod is a mask */
+        const int32_t hm = h - 1;
+        for (int y = ya; y < yb; y++) {
+            int32_t t = (int32_t)(tbase + (int64_t)y * tstep);
+            put(f, x, y, cm[px[((t >> 16) & hm) * w]]);
+        }
+    } else {
+        for (int y = ya; y < yb; y++) {
+            int32_t t = (int32_t)(tbase + (int64_t)y * tstep);
+            int32_t v = floormod32((int32_t)asr64(t, 16), h);
+            put(f, x, y, cm[px[v * w]]);
+        }
     }
 }
 
@@ -501,6 +525,9 @@ static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *po
     f.tx = scratch; f.tz = f.tx + sc->nverts;
     f.ctop = f.tz + sc->nverts; f.cbot = f.ctop + W;
     f.yslope = (uint32_t *)(f.cbot + W);
+    f.prow = f.yslope + H;
+    f.prow_key = (int64_t *)(((uintptr_t)(f.prow + 5 * (size_t)H) + 7) & ~(uintptr_t)7);
+    memset(f.prow_key, 0, sizeof(int64_t) * (size_t)H);
     b2o_sincos_q30(pose->angle, &f.cosq, &f.sinq);
     f.invF = (uint32_t)(4294967296ULL / (uint64_t)vw->F);
     memset(fb, 0, (size_t)W * H);                              /* void index = 0 */
@@ -540,7 +567,8 @@ int b2o_render_t(const uint8_t *scene_blob, const b2o_view *vw, const b2o_pose *
     if (scene_bind(&sc, scene_blob) != 0) return -1;
     if (vw->W < 1 || vw->H < 1 || vw->W > 4096 || vw->H > 2160 || vw->F < 2 || vw->FY2 < 2) return -2;
     const size_t npix = (size_t)vw->W * vw->H;
-    const size_t scratch_ints = 2 * (size_t)sc.nverts + 2 * (size_t)vw->W + (size_t)vw->H + 16;
+    const size_t scratch_ints = 2 * (size_t)sc.nverts + 2 * (size_t)vw->W + (size_t)vw->H + 16
+                              + 5 * (size_t)vw->H + 2 * (size_t)vw->H + 4;      /* + plane-row memo (5 words + one int64 per row) */
     int err = 0;
     if (nthreads < 1) nthreads = 1;
 #pragma omp parallel num_threads(nthreads)

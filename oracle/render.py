@@ -53,11 +53,15 @@ def make_pose(x: float, y: float, z: float, angle_deg: float) -> np.ndarray:
 
 
 def render(blob: bytes, view: View, poses: np.ndarray, rgba: bool = False, threads: int = 1,
-           seg_hits: bool = False, tics: int = 0):
+           seg_hits: bool = False, tics: int = 0, out: np.ndarray = None):
+    """`out`: optional (n, H, W) uint8 array to render into (timing loops reuse it, so that a step does not pay for
+    first-touch page faults of a fresh allocation)."""
     poses = np.ascontiguousarray(poses, dtype=POSE)
     n = len(poses)
     W, H = view.W, view.H
-    fb = np.empty((n, H, W), dtype=np.uint8)
+    if out is not None:
+        assert out.dtype == np.uint8 and out.shape == (n, H, W) and out.flags.c_contiguous
+    fb = out if out is not None else np.empty((n, H, W), dtype=np.uint8)
     out_rgba = np.empty((n, H, W), dtype=np.uint32) if rgba else None
     nsegs = int(np.frombuffer(blob, dtype="<u4", count=32)[6])
     hits = np.zeros((n, nsegs), dtype=np.int32) if seg_hits else None

@@ -60,7 +60,7 @@ void free_renderer(b2d_renderer *r) {
     for (cudaEvent_t e : r->prof_events) cudaEventDestroy(e);
     if (r->h_poses) cudaFreeHost(r->h_poses);
     if (r->render_stream) cudaStreamDestroy(r->render_stream);
-    if (r->copy_stream) cudaStreamDestroy(r->copy_stream);
+    for (int i = 0; i < 2; i++) if (r->copy_stream[i]) cudaStreamDestroy(r->copy_stream[i]);
     for (int i = 0; i < 2; i++) {
         if (r->d_work[i]) cudaFree(r->d_work[i]);
         if (r->d_frames[i]) cudaFree(r->d_frames[i]);
@@ -497,7 +497,7 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
     const size_t npix = (size_t)r->view.W * r->view.H;
     if (!r->render_stream) {
         CU(cudaStreamCreateWithFlags(&r->render_stream, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&r->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) CU(cudaStreamCreateWithFlags(&r->copy_stream[i], cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
             CU(cudaEventCreateWithFlags(&r->rendered[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&r->copied[i], cudaEventDisableTiming));
@@ -521,15 +521,15 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
         int rc = enqueue_frames(r, r->d_poses, cnt, r->d_index[buf], rgba_fb ? r->d_rgba[buf] : nullptr, r->render_stream);
         if (rc != B2D_OK) return rc;
         CU(cudaEventRecord(r->rendered[buf], r->render_stream));
-        CU(cudaStreamWaitEvent(r->copy_stream, r->rendered[buf], 0));
-        CU(cudaMemcpyAsync(index_fb + done * npix, r->d_index[buf], npix * (size_t)cnt, cudaMemcpyDeviceToHost, r->copy_stream));
+        CU(cudaStreamWaitEvent(r->copy_stream[buf], r->rendered[buf], 0));
+        CU(cudaMemcpyAsync(index_fb + done * npix, r->d_index[buf], npix * (size_t)cnt, cudaMemcpyDeviceToHost, r->copy_stream[buf]));
         if (rgba_fb)
-            CU(cudaMemcpyAsync(rgba_fb + done * npix, r->d_rgba[buf], npix * 4 * (size_t)cnt, cudaMemcpyDeviceToHost, r->copy_stream));
-        CU(cudaEventRecord(r->copied[buf], r->copy_stream));
+            CU(cudaMemcpyAsync(rgba_fb + done * npix, r->d_rgba[buf], npix * 4 * (size_t)cnt, cudaMemcpyDeviceToHost, r->copy_stream[buf]));
+        CU(cudaEventRecord(r->copied[buf], r->copy_stream[buf]));
         done += (size_t)cnt;
         b++;
     }
-    CU(cudaStreamSynchronize(r->copy_stream));
+    for (int i = 0; i < 2; i++) CU(cudaStreamSynchronize(r->copy_stream[i]));
     CU(cudaStreamSynchronize(r->render_stream));
     int32_t status = 0;
     CU(cudaMemcpy(&status, r->d_status, sizeof status, cudaMemcpyDeviceToHost));

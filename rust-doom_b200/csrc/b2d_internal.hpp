@@ -48,7 +48,7 @@ struct b2d_renderer {
     uint8_t *d_index[2] = {nullptr, nullptr};
     uint32_t *d_rgba[2] = {nullptr, nullptr};
     Pose *h_poses = nullptr;        // pinned
-    cudaStream_t render_stream = nullptr, copy_stream = nullptr;
+    cudaStream_t render_stream = nullptr, copy_stream[2] = {nullptr, nullptr};   // one copy stream per staging buffer
     cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     std::vector<uint8_t> h_blob;    // host copy of the scene, kept only when it has time-dependent content
     uint32_t tics = 0;

@@ -34,6 +34,47 @@ def gather_chunks(per_rank: int, chunk_frames: int) -> Iterator[Tuple[int, int]]
         c0 += chunk_frames
 
 
+def sharded_schedule(n_total: int, world: int, chunk_frames: int, max_batch: int = 1 << 30):
+    """The chunk plan of b2d_render_sharded (csrc/b2d_sharded.cu), restated: per = ceil(n_total / world) poses per rank
+    (a short last block is padded by repeating the job's last pose), chunks of min(chunk_frames, max_batch, per) frames.
+    Returns (per, [(first_local_pose, frames_per_rank), ...])."""
+    per = (n_total + world - 1) // world
+    chunk = min(chunk_frames or 256, max_batch, per) if per else 0
+    plan = []
+    first = 0
+    while first < per:
+        cnt = min(chunk, per - first)
+        plan.append((first, cnt))
+        first += cnt
+    return per, plan
+
+
+def padded_block(poses: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """Rank `rank`'s block of the job as b2d_render_sharded renders it: poses[rank*per + i], indices past the end
+    clamped to the last pose."""
+    n = len(poses)
+    per = (n + world - 1) // world
+    idx = np.minimum(rank * per + np.arange(per), n - 1)
+    return poses[idx]
+
+
+def sharded_gather_emulated(local_frames, n_total: int, chunk_frames: int, on_chunk, group=None):
+    """CPU stand-in (gloo) for the exchange of b2d_render_sharded, chunk for chunk and in the same buffer layout: for
+    every chunk, `on_chunk(k, first_local_pose, frames_per_rank, gathered)` with gathered[q, j] = frame j of rank q's
+    slice.  `local_frames` is this rank's padded block [per, H, W] (torch uint8)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    per, plan = sharded_schedule(n_total, world, chunk_frames)
+    assert local_frames.shape[0] == per
+    for k, (first, cnt) in enumerate(plan):
+        send = local_frames[first:first + cnt].contiguous()
+        lst = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(lst, send, group=group)
+        on_chunk(k, first, cnt, torch.stack(lst))
+
+
 def all_gather_frames(local, n_total: int, chunk_frames: int = 256, group=None, out=None):
     """All-gather per-rank frame blocks [per_rank_valid, H, W] (torch uint8) into global pose order.
 

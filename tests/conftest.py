@@ -42,6 +42,12 @@ def b2d():
 
 @pytest.fixture(scope="session")
 def synth_wad():
+    """The level every generic test runs on: a generated two-map IWAD, or -- when B2D_IWAD=/path/doom1.wad is set -- that
+    file, so that the whole suite (oracle, scene compiler, hostcheck, -m gpu) runs on a real IWAD's first level."""
+    iwad = os.environ.get("B2D_IWAD")
+    if iwad:
+        with open(iwad, "rb") as f:
+            return f.read()
     from rust_doom_b200 import synthwad
     return synthwad.build_iwad(1, ("E1M1", "E1M2"))
 
@@ -89,6 +95,13 @@ def hostcheck():
 
     run.lib = lib
     return run
+
+
+def oracle_blob(wad_bytes: bytes, level: int = 0) -> bytes:
+    """The scene compiled by the ORACLE's own loader + compiler (oracle/wad.py, oracle/scene.py), independent of libb2d."""
+    from oracle import scene, wad
+    a = wad.Archive(wad_bytes)
+    return scene.compile_scene(a, wad.TextureDirectory(a), level)
 
 
 def sample_poses(b2d_mod, scene, n, seed):

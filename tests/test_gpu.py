@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import render
-from tests.conftest import sample_poses
+from tests.conftest import oracle_blob, sample_poses
 
 pytestmark = pytest.mark.gpu
 
@@ -43,13 +43,14 @@ def test_gpu_matches_oracle_odd_width(b2d, product_scene):
         _assert_same(ofb, gfb, "%dx%d" % (w, h))
 
 
-def test_gpu_matches_oracle_1080p_and_4k(b2d, product_scene):
+def test_gpu_matches_oracle_1080p_and_4k(b2d, product_scene, oracle_scene):
+    """The oracle renders from the scene ITS OWN compiler built (oracle/scene.py), the GPU from libb2d's."""
     poses = sample_poses(b2d, product_scene, 10, 33)
     gfb = b2d.Renderer(product_scene, b2d.make_view(1920, 1080), max_batch=16).render(poses)
-    ofb = render.render(product_scene.blob, render.make_view(1920, 1080), poses, threads=8)
+    ofb = render.render(oracle_scene, render.make_view(1920, 1080), poses, threads=8)
     _assert_same(ofb, gfb, "1080p")
     gfb = b2d.Renderer(product_scene, b2d.make_view(3840, 2160), max_batch=4).render(poses[:3])
-    ofb = render.render(product_scene.blob, render.make_view(3840, 2160), poses[:3], threads=8)
+    ofb = render.render(oracle_scene, render.make_view(3840, 2160), poses[:3], threads=8)
     _assert_same(ofb, gfb, "4K")
 
 
@@ -158,14 +159,15 @@ def test_config3_all_e1_maps_batched_1080p(b2d):
     """configs[2]: every E1 map, 1920x1080, one renderer per map, frames vs oracle."""
     from rust_doom_b200 import poses as P
     from rust_doom_b200 import synthwad
-    arch = b2d.Archive.from_bytes(synthwad.build_iwad(1, synthwad.E1_MAPS, map_seeds=list(range(11, 20))))
+    data = synthwad.build_iwad(1, synthwad.E1_MAPS, map_seeds=list(range(11, 20)))
+    arch = b2d.Archive.from_bytes(data)
     assert arch.num_levels() == 9
     view = b2d.make_view(1920, 1080)
     for lvl in range(9):
         sc = b2d.Scene(arch, lvl)
         poses = P.flythrough_poses(sc, 3, 2)
         gfb = b2d.Renderer(sc, view, max_batch=4).render(poses)
-        ofb = render.render(sc.blob, render.make_view(1920, 1080), poses, threads=8)
+        ofb = render.render(oracle_blob(data, lvl), render.make_view(1920, 1080), poses, threads=8)   # the oracle's own scene
         _assert_same(ofb, gfb, "E1M%d" % (lvl + 1))
 
 
@@ -173,17 +175,18 @@ def test_config4_doom2_maps_4k(b2d):
     """configs[3]: MAP01-MAP10 stand-ins at 3840x2160 (one map per GPU in the real config)."""
     from rust_doom_b200 import poses as P
     from rust_doom_b200 import synthwad
-    arch = b2d.Archive.from_bytes(synthwad.build_iwad(2, synthwad.MAP_NAMES_DOOM2, map_seeds=list(range(21, 31))))
+    data = synthwad.build_iwad(2, synthwad.MAP_NAMES_DOOM2, map_seeds=list(range(21, 31)))
+    arch = b2d.Archive.from_bytes(data)
     view = b2d.make_view(3840, 2160)
     for lvl in (0, 4, 9):
         sc = b2d.Scene(arch, lvl)
         poses = P.flythrough_poses(sc, 2, 2)
         gfb = b2d.Renderer(sc, view, max_batch=2).render(poses)
-        ofb = render.render(sc.blob, render.make_view(3840, 2160), poses, threads=8)
+        ofb = render.render(oracle_blob(data, lvl), render.make_view(3840, 2160), poses, threads=8)
         _assert_same(ofb, gfb, "MAP%02d" % (lvl + 1))
 
 
-def test_config5_random_poses_1080p(b2d, product_scene):
+def test_config5_random_poses_1080p(b2d, product_scene, oracle_scene):
     """configs[4]: random poses (splitmix64, sector_at acceptance); 512 rendered, every 32nd checked vs oracle,
     all checked for determinism across two launches."""
     import torch
@@ -197,7 +200,7 @@ def test_config5_random_poses_1080p(b2d, product_scene):
     r.render_device(dp.data_ptr(), 512, bb.data_ptr())
     torch.cuda.synchronize()
     assert torch.equal(a, bb)
-    ofb = render.render(product_scene.blob, render.make_view(1920, 1080), poses[::32], threads=8)
+    ofb = render.render(oracle_scene, render.make_view(1920, 1080), poses[::32], threads=8)
     assert np.array_equal(a[::32].cpu().numpy(), ofb)
 
 
@@ -285,14 +288,16 @@ def test_gpu_full_benchmark_workload_matches_oracle(b2d, product_scene):
     import os
     from rust_doom_b200 import poses as P
     from rust_doom_b200 import synthwad
-    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",))), 0)
+    data = synthwad.build_iwad(1, ("E1M1",))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0)
+    oblob = oracle_blob(data, 0)
     poses = P.flythrough_poses(sc, 1000, 2)
     r = b2d.Renderer(sc, b2d.make_view(1920, 1080), max_batch=250)
     gfb = r.render(poses)
-    threads = os.cpu_count() or 8
+    threads = len(os.sched_getaffinity(0))
     bad = []
     for c0 in range(0, 1000, 250):
-        ofb = render.render(sc.blob, render.make_view(1920, 1080), poses[c0:c0 + 250], threads=threads)
+        ofb = render.render(oblob, render.make_view(1920, 1080), poses[c0:c0 + 250], threads=threads)
         bad += [c0 + i for i in range(250) if not np.array_equal(ofb[i], gfb[c0 + i])]
     assert not bad, "frames differ: %s" % bad[:10]
 
@@ -433,3 +438,130 @@ def test_gpu_random_campaign_short():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main(cases=40, seed=2024) == 0
+
+
+def test_gpu_status_is_sticky_and_reports_masked_overflow(b2d):
+    """b2d_renderer_status: the device-resident entry points cannot report incomplete frames themselves; the sticky bits
+    can.  Force the masked-entry arena to a single chunk (B2D_MASKED_CHUNKS=1): bit 8 must come up, be cleared by the
+    read, and the frames of a normally sized renderer of the same level must be complete and exact."""
+    import torch
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=45, thing_pct=60))), 0)
+    poses = sample_poses(b2d, sc, 16, 77)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    out = torch.empty((16, 200, 320), dtype=torch.uint8, device="cuda")
+    os.environ["B2D_MASKED_CHUNKS"] = "1"
+    try:
+        small = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=16)
+    finally:
+        del os.environ["B2D_MASKED_CHUNKS"]
+    assert small.status() == 0
+    small.render_device(dp.data_ptr(), 16, out.data_ptr())
+    assert small.status() & 8, "arena of one chunk did not overflow"
+    assert small.status() == 0, "status is cleared by the read"
+    with pytest.raises(b2d.B2dError):
+        small.render(poses)                                   # the host path reports the same condition as an error
+    r = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=16)
+    r.render_device(dp.data_ptr(), 16, out.data_ptr())
+    assert r.status() == 0
+    _assert_same(render.render(sc.blob, render.make_view(320, 200), poses, threads=8), out.cpu().numpy(), "arena")
+
+
+def test_gpu_two_rasters_in_flight_share_the_masked_arena(b2d):
+    """rasters of a level with masked content enqueued on two streams used to share one scratch list.  They
+    are now ordered through an event: both batches come out exact."""
+    import torch
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(2, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=40, thing_pct=50))), 0)
+    view = b2d.make_view(640, 400)
+    r = b2d.Renderer(sc, view, max_batch=24)
+    batches = [sample_poses(b2d, sc, 24, 900 + k) for k in range(4)]
+    dps = [torch.from_numpy(p.view(np.int32).reshape(-1, 4).copy()).cuda() for p in batches]
+    outs = [torch.empty((24, 400, 640), dtype=torch.uint8, device="cuda") for _ in batches]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    for k in range(4):
+        r.render_device(dps[k].data_ptr(), 24, outs[k].data_ptr(), 0, streams[k & 1].cuda_stream)
+    torch.cuda.synchronize()
+    assert r.status() == 0
+    for k in range(4):
+        _assert_same(render.render(sc.blob, render.make_view(640, 400), batches[k], threads=8), outs[k].cpu().numpy(), "batch %d" % k)
+
+
+def test_gpu_set_time_async_is_stream_ordered(b2d):
+    """b2d_renderer_set_time_async: no host-side synchronisation; batches enqueued before the call see the old time,
+    batches after it the new one -- on the same stream and on another stream."""
+    import torch
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(anim=True, mid_pct=15))), 0)
+    poses = sample_poses(b2d, sc, 8, 55)
+    r = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=8)
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    times = [0, 8, 17, 1000, 9, 0, 123456]
+    outs = [torch.empty((8, 200, 320), dtype=torch.uint8, device="cuda") for _ in times]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for k, t in enumerate(times):
+        st = (s1, s2)[k % 2]
+        r.set_time_async(t, st.cuda_stream)
+        r.render_device(dp.data_ptr(), 8, outs[k].data_ptr(), 0, (s2, s1)[k % 2].cuda_stream if k % 3 == 0 else st.cuda_stream)
+    torch.cuda.synchronize()
+    assert r.status() == 0
+    oview = render.make_view(320, 200)
+    for k, t in enumerate(times):
+        _assert_same(render.render(sc.blob, oview, poses, threads=8, tics=t), outs[k].cpu().numpy(), "tics %d (step %d)" % (t, k))
+
+
+def test_gpu_sharded_render_world1_and_checksums(b2d, product_scene, oracle_scene):
+    """b2d_render_sharded through the C ABI with a one-rank NCCL communicator: chunked render into the in-place
+    all-gather buffer, gather + consumer streams; every gathered frame's device checksum equals the host restatement on
+    the oracle's frame (chunk not dividing the job, a short last chunk, all three modes)."""
+    import torch
+    from rust_doom_b200 import jobs
+    poses = sample_poses(b2d, product_scene, 23, 97)
+    comm = jobs.single_comm(0)
+    assert comm.nccl_version >= 21900
+    view = b2d.make_view(640, 400)
+    r = b2d.Renderer(product_scene, view, max_batch=8)
+    npix = 640 * 400
+    table = jobs.ChecksumTable(1, 23, npix, torch.device("cuda", 0))
+    seen = []
+
+    def on_chunk(k, first, cnt, ptr, ranks, stream):
+        seen.append((k, first, cnt, ranks))
+        table.on_chunk(k, first, cnt, ptr, ranks, stream)
+
+    st = r.render_sharded(comm, poses, 5, b2d._lib.SHARD_RENDER_GATHER, on_chunk)
+    assert st["chunks"] == 5 and st["frames_local"] == 23 and st["frames_gathered"] == 23
+    assert seen == [(0, 0, 5, 1), (1, 5, 5, 1), (2, 10, 5, 1), (3, 15, 5, 1), (4, 20, 3, 1)]
+    assert r.status() == 0
+    ofb = render.render(oracle_scene, render.make_view(640, 400), poses, threads=8)
+    want = np.array([b2d.frame_checksum(ofb[i]) for i in range(23)], np.uint32)
+    assert np.array_equal(table.host()[0], want)
+    for mode in (b2d._lib.SHARD_RENDER_ONLY, b2d._lib.SHARD_GATHER_ONLY):
+        st = r.render_sharded(comm, poses, 8, mode)
+        assert st["chunks"] == 3 and st["total_ms"] > 0
+    # the checksum kernel on an unaligned frame size
+    odd = torch.from_numpy(ofb.reshape(-1)[:3 * 1003].copy()).cuda()
+    outc = torch.zeros(3, dtype=torch.int32, device="cuda")
+    b2d.frame_checksums_device(odd.data_ptr(), 3, 1003, outc.data_ptr())
+    torch.cuda.synchronize()
+    assert outc.cpu().numpy().view(np.uint32).tolist() == [b2d.frame_checksum(ofb.reshape(-1)[i * 1003:(i + 1) * 1003]) for i in range(3)]
+    comm.close()
+
+
+def test_gpu_suite_runs_on_a_supplied_iwad(tmp_path):
+    """B2D_IWAD hook: with the variable set, the generic fixtures load that file instead of the generated level.  Kept
+    alive with a generated IWAD written to disk (no real doom1.wad exists here): a sub-run of this suite must pass."""
+    import subprocess
+    import sys
+    from rust_doom_b200 import synthwad
+    path = tmp_path / "custom.wad"
+    path.write_bytes(synthwad.build_iwad(9, ("E1M1", "E1M2"), cfg=synthwad.SynthConfig(mid_pct=10, thing_pct=10)))
+    env = dict(os.environ, B2D_IWAD=str(path))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "tests/test_gpu.py", "-k",
+                          "320x200 or odd_width or device_and_host or config5"], cwd=root, env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "4 passed" in res.stdout

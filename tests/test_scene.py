@@ -1,5 +1,7 @@
 """Scene compiler: the product's C++ compiler must emit the same bytes as the oracle's restatement of
 LevelWalker (wad/src/visitor.rs:711-937) for every map, plus spot checks of the pegging rules."""
+import os
+
 import numpy as np
 import pytest
 
@@ -223,3 +225,23 @@ def test_light_effect_parameters_and_hand_values():
     assert set(vals) == {0, 255} and 0.02 < vals.count(0) / len(vals) < 0.12
     # static sector: clamped, truncated
     assert S.light_byte_at((S.LIGHT_NONE, f(144 >> 3) / f(31.0), f(0), f(0), f(0), f(0)), 99) == W.light_byte(144, 0)
+
+
+def test_fixture_blob_identical(product_scene, oracle_scene):
+    """The level every generic test runs on (generated, or B2D_IWAD): both scene compilers give the same bytes."""
+    assert product_scene.blob == oracle_scene
+
+
+def test_suite_runs_on_a_supplied_iwad(tmp_path):
+    """B2D_IWAD hook (CPU tier): the generic fixtures take their level from the file the variable names.  A generated
+    IWAD on disk stands in for doom1.wad: the scene-compiler and hostcheck tests must pass on it."""
+    import subprocess
+    import sys
+    from rust_doom_b200 import synthwad
+    path = tmp_path / "custom.wad"
+    path.write_bytes(synthwad.build_iwad(9, ("E1M1", "E1M2"), cfg=synthwad.SynthConfig(mid_pct=10, thing_pct=10)))
+    env = dict(os.environ, B2D_IWAD=str(path))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "not gpu", "tests/test_scene.py", "tests/test_hostcheck.py",
+                          "-k", "fixture_blob_identical or sector_at_agrees or hostcheck_320x200 or hostcheck_odd_sizes"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
