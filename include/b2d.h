@@ -85,6 +85,42 @@ int b2d_wad_name(const void *bytes, size_t size, char name_out[8]);
 
 /* ---- scene (level + textures -> GPU-ready arrays) ------------------------------------------ */
 int b2d_scene_create(const b2d_archive *a, int level_index, b2d_scene **out);
+/* The same scene from buffers the host already owns -- what a Rust `GpuRenderer: System` has after
+ * `WadSystem::create` (game/src/wad_system.rs:18-23,72-114): the level's eight raw lumps (wad::Level keeps exactly
+ * these vectors, wad/src/level.rs:22-31) and the TextureDirectory's decoded images (wad/src/tex.rs:109-135:
+ * `texture(name)` -> row-major u16 image, a non-zero high byte = transparent, wad/src/image.rs:11-37; `flat(name)` ->
+ * 4096 bytes; `colormap(i)`, `palette(0)`).  Nothing is parsed twice: no WAD path, no directory, no PNAMES/TEXTUREx
+ * here.  Inputs are caller-owned and copied.  `textures` must hold every wall texture the level's sidedefs name, the
+ * level's sky texture and the sprite images of its things (names the level uses but the list lacks render as
+ * missing, as in the reference: visitor.rs:857-860); duplicates: the later entry wins (archive.rs:85). */
+typedef struct b2d_lump {
+    const void *data;
+    size_t size;
+} b2d_lump;
+typedef struct b2d_level_lumps {
+    char name[8];               /* level marker name ("E1M1", "MAP01"; NUL padded): selects the sky (wad/src/meta.rs:156-172) */
+    b2d_lump things, linedefs, sidedefs, vertexes, segs, ssectors, nodes, sectors;
+} b2d_level_lumps;
+typedef struct b2d_image {
+    char name[8];
+    int32_t width, height;
+    const uint16_t *pixels;     /* width*height, row-major */
+} b2d_image;
+typedef struct b2d_flat {
+    char name[8];
+    const uint8_t *pixels;      /* 4096 bytes */
+} b2d_flat;
+typedef struct b2d_textures {
+    const b2d_image *textures;  /* composed wall textures, then sprites (tex.rs:81-95: one name -> image map) */
+    size_t n_textures;
+    const b2d_flat *flats;
+    size_t n_flats;
+    const uint8_t *colormaps;   /* n_colormaps x 256 (COLORMAP; rows 0..31 are used) */
+    size_t n_colormaps;
+    const uint8_t *palette;     /* 768 bytes: PLAYPAL[0] */
+} b2d_textures;
+int b2d_scene_create_from_lumps(const b2d_level_lumps *level, const b2d_textures *tex, b2d_scene **out);
+
 int b2d_scene_info_get(const b2d_scene *s, b2d_scene_info *out);
 /* Read-only access to the compiled "B2DS" blob (layout in DESIGN.md); valid until destroy. */
 const void *b2d_scene_blob(const b2d_scene *s, size_t *size_out);
@@ -192,6 +228,12 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
  * (position sensitive, order independent).  Used to validate gathered frames without moving them to the host. */
 int b2d_frame_checksums_device(const uint8_t *d_frames, size_t n_frames, size_t frame_bytes, uint32_t *d_out,
                                void *cuda_stream);
+
+/* Device memory for hosts that do not link a CUDA library themselves (the compiled CLI; a Rust binding would use its
+ * cuda-sys crate instead): allocate / free on `device`, and a synchronous device -> host copy. */
+int b2d_device_alloc(int device, size_t bytes, void **d_out);
+int b2d_device_free(int device, void *d_ptr);
+int b2d_device_download(int device, void *host_dst, const void *d_src, size_t bytes);
 
 /* Introspection for tests/profiling: copies the BSP-walk worklist of the LAST b2d_render_device
  * batch to the host.  counts_out[n], and for frame i seg ids seg_ids_out[i*stride .. +counts[i]). */

@@ -100,13 +100,52 @@ class Archive:
 
 
 class Scene:
-    def __init__(self, archive: Archive, level_index: int = 0):
-        h = ctypes.c_void_p()
-        _check(_lib.load().b2d_scene_create(archive._h, level_index, ctypes.byref(h)))
+    def __init__(self, archive: Optional[Archive], level_index: int = 0, _handle=None):
+        h = _handle if _handle is not None else ctypes.c_void_p()
+        if _handle is None:
+            _check(_lib.load().b2d_scene_create(archive._h, level_index, ctypes.byref(h)))
         self._h = h
         info = _lib.SceneInfo()
         _check(_lib.load().b2d_scene_info_get(self._h, ctypes.byref(info)))
         self.info = info
+
+    LUMP_ORDER = ("things", "linedefs", "sidedefs", "vertexes", "segs", "ssectors", "nodes", "sectors")
+
+    @classmethod
+    def from_lumps(cls, name: bytes, lumps, textures, flats, colormaps, palette: bytes) -> "Scene":
+        """b2d_scene_create_from_lumps: the scene from buffers a host that has already parsed the WAD owns
+        (game::WadSystem's pub fields).  lumps: dict of the eight raw level lumps (bytes); textures: iterable of
+        (name, uint16 array [h, w], hi byte != 0 = transparent); flats: iterable of (name, 4096 bytes); colormaps:
+        iterable of 256-byte rows; palette: 768 bytes (PLAYPAL[0])."""
+        keep = []                                             # buffers must outlive the call (they are copied inside)
+        ll = _lib.LevelLumps()
+        ll.name = name[:8]
+        for key in cls.LUMP_ORDER:
+            raw = bytes(lumps[key])
+            buf = ctypes.create_string_buffer(raw, len(raw)) if raw else None
+            keep.append(buf)
+            setattr(ll, key, _lib.Lump(ctypes.addressof(buf) if buf is not None else None, len(raw)))
+        tex = list(textures)
+        imgs = (_lib.ImageDesc * max(len(tex), 1))()
+        for i, (nm, px) in enumerate(tex):
+            a = np.ascontiguousarray(px, dtype=np.uint16)
+            keep.append(a)
+            imgs[i].name, imgs[i].width, imgs[i].height, imgs[i].pixels = nm[:8], a.shape[1], a.shape[0], a.ctypes.data
+        fl = list(flats)
+        fds = (_lib.FlatDesc * max(len(fl), 1))()
+        for i, (nm, data) in enumerate(fl):
+            b = ctypes.create_string_buffer(bytes(data)[:4096].ljust(4096, b"\0"), 4096)
+            keep.append(b)
+            fds[i].name, fds[i].pixels = nm[:8], ctypes.addressof(b)
+        cm = b"".join(bytes(c)[:256].ljust(256, b"\0") for c in colormaps)
+        cmb = ctypes.create_string_buffer(cm, len(cm)) if cm else None
+        pal = ctypes.create_string_buffer(bytes(palette)[:768].ljust(768, b"\0"), 768)
+        t = _lib.Textures(imgs, len(tex), fds, len(fl), ctypes.addressof(cmb) if cmb is not None else None, len(cm) // 256,
+                          ctypes.addressof(pal))
+        h = ctypes.c_void_p()
+        _check(_lib.load().b2d_scene_create_from_lumps(ctypes.byref(ll), ctypes.byref(t), ctypes.byref(h)))
+        del keep
+        return cls(None, 0, _handle=h)
 
     @property
     def blob(self) -> bytes:

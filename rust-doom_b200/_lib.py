@@ -27,13 +27,13 @@ class SceneInfo(ctypes.Structure):
 
 EXPORTS = [
     "b2d_last_error", "b2d_archive_open", "b2d_archive_open_memory", "b2d_archive_num_levels",
-    "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_info_get",
+    "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_create_from_lumps", "b2d_scene_info_get",
     "b2d_scene_blob", "b2d_scene_sector_at", "b2d_scene_destroy", "b2d_view_init", "b2d_renderer_create",
     "b2d_renderer_destroy", "b2d_renderer_set_time", "b2d_renderer_set_time_async", "b2d_renderer_status", "b2d_render", "b2d_render_device", "b2d_walk_device",
     "b2d_raster_device", "b2d_palette_lut_device",
     "b2d_debug_worklist", "b2d_launch_count", "b2d_profile_enable", "b2d_profile_read",
     "b2d_comm_unique_id", "b2d_comm_create", "b2d_comm_destroy", "b2d_comm_info", "b2d_render_sharded",
-    "b2d_frame_checksums_device",
+    "b2d_frame_checksums_device", "b2d_device_alloc", "b2d_device_free", "b2d_device_download",
 ]
 
 COMM_ID_BYTES = 128
@@ -50,6 +50,28 @@ class ShardedStats(ctypes.Structure):
 # void fn(void *user, int chunk, size_t first_local_pose, size_t frames_per_rank, const uint8_t *d_frames, int ranks, void *stream)
 CHUNK_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p,
                             ctypes.c_int, ctypes.c_void_p)
+
+class Lump(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("size", ctypes.c_size_t)]
+
+
+class LevelLumps(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 8)] + [(n, Lump) for n in ("things", "linedefs", "sidedefs", "vertexes", "segs", "ssectors", "nodes", "sectors")]
+
+
+class ImageDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 8), ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("pixels", ctypes.c_void_p)]
+
+
+class FlatDesc(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char * 8), ("pixels", ctypes.c_void_p)]
+
+
+class Textures(ctypes.Structure):
+    _fields_ = [("textures", ctypes.POINTER(ImageDesc)), ("n_textures", ctypes.c_size_t), ("flats", ctypes.POINTER(FlatDesc)),
+                ("n_flats", ctypes.c_size_t), ("colormaps", ctypes.c_void_p), ("n_colormaps", ctypes.c_size_t),
+                ("palette", ctypes.c_void_p)]
+
 
 _lib = None
 
@@ -77,6 +99,7 @@ def load() -> ctypes.CDLL:
     L.b2d_archive_close.restype = None
     L.b2d_wad_name.argtypes = [vp, cs, ctypes.c_char_p]
     L.b2d_scene_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    L.b2d_scene_create_from_lumps.argtypes = [ctypes.POINTER(LevelLumps), ctypes.POINTER(Textures), ctypes.POINTER(vp)]
     L.b2d_scene_info_get.argtypes = [vp, ctypes.POINTER(SceneInfo)]
     L.b2d_scene_blob.argtypes = [vp, ctypes.POINTER(cs)]
     L.b2d_scene_blob.restype = vp

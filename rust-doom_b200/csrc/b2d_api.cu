@@ -248,24 +248,72 @@ int b2d_wad_name(const void *bytes, size_t size, char name_out[8]) {
 }
 
 // ---- scene -----------------------------------------------------------------------------------
+namespace {
+void fill_scene_info(b2d_scene *s) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(s->blob.data());
+    b2d_scene_info &i = s->info;
+    i.n_verts = (int32_t)h[H_NVERTS]; i.n_nodes = (int32_t)h[H_NNODES]; i.n_ssectors = (int32_t)h[H_NSSECTORS];
+    i.n_segs = (int32_t)h[H_NSEGS]; i.n_sectors = (int32_t)h[H_NSECTORS]; i.n_textures = (int32_t)h[H_NTEX];
+    i.n_flats = (int32_t)h[H_NFLATS]; i.blob_bytes = (int32_t)h[H_TOTAL];
+    i.n_masked_mids = (int32_t)h[H_NMIDS]; i.n_sprites = (int32_t)h[H_NSPRITES];
+    i.has_start = (int32_t)h[H_HAS_START];
+    i.start.x = (int32_t)h[H_START_X] * 65536; i.start.y = (int32_t)h[H_START_Y] * 65536;
+    i.start.z = (int32_t)h[H_START_Z] * 65536;
+    i.start.angle = (uint32_t)(((uint64_t)h[H_START_ANGLE] << 32) / 360u);
+    i.min_height = (int32_t)h[H_MIN_H]; i.max_height = (int32_t)h[H_MAX_H];
+}
+}  // namespace
+
 int b2d_scene_create(const b2d_archive *a, int level_index, b2d_scene **out) {
     if (!a || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
     return guarded([&] {
         auto s = std::make_unique<b2d_scene>();
         TextureDirectory td = TextureDirectory::load(*a->wad);
-        s->blob = compile_scene(*a->wad, td, level_index);
         s->level = Level::load(*a->wad, level_index);
-        const uint32_t *h = reinterpret_cast<const uint32_t *>(s->blob.data());
-        b2d_scene_info &i = s->info;
-        i.n_verts = (int32_t)h[H_NVERTS]; i.n_nodes = (int32_t)h[H_NNODES]; i.n_ssectors = (int32_t)h[H_NSSECTORS];
-        i.n_segs = (int32_t)h[H_NSEGS]; i.n_sectors = (int32_t)h[H_NSECTORS]; i.n_textures = (int32_t)h[H_NTEX];
-        i.n_flats = (int32_t)h[H_NFLATS]; i.blob_bytes = (int32_t)h[H_TOTAL];
-        i.n_masked_mids = (int32_t)h[H_NMIDS]; i.n_sprites = (int32_t)h[H_NSPRITES];
-        i.has_start = (int32_t)h[H_HAS_START];
-        i.start.x = (int32_t)h[H_START_X] * 65536; i.start.y = (int32_t)h[H_START_Y] * 65536;
-        i.start.z = (int32_t)h[H_START_Z] * 65536;
-        i.start.angle = (uint32_t)(((uint64_t)h[H_START_ANGLE] << 32) / 360u);
-        i.min_height = (int32_t)h[H_MIN_H]; i.max_height = (int32_t)h[H_MAX_H];
+        s->blob = compile_scene(s->level, td);
+        fill_scene_info(s.get());
+        *out = s.release();
+        return B2D_OK;
+    });
+}
+
+int b2d_scene_create_from_lumps(const b2d_level_lumps *lv, const b2d_textures *tex, b2d_scene **out) {
+    if (!lv || !tex || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    if ((tex->n_textures && !tex->textures) || (tex->n_flats && !tex->flats) || (tex->n_colormaps && !tex->colormaps))
+        return fail(B2D_ERR_INVALID_ARG, "null texture table");
+    return guarded([&] {
+        auto s = std::make_unique<b2d_scene>();
+        const b2d_lump *src[8] = {&lv->things, &lv->linedefs, &lv->sidedefs, &lv->vertexes, &lv->segs, &lv->ssectors, &lv->nodes, &lv->sectors};
+        RawLump lumps[8];
+        for (int k = 0; k < 8; k++) { lumps[k].data = static_cast<const uint8_t *>(src[k]->data); lumps[k].size = src[k]->size; }
+        s->level = Level::from_lumps(make_name(reinterpret_cast<const uint8_t *>(lv->name), 8), lumps);
+        // a TextureDirectory filled from the caller's decoded images instead of PNAMES / TEXTUREx / F_START..F_END
+        TextureDirectory td;
+        td.textures.reserve(tex->n_textures);
+        for (size_t i = 0; i < tex->n_textures; i++) {
+            const b2d_image &im = tex->textures[i];
+            if (im.width < 1 || im.height < 1 || im.width > 4096 || im.height > 4096 || !im.pixels)      // image.rs:9,49-52
+                throw WadError(kErrCorrupt, "texture image out of range (1..4096 x 1..4096)");
+            Image img;
+            img.w = im.width; img.h = im.height;
+            img.px.assign(im.pixels, im.pixels + (size_t)im.width * (size_t)im.height);
+            td.texture_index[make_name(reinterpret_cast<const uint8_t *>(im.name), 8)] = (int)td.textures.size();   // later wins
+            td.textures.push_back(std::move(img));
+        }
+        td.own_flats.resize(tex->n_flats);
+        for (size_t i = 0; i < tex->n_flats; i++) {
+            if (!tex->flats[i].pixels) throw WadError(kErrCorrupt, "null flat");
+            std::memcpy(td.own_flats[i].data(), tex->flats[i].pixels, 4096);
+            td.flat_index[make_name(reinterpret_cast<const uint8_t *>(tex->flats[i].name), 8)] = (int)i;
+        }
+        td.colormaps.resize(tex->n_colormaps);
+        for (size_t i = 0; i < tex->n_colormaps; i++) std::memcpy(td.colormaps[i].data(), tex->colormaps + 256 * i, 256);
+        if (tex->palette) {
+            td.palettes.resize(1);
+            std::memcpy(td.palettes[0].data(), tex->palette, 768);
+        }
+        s->blob = compile_scene(s->level, td);
+        fill_scene_info(s.get());
         *out = s.release();
         return B2D_OK;
     });
@@ -548,6 +596,28 @@ int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_
     CU(cudaSetDevice(r->device));
     CU(launch_palette(r->ds.palette, d_index, d_rgba, n_pixels, static_cast<cudaStream_t>(cuda_stream)));
     r->launches += 1;
+    return B2D_OK;
+}
+
+int b2d_device_alloc(int device, size_t bytes, void **d_out) {
+    if (!d_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(d_out, bytes ? bytes : 1));
+    CU(cudaMemset(*d_out, 0, bytes));
+    return B2D_OK;
+}
+
+int b2d_device_free(int device, void *d_ptr) {
+    CU(cudaSetDevice(device));
+    CU(cudaFree(d_ptr));
+    return B2D_OK;
+}
+
+int b2d_device_download(int device, void *host_dst, const void *d_src, size_t bytes) {
+    if (!host_dst || !d_src) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(host_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return B2D_OK;
 }
 

@@ -136,7 +136,10 @@ int sector_at(const Level &lv, double x, double y, int *subsector_out) {
 }
 
 std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &td, int level_index) {
-    const Level lv = Level::load(wad, level_index);
+    return compile_scene(Level::load(wad, level_index), td);
+}
+
+std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) {
     const int nverts = (int)lv.vertices.size(), nsegs = (int)lv.segs.size();
     const int nsect = (int)lv.sectors.size(), nss = (int)lv.subsectors.size(), nnodes = (int)lv.nodes.size();
 

@@ -166,6 +166,7 @@ inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, S
 }
 
 std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &tex, int level_index);
+std::vector<uint8_t> compile_scene(const Level &level, const TextureDirectory &tex);
 
 // LevelWalker::sector_at on the raw level (visitor.rs:1028-1060); -1 if outside.
 int sector_at(const Level &level, double x, double y, int *subsector_out = nullptr);

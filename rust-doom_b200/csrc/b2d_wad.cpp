@@ -131,12 +131,11 @@ const uint8_t *Archive::lump_data(int index) const {
 namespace {
 
 template <typename T, size_t kSize, typename Fn>
-std::vector<T> decode_vec(const Archive &wad, int index, Fn decode_one) {
-    const Lump &l = wad.lump(index);
-    if (l.size <= 0 || (size_t)l.size % kSize != 0)
-        corrupt("bad lump size for '" + name_str(l.name) + "'");        // archive.rs:178-181
-    const uint8_t *p = wad.lump_data(index);
-    size_t n = (size_t)l.size / kSize;
+std::vector<T> decode_vec(const RawLump &l, const char *what, Fn decode_one) {
+    if (l.size == 0 || l.size % kSize != 0 || !l.data)
+        corrupt(std::string("bad lump size for '") + what + "'");        // archive.rs:178-181
+    const uint8_t *p = l.data;
+    size_t n = l.size / kSize;
     std::vector<T> out(n);
     for (size_t i = 0; i < n; i++) out[i] = decode_one(p + i * kSize);
     return out;
@@ -146,39 +145,49 @@ std::vector<T> decode_vec(const Archive &wad, int index, Fn decode_one) {
 
 Level Level::load(const Archive &wad, int level_index) {
     int start = wad.level_lump_index(level_index);
+    RawLump lumps[8];
+    for (int k = 0; k < 8; k++) {               // THINGS .. SECTORS at fixed offsets from the marker (level.rs:13-20)
+        const Lump &l = wad.lump(start + 1 + k);
+        lumps[k].size = l.size > 0 ? (size_t)l.size : 0;
+        lumps[k].data = wad.lump_data(start + 1 + k);
+    }
+    return from_lumps(wad.lump(start).name, lumps);
+}
+
+Level Level::from_lumps(const Name &name, const RawLump lumps[8]) {
     Level lv;
-    lv.name = wad.lump(start).name;
-    lv.things = decode_vec<Thing, 10>(wad, start + 1, [](const uint8_t *p) {
+    lv.name = name;
+    lv.things = decode_vec<Thing, 10>(lumps[0], "THINGS", [](const uint8_t *p) {
         return Thing{rd_i16(p), rd_i16(p + 2), rd_i16(p + 4), rd_u16(p + 6), rd_u16(p + 8)};
     });
-    lv.linedefs = decode_vec<Linedef, 14>(wad, start + 2, [](const uint8_t *p) {
+    lv.linedefs = decode_vec<Linedef, 14>(lumps[1], "LINEDEFS", [](const uint8_t *p) {
         return Linedef{rd_u16(p), rd_u16(p + 2), rd_u16(p + 4), rd_u16(p + 6), rd_u16(p + 8),
                        rd_i16(p + 10), rd_i16(p + 12)};
     });
-    lv.sidedefs = decode_vec<Sidedef, 30>(wad, start + 3, [](const uint8_t *p) {
+    lv.sidedefs = decode_vec<Sidedef, 30>(lumps[2], "SIDEDEFS", [](const uint8_t *p) {
         Sidedef s;
         s.xoff = rd_i16(p); s.yoff = rd_i16(p + 2);
         s.upper = make_name(p + 4, 8); s.lower = make_name(p + 12, 8); s.middle = make_name(p + 20, 8);
         s.sector = rd_u16(p + 28);
         return s;
     });
-    lv.vertices = decode_vec<Vertex, 4>(wad, start + 4, [](const uint8_t *p) {
+    lv.vertices = decode_vec<Vertex, 4>(lumps[3], "VERTEXES", [](const uint8_t *p) {
         return Vertex{rd_i16(p), rd_i16(p + 2)};
     });
-    lv.segs = decode_vec<Seg, 12>(wad, start + 5, [](const uint8_t *p) {
+    lv.segs = decode_vec<Seg, 12>(lumps[4], "SEGS", [](const uint8_t *p) {
         return Seg{rd_u16(p), rd_u16(p + 2), rd_u16(p + 4), rd_u16(p + 6), rd_u16(p + 8), rd_u16(p + 10)};
     });
-    lv.subsectors = decode_vec<Subsector, 4>(wad, start + 6, [](const uint8_t *p) {
+    lv.subsectors = decode_vec<Subsector, 4>(lumps[5], "SSECTORS", [](const uint8_t *p) {
         return Subsector{rd_u16(p), rd_u16(p + 2)};
     });
-    lv.nodes = decode_vec<Node, 28>(wad, start + 7, [](const uint8_t *p) {
+    lv.nodes = decode_vec<Node, 28>(lumps[6], "NODES", [](const uint8_t *p) {
         Node n;
         n.x = rd_i16(p); n.y = rd_i16(p + 2); n.dx = rd_i16(p + 4); n.dy = rd_i16(p + 6);
         for (int k = 0; k < 4; k++) { n.rbox[k] = rd_i16(p + 8 + 2 * k); n.lbox[k] = rd_i16(p + 16 + 2 * k); }
         n.right = rd_u16(p + 24); n.left = rd_u16(p + 26);
         return n;
     });
-    lv.sectors = decode_vec<Sector, 26>(wad, start + 8, [](const uint8_t *p) {
+    lv.sectors = decode_vec<Sector, 26>(lumps[7], "SECTORS", [](const uint8_t *p) {
         Sector s;
         s.floor = rd_i16(p); s.ceil = rd_i16(p + 2);
         s.floor_tex = make_name(p + 4, 8); s.ceil_tex = make_name(p + 12, 8);
@@ -281,6 +290,7 @@ const Image *TextureDirectory::texture(const Name &n) const {
 const uint8_t *TextureDirectory::flat(const Name &n) const {
     auto it = flat_index.find(n);
     if (it == flat_index.end()) return nullptr;
+    if (!wad) return (size_t)it->second < own_flats.size() ? own_flats[(size_t)it->second].data() : nullptr;
     if (wad->lump(it->second).size < 4096) return nullptr;
     return wad->lump_data(it->second);
 }

@@ -71,6 +71,8 @@ private:
     std::vector<int> levels_;
 };
 
+struct RawLump { const uint8_t *data = nullptr; size_t size = 0; };
+
 struct Level {
     Name name;
     std::vector<Thing> things;
@@ -83,6 +85,9 @@ struct Level {
     std::vector<Sector> sectors;
 
     static Level load(const Archive &wad, int level_index);
+    // the eight level lumps as raw bytes, in marker order: THINGS, LINEDEFS, SIDEDEFS, VERTEXES, SEGS, SSECTORS, NODES,
+    // SECTORS (wad/src/level.rs:13-31) -- what a host that has already parsed the WAD hands over
+    static Level from_lumps(const Name &name, const RawLump lumps[8]);
     int seg_sidedef(const Seg &s) const;          // -1 if none (level.rs:101-109)
     int seg_back_sidedef(const Seg &s) const;     // level.rs:111-119
     int sector_min_light(int sector_id) const;    // level.rs:163-182
@@ -104,7 +109,8 @@ struct TextureDirectory {
     std::vector<Image> patch_images;
     std::unordered_map<Name, int, NameHash> texture_index;   // name -> textures[] (later wins)
     std::vector<Image> textures;
-    std::unordered_map<Name, int, NameHash> flat_index;      // name -> flat lump index in archive
+    std::unordered_map<Name, int, NameHash> flat_index;      // name -> flat lump index in archive (or into own_flats)
+    std::vector<std::array<uint8_t, 4096>> own_flats;        // flats handed over by the caller (wad == nullptr)
     const Archive *wad = nullptr;
 
     static TextureDirectory load(const Archive &wad);

@@ -116,3 +116,20 @@ def test_compiled_cli_renders_the_same_frames_as_the_python_mirror(tmp_path, b2d
     rgba = r.render(poses, rgba=True)[1]
     want = b"".join(cli.encode_ppm(cli.rgba_to_rgb(rgba[i])) for i in range(4))
     assert stream.read_bytes() == want
+
+
+@pytest.mark.gpu
+def test_compiled_cli_sharded_world1(tmp_path):
+    """The compiled front end drives b2d_render_sharded (communicator from a unique-id file, checksum consumer,
+    b2d_renderer_status) through nothing but include/b2d.h; a one-rank run must gather every frame."""
+    import os
+    import subprocess
+    from rust_doom_b200 import build, synthwad
+    wad = tmp_path / "t.wad"
+    wad.write_bytes(synthwad.build_iwad(1, ("E1M1",)))
+    exe = build.build_cli()
+    res = subprocess.run([exe, "--iwad", str(wad), "--resolution", "320x200", "--poses", "10", "--world", "1", "--rank", "0",
+                          "--chunk", "4", "--id-file", str(tmp_path / "id")], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ))
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "rank 0/1: 10 frames gathered in 3 chunk(s)" in res.stdout

@@ -245,3 +245,28 @@ def test_suite_runs_on_a_supplied_iwad(tmp_path):
     res = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "not gpu", "tests/test_scene.py", "tests/test_hostcheck.py",
                           "-k", "fixture_blob_identical or sector_at_agrees or hostcheck_320x200 or hostcheck_odd_sizes"], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("seed,maps,level,cfg", [(1, ("E1M1", "E1M2"), 1, {}), (5, ("MAP03",), 0, dict(mid_pct=30, thing_pct=40, anim=True, odd_tex=True))])
+def test_scene_from_lumps_equals_scene_from_wad(b2d, seed, maps, level, cfg):
+    """b2d_scene_create_from_lumps ('caller-owned raw lump bytes + composed textures + COLORMAP + PLAYPAL[0]'):
+    a host that has parsed the WAD itself -- here the oracle's loader stands in for rust-doom's wad crate -- hands over
+    the level's eight lumps and its decoded images; the compiled scene is byte-identical to the one built from the
+    WAD file, and so is sector_at."""
+    from rust_doom_b200 import synthwad
+    data = synthwad.build_iwad(seed, maps, cfg=synthwad.SynthConfig(**cfg))
+    a = W.Archive(data)
+    td = W.TextureDirectory(a)
+    marker = a.levels[level]
+    lumps = {key: a.read(marker + 1 + k) for k, key in enumerate(b2d.Scene.LUMP_ORDER)}
+    sc = b2d.Scene.from_lumps(a.lumps[marker][0], lumps, list(td.textures.items()), list(td.flats.items()), td.colormaps, td.palettes[0])
+    ref = b2d.Scene(b2d.Archive.from_bytes(data), level)
+    assert sc.blob == ref.blob
+    assert sc.info.n_segs == ref.info.n_segs and sc.info.has_start == ref.info.has_start
+    assert sc.start_pose.tobytes() == ref.start_pose.tobytes()
+    assert sc.sector_at(100.0, 50.0) == ref.sector_at(100.0, 50.0)
+    # errors follow wad::ErrorKind::CorruptWad: a lump whose size is not a multiple of the record size
+    bad = dict(lumps, segs=lumps["segs"][:-1])
+    with pytest.raises(b2d.B2dError) as e:
+        b2d.Scene.from_lumps(a.lumps[marker][0], bad, [], [], td.colormaps, td.palettes[0])
+    assert e.value.code == b2d.ERR_CORRUPT_WAD
