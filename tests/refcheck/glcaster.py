@@ -53,7 +53,9 @@ def _sector_at_vec(level: W.Level, px: np.ndarray, py: np.ndarray) -> np.ndarray
 
 def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width: int, height: int,
            x: float, y: float, z: float, angle_deg: float, fov_deg: float = 65.0, focal2=None,
-           tics: int = 0) -> np.ndarray:
+           tics: int = 0, cols=None, debug: bool = False):
+    """`cols`: optional subset of screen columns to cast (the result then has shape (height, len(cols))); `debug`: also
+    return, per pixel, which image / texel / colormap row / surface produced it (for classifying differences)."""
     level = W.Level(archive, level_index)
     from oracle.anim_table import FLATS as ANIM_FLATS, WALLS as ANIM_WALLS
 
@@ -80,14 +82,29 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
     fx, fy = math.cos(a), math.sin(a)                     # forward (wad x east, y north)
     rx, ry = math.sin(a), -math.cos(a)                    # right
     xs = (np.arange(W_) + 0.5) / W_ * 2.0 - 1.0
+    if cols is not None:
+        xs = xs[np.asarray(cols, dtype=np.int64)]
+    WC = len(xs)
     ys = 1.0 - (np.arange(H_) + 0.5) / H_ * 2.0
     ndx, ndy = np.meshgrid(xs, ys)
     # ray direction with unit forward component: depth along forward = t
     dx = fx + rx * ndx * tanx
     dy = fy + ry * ndx * tanx
     dz = ndy * tany
-    npx = W_ * H_
+    npx = WC * H_
     dx, dy, dz = dx.reshape(-1), dy.reshape(-1), dz.reshape(-1)
+    images, image_ids = [], {}
+    d_img = np.full(npx, -1, dtype=np.int32)
+    d_u = np.zeros(npx, dtype=np.int32)
+    d_v = np.zeros(npx, dtype=np.int32)
+    d_row = np.zeros(npx, dtype=np.int32)
+    d_surf = np.full(npx, -1, dtype=np.int64)
+
+    def image_id(key, arr):
+        if key not in image_ids:
+            image_ids[key] = len(images)
+            images.append(np.asarray(arr))
+        return image_ids[key]
     best_t = np.full(npx, np.inf)
     out = np.zeros(npx, dtype=np.uint8)                   # void = 0, as in the oracle
     kind = np.zeros(npx, dtype=np.int8)                   # 0 none, 1 wall, 2 flat, 3 sky
@@ -113,7 +130,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         light = v * 2.0 - dist
         return np.clip(np.floor((1.0 - light) * 32.0), 0, 31).astype(np.int64)
 
-    def sky_pixels(mask):
+    def sky_pixels(mask, record=True):
         """sky.vert:9-16, sky.frag:12-26 at pitch 0: uv = (ndc.x - 4*yaw/pi, 1 - ndc.y), mirrored below."""
         name = S.sky_for(level.name)
         img = tex.textures.get(name)
@@ -125,6 +142,9 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         v = np.where(v >= 1.0, 1.0 - v, v)
         ui = np.floor((u - np.floor(u)) * sw).astype(np.int64) % sw
         vi = np.floor((v - np.floor(v)) * sh).astype(np.int64) % sh
+        if record:
+            d_img[mask] = image_id(("tex", name), img)
+            d_u[mask], d_v[mask], d_row[mask], d_surf[mask] = ui, vi, 0, 3000000
         return cmaps[0][(img[vi, ui] & 0xFF).astype(np.int64)]
 
     # ---- walls -----------------------------------------------------------------------------------------
@@ -248,7 +268,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
                 elif peg == "bottomfloat":
                     low, high = high0 + yoff - th, high0 + yoff
                 pieces.append((low, high, mname, (th - (high - low)) if peg == "bottom" else 0.0))
-        for (low, high, name, t_high) in pieces:
+        for pi, (low, high, name, t_high) in enumerate(pieces):
             if low >= high:
                 continue
             hit = ok & (hz >= low) & (hz < high) & (t < best_t)
@@ -278,6 +298,8 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
             best_t[idx] = t[hit][opaque]
             out[idx] = val[opaque]
             kind[idx] = 1
+            d_img[idx] = image_id(("tex", anim_name(name, ANIM_WALLS, tex.textures)), img)
+            d_u[idx], d_v[idx], d_row[idx], d_surf[idx] = ui[opaque], vi[opaque], rows[opaque], si * 8 + pi
 
     # ---- decoration sprites: billboards at constant view depth ---------------------------------------------
     from oracle.thing_table import THINGS
@@ -311,7 +333,8 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         hit = (u >= 0) & (u < sw) & (v >= 0) & (v < sh) & (cz < best_t)
         if not hit.any():
             continue
-        texel = img[np.floor(v[hit]).astype(np.int64), np.floor(u[hit]).astype(np.int64)]
+        sui, svi = np.floor(u[hit]).astype(np.int64), np.floor(v[hit]).astype(np.int64)
+        texel = img[svi, sui]
         vb = sector_byte[sec] / 255.0
         dist = min(1.0, 1.0 - 1.0 / (cz / 100.0 + 1.0))
         light = min(vb, vb * 2.0 - dist)                      # sprite.frag:24-26
@@ -321,6 +344,9 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         best_t[idx] = cz
         out[idx] = cmaps[row][(texel[opaque] & 0xFF).astype(np.int64)]
         kind[idx] = 4
+        d_img[idx] = image_id(("sprite", id(img)), img)
+        d_u[idx], d_v[idx], d_row[idx] = sui[opaque], svi[opaque], row
+        d_surf[idx] = 1000000 + int(th["x"]) * 65536 + int(th["y"])
 
     # ---- flats: one horizontal plane per distinct height -------------------------------------------------
     floor_h = np.array([min_h if W.is_sky_flat(floor_name[i]) else int(secs[i]["floor"]) for i in range(len(secs))], dtype=np.float64)
@@ -344,6 +370,11 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
             names = ceil_name if is_ceiling else floor_name
             vals = np.zeros(len(idx), dtype=np.uint8)
             knd = np.full(len(idx), 2, dtype=np.int8)
+            f_img = np.full(len(idx), -1, dtype=np.int32)
+            f_u = np.zeros(len(idx), dtype=np.int32)
+            f_v = np.zeros(len(idx), dtype=np.int32)
+            f_row = np.zeros(len(idx), dtype=np.int32)
+            f_surf = 2000000 + sec * 2 + (1 if is_ceiling else 0)
             for sid in np.unique(sec):
                 m = sec == sid
                 name = names[sid]
@@ -359,10 +390,18 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
                 v = np.floor(hx[m]).astype(np.int64) % 64
                 rows = palette_row(sec_light[sid], tt[m])
                 vals[m] = cmaps[rows, fl[u + 64 * v].astype(np.int64)]
+                f_img[m] = image_id(("flat", anim_name(name, ANIM_FLATS, tex.flats)), fl.reshape(64, 64).astype(np.uint16))
+                f_u[m], f_v[m], f_row[m] = u, v, rows
             best_t[idx] = tt
             out[idx] = vals
             kind[idx] = knd
+            d_img[idx], d_u[idx], d_v[idx], d_row[idx], d_surf[idx] = f_img, f_u, f_v, f_row, f_surf
     sky = kind == 3
     if sky.any():
         out[sky] = sky_pixels(sky)
-    return out.reshape(H_, W_), kind.reshape(H_, W_)
+    if debug:
+        sky_all = sky_pixels(np.ones(npx, dtype=bool), record=False).reshape(H_, WC)   # what the sky would show at each pixel
+        dbg = {"images": images, "cmaps": cmaps, "sky_all": sky_all, "kind": kind.reshape(H_, WC), "img": d_img.reshape(H_, WC), "u": d_u.reshape(H_, WC), "v": d_v.reshape(H_, WC),
+               "row": d_row.reshape(H_, WC), "surf": d_surf.reshape(H_, WC)}
+        return out.reshape(H_, WC), kind.reshape(H_, WC), dbg
+    return out.reshape(H_, WC), kind.reshape(H_, WC)
