@@ -14,6 +14,7 @@
  *                                                compiler into texA/tA/hA, texB/tB/hB, otop/obot)
  *   - wall texel  tex[(s mod w) + (t mod h)*w]   assets/shaders/static.frag:19-22 (floor-mod)
  *   - flat texel  flat[(wad_y mod 64) + 64*(wad_x mod 64)]   game/src/level.rs:537-549
+ *                 at the map position eye + z(row) * dir(column)
  *   - colormap row = clamp(floor((1-light)*32),0,31), light = 2*b/255 - (1 - 0.9/(w+0.9)),
  *     w = view depth / 100                       assets/shaders/static.vert:41-43, static.frag:15-27,
  *                                                wad/src/tex.rs:137-166
@@ -172,7 +173,7 @@ typedef struct {
      * one after the other and share their floor / ceiling plane, so the 64-bit set-up runs once per row per plane, not
      * once per pixel (same values: this is a memo, not a different formula). */
     int64_t *prow_key;        /* (h << 9 | lightb) + 1, 0 = empty */
-    uint32_t *prow;           /* 5 words per row: baseU, stepU, baseV, stepV, 256 * light row */
+    uint32_t *prow;           /* 2 words per row: view depth Q8, 256 * light row */
 } Frame;
 
 static inline void put(Frame *f, int x, int y, uint8_t v) {
@@ -236,30 +237,27 @@ static void draw_plane(Frame *f, int x, int ya, int yb, int32_t h, int32_t flat,
     int64_t hrel = clamp64(((int64_t)h << 16) - f->pose.z, -((int64_t)1 << 27), (int64_t)1 << 27);
     uint64_t a = (uint64_t)(hrel < 0 ? -hrel : hrel);
     const int64_t key = (((int64_t)h << 9) | (int64_t)(lightb & 0x1FF)) + 1;
+    /* direction of this column's ray, Q18: (cos*F + sin*c2)/F, (sin*F - cos*c2)/F with c2 = 2x+1-W */
+    const int64_t c2 = 2 * (int64_t)x + 1 - W;
+    const int64_t nx = asr64((int64_t)f->cosq * f->vw.F + (int64_t)f->sinq * c2, 4);
+    const int64_t ny = asr64((int64_t)f->sinq * f->vw.F - (int64_t)f->cosq * c2, 4);
+    const uint32_t ax = (uint32_t)(int32_t)asr64(nx * (int64_t)f->invF, 40);
+    const uint32_t ay = (uint32_t)(int32_t)asr64(ny * (int64_t)f->invF, 40);
+    const uint32_t bu = (uint32_t)f->pose.x << 10, bv = (uint32_t)f->pose.y << 10;
     for (int y = ya; y < yb; y++) {
-        uint32_t *pr = f->prow + 5 * (size_t)y;
+        uint32_t *pr = f->prow + 2 * (size_t)y;
         if (f->prow_key[y] != key) {
             uint64_t zz = (a * f->yslope[y]) >> 16;
             int32_t z16 = zz > 0x7FFFFFFFull ? 0x7FFFFFFF : (int32_t)zz;
-            int32_t fxw = (int32_t)asr64((int64_t)z16 * f->cosq, 30);
-            int32_t fyw = (int32_t)asr64((int64_t)z16 * f->sinq, 30);
-            int64_t Rx = fyw, Ry = -(int64_t)fxw;                 /* right = (sin, -cos) scaled by z */
-            uint32_t stepU = (uint32_t)(uint64_t)asr64(Rx * (int64_t)f->invF, 21);
-            uint32_t halfU = (uint32_t)(uint64_t)asr64(Rx * (int64_t)f->invF, 22);
-            uint32_t stepV = (uint32_t)(uint64_t)asr64(Ry * (int64_t)f->invF, 21);
-            uint32_t halfV = (uint32_t)(uint64_t)asr64(Ry * (int64_t)f->invF, 22);
-            pr[0] = ((uint32_t)(f->pose.x + fxw) << 10) + (uint32_t)(1 - W) * halfU;
-            pr[1] = stepU;
-            pr[2] = ((uint32_t)(f->pose.y + fyw) << 10) + (uint32_t)(1 - W) * halfV;
-            pr[3] = stepV;
+            pr[0] = (uint32_t)(z16 >> 8);                         /* view depth of the row on this plane, Q8 */
             int32_t z8 = z16 >> 13; if (z8 > 65535) z8 = 65535;
-            pr[4] = 256u * (uint32_t)light_row(lightb, z8);
+            pr[1] = 256u * (uint32_t)light_row(lightb, z8);
             f->prow_key[y] = key;
         }
-        uint32_t U = pr[0] + (uint32_t)x * pr[1];             /* wad x, Q26 mod 64 */
-        uint32_t V = pr[2] + (uint32_t)x * pr[3];             /* wad y */
+        uint32_t U = bu + pr[0] * ax;                             /* wad x, Q26 mod 64 */
+        uint32_t V = bv + pr[0] * ay;                             /* wad y */
         uint8_t texel = px[((U >> 26) << 6) | (V >> 26)];
-        put(f, x, y, sc->colormap[pr[4] + texel]);
+        put(f, x, y, sc->colormap[pr[1] + texel]);
     }
 }
 
@@ -526,7 +524,7 @@ static void render_frame(const Scene *sc, const b2o_view *vw, const b2o_pose *po
     f.ctop = f.tz + sc->nverts; f.cbot = f.ctop + W;
     f.yslope = (uint32_t *)(f.cbot + W);
     f.prow = f.yslope + H;
-    f.prow_key = (int64_t *)(((uintptr_t)(f.prow + 5 * (size_t)H) + 7) & ~(uintptr_t)7);
+    f.prow_key = (int64_t *)(((uintptr_t)(f.prow + 2 * (size_t)H) + 7) & ~(uintptr_t)7);
     memset(f.prow_key, 0, sizeof(int64_t) * (size_t)H);
     b2o_sincos_q30(pose->angle, &f.cosq, &f.sinq);
     f.invF = (uint32_t)(4294967296ULL / (uint64_t)vw->F);

@@ -295,9 +295,8 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
 struct RasterCtx {
     const DeviceScene *sc;
     uint32_t pal_s;            // ... of the palette (rgba only)
-    uint32_t row4_s, row1_s;   // ... of this warp's 32-entry staging of per-row plane constants
-    uint4 *row4;               // generic pointers to the same staging (for the lane-parallel writes)
-    uint32_t *row1;
+    uint2 *rowz;               // this warp's 32-entry staging of per-row plane constants {depth Q8, plane offset / 64}
+    PlaneDir dir;              // direction of this lane's column ray (Q18), for the flat texel
     uint8_t *fb;               // &index_fb[frame][0][x]
     uint32_t *rgba;            // &rgba_fb[frame][0][x] or nullptr
     int W, H, x, lane;
@@ -390,36 +389,34 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
     const int Wc = kW ? kW : c.W;
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
-    const uint32_t xx = (uint32_t)c.x;
+    const uint32_t bu = (uint32_t)fc.pose.x << 10, bv = (uint32_t)fc.pose.y << 10;
+    const uint32_t ax = (uint32_t)c.dir.ax, ay = (uint32_t)c.dir.ay;
     for (int yc = y0; yc < y1; yc += 32) {
-        // lane j prepares the texture-mapping constants of row yc+j (64-bit maths, once per row per warp)
+        // lane j prepares the constants of row yc+j (64-bit maths, once per row per warp): view depth and plane offset
         int yy = yc + c.lane;
         if (yy < y1) {
-            PlaneRow pr = plane_row(habs, sc.yslope[yy], fc, vw, sc.invF);
-            c.row4[c.lane] = make_uint4(pr.baseU, pr.stepU, pr.baseV, pr.stepV);
+            const PlaneRow pr = plane_row(habs, sc.yslope[yy]);
             // plane + flat offset / 64: the texel offset is then two instructions, LEA.HI (cm6 + (U >> 26)) and a funnel
             // shift ((.) << 6 | V >> 26)
-            c.row1[c.lane] = (sc.lit_flat_stride >> 6) * (uint32_t)light_row(lightb, pr.z8) + 64u * (uint32_t)flat;
+            c.rowz[c.lane] = make_uint2(pr.z8q, (sc.lit_flat_stride >> 6) * (uint32_t)light_row(lightb, pr.z8) + 64u * (uint32_t)flat);
         }
         __syncwarp();
         const int rows = min(32, y1 - yc);
         int j = 0;
         for (; j + kBatch <= rows; j += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
-            uint32_t v[kBatch], cm[kBatch];
+            uint32_t v[kBatch];
 #pragma unroll
             for (int k = 0; k < kBatch; k++) {
-                const uint4 r4 = c.row4[j + k];                               // shared-memory broadcast
-                cm[k] = c.row1[j + k];
-                v[k] = __ldg(px + flat_offset(cm[k], r4.x + xx * r4.y, r4.z + xx * r4.w));   // always in bounds
+                const uint2 rz = c.rowz[j + k];                               // shared-memory broadcast: one 64-bit word per row
+                v[k] = __ldg(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay));   // always in bounds
             }
             const int y = yc + j;
             store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
         }
         for (; j < rows; j++, p8 += Wc, p32 += Wc) {
-            const uint4 r4 = c.row4[j];
-            const uint32_t cm = c.row1[j];
+            const uint2 rz = c.rowz[j];
             const int y = yc + j;
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + flat_offset(cm, r4.x + xx * r4.y, r4.z + xx * r4.w)));
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay)));
         }
         __syncwarp();
     }
@@ -708,8 +705,7 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
                   const SegFrame *__restrict__ work, int stride, int n, int strips,
                   uint8_t *__restrict__ index_fb, uint32_t *__restrict__ rgba_fb) {
     __shared__ uint32_t s_pal[kRgba ? 256 : 1];
-    __shared__ uint4 s_row4[kWarps][32];
-    __shared__ uint32_t s_row1[kWarps][32];
+    __shared__ uint2 s_rowz[kWarps][32];
     __shared__ uint32_t s_chunks[kMasked ? kWarps : 1][kMasked ? kMaskedCapMax / kMaskedChunk : 1];
     if (kRgba) {   // the palette into shared memory (colours come pre-lit from global memory: no colormap here)
         for (int i = threadIdx.x; i < 256; i += blockDim.x) s_pal[i] = sc.palette[i];
@@ -728,9 +724,8 @@ b2d_raster_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant_
     RasterCtx c;
     c.sc = &sc;
     c.pal_s = (uint32_t)__cvta_generic_to_shared(s_pal);
-    c.row4 = s_row4[threadIdx.x >> 5]; c.row1 = s_row1[threadIdx.x >> 5];
-    c.row4_s = (uint32_t)__cvta_generic_to_shared(c.row4);
-    c.row1_s = (uint32_t)__cvta_generic_to_shared(c.row1);
+    c.rowz = s_rowz[threadIdx.x >> 5];
+    c.dir = plane_dir(fc, vw, inside ? x : 0, sc.invF);
     c.fb = index_fb + (size_t)frame * W * H + (inside ? x : 0);
     c.rgba = kRgba ? rgba_fb + (size_t)frame * W * H + (inside ? x : 0) : nullptr;
     c.W = W; c.H = H; c.x = x; c.lane = lane;

@@ -256,26 +256,32 @@ B2D_HD int32_t wall_hrel(int32_t h, int32_t pose_z) {
     return (int32_t)clampv<int64_t>(((int64_t)h << 16) - pose_z, -((int64_t)1 << 27), (int64_t)1 << 27);
 }
 
-// Texture mapping of one screen row of a horizontal plane: U(x) = baseU + x*stepU (wad x, Q26 mod 64),
-// V likewise for wad y; z8 = depth of the row for lighting.
-struct PlaneRow { uint32_t baseU, stepU, baseV, stepV; int32_t z8; };
-B2D_HD PlaneRow plane_row(uint32_t habs, uint32_t yslope, const FrameConst &f, const View &vw, uint32_t invF) {
+// Texture mapping of a horizontal plane: the map position under pixel (x, y) is eye + z(y) * dir(x) with
+// z the view depth of screen row y on the plane and dir(x) = forward + right * (2x+1-W)/F the direction of column x's ray
+// (unit forward component).  Per column (once per frame): dir in Q18.  Per row and plane: z in Q8 and the light row.
+// Per pixel: U = (pose.x << 10) + z * dirx, V likewise -- two 32-bit multiply-adds, Q26 modulo 64 texels by wrap-around.
+struct PlaneDir { int32_t ax, ay; };                     // Q18
+B2D_HD PlaneDir plane_dir(const FrameConst &f, const View &vw, int x, uint32_t invF) {
+    const int64_t c2 = 2 * (int64_t)x + 1 - vw.W;
+    // (cos*F + sin*c2) / F and (sin*F - cos*c2) / F, Q30 -> Q18 through invF = floor(2^32 / F); >> 4 first keeps 64 bits
+    const int64_t nx = ((int64_t)f.cosq * vw.F + (int64_t)f.sinq * c2) >> 4;
+    const int64_t ny = ((int64_t)f.sinq * vw.F - (int64_t)f.cosq * c2) >> 4;
+    PlaneDir d;
+    d.ax = (int32_t)((nx * (int64_t)invF) >> 40);
+    d.ay = (int32_t)((ny * (int64_t)invF) >> 40);
+    return d;
+}
+struct PlaneRow { uint32_t z8q; int32_t z8; };           // depth Q8 (for the texel), depth in 1/8 units (for the light row)
+B2D_HD PlaneRow plane_row(uint32_t habs, uint32_t yslope) {
     PlaneRow pr;
     uint64_t zz = ((uint64_t)habs * yslope) >> 16;
     int32_t z16 = zz > 0x7FFFFFFFull ? 0x7FFFFFFF : (int32_t)zz;
-    int32_t fxw = (int32_t)(((int64_t)z16 * f.cosq) >> 30);
-    int32_t fyw = (int32_t)(((int64_t)z16 * f.sinq) >> 30);
-    int64_t Rx = fyw, Ry = -(int64_t)fxw;
-    pr.stepU = (uint32_t)(uint64_t)((Rx * (int64_t)invF) >> 21);
-    uint32_t halfU = (uint32_t)(uint64_t)((Rx * (int64_t)invF) >> 22);
-    pr.stepV = (uint32_t)(uint64_t)((Ry * (int64_t)invF) >> 21);
-    uint32_t halfV = (uint32_t)(uint64_t)((Ry * (int64_t)invF) >> 22);
-    pr.baseU = ((uint32_t)(f.pose.x + fxw) << 10) + (uint32_t)(1 - vw.W) * halfU;
-    pr.baseV = ((uint32_t)(f.pose.y + fyw) << 10) + (uint32_t)(1 - vw.W) * halfV;
+    pr.z8q = (uint32_t)(z16 >> 8);
     int32_t z8 = z16 >> 13;
     pr.z8 = z8 > 65535 ? 65535 : z8;
     return pr;
 }
+B2D_HD uint32_t plane_u(int32_t pose_xy, uint32_t z8q, int32_t a) { return ((uint32_t)pose_xy << 10) + z8q * (uint32_t)a; }
 B2D_HD uint32_t flat_index(uint32_t U, uint32_t V) { return ((U >> 26) << 6) | (V >> 26); }
 // the same index on top of a plane/flat offset given in units of 64 bytes: ((cm6 + (U >> 26)) << 6) | (V >> 26)
 B2D_HD uint32_t flat_offset(uint32_t cm6, uint32_t U, uint32_t V) {

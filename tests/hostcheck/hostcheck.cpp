@@ -216,11 +216,11 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
         if (flat < 0 || flat >= sc.nflats) { fill_void(x, ya, yb); return; }
         const uint8_t *px = sc.lit_flats;
         uint32_t habs = plane_habs(h, fc.pose.z);
+        const PlaneDir dir = plane_dir(fc, vw, x, invF);
         for (int y = ya; y < yb; y++) {
-            PlaneRow pr = plane_row(habs, yslope[(size_t)y], fc, vw, invF);
+            PlaneRow pr = plane_row(habs, yslope[(size_t)y]);
             const uint32_t cm6 = (sc.lit_flat_stride >> 6) * (uint32_t)light_row(lightb, pr.z8) + 64u * (uint32_t)flat;
-            uint32_t U = pr.baseU + (uint32_t)x * pr.stepU, V = pr.baseV + (uint32_t)x * pr.stepV;
-            put(x, y, px[flat_offset(cm6, U, V)]);
+            put(x, y, px[flat_offset(cm6, plane_u(fc.pose.x, pr.z8q, dir.ax), plane_u(fc.pose.y, pr.z8q, dir.ay))]);
         }
     };
     auto draw_wall = [&](int x, int ya, int yb, int32_t tex, int32_t tA, int32_t hA, int32_t ucol, int32_t iscale, int row) {
