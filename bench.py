@@ -301,7 +301,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "4k", "rich"])
     ap.add_argument("--poses", type=int, default=0, help="poses per map / per job (0 = the configuration's own count)")
     ap.add_argument("--chunk", type=int, default=256, help="c5: frames per rank per all-gather chunk")
-    ap.add_argument("--batch", type=int, default=0, help="c3/c4/4k: frames per launch (0 = 125 at 1080p, 100 at 4K)")
+    ap.add_argument("--batch", type=int, default=0, help="c3/c4/4k/rich: frames per launch (0 = 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
@@ -398,9 +398,9 @@ def main():
     # ================================================================== c3 / c4 / 4k / rich: several maps or other shapes
     if cfg in ("c3", "c4", "4k", "rich"):
         mine = jobs.map_assignment(len(maps), world)[rank] if cfg == "c4" else list(range(len(maps)))
-        batch = args.batch or (100 if width > 1920 else 125)
-        if cfg == "rich":
-            batch = args.batch or min(n, 500)
+        # frames per launch: the BSP walk is one latency-bound wave (~0.1 ms whatever the batch), so batches are large;
+        # c3 still interleaves the nine renderers batch by batch
+        batch = args.batch or min(n, 500)
         scenes, poses = [], []
         for m in mine:
             mapname, seed, scfg, kind, pseed = maps[m]

@@ -498,7 +498,9 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
         j = k
         while j < len(sprite_rows) and sprite_rows[j][0] == ssid:
             j += 1
-        cnt = min(j - k, 255)
+        if j - k > 255:
+            raise W.WadError("more than 255 decoration things in one subsector")
+        cnt = j - k
         ssectors[ssid, 3] = k | (cnt << 24)
         k = j
 
@@ -634,7 +636,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
         sx, sy = int(t["x"]) - 32, int(t["y"])
         sz = int(level.sectors[sec]["floor"]) + 50 + 12
         sang = int(ang) % 360
-        break   # visit_marker overwrites on every player-1 start; doom maps have exactly one
+        # no break: visit_marker overwrites start_pos on every player-1 start -- the LAST one wins (level.rs:757-762)
 
     # --- assemble ---------------------------------------------------------------------------------
     parts = [("verts", verts.astype("<i4").tobytes()), ("nodes", (nodes & 0xFFFFFFFF).astype("<u4").tobytes()),

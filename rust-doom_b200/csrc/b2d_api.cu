@@ -624,16 +624,18 @@ int b2d_device_download(int device, void *host_dst, const void *d_src, size_t by
 int b2d_debug_worklist(b2d_renderer *r, size_t n, int32_t *counts_out, int32_t *seg_ids_out, size_t stride) {
     if (!r || !counts_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
     if (n > (size_t)r->max_batch) return fail(B2D_ERR_INVALID_ARG, "n exceeds max_batch");
+    const int slot = r->last_slot;
+    if (!r->d_frames[slot] || n > (size_t)r->slot_n[slot]) return fail(B2D_ERR_INVALID_ARG, "n exceeds the frames of the last walked batch");
     CU(cudaSetDevice(r->device));
     CU(cudaDeviceSynchronize());
     std::vector<FrameConst> frames(n);
-    const int slot = r->last_slot;
     CU(cudaMemcpy(frames.data(), r->d_frames[slot], sizeof(FrameConst) * n, cudaMemcpyDeviceToHost));
     std::vector<SegFrame> work;
     for (size_t i = 0; i < n; i++) {
         counts_out[i] = frames[i].status ? -frames[i].status : frames[i].count;
         if (!seg_ids_out) continue;
-        size_t c = (size_t)frames[i].count;
+        size_t c = frames[i].count > 0 ? (size_t)frames[i].count : 0;
+        if (c > (size_t)r->stride) c = (size_t)r->stride;
         work.resize(c);
         if (c) CU(cudaMemcpy(work.data(), r->d_work[slot] + i * (size_t)r->stride, sizeof(SegFrame) * c, cudaMemcpyDeviceToHost));
         for (size_t k = 0; k < c && k < stride; k++) seg_ids_out[i * stride + k] = work[k].seg;

@@ -106,9 +106,6 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     extern __shared__ __align__(16) uint8_t smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int frame = blockIdx.x;
-    if (frame >= n) return;                       // whole CTA
-
     const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss, sc.nsprites);
     uint8_t *base = smem;
     __shared__ int s_count, s_status;
@@ -123,6 +120,10 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     uint32_t *stack = reinterpret_cast<uint32_t *>(base + L.off_stack);
     uint16_t *list = reinterpret_cast<uint16_t *>(base + L.off_list);
 
+    // One frame per CTA when the grid has a CTA per frame; a smaller (persistent) grid loops: that is the form for running
+    // under another batch's raster -- a CTA per SM keeps the walk's footprint at 1/8 of the register file while it takes
+    // a few frame latencies, all hidden behind the raster (launch_walk, B2D_TUNE bit 2).
+    for (int frame = blockIdx.x; frame < n; frame += gridDim.x) {
     FrameConst fc;
     frame_setup(poses[frame], fc);
 
@@ -278,6 +279,8 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 6; i++) fc.pad[i] = 0;
         frames[frame] = fc;
+    }
+    __syncthreads();                              // the next frame of this CTA reuses the shared-memory tables
     }
 }
 
@@ -848,7 +851,9 @@ b2d_palette_kernel(const uint32_t *__restrict__ palette, const uint8_t *__restri
     __shared__ uint32_t s_pal[256];
     s_pal[threadIdx.x] = palette[threadIdx.x];
     __syncthreads();
-    const size_t nvec = n_pixels / 16;
+    // 128-bit path only for 16-byte aligned buffers (a caller may pass &index_fb[i*W*H] with W*H % 16 != 0)
+    const bool aligned = ((reinterpret_cast<uintptr_t>(index) | reinterpret_cast<uintptr_t>(rgba)) & 15) == 0;
+    const size_t nvec = aligned ? n_pixels / 16 : 0;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
         uint4 in = __ldcs(reinterpret_cast<const uint4 *>(index) + i);
@@ -883,7 +888,8 @@ cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_pos
         cudaError_t e = cudaFuncSetAttribute(b2d_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    const int blocks = n, warps = 4;
+    // B2D_TUNE bit 2 (4): persistent grid, one CTA per SM, for the overlapped mode (b2d_walk_device under a raster)
+    const int blocks = ((sc.tune & 4u) && n > 148) ? 148 : n, warps = 4;
     b2d_walk_kernel<<<blocks, warps * 32, smem, stream>>>(sc, vw, d_poses, n, d_frames, d_work, stride);
     return cudaGetLastError();
 }

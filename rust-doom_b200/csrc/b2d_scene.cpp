@@ -80,6 +80,9 @@ struct BlobWriter {
     std::vector<uint8_t> bytes;
     BlobWriter() : bytes(4 * H_COUNT, 0) {}
     uint32_t append(const void *p, size_t n) {
+        // every offset and size in the header is 32-bit, and the device side indexes with 32-bit offsets: a level whose
+        // textures would push the blob past 2 GiB (TEXTUREx entries are 22 bytes and can declare 4096x4096 images) is refused
+        if (bytes.size() + n > (size_t)0x7FFFFFF0) throw WadError(kErrCorrupt, "compiled scene exceeds 2 GiB (texture data too large)");
         uint32_t off = (uint32_t)bytes.size();
         const uint8_t *b = static_cast<const uint8_t *>(p);
         bytes.insert(bytes.end(), b, b + n);
@@ -385,7 +388,9 @@ std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) 
     for (size_t k = 0; k < sprite_rows.size();) {
         size_t j = k;
         while (j < sprite_rows.size() && sprite_rows[j].ss == sprite_rows[k].ss) j++;
-        size_t cnt = j - k < 255 ? j - k : 255;
+        if (j - k > 255)      // the count shares a word with the first index: refuse instead of dropping sprites silently
+            throw WadError(kErrCorrupt, "more than 255 decoration things in one subsector");
+        size_t cnt = j - k;
         ssectors[(size_t)sprite_rows[k].ss].sprites = (int32_t)(k | (cnt << 24));
         k = j;
     }
@@ -522,7 +527,8 @@ std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) 
         sx = t.x - 32; sy = t.y;
         sz = lv.sectors[(size_t)sec].floor + 50 + 12;
         sang = (((int)yaw % 360) + 360) % 360;
-        break;
+        // no break: visit_marker overwrites start_pos on every player-1 start, so the LAST one wins
+        // (game/src/level.rs:757-762) -- maps with voodoo dolls have several
     }
 
     BlobWriter w;

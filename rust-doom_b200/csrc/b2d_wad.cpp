@@ -344,6 +344,7 @@ TextureDirectory TextureDirectory::load(const Archive &wad) {
         if (!p || size < 4) corrupt("missing number of textures");
         uint32_t n = rd_u32(p);
         if (4ull * n >= size - 4) corrupt("textures lump too small for offsets");
+        size_t decoded_px = 0;                 // a 22-byte entry can declare 4096x4096: cap what a tiny lump can make us allocate
         for (uint32_t i = 0; i < n; i++) {
             size_t off = rd_u32(p + 4 + 4 * (size_t)i);
             if (off >= size) corrupt("textures lump too small for offsets");
@@ -353,6 +354,8 @@ TextureDirectory TextureDirectory::load(const Archive &wad) {
             int w = rd_u16(p + off + 12), h = rd_u16(p + off + 14);
             int np = rd_u16(p + off + 20);
             if (w > 4096 || h > 4096) continue;
+            decoded_px += (size_t)w * (size_t)h;
+            if (decoded_px > ((size_t)1 << 28)) corrupt("composed textures exceed 256 Mpixel");
             Image img = Image::blank(w, h);
             size_t q = off + 22;
             for (int k = 0; k < np; k++) {

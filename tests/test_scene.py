@@ -270,3 +270,28 @@ def test_scene_from_lumps_equals_scene_from_wad(b2d, seed, maps, level, cfg):
     with pytest.raises(b2d.B2dError) as e:
         b2d.Scene.from_lumps(a.lumps[marker][0], bad, [], [], td.colormaps, td.palettes[0])
     assert e.value.code == b2d.ERR_CORRUPT_WAD
+
+
+def test_last_player_start_wins(b2d):
+    """game/src/level.rs:757-762 overwrites start_pos on every player-1 start marker: with several (voodoo dolls) the
+    LAST one in THINGS is the spawn.  Turn the last decoration thing of a generated level into a second type-1 thing."""
+    import struct
+    from rust_doom_b200 import synthwad
+    data = bytearray(synthwad.build_iwad(4, ("E1M1",), cfg=synthwad.SynthConfig(thing_pct=40)))
+    a = W.Archive(bytes(data))
+    _, pos, size = a.lumps[a.levels[0] + 1]                   # THINGS: 10-byte records
+    n = size // 10
+    first = [i for i in range(n) if struct.unpack_from("<h", data, pos + 10 * i + 6)[0] == 1]
+    assert len(first) == 1
+    # the last thing that stands inside the level becomes a second player-1 start
+    lv = W.Level(a, 0)
+    cand = [i for i in range(n) if i != first[0] and S.sector_at(lv, float(lv.things[i]["x"]), float(lv.things[i]["y"])) >= 0]
+    k = max(cand)
+    assert k > first[0]
+    struct.pack_into("<h", data, pos + 10 * k + 6, 1)
+    x, y, ang = struct.unpack_from("<hhh", data, pos + 10 * k)
+    a2 = W.Archive(bytes(data))
+    ob = S.compile_scene(a2, W.TextureDirectory(a2), 0)
+    sc = b2d.Scene(b2d.Archive.from_bytes(bytes(data)), 0)
+    assert sc.blob == ob
+    assert sc.info.has_start and sc.info.start.x == (x - 32) * 65536 and sc.info.start.y == y * 65536

@@ -1,0 +1,20 @@
+#!/bin/bash
+TAG=${1:-r2c}
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q -k "not full_benchmark and not campaign" > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_$TAG.log
+tail -3 gpurun_out/pytest_$TAG.log
+run() { name=$1; shift; timeout 600 "$@" > gpurun_out/bench_${TAG}_$name.json 2> gpurun_out/bench_${TAG}_$name.err; echo "$name rc=$?"; python - <<PY
+import json
+try:
+    d=json.load(open("gpurun_out/bench_${TAG}_$name.json")); r=d.get("roofline") or {}
+    print("$name: %.0f fps  ms/step %.4f raster %s walk %s frac %s" % (d["value"], d["ms_per_step"], r.get("avg_launch_ms"), r.get("walk_avg_launch_ms"), r.get("frac")))
+except Exception as e: print("$name: no result", e)
+PY
+tail -2 gpurun_out/bench_${TAG}_$name.err; }
+Q="--no-e2e --no-cpu-baseline --steps 60 --warmup 3"
+run c2 python bench.py $Q
+run c2pipe python bench.py $Q --pipeline
+B2D_TUNE=4 run c2pipe4 python bench.py $Q --pipeline
+run c3 python bench.py --config c3 --steps 5 --warmup 3
+run 4k python bench.py --config 4k --steps 20 --warmup 3
+run rich python bench.py --config rich --steps 20 --warmup 3
