@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2d.so")
+LIB_PATH = os.environ.get("B2D_LIB") or os.path.join(_HERE, "libb2d.so")      # B2D_LIB: A/B another build of the library
 
 
 class Pose(ctypes.Structure):

@@ -13,6 +13,7 @@ PY
 tail -2 gpurun_out/bench_${TAG}_$name.err; }
 Q="--no-e2e --no-cpu-baseline --steps 60 --warmup 3"
 run c2 python bench.py $Q
+B2D_LIB=$PWD/rust-doom_b200/libb2d_prev.so run c2prev python bench.py $Q
 run c2pipe python bench.py $Q --pipeline
 B2D_TUNE=4 run c2pipe4 python bench.py $Q --pipeline
 run c3 python bench.py --config c3 --steps 5 --warmup 3
