@@ -497,9 +497,22 @@ static void walk(Frame *f, uint32_t child, int depth) {
         if ((int)id >= sc->nss) return;
         const int32_t *ss = sc->ssectors + 4 * id;
         if (ss[2] < 0) return;
-        {   /* decoration things of this subsector: in front of its far segs, behind everything drawn so far */
+        {   /* decoration things of this subsector: in front of its far segs, behind everything drawn so far; among
+             * themselves nearest first (they are drawn back to front, so the nearer billboard ends up on top, as a depth
+             * test would have it: sprite.vert:40-42 puts a billboard at one view depth); ties keep the stored order */
             int first = ss[3] & 0xFFFFFF, cnt = (ss[3] >> 24) & 0xFF;
-            for (int i = 0; i < cnt && first + i < sc->nsprites; i++) record_sprite(f, first + i);
+            if (first + cnt > sc->nsprites) cnt = sc->nsprites > first ? sc->nsprites - first : 0;
+            int64_t cz[256];
+            int order[256];
+            for (int i = 0; i < cnt; i++) {
+                const int32_t *SP = sc->sprites + 8 * (first + i);
+                int64_t dx = ((int64_t)SP[0] << 8) - asr64(f->pose.x, 8), dy = ((int64_t)SP[1] << 8) - asr64(f->pose.y, 8);
+                cz[i] = asr64(dx * f->cosq + dy * f->sinq, 30);
+                int k = i;
+                while (k > 0 && cz[order[k - 1]] > cz[i]) { order[k] = order[k - 1]; k--; }     /* stable insertion sort */
+                order[k] = i;
+            }
+            for (int i = 0; i < cnt; i++) record_sprite(f, first + order[i]);
         }
         for (int i = 0; i < ss[1]; i++) draw_seg(f, ss[0] + i);
         return;

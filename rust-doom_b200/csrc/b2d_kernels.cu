@@ -74,7 +74,7 @@ __device__ __forceinline__ void mark_solid(uint32_t *mask, int lane, int lo, int
 __host__ __device__ inline size_t align16(size_t v) { return (v + 15) & ~(size_t)15; }
 
 struct WalkSmem {
-    size_t off_tx, off_tz, off_segr, off_boxr, off_node, off_ssec, off_sprr, off_mask, off_stack, off_list, total;
+    size_t off_tx, off_tz, off_segr, off_boxr, off_node, off_ssec, off_sprr, off_sprz, off_mask, off_stack, off_list, total;
 };
 __host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnodes, int nss, int nsprites) {
     WalkSmem L;
@@ -86,6 +86,7 @@ __host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnode
     L.off_node = o; o = align16(o + 32 * (size_t)nnodes);     // {x,y,dx,dy,rchild,lchild,-,-} per node
     L.off_ssec = o; o = align16(o + 16 * (size_t)nss);        // SSectorRec copies
     L.off_sprr = o; o = align16(o + 4 * (size_t)nsprites);    // packed column range per sprite
+    L.off_sprz = o; o = align16(o + 4 * (size_t)nsprites);    // view depth per sprite (ordering inside a subsector)
     L.off_mask = o; o = align16(o + 4 * kMaskWords);
     L.off_stack = o; o = align16(o + 4 * kStackDepth);
     L.off_list = o; o = align16(o + 2 * ((size_t)nsegs + (size_t)nsprites));
@@ -116,6 +117,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     int4 *node_s = reinterpret_cast<int4 *>(base + L.off_node);       // traversal reads shared memory, not L2
     int4 *ssec_s = reinterpret_cast<int4 *>(base + L.off_ssec);
     uint32_t *sprr = reinterpret_cast<uint32_t *>(base + L.off_sprr);
+    int32_t *sprz = reinterpret_cast<int32_t *>(base + L.off_sprz);
     uint32_t *mask = reinterpret_cast<uint32_t *>(base + L.off_mask);
     uint32_t *stack = reinterpret_cast<uint32_t *>(base + L.off_stack);
     uint16_t *list = reinterpret_cast<uint16_t *>(base + L.off_list);
@@ -169,9 +171,11 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         const SpriteRec &P = sc.sprites[i];
         SpriteFrame sp;
         uint32_t packed = 0;
+        sp.cz = 0;
         if (P.tex >= 0 && P.tex < sc.ntex && sprite_setup(fc, vw, P.x, P.y, (int32_t)sc.tex[P.tex].w, sp))
             packed = pack_range(sp.lo, sp.hi, kVisBit);
         sprr[i] = packed;
+        sprz[i] = (int32_t)sp.cz;
     }
     // solid-column mask: columns >= W start out solid
     for (int w = tid; w < kMaskWords; w += nthr) mask[w] = ~word_bits(w, 0, vw.W - 1);
@@ -193,17 +197,39 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
             SSectorRec ss;
             ss.first_seg = ssv.x; ss.num_segs = ssv.y; ss.sector = ssv.z; ss.sprites = ssv.w;
             if (ss.sector < 0) continue;
-            {   // the subsector's decoration sprites come first: they stand in front of its far segs
-                const int sfirst = ss.sprites & 0xFFFFFF, scnt = (ss.sprites >> 24) & 0xFF;
+            {   // the subsector's decoration sprites come first: they stand in front of its far segs.  Among themselves
+                // nearest first (drawn back to front, the nearer billboard ends up on top); ties keep the stored order.
+                // A lane's slot = the number of visible sprites of the subsector that sort before its own.
+                const int sfirst = ss.sprites & 0xFFFFFF;
+                int scnt = (ss.sprites >> 24) & 0xFF;
+                if (sfirst + scnt > sc.nsprites) scnt = sc.nsprites > sfirst ? sc.nsprites - sfirst : 0;
+                int nvis = 0;
                 for (int k0 = 0; k0 < scnt; k0 += 32) {
-                    int k = k0 + lane, pi = sfirst + k;
-                    uint32_t r = (k < scnt && pi < sc.nsprites) ? sprr[pi] : 0u;
-                    bool vis = (r & kVisBit) && lane_range_open(mask, range_lo(r), range_hi(r));
-                    unsigned m = __ballot_sync(kFull, vis);
-                    int pos = count + __popc(m & ((1u << lane) - 1u));
+                    const int k = k0 + lane, pi = sfirst + k;
+                    const uint32_t r = k < scnt ? sprr[pi] : 0u;
+                    const bool vis = (r & kVisBit) && lane_range_open(mask, range_lo(r), range_hi(r));
+                    int rank = 0, total = 0;
+                    const int32_t myz = vis ? sprz[pi] : 0;
+                    for (int j0 = 0; j0 < scnt; j0 += 32) {                 // warp-uniform loop over all sprites of the subsector
+                        const int j = j0 + lane, pj = sfirst + j;
+                        const uint32_t rj = j < scnt ? sprr[pj] : 0u;
+                        const bool vj = (rj & kVisBit) && lane_range_open(mask, range_lo(rj), range_hi(rj));
+                        const int32_t zj = vj ? sprz[pj] : 0;
+                        unsigned mj = __ballot_sync(kFull, vj);
+                        total += __popc(mj);
+                        while (mj) {
+                            const int b = __ffs(mj) - 1;
+                            mj &= mj - 1;
+                            const int32_t zb = __shfl_sync(kFull, zj, b);
+                            const int jb = j0 + b;
+                            if (vis && (zb < myz || (zb == myz && jb < k))) rank++;
+                        }
+                    }
+                    const int pos = count + rank;
                     if (vis && pos < sc.nsegs + sc.nsprites) list[pos] = (uint16_t)(sc.nsegs + pi);
-                    count = min(count + __popc(m), sc.nsegs + sc.nsprites);
+                    nvis = total;
                 }
+                count = min(count + nvis, sc.nsegs + sc.nsprites);
                 __syncwarp();
             }
             for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {

@@ -109,12 +109,15 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
         if (r.vis) { r.lo = lo; r.hi = hi; }
     }
     std::vector<Range> sprr((size_t)sc.nsprites);
+    std::vector<int32_t> sprz((size_t)sc.nsprites, 0);
     for (int i = 0; i < sc.nsprites; i++) {
         const SpriteRec &P = sc.sprites[i];
         SpriteFrame sp;
+        sp.cz = 0;
         if (P.tex >= 0 && P.tex < sc.ntex && sprite_setup(fc, vw, P.x, P.y, (int32_t)sc.tex[P.tex].w, sp)) {
             sprr[(size_t)i].vis = true; sprr[(size_t)i].lo = sp.lo; sprr[(size_t)i].hi = sp.hi;
         }
+        sprz[(size_t)i] = (int32_t)sp.cz;
     }
     std::vector<char> solid((size_t)vw.W, 0);
     auto range_open = [&](int lo, int hi) {
@@ -137,10 +140,13 @@ void walk(const HostScene &sc, const View &vw, const Pose &pose, FrameConst &fc,
             if (ss.sector < 0) continue;
             {
                 const int sfirst = ss.sprites & 0xFFFFFF, scnt = (ss.sprites >> 24) & 0xFF;
+                std::vector<int> vis;                 // nearest first, ties in stored order (as the walk kernel ranks them)
                 for (int k = 0; k < scnt && sfirst + k < sc.nsprites; k++) {
                     const Range &r = sprr[(size_t)(sfirst + k)];
-                    if (r.vis && range_open(r.lo, r.hi)) list.push_back(sc.nsegs + sfirst + k);
+                    if (r.vis && range_open(r.lo, r.hi)) vis.push_back(sfirst + k);
                 }
+                std::stable_sort(vis.begin(), vis.end(), [&](int a, int b) { return sprz[(size_t)a] < sprz[(size_t)b]; });
+                for (int pi : vis) list.push_back(sc.nsegs + pi);
             }
             for (int k0 = 0; k0 < ss.num_segs; k0 += 32) {
                 std::vector<int> emitted;

@@ -12,8 +12,9 @@ A differing pixel is *explained* when the oracle's value is what the reference's
 Three more categories are *deviations*, counted separately and bounded tightly by the tests:
   sky_hack      next to a sky surface the oracle shows the sky (at the pixel's own sky coordinates): a sky ceiling hides
                 what pokes above it, as in Doom; the reference's sky polygon sits at level max + 512 and would not
-  sprite_order  billboards are ordered and clipped per subsector / column window instead of depth-tested per pixel: two
-                overlapping sprites of one subsector (stored order), a sprite that pokes into a wall
+  sprite_order  billboards are clipped by the column windows open when their subsector is entered instead of being
+                depth-tested per pixel: a sprite that pokes into a wall, or overlaps a sprite of a neighbouring subsector
+                (within a subsector they are depth-sorted)
   sliver        an edge pixel showing a third surface of which the caster has no pixel nearby, or a one-pixel-wide run
                 (both neighbours across it agree): a surface seen edge-on that one renderer gives a column and the other none
 Everything else -- a differing pixel away from any edge that no adjacent sample explains -- is *unexplained* and fails."""

@@ -53,7 +53,7 @@ class Tally:
         assert s["texel"] + s["silhouette"] + s["minified"] + s["sky_hack"] + s["sprite_order"] + s["sliver"] == s["differing"]
         assert s["differing"] < 0.01 * self.px, s                       # rounding residue: well under 1 % of the pixels
         assert s["sky_hack"] <= 2e-4 * self.px and s["sliver"] <= 2e-4 * self.px, s
-        assert s["sprite_order"] <= 1e-3 * self.px, s
+        assert s["sprite_order"] <= 2e-4 * self.px, s
 
 
 def _frame(a, tex, blob, W_, H_, pose, tics=0, cols=None):
