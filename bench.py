@@ -305,8 +305,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
-    ap.add_argument("--pipeline", action="store_true",
-                    help="c2: b2d_walk_device / b2d_raster_device on two streams instead of one b2d_render_device call per step")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="c2: one b2d_render_device call per step (BSP walk, then raster of the same batch, one stream) instead of "
+                         "the default b2d_walk_device / b2d_raster_device pair on two streams (the walk of the next batch runs as a "
+                         "one-CTA-per-SM background grid under this batch's raster)")
     ap.add_argument("--rgba", action="store_true", help="c2: also materialise RGBA8 frames in HBM (5 B/pixel; not the headline config)")
     ap.add_argument("--gather-frames", type=int, default=0, help="c2, N>1: frames per rank in a separate all-gather timing (0 = off; see --config c5)")
     args = ap.parse_args()
@@ -472,7 +474,7 @@ def main():
     d_rgba = torch.empty((n, height, width), dtype=torch.int32, device=dev) if args.rgba else None
     stream = torch.cuda.current_stream().cuda_stream
 
-    pipelined = args.pipeline
+    pipelined = not args.no_pipeline
     walk_stream = torch.cuda.Stream(device=dev, priority=-1) if pipelined else None
     pending = [r.walk_device(d_poses.data_ptr(), n, walk_stream.cuda_stream)] if pipelined else None
 
@@ -579,7 +581,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": bench_config(desc + (", + RGBA8 framebuffer" if args.rgba else ""), n, world, scene.info),
-            "step": ("raster of this batch + BSP walk of the next batch, two streams (b2d_walk_device / b2d_raster_device)" if pipelined
+            "step": ("raster of this batch + BSP walk of the NEXT batch on two streams (b2d_walk_device / b2d_raster_device): every step "
+                     "runs one walk and one raster of 1000 poses, the walk as a background grid under the raster; roofline.avg_launch_ms is "
+                     "the raster's duration WITH that walk co-resident" if pipelined
                      else "BSP walk then raster of one batch, one stream (b2d_render_device)"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "allgather": allgather}))

@@ -87,7 +87,7 @@ void free_renderer(b2d_renderer *r) {
 // BSP walk of a batch into the next worklist slot, on `stream`.  The slot's previous raster (if any, on whatever
 // stream) is awaited through an event, so a caller may run walks and rasters on two streams and have the walk of
 // batch k+1 overlap the raster of batch k.
-int walk_into_slot(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t stream, int64_t *ticket_out) {
+int walk_into_slot(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t stream, int64_t *ticket_out, bool background = false) {
     const int slot = (int)(r->next_ticket & 1);
     if (!r->slot_rastered[slot]) return fail(B2D_ERR_INVALID_ARG, "both worklist slots hold batches that were walked but not rastered yet");
     if (!r->d_frames[slot]) {
@@ -106,7 +106,7 @@ int walk_into_slot(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t str
         for (auto &e : ev) CU(cudaEventCreate(&e));
         CU(cudaEventRecord(ev[0], stream));
     }
-    CU(launch_walk(r->ds, r->view, d_poses, n, r->d_frames[slot], r->d_work[slot], r->stride, stream));
+    CU(launch_walk(r->ds, r->view, d_poses, n, r->d_frames[slot], r->d_work[slot], r->stride, stream, background));
     if (r->profiling) {
         CU(cudaEventRecord(ev[1], stream));
         for (auto e : ev) r->prof_events.push_back(e);
@@ -529,7 +529,7 @@ int b2d_walk_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, void *cu
     if (!r || !d_poses || !ticket_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
     if (n == 0 || n > (size_t)r->max_batch) return fail(B2D_ERR_INVALID_ARG, "n must be in 1..max_batch");
     CU(cudaSetDevice(r->device));
-    return walk_into_slot(r, reinterpret_cast<const Pose *>(d_poses), (int)n, static_cast<cudaStream_t>(cuda_stream), ticket_out);
+    return walk_into_slot(r, reinterpret_cast<const Pose *>(d_poses), (int)n, static_cast<cudaStream_t>(cuda_stream), ticket_out, true);
 }
 
 int b2d_raster_device(b2d_renderer *r, int64_t ticket, uint8_t *d_index_fb, uint32_t *d_rgba_fb, void *cuda_stream) {

@@ -929,7 +929,7 @@ b2d_palette_kernel(const uint32_t *__restrict__ palette, const uint8_t *__restri
 size_t walk_smem_per_warp(const DeviceScene &sc) { return walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss, sc.nsprites).total; }
 
 cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
-                        FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream) {
+                        FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream, bool background) {
     if (n <= 0) return cudaSuccess;
     const size_t smem = walk_smem_per_warp(sc);          // one frame per CTA
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
@@ -937,8 +937,11 @@ cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_pos
         cudaError_t e = cudaFuncSetAttribute(b2d_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    // B2D_TUNE bit 2 (4): persistent grid, one CTA per SM, for the overlapped mode (b2d_walk_device under a raster)
-    const int blocks = ((sc.tune & 4u) && n > 148) ? 148 : n, warps = 4;
+    // background (b2d_walk_device: the walk of the NEXT batch, meant to run under another batch's raster): a persistent grid
+    // of one CTA per SM.  It takes n/148 frame latencies instead of one, but holds 1/8 of the register file instead of
+    // 7/8, so the raster keeps 28 of its 32 warps per SM while the walk hides behind it (measured: profiles/README.md).
+    // B2D_TUNE bit 2 (4) turns it off for A/B.
+    const int blocks = (background && !(sc.tune & 4u) && n > 148) ? 148 : n, warps = 4;
     b2d_walk_kernel<<<blocks, warps * 32, smem, stream>>>(sc, vw, d_poses, n, d_frames, d_work, stride);
     return cudaGetLastError();
 }

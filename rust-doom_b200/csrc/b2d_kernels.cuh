@@ -40,7 +40,7 @@ struct DeviceScene {
     uint32_t masked_chunks;      // arena capacity in chunks (exhausted -> status bit 8)
     int32_t masked_cap;          // entries one 32-column strip can defer per frame (more -> status bit 8)
     uint32_t tune;               // A/B switches for profiles/ (env B2D_TUNE, default 0): 1 no incremental wall path,
-                                 // 2 no 16-row batches, 4 persistent BSP-walk grid (one CTA per SM)
+                                 // 2 no 16-row batches, 4 no persistent grid for background walks
 };
 
 // masked middle textures + sprites one 32-column strip can defer per frame: min(masked mids + sprites of the level,
@@ -54,7 +54,7 @@ size_t walk_smem_per_warp(const DeviceScene &sc);
 // Kernel 1: front-to-back BSP walk, one CTA per frame.  Writes frames[i] and up to `stride`
 // worklist entries per frame at work[i*stride ...].
 cudaError_t launch_walk(const DeviceScene &sc, const View &vw, const Pose *d_poses, int n,
-                        FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream);
+                        FrameConst *d_frames, SegFrame *d_work, int stride, cudaStream_t stream, bool background = false);
 
 // Kernel 2: wall-column / flat-span / sky rasteriser, one warp per (frame, 32-column strip).
 // Writes every pixel of d_index_fb exactly once; if d_rgba != nullptr also the palette-mapped RGBA8.
