@@ -76,6 +76,12 @@ const char *b2d_last_error(void);
 /* ---- wad::Archive ----------------------------------------------------------------------- */
 int b2d_archive_open(const char *wad_path, b2d_archive **out);
 int b2d_archive_open_memory(const void *bytes, size_t size, b2d_archive **out);
+/* IWAD + PWAD overlays (files[0] is the IWAD, the rest are PWADs applied in order; the reference itself opens IWADs only,
+ * wad/src/archive.rs:69-72): PWAD lumps are appended to the directory, so a later lump of a name wins every by-name
+ * lookup (PNAMES, TEXTUREx, patches, PLAYPAL ...); a level whose name exists replaces that level in place, new names
+ * are appended; flats / sprites between a PWAD's FF_START..FF_END / SS_START..SS_END (or F_/S_) markers join the IWAD's. */
+int b2d_archive_open_files(const char *const *paths, int n_paths, b2d_archive **out);
+int b2d_archive_open_memory_files(const void *const *bytes, const size_t *sizes, int n_files, b2d_archive **out);
 int b2d_archive_num_levels(const b2d_archive *a);
 int b2d_archive_level_name(const b2d_archive *a, int level_index, char name_out[9]);
 void b2d_archive_close(b2d_archive *a);

@@ -86,27 +86,67 @@ def _raw_name(b: bytes) -> bytes:
 # archive  (wad/src/archive.rs:36-106, 172-242)
 # ---------------------------------------------------------------------------------------------
 class Archive:
-    def __init__(self, data: bytes):
+    def __init__(self, data: bytes, overlays=()):
+        """`data` is the IWAD (all the reference opens, archive.rs:69-72).  `overlays`: PWAD files applied in order, Doom-engine
+        style -- their lumps are appended to the directory (a later lump of a name wins every by-name lookup), a level of
+        an existing name replaces that level in place, new level names are appended, and flats / sprites between a PWAD's
+        FF_START..FF_END / SS_START..SS_END (or F_START / S_START) markers are added to the IWAD's."""
         self.data = data
+        self.files: List[bytes] = []
+        self.file_ranges: List[Tuple[int, int]] = []
+        self.lumps: List[Tuple[bytes, int, int]] = []          # (name, offset, size)
+        self.lump_file: List[int] = []
+        self.index_map: Dict[bytes, int] = {}                  # later duplicate wins (archive.rs:85)
+        self.levels: List[int] = []
+        for k, blob in enumerate((data,) + tuple(overlays)):
+            self._add_file(blob, k == 0)
+
+    def _add_file(self, data: bytes, iwad: bool) -> None:
         if len(data) < 12:
             raise WadError("bad wad header")
         ident, num_lumps, info_off = struct.unpack_from("<4sii", data, 0)
-        if ident != b"IWAD":                                   # archive.rs:69-72
+        if ident != (b"IWAD" if iwad else b"PWAD"):            # archive.rs:69-72
             raise WadError("bad wad header identifier %r" % ident)
-        self.lumps: List[Tuple[bytes, int, int]] = []          # (name, offset, size)
-        self.index_map: Dict[bytes, int] = {}                  # later duplicate wins (archive.rs:85)
-        self.levels: List[int] = []
         if info_off < 0 or info_off + 16 * num_lumps > len(data) or num_lumps < 0:
             raise WadError("bad lump info table")
+        fi = len(self.files)
+        self.files.append(data)
+        first = len(self.lumps)
         for i in range(num_lumps):
             pos, size, raw = struct.unpack_from("<ii8s", data, info_off + 16 * i)
             name = wad_name(raw)                               # invalid byte fails the open
             self.index_map[name] = len(self.lumps)
             self.lumps.append((name, pos, size))
+            self.lump_file.append(fi)
             if name == b"THINGS\0\0":                          # archive.rs:92-97
                 if i == 0:
                     raise WadError("THINGS lump without a level marker")
-                self.levels.append(i - 1)
+                marker = first + i - 1
+                same = [k for k, lv in enumerate(self.levels) if self.lumps[lv][0] == self.lumps[marker][0]]
+                if same:
+                    for k in same:
+                        self.levels[k] = marker
+                else:
+                    self.levels.append(marker)
+        self.file_ranges.append((first, len(self.lumps)))
+
+    def marker_ranges(self, starts, ends) -> List[Tuple[int, int]]:
+        """[first, last) lump ranges between the start / end markers of every file that has them (the IWAD must)."""
+        starts = [wad_name(x) for x in starts]
+        ends = [wad_name(x) for x in ends]
+        out = []
+        for f, (lo, hi) in enumerate(self.file_ranges):
+            a = b = -1
+            for i in range(lo, hi):
+                if self.lumps[i][0] in starts:
+                    a = i
+                if self.lumps[i][0] in ends:
+                    b = i
+            if f == 0 and (a < 0 or b < 0):
+                raise WadError("missing required lump %r" % (starts[0] if a < 0 else ends[0]))
+            if a >= 0 and b >= 0:
+                out.append((a, b))
+        return out
 
     @classmethod
     def open(cls, path: str) -> "Archive":
@@ -137,9 +177,10 @@ class Archive:
         _, pos, size = self.lumps[index]
         if size == 0:
             return b""
-        if pos < 0 or size < 0 or pos + size > len(self.data):   # i32 -> usize wrap makes the read fail
+        data = self.files[self.lump_file[index]]
+        if pos < 0 or size < 0 or pos + size > len(data):        # i32 -> usize wrap makes the read fail
             raise WadError("lump %d out of file bounds" % index)
-        return self.data[pos:pos + size]
+        return data[pos:pos + size]
 
     def decode_vec(self, index: int, dtype: np.dtype) -> np.ndarray:
         """LumpReader::decode_vec: size > 0 and a multiple of the element size (archive.rs:172-190)."""
@@ -236,6 +277,7 @@ def decode_picture(buf: bytes) -> Tuple[np.ndarray, int, int]:
         p = offs[x]
         if p >= n:
             raise WadError("invalid image column offset in %d" % x)
+        last_row = -1
         while True:
             if p >= n:
                 raise WadError("unfinished image column %d" % x)
@@ -243,6 +285,11 @@ def decode_picture(buf: bytes) -> Tuple[np.ndarray, int, int]:
             p += 1
             if row == 255:
                 break
+            # tall patches (DeePsea convention): a post whose topdelta does not exceed the previous post's is relative to
+            # it; stock patches have strictly increasing posts, so this changes nothing the reference can represent
+            if last_row >= 0 and row <= last_row:
+                row += last_row
+            last_row = row
             if p >= n:
                 raise WadError("missing image run length")
             ln = buf[p]
@@ -299,23 +346,21 @@ class TextureDirectory:
                 continue
             self._read_textures(wad.read(idx))
         self.flats: "OrderedDict[bytes, bytes]" = OrderedDict()
-        start = wad.required(b"F_START")
-        end = wad.required(b"F_END")
-        for i in range(start, end):
-            name, _, size = wad.lumps[i]
-            if size == 0:
-                continue
-            self.flats[name] = wad.read(i)
+        for start, end in wad.marker_ranges((b"F_START", b"FF_START"), (b"F_END", b"FF_END")):
+            for i in range(start, end):
+                name, _, size = wad.lumps[i]
+                if size == 0:
+                    continue
+                self.flats[name] = wad.read(i)          # a PWAD's flat of the same name wins
         # sprites share the texture map and may shadow a texture name (tex.rs:475-497)
-        s0 = wad.required(b"S_START") + 1
-        s1 = wad.required(b"S_END")
-        for i in range(s0, s1):
-            buf = wad.read(i)                       # a read failure fails the load (tex.rs:484-485)
-            try:
-                px, _, _ = decode_picture(buf)
-            except WadError:
-                continue                            # a decode failure skips the sprite (tex.rs:486-493)
-            self.textures[wad.lumps[i][0]] = px
+        for s0, s1 in wad.marker_ranges((b"S_START", b"SS_START"), (b"S_END", b"SS_END")):
+            for i in range(s0 + 1, s1):
+                buf = wad.read(i)                       # a read failure fails the load (tex.rs:484-485)
+                try:
+                    px, _, _ = decode_picture(buf)
+                except WadError:
+                    continue                            # a decode failure skips the sprite (tex.rs:486-493)
+                self.textures[wad.lumps[i][0]] = px
 
     @staticmethod
     def _read_patches(wad: Archive):

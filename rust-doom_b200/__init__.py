@@ -64,14 +64,27 @@ class Archive:
         self._h = handle
 
     @classmethod
-    def open(cls, path: str) -> "Archive":
+    def open(cls, path: str, pwads=()) -> "Archive":
+        """IWAD at `path`; `pwads`: PWAD files applied on top, in order (b2d_archive_open_files)."""
         h = ctypes.c_void_p()
+        if pwads:
+            paths = [path.encode()] + [p.encode() for p in pwads]
+            arr = (ctypes.c_char_p * len(paths))(*paths)
+            _check(_lib.load().b2d_archive_open_files(arr, len(paths), ctypes.byref(h)))
+            return cls(h)
         _check(_lib.load().b2d_archive_open(path.encode(), ctypes.byref(h)))
         return cls(h)
 
     @classmethod
-    def from_bytes(cls, data: bytes) -> "Archive":
+    def from_bytes(cls, data: bytes, overlays=()) -> "Archive":
         h = ctypes.c_void_p()
+        if overlays:
+            blobs = [bytes(data)] + [bytes(o) for o in overlays]
+            bufs = [(ctypes.c_char * max(len(b), 1)).from_buffer_copy(b.ljust(1, b"\0")) for b in blobs]
+            ptrs = (ctypes.c_void_p * len(bufs))(*[ctypes.addressof(b) for b in bufs])
+            sizes = (ctypes.c_size_t * len(bufs))(*[len(b) for b in blobs])
+            _check(_lib.load().b2d_archive_open_memory_files(ptrs, sizes, len(bufs), ctypes.byref(h)))
+            return cls(h)
         buf = (ctypes.c_char * len(data)).from_buffer_copy(data) if len(data) else (ctypes.c_char * 1)()
         _check(_lib.load().b2d_archive_open_memory(ctypes.addressof(buf), len(data), ctypes.byref(h)))
         return cls(h)

@@ -26,7 +26,7 @@ class SceneInfo(ctypes.Structure):
 
 
 EXPORTS = [
-    "b2d_last_error", "b2d_archive_open", "b2d_archive_open_memory", "b2d_archive_num_levels",
+    "b2d_last_error", "b2d_archive_open", "b2d_archive_open_memory", "b2d_archive_open_files", "b2d_archive_open_memory_files", "b2d_archive_num_levels",
     "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_create_from_lumps", "b2d_scene_info_get",
     "b2d_scene_blob", "b2d_scene_sector_at", "b2d_scene_destroy", "b2d_view_init", "b2d_renderer_create",
     "b2d_renderer_destroy", "b2d_renderer_set_time", "b2d_renderer_set_time_async", "b2d_renderer_status", "b2d_render", "b2d_render_device", "b2d_walk_device",
@@ -93,6 +93,8 @@ def load() -> ctypes.CDLL:
     L.b2d_last_error.restype = ctypes.c_char_p
     L.b2d_archive_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(vp)]
     L.b2d_archive_open_memory.argtypes = [vp, cs, ctypes.POINTER(vp)]
+    L.b2d_archive_open_files.argtypes = [ctypes.POINTER(ctypes.c_char_p), ci, ctypes.POINTER(vp)]
+    L.b2d_archive_open_memory_files.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(cs), ci, ctypes.POINTER(vp)]
     L.b2d_archive_num_levels.argtypes = [vp]
     L.b2d_archive_level_name.argtypes = [vp, ci, ctypes.c_char_p]
     L.b2d_archive_close.argtypes = [vp]

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -216,6 +217,37 @@ int b2d_archive_open_memory(const void *bytes, size_t size, b2d_archive **out) {
         const uint8_t *p = static_cast<const uint8_t *>(bytes);
         auto a = std::make_unique<b2d_archive>();
         a->wad = std::make_unique<Archive>(std::vector<uint8_t>(p, p + size));
+        *out = a.release();
+        return B2D_OK;
+    });
+}
+
+int b2d_archive_open_files(const char *const *paths, int n_paths, b2d_archive **out) {
+    if (!paths || !out || n_paths < 1) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        std::vector<std::string> ps;
+        for (int i = 0; i < n_paths; i++) {
+            if (!paths[i]) throw std::invalid_argument("null path");
+            ps.emplace_back(paths[i]);
+        }
+        auto a = std::make_unique<b2d_archive>();
+        a->wad = std::make_unique<Archive>(Archive::open(ps));
+        *out = a.release();
+        return B2D_OK;
+    });
+}
+
+int b2d_archive_open_memory_files(const void *const *bytes, const size_t *sizes, int n_files, b2d_archive **out) {
+    if (!bytes || !sizes || !out || n_files < 1) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return guarded([&] {
+        std::vector<std::vector<uint8_t>> files;
+        for (int i = 0; i < n_files; i++) {
+            if (!bytes[i]) throw std::invalid_argument("null file");
+            const uint8_t *p = static_cast<const uint8_t *>(bytes[i]);
+            files.emplace_back(p, p + sizes[i]);
+        }
+        auto a = std::make_unique<b2d_archive>();
+        a->wad = std::make_unique<Archive>(std::move(files));
         *out = a.release();
         return B2D_OK;
     });

@@ -432,31 +432,15 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         __syncwarp();
         const int rows = min(32, y1 - yc);
         int j = 0;
-        if (rows >= kBatch) {
-            // software pipelined over the block's batches: the eight gathers of batch b+1 are in flight while batch b is stored
+        for (; j + kBatch <= rows; j += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
             uint32_t v[kBatch];
 #pragma unroll
             for (int k = 0; k < kBatch; k++) {
-                const uint2 rz = c.rowz[k];                                   // shared-memory broadcast: one 64-bit word per row
+                const uint2 rz = c.rowz[j + k];                               // shared-memory broadcast: one 64-bit word per row
                 v[k] = __ldg(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay));   // always in bounds
             }
-            for (; j + kBatch <= rows; j += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
-                uint32_t nv[kBatch];
-                const bool more = j + 2 * kBatch <= rows;                     // warp-uniform
-                if (more) {
-#pragma unroll
-                    for (int k = 0; k < kBatch; k++) {
-                        const uint2 rz = c.rowz[j + kBatch + k];
-                        nv[k] = __ldg(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay));
-                    }
-                }
-                const int y = yc + j;
-                store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
-                if (more) {
-#pragma unroll
-                    for (int k = 0; k < kBatch; k++) v[k] = nv[k];
-                }
-            }
+            const int y = yc + j;
+            store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
         }
         for (; j < rows; j++, p8 += Wc, p32 += Wc) {
             const uint2 rz = c.rowz[j];
@@ -477,22 +461,15 @@ __device__ __forceinline__ void wall_fast_loop(const RasterCtx &c, const uint8_t
     uint8_t *p8 = c.fb + (size_t)y0 * Wc;
     uint32_t *p32 = kRgba ? c.rgba + (size_t)y0 * Wc : nullptr;
     asm("" : "+l"(plq));       // keep the column's plane pointer whole: one IMAD.WIDE per load instead of re-adding the base
-    // software pipelined: the two words of the NEXT batch are requested before this batch's selects and stores, so the load
-    // latency (L1 ~30, L2 ~250 cycles) hides behind 3-4 instructions per row instead of stalling every batch
-    uint32_t q1 = q + 1u == nq ? 0u : q + 1u;
-    uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q * w4));
-    uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q1 * w4));
 #pragma unroll 1
     for (int y = y0; y < y1; y += R, p8 += (size_t)R * Wc, p32 += (size_t)R * Wc) {
-        const uint32_t acc0 = acc;
-        wall_advance(acc, q, ts29, (uint32_t)R, nq);
-        q1 = q + 1u == nq ? 0u : q + 1u;
-        const uint32_t n0 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q * w4));     // always in bounds
-        const uint32_t n1 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q1 * w4));
+        const uint32_t q1 = q + 1u == nq ? 0u : q + 1u;
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q * w4));
+        const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q1 * w4));
         if (y >= full_lo && y + R <= full_hi) {
 #pragma unroll
             for (int k = 0; k < R; k++) {
-                uint32_t v = pick_byte(w0, w1, wall_sel(acc0, ts29, (uint32_t)k));
+                uint32_t v = pick_byte(w0, w1, wall_sel(acc, ts29, (uint32_t)k));
                 if (kRgba) v &= 0xFFu;
                 put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, true, v);
             }
@@ -500,12 +477,12 @@ __device__ __forceinline__ void wall_fast_loop(const RasterCtx &c, const uint8_t
             const uint32_t m = row_mask(y, ya, yb, R);
 #pragma unroll
             for (int k = 0; k < R; k++) {
-                uint32_t v = pick_byte(w0, w1, wall_sel(acc0, ts29, (uint32_t)k));
+                uint32_t v = pick_byte(w0, w1, wall_sel(acc, ts29, (uint32_t)k));
                 if (kRgba) v &= 0xFFu;
                 put_px<kRgba>(c, p8 + (size_t)k * Wc, kRgba ? p32 + (size_t)k * Wc : nullptr, (m >> k) & 1u, v);
             }
         }
-        w0 = n0; w1 = n1;
+        wall_advance(acc, q, ts29, (uint32_t)R, nq);
     }
 }
 

@@ -59,31 +59,68 @@ bool is_sky_flat(const Name &n) {
 }
 
 // ------------------------------------------------------------------------------------ Archive
-Archive::Archive(std::vector<uint8_t> data) : data_(std::move(data)) {
-    if (data_.size() < 12) corrupt("bad wad header");
-    if (std::memcmp(data_.data(), "IWAD", 4) != 0) corrupt("bad wad header identifier (IWAD required)");
-    int32_t num = rd_i32(&data_[4]);
-    int32_t table = rd_i32(&data_[8]);
-    if (num < 0 || table < 0 || (uint64_t)table + 16ull * (uint64_t)num > data_.size())
+Archive::Archive(std::vector<uint8_t> data) { add_file(data, true); }
+
+Archive::Archive(std::vector<std::vector<uint8_t>> files) {
+    if (files.empty()) corrupt("no wad file");
+    for (size_t i = 0; i < files.size(); i++) add_file(files[i], i == 0);
+}
+
+void Archive::add_file(const std::vector<uint8_t> &file, bool iwad) {
+    if (file.size() < 12) corrupt("bad wad header");
+    if (std::memcmp(file.data(), iwad ? "IWAD" : "PWAD", 4) != 0)
+        corrupt(iwad ? "bad wad header identifier (IWAD required)" : "bad wad header identifier (PWAD required for an overlay)");
+    int32_t num = rd_i32(&file[4]);
+    int32_t table = rd_i32(&file[8]);
+    if (num < 0 || table < 0 || (uint64_t)table + 16ull * (uint64_t)num > file.size())
         corrupt("lump info table out of bounds");
+    const int64_t base = (int64_t)data_.size();                  // lump positions become offsets into the concatenation
+    data_.insert(data_.end(), file.begin(), file.end());
     static const Name things = make_name("THINGS");
-    lumps_.reserve((size_t)num);
+    const int first = (int)lumps_.size();
+    lumps_.reserve(lumps_.size() + (size_t)num);
     for (int32_t i = 0; i < num; i++) {
-        const uint8_t *e = &data_[(size_t)table + 16u * (size_t)i];
+        const uint8_t *e = &file[(size_t)table + 16u * (size_t)i];
         Lump l;
         l.pos = rd_i32(e);
         l.size = rd_i32(e + 4);
+        // a lump must lie inside its own file (a position past it would alias the next file of the concatenation)
+        if (l.size > 0 && (l.pos < 0 || (uint64_t)l.pos + (uint64_t)l.size > file.size())) l.pos = -1;
+        else if (l.pos >= 0) l.pos += base;
         l.name = make_name(e + 8, 8);       // an invalid name fails the whole open (name.rs:132-139)
         index_[l.name] = (int)lumps_.size();
         lumps_.push_back(l);
         if (l.name == things) {
             if (i == 0) corrupt("THINGS lump without level marker");
-            levels_.push_back(i - 1);
+            const int marker = first + i - 1;
+            bool replaced = false;
+            for (int &lv : levels_)
+                if (lumps_[(size_t)lv].name == lumps_[(size_t)marker].name) { lv = marker; replaced = true; }
+            if (!replaced) levels_.push_back(marker);
         }
     }
+    files_.emplace_back(first, (int)lumps_.size());
 }
 
-Archive Archive::open(const std::string &path) {
+std::vector<std::pair<int, int>> Archive::marker_ranges(const char *start, const char *start2, const char *end,
+                                                       const char *end2) const {
+    const Name s1 = make_name(start), s2 = make_name(start2), e1 = make_name(end), e2 = make_name(end2);
+    std::vector<std::pair<int, int>> out;
+    for (size_t f = 0; f < files_.size(); f++) {
+        int a = -1, b = -1;
+        for (int i = files_[f].first; i < files_[f].second; i++) {
+            const Name &n = lumps_[(size_t)i].name;
+            if (n == s1 || n == s2) a = i;                       // the later duplicate wins, as a by-name lookup would
+            if (n == e1 || n == e2) b = i;
+        }
+        if (f == 0 && (a < 0 || b < 0)) corrupt(std::string("missing required lump ") + (a < 0 ? start : end));
+        if (a >= 0 && b >= 0) out.emplace_back(a, b);
+    }
+    return out;
+}
+
+namespace {
+std::vector<uint8_t> read_file(const std::string &path) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) throw WadError(kErrIo, "cannot open wad file '" + path + "'");
     std::vector<uint8_t> data;
@@ -93,7 +130,16 @@ Archive Archive::open(const std::string &path) {
     bool bad = std::ferror(f) != 0;
     std::fclose(f);
     if (bad) throw WadError(kErrIo, "error reading wad file '" + path + "'");
-    return Archive(std::move(data));
+    return data;
+}
+}  // namespace
+
+Archive Archive::open(const std::string &path) { return Archive(read_file(path)); }
+
+Archive Archive::open(const std::vector<std::string> &paths) {
+    std::vector<std::vector<uint8_t>> files;
+    for (const std::string &p : paths) files.push_back(read_file(p));
+    return Archive(std::move(files));
 }
 
 const Name &Archive::level_name(int level_index) const { return lumps_.at((size_t)level_lump_index(level_index)).name; }
@@ -246,10 +292,16 @@ Image Image::decode(const uint8_t *buf, size_t size) {
     for (int x = 0; x < im.w; x++) {
         size_t p = rd_u32(buf + 8 + 4 * (size_t)x);
         if (p >= size) corrupt("invalid image column offset");
+        int last_row = -1;
         for (;;) {
             if (p >= size) corrupt("unfinished image column");
             unsigned row = buf[p++];
             if (row == 255) break;
+            // tall patches (DeePsea convention, used by PWAD textures taller than 254 rows): a post whose topdelta does not
+            // exceed the previous post's is relative to it.  Posts of a stock patch are strictly increasing, so nothing
+            // changes for the pictures the reference (image.rs:73-157, absolute offsets only) can represent.
+            if (last_row >= 0 && (int)row <= last_row) row += (unsigned)last_row;
+            last_row = (int)row;
             if (p >= size) corrupt("missing image run length");
             unsigned len = buf[p++];
             if ((int)(row + len) > im.h) corrupt("image run too big");
@@ -373,16 +425,16 @@ TextureDirectory TextureDirectory::load(const Archive &wad) {
         }
     }
     {   // flats (tex.rs:594-606)
-        int s = wad.require("F_START"), e = wad.require("F_END");
-        for (int i = s; i < e; i++)
-            if (wad.lump(i).size != 0) {
-                (void)wad.lump_data(i);                        // read_bytes()? : out-of-file lumps fail the load
-                td.flat_index[wad.lump(i).name] = i;
-            }
+        for (const auto &rg : wad.marker_ranges("F_START", "FF_START", "F_END", "FF_END"))
+            for (int i = rg.first; i < rg.second; i++)
+                if (wad.lump(i).size != 0) {
+                    (void)wad.lump_data(i);                    // read_bytes()? : out-of-file lumps fail the load
+                    td.flat_index[wad.lump(i).name] = i;       // a PWAD's flat of the same name wins
+                }
     }
     {   // sprites share the texture name space and may shadow a texture (tex.rs:475-497)
-        int s = wad.require("S_START") + 1, e = wad.require("S_END");
-        for (int i = s; i < e; i++) {
+        for (const auto &rg : wad.marker_ranges("S_START", "SS_START", "S_END", "SS_END"))
+        for (int i = rg.first + 1; i < rg.second; i++) {
             const uint8_t *bytes = wad.lump_data(i);           // read failure propagates (tex.rs:484-485)
             try {
                 Image im = Image::decode(bytes, (size_t)wad.lump(i).size);

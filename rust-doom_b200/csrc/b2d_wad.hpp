@@ -52,8 +52,17 @@ struct Node { int16_t x, y, dx, dy; int16_t rbox[4], lbox[4]; uint16_t right, le
 
 class Archive {
 public:
+    // files[0] is the IWAD (the reference opens nothing else: archive.rs:69-72); further files are PWADs applied in order,
+    // Doom-engine style: their lumps are appended to the directory, so a later lump of the same name wins every by-name
+    // lookup (PNAMES, TEXTUREx, patches, PLAYPAL ...), a level of an existing name replaces that level in place, new
+    // level names are appended, and flats / sprites between a PWAD's own FF_START..FF_END / SS_START..SS_END (or
+    // F_START / S_START) markers are added to the IWAD's.
     explicit Archive(std::vector<uint8_t> data);
+    explicit Archive(std::vector<std::vector<uint8_t>> files);
     static Archive open(const std::string &path);
+    static Archive open(const std::vector<std::string> &paths);
+    // lump index ranges [first, last) between the start / end markers of every file that has them (the IWAD must)
+    std::vector<std::pair<int, int>> marker_ranges(const char *start, const char *start2, const char *end, const char *end2) const;
 
     int num_levels() const { return (int)levels_.size(); }
     const Name &level_name(int level_index) const;
@@ -65,7 +74,9 @@ public:
     const uint8_t *lump_data(int index) const;     // nullptr for virtual (size 0) lumps
 
 private:
+    void add_file(const std::vector<uint8_t> &file, bool iwad);
     std::vector<uint8_t> data_;
+    std::vector<std::pair<int, int>> files_;       // [first lump, one past last lump) per file
     std::vector<Lump> lumps_;
     std::unordered_map<Name, int, NameHash> index_;
     std::vector<int> levels_;

@@ -142,3 +142,100 @@ def test_blit_clipping_and_mask():
     W.blit(d3, src, 4, 0, False)          # fully out of bounds
     W.blit(d3, src, -9, 0, False)
     assert not d3.any()
+
+
+def _encode_tall_picture(img):
+    """Picture lump for an image taller than 254 rows, DeePsea style: a post whose topdelta is not above the previous
+    post's is relative to it (runs of at most 100 rows; the second post of a column at absolute row 300 is written as
+    topdelta 300 - 200 = 100 <= 200)."""
+    import struct
+    h, w = img.shape
+    cols = []
+    for x in range(w):
+        out = bytearray()
+        last = -1
+        for y0 in range(0, h, 100):
+            run = bytes(int(v) & 0xFF for v in img[y0:min(h, y0 + 100), x])
+            if y0 <= 254 and y0 > last:
+                top = y0                     # absolute while it fits and increases
+            else:
+                top = y0 - last              # relative to the previous post
+                assert 0 < top <= last and top < 255
+            out += bytes([top, len(run), 0]) + run + b"\0"
+            last = y0
+        out += b"\xff"
+        cols.append(bytes(out))
+    offs, pos = [], 8 + 4 * w
+    for c in cols:
+        offs.append(pos)
+        pos += len(c)
+    return struct.pack("<HHhh", w, h, 0, 0) + struct.pack("<%dI" % w, *offs) + b"".join(cols)
+
+
+def test_pwad_overlay_and_tall_patches(b2d):
+    """IWAD + PWAD (wad/src/archive.rs:69-72 rejects PWADs): a PWAD replaces E1M1, adds a level, overrides a
+    flat between FF_START/FF_END, brings its own PNAMES / TEXTURE1 with a 64x420 texture built from a tall patch
+    (relative posts).  Product and oracle loaders agree: level list, compiled scenes byte for byte, decoded tall texture."""
+    import struct
+    from oracle import scene as S
+    from rust_doom_b200 import synthwad
+    iwad = synthwad.build_iwad(1, ("E1M1", "E1M2"))
+    donor = W.Archive(synthwad.build_iwad(7, ("E1M1",)))
+    donor2 = W.Archive(synthwad.build_iwad(8, ("E1M1",)))
+
+    def level_lumps(arch, new_name, rename=None):
+        m = arch.levels[0]
+        out = [(new_name, b"")]
+        for k in range(1, 11):
+            name, _, _ = arch.lumps[m + k]
+            if name in (b"THINGS\0\0", b"LINEDEFS", b"SIDEDEFS", b"VERTEXES", b"SEGS\0\0\0\0", b"SSECTORS", b"NODES\0\0\0", b"SECTORS\0",
+                        b"REJECT\0\0", b"BLOCKMAP"):
+                data = arch.read(m + k)
+                if rename and name == b"SIDEDEFS":
+                    for old, new in rename.items():
+                        data = data.replace(old, new)
+                out.append((name.rstrip(b"\0").decode(), data))
+        return out
+
+    rng = np.random.default_rng(5)
+    tall = rng.integers(1, 250, (420, 64)).astype(np.int16)
+    base = W.Archive(iwad)
+    pn = base.read(base.required(b"PNAMES"))
+    npn = struct.unpack_from("<I", pn, 0)[0]
+    pnames = struct.pack("<I", npn + 1) + pn[4:] + b"TALLP\0\0\0"
+    t1 = base.read(base.required(b"TEXTURE1"))
+    ntex = struct.unpack_from("<I", t1, 0)[0]
+    offs = list(struct.unpack_from("<%dI" % ntex, t1, 4))
+    bodies = t1[4 + 4 * ntex:]
+    newtex = struct.pack("<8sIHHIH", b"TALLTEX\0", 0, 64, 420, 0, 1) + struct.pack("<hhHHH", 0, 0, npn, 1, 0)
+    offs = [o + 4 for o in offs] + [4 + 4 * (ntex + 1) + len(bodies)]
+    texture1 = struct.pack("<I", ntex + 1) + struct.pack("<%dI" % (ntex + 1), *offs) + bodies + newtex
+    new_floor = bytes(rng.integers(0, 256, 4096, dtype=np.uint8))
+    lumps = (level_lumps(donor, "E1M1", rename={b"BRICK1\0\0": b"TALLTEX\0"}) + level_lumps(donor2, "E1M9")
+             + [("PNAMES", pnames), ("TEXTURE1", texture1), ("PP_START", b""), ("TALLP", _encode_tall_picture(tall)), ("PP_END", b""),
+                ("FF_START", b""), ("FLOOR1", new_floor), ("FF_END", b"")])
+    pwad = synthwad.assemble_wad(lumps, ident=b"PWAD")
+
+    oa = W.Archive(iwad, overlays=(pwad,))
+    pa = b2d.Archive.from_bytes(iwad, overlays=(pwad,))
+    assert [n.rstrip(b"\0").decode() for n in (oa.level_name(i) for i in range(oa.num_levels()))] == ["E1M1", "E1M2", "E1M9"]
+    assert pa.level_names() == ["E1M1", "E1M2", "E1M9"]
+    otd = W.TextureDirectory(oa)
+    assert np.array_equal(otd.textures[b"TALLTEX\0"], tall.astype(np.uint16))       # tall patch decoded, relative posts and all
+    assert otd.flats[b"FLOOR1\0\0"] == new_floor
+    uses_tall = False
+    for lvl in range(3):
+        ob = S.compile_scene(oa, otd, lvl)
+        assert b2d.Scene(pa, lvl).blob == ob, "level %d" % lvl
+        if lvl == 0:
+            uses_tall = any(int(t[2]) == 420 for t in S.section(ob, "textures"))
+    assert uses_tall, "the replaced E1M1 does not use the tall texture"
+    # E1M1 is the PWAD's level now (E1M2 is still the IWAD's own)
+    assert b2d.Scene(pa, 0).info.n_segs == b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(7, ("E1M1",))), 0).info.n_segs
+    # an overlay must be a PWAD, the base an IWAD
+    with pytest.raises(b2d.B2dError):
+        b2d.Archive.from_bytes(iwad, overlays=(iwad,))
+    with pytest.raises(W.WadError):
+        W.Archive(iwad, overlays=(iwad,))
+    with pytest.raises(b2d.B2dError):
+        b2d.Archive.from_bytes(pwad)
