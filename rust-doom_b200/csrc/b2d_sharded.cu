@@ -19,6 +19,7 @@
 
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "b2d_internal.hpp"
 
@@ -29,6 +30,7 @@ typedef struct ncclComm *ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef void *ncclWindow_t;
 constexpr int kNcclUint8 = 1;        // ncclUint8 / ncclChar enum value
+constexpr int kNcclInt32 = 2, kNcclSum = 0;
 constexpr int kWinCollSymmetric = 1; // NCCL_WIN_COLL_SYMMETRIC
 
 struct Nccl {
@@ -40,6 +42,7 @@ struct Nccl {
     int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*MemAlloc)(void **, size_t) = nullptr;                       // optional
     int (*MemFree)(void *) = nullptr;
     int (*CommRegister)(ncclComm_t, void *, size_t, void **) = nullptr;
@@ -68,6 +71,7 @@ Nccl &nccl() {
         B2D_NCCL_SYM(CommInitRank, "ncclCommInitRank");
         B2D_NCCL_SYM(CommDestroy, "ncclCommDestroy");
         B2D_NCCL_SYM(AllGather, "ncclAllGather");
+        B2D_NCCL_SYM(AllReduce, "ncclAllReduce");
         B2D_NCCL_SYM(MemAlloc, "ncclMemAlloc");
         B2D_NCCL_SYM(MemFree, "ncclMemFree");
         B2D_NCCL_SYM(CommRegister, "ncclCommRegister");
@@ -144,6 +148,14 @@ struct b2d_comm {
     ncclWindow_t win[2] = {nullptr, nullptr};
     const char *registration = "none";
     cudaStream_t render_stream = nullptr, gather_stream = nullptr, consume_stream = nullptr;
+    // copy-engine transport (B2D_GATHER=ce): every rank pushes its slice into the peers' buffers with cudaMemcpyAsync over
+    // CUDA-IPC mappings -- no SM is used for the exchange; two tiny NCCL all-reduces per chunk order it across ranks
+    bool ce = false;
+    std::vector<uint8_t *> peer[2];                 // [buffer][rank]: that rank's buffer as mapped here (own rank: buf[b])
+    std::vector<cudaStream_t> push_stream;          // one per peer
+    std::vector<cudaEvent_t> push_done;
+    cudaEvent_t push_go = nullptr;
+    int32_t *d_token = nullptr;
     Pose *d_poses = nullptr, *h_poses = nullptr;
     size_t poses_cap = 0;
 };
@@ -152,6 +164,11 @@ namespace {
 
 void release_buffers(b2d_comm *c) {
     Nccl &n = nccl();
+    for (int i = 0; i < 2; i++) {
+        for (size_t q = 0; q < c->peer[i].size(); q++)
+            if ((int)q != c->rank && c->peer[i][q]) cudaIpcCloseMemHandle(c->peer[i][q]);
+        c->peer[i].clear();
+    }
     for (int i = 0; i < 2; i++) {
         if (!c->buf[i]) continue;
         if (c->win[i] && n.CommWindowDeregister) n.CommWindowDeregister(c->comm, c->win[i]);
@@ -166,7 +183,9 @@ int ensure_buffers(b2d_comm *c, size_t bytes) {
     if (c->buf_bytes >= bytes) return B2D_OK;
     Nccl &n = nccl();
     release_buffers(c);
-    const bool want_reg = !getenv("B2D_NCCL_NO_REGISTER");
+    const char *tr = getenv("B2D_GATHER");
+    c->ce = tr && std::strcmp(tr, "ce") == 0 && c->world > 1 && n.AllReduce;
+    const bool want_reg = !getenv("B2D_NCCL_NO_REGISTER") && !c->ce;      // IPC needs plain cudaMalloc memory
     c->nccl_mem = want_reg && n.MemAlloc && n.MemFree;
     c->registration = "none";
     for (int i = 0; i < 2; i++) {
@@ -193,7 +212,69 @@ int ensure_buffers(b2d_comm *c, size_t bytes) {
         }
         cudaGetLastError();
     }
+    if (c->ce) {
+        // exchange the IPC handles of both buffers (NCCL all-gather of 2 x 64 bytes per rank) and map the peers' buffers
+        const size_t hb = sizeof(cudaIpcMemHandle_t);
+        std::vector<uint8_t> mine(2 * hb), all(2 * hb * (size_t)c->world);
+        for (int i = 0; i < 2; i++) {
+            cudaIpcMemHandle_t h;
+            B2D_CU(cudaIpcGetMemHandle(&h, c->buf[i]));
+            std::memcpy(&mine[(size_t)i * hb], &h, hb);
+        }
+        uint8_t *d_h = nullptr;
+        B2D_CU(cudaMalloc(&d_h, all.size()));
+        B2D_CU(cudaMemcpy(d_h + (size_t)c->rank * 2 * hb, mine.data(), 2 * hb, cudaMemcpyHostToDevice));
+        int nrc = n.AllGather(d_h + (size_t)c->rank * 2 * hb, d_h, 2 * hb, kNcclUint8, c->comm, c->gather_stream);
+        if (nrc != 0) { cudaFree(d_h); return nccl_fail(nrc, "ncclAllGather (ipc handles)"); }
+        B2D_CU(cudaStreamSynchronize(c->gather_stream));
+        B2D_CU(cudaMemcpy(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost));
+        cudaFree(d_h);
+        for (int i = 0; i < 2; i++) {
+            c->peer[i].assign((size_t)c->world, nullptr);
+            for (int q = 0; q < c->world; q++) {
+                if (q == c->rank) { c->peer[i][(size_t)q] = c->buf[i]; continue; }
+                cudaIpcMemHandle_t h;
+                std::memcpy(&h, &all[((size_t)q * 2 + (size_t)i) * hb], hb);
+                void *p = nullptr;
+                B2D_CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                c->peer[i][(size_t)q] = static_cast<uint8_t *>(p);
+            }
+        }
+        if (c->push_stream.empty()) {
+            c->push_stream.resize((size_t)c->world, nullptr);
+            c->push_done.resize((size_t)c->world, nullptr);
+            for (int q = 0; q < c->world; q++) {
+                if (q == c->rank) continue;
+                B2D_CU(cudaStreamCreateWithFlags(&c->push_stream[(size_t)q], cudaStreamNonBlocking));
+                B2D_CU(cudaEventCreateWithFlags(&c->push_done[(size_t)q], cudaEventDisableTiming));
+            }
+            B2D_CU(cudaEventCreateWithFlags(&c->push_go, cudaEventDisableTiming));
+            B2D_CU(cudaMalloc(&c->d_token, sizeof(int32_t)));
+            B2D_CU(cudaMemset(c->d_token, 0, sizeof(int32_t)));
+        }
+        c->registration = "copy engines: cudaMemcpyAsync pushes over CUDA-IPC peer mappings";
+    }
     c->buf_bytes = bytes;
+    return B2D_OK;
+}
+
+// copy-engine all-gather of one chunk (see b2d_comm::ce).  Enqueued on the gather stream after `rendered`.
+int ce_gather(b2d_comm *c, int b, size_t slice_off, size_t bytes) {
+    Nccl &n = nccl();
+    // 1. every rank's buffer b is free again (each rank enqueues this after the event that says so locally)
+    B2D_NC(n.AllReduce(c->d_token, c->d_token, 1, kNcclInt32, kNcclSum, c->comm, c->gather_stream));
+    B2D_CU(cudaEventRecord(c->push_go, c->gather_stream));
+    // 2. push my slice into every peer's buffer, one stream (one copy engine queue) per peer
+    for (int k = 1; k < c->world; k++) {
+        const int q = (c->rank + k) % c->world;                        // stagger the targets across ranks
+        cudaStream_t ps = c->push_stream[(size_t)q];
+        B2D_CU(cudaStreamWaitEvent(ps, c->push_go, 0));
+        B2D_CU(cudaMemcpyAsync(c->peer[b][(size_t)q] + slice_off, c->buf[b] + slice_off, bytes, cudaMemcpyDeviceToDevice, ps));
+        B2D_CU(cudaEventRecord(c->push_done[(size_t)q], ps));
+        B2D_CU(cudaStreamWaitEvent(c->gather_stream, c->push_done[(size_t)q], 0));
+    }
+    // 3. everybody's pushes have landed
+    B2D_NC(n.AllReduce(c->d_token, c->d_token, 1, kNcclInt32, kNcclSum, c->comm, c->gather_stream));
     return B2D_OK;
 }
 
@@ -242,6 +323,10 @@ void b2d_comm_destroy(b2d_comm *c) {
     if (c->render_stream) cudaStreamDestroy(c->render_stream);
     if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
     if (c->consume_stream) cudaStreamDestroy(c->consume_stream);
+    for (cudaStream_t ps : c->push_stream) if (ps) cudaStreamDestroy(ps);
+    for (cudaEvent_t e : c->push_done) if (e) cudaEventDestroy(e);
+    if (c->push_go) cudaEventDestroy(c->push_go);
+    if (c->d_token) cudaFree(c->d_token);
     if (c->comm) nccl().CommDestroy(c->comm);
     delete c;
 }
@@ -335,7 +420,10 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
         if (do_gather) {
             B2D_CU(cudaStreamWaitEvent(c->gather_stream, rendered[b], 0));
             B2D_CU(cudaEventRecord(gt[2 * k], c->gather_stream));
-            if (world > 1 || !getenv("B2D_SKIP_SELF_GATHER")) {
+            if (c->ce) {
+                result = ce_gather(c, b, rank * cnt * npix, cnt * npix);
+                if (result != B2D_OK) break;
+            } else {
                 int nrc = n.AllGather(slice, c->buf[b], cnt * npix, kNcclUint8, c->comm, c->gather_stream);
                 if (nrc != 0) { result = nccl_fail(nrc, "ncclAllGather"); break; }
             }

@@ -7,8 +7,9 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 run() { name=$1; shift; timeout 900 "$@" > gpurun_out/bench_${TAG}_$name.json 2> gpurun_out/bench_${TAG}_$name.err; echo "$name rc=$?"; tail -c 2500 gpurun_out/bench_${TAG}_$name.json; echo; grep -v "^W0\|^\*\*\*\|OMP_NUM_THREADS" gpurun_out/bench_${TAG}_$name.err | tail -5; }
 for w in "$@"; do
   case $w in
-    c5small) NCCL_DEBUG=WARN run c5small $TR bench.py --gpus $N --config c5 --poses 8000 --chunk 250 --steps 1 ;;
-    c5) run c5 $TR bench.py --gpus $N --config c5 --chunk 256 --steps 2 ;;
+    c5small) NCCL_DEBUG=WARN run c5small $TR bench.py --gpus $N --config c5 --poses 8000 --chunk 250 --steps 1 --transports window,plain,ce ;;
+    c5) run c5 $TR bench.py --gpus $N --config c5 --chunk 256 --steps 2 --transports window,plain,ce ;;
+    c5chan) NCCL_MIN_NCHANNELS=32 run c5chan $TR bench.py --gpus $N --config c5 --chunk 256 --steps 2 --transports window,plain ;;
     c5big) run c5big $TR bench.py --gpus $N --config c5 --chunk 512 --steps 2 ;;
     c5noreg) B2D_NCCL_NO_REGISTER=1 run c5noreg $TR bench.py --gpus $N --config c5 --chunk 256 --steps 2 ;;
     c5nowin) B2D_NCCL_NO_WINDOW=1 run c5nowin $TR bench.py --gpus $N --config c5 --chunk 256 --steps 2 ;;
