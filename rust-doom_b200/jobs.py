@@ -203,21 +203,30 @@ def run_maps(scenes: Sequence[Scene], poses: Sequence[np.ndarray], width: int, h
     outs = [torch.empty((len(p), height, width), dtype=torch.uint8, device=dev) for p in poses]
     stream = torch.cuda.current_stream().cuda_stream
 
+    # the launches of one pass, in order: (map, first pose, count); c3 interleaves the maps batch by batch
+    items = []
+    if interleave:
+        for b0 in range(0, nmax, batch):
+            for m in range(len(rs)):
+                if b0 < len(poses[m]):
+                    items.append((m, b0, min(batch, len(poses[m]) - b0)))
+    else:
+        for m in range(len(rs)):
+            for b0 in range(0, len(poses[m]), batch):
+                items.append((m, b0, min(batch, len(poses[m]) - b0)))
+    walk_stream = torch.cuda.Stream(device=dev, priority=-1)
+
+    def walk(i):
+        m, b0, cnt = items[i]
+        return rs[m].walk_device(d_poses[m].data_ptr() + 16 * b0, cnt, walk_stream.cuda_stream)
+
     def one_pass():
-        if interleave:
-            for b0 in range(0, nmax, batch):
-                for m, r in enumerate(rs):
-                    n = len(poses[m])
-                    if b0 >= n:
-                        continue
-                    cnt = min(batch, n - b0)
-                    r.render_device(d_poses[m].data_ptr() + 16 * b0, cnt, outs[m].data_ptr() + npix * b0, 0, stream)
-        else:
-            for m, r in enumerate(rs):
-                n = len(poses[m])
-                for b0 in range(0, n, batch):
-                    cnt = min(batch, n - b0)
-                    r.render_device(d_poses[m].data_ptr() + 16 * b0, cnt, outs[m].data_ptr() + npix * b0, 0, stream)
+        # pipelined like bench.py's c2 step: the BSP walk of item i+1 (a background grid) runs under the raster of item i
+        ticket = walk(0)
+        for i, (m, b0, cnt) in enumerate(items):
+            rs[m].raster_device(ticket, outs[m].data_ptr() + npix * b0, 0, stream)
+            if i + 1 < len(items):
+                ticket = walk(i + 1)
 
     for _ in range(max(warmup, 1)):
         one_pass()
