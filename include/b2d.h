@@ -169,6 +169,16 @@ int b2d_renderer_status(b2d_renderer *r, int32_t *bits_out);
  * (R in the low byte).  n may exceed max_batch; it is processed in batches. */
 int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_fb, uint32_t *rgba_fb);
 
+/* Per-pose level time (poses (x, y, z, yaw, t)): pose i is rendered at level time tics[i] (HOST array).  A batch
+ * shares its scene tables, so consecutive poses are launched together as long as their tables are byte-identical
+ * (equal tics, or tics that change nothing: inside one 8-tic animation frame of a level without light effects or
+ * scrolling walls) and the tables are re-uploaded in stream order where they change; a timeline sorted by time costs
+ * one launch per table change, an unsorted one a launch per pose.  Leaves the renderer at the last pose's time.
+ * tics == NULL in b2d_render_timed is b2d_render. */
+int b2d_render_timed(b2d_renderer *r, const b2d_pose *poses, const uint32_t *tics, size_t n, uint8_t *index_fb, uint32_t *rgba_fb);
+int b2d_render_device_timed(b2d_renderer *r, const b2d_pose *d_poses, const uint32_t *tics, size_t n, uint8_t *d_index_fb,
+                            uint32_t *d_rgba_fb, void *cuda_stream);
+
 /* Device-resident: poses, index_fb and rgba_fb (nullable) are DEVICE pointers on the renderer's
  * device; work is enqueued on `cuda_stream` (a cudaStream_t, NULL = default stream) and NOT
  * synchronised.  n <= max_batch. */

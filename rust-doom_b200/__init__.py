@@ -296,6 +296,23 @@ class Renderer:
                                       out_rgba.ctypes.data if rgba else None))
         return (out_index, out_rgba) if rgba else out_index
 
+    def render_timed(self, poses: np.ndarray, tics, rgba: bool = False):
+        """b2d_render_timed: pose i at level time tics[i] (per-pose time)."""
+        poses = np.ascontiguousarray(poses, dtype=POSE_DTYPE)
+        t = np.ascontiguousarray(tics, dtype=np.uint32)
+        assert len(t) == len(poses)
+        n = len(poses)
+        out_index = np.empty((n, self.height, self.width), dtype=np.uint8)
+        out_rgba = np.empty((n, self.height, self.width), dtype=np.uint32) if rgba else None
+        _check(_lib.load().b2d_render_timed(self._h, poses.ctypes.data, t.ctypes.data, n, out_index.ctypes.data,
+                                            out_rgba.ctypes.data if rgba else None))
+        return (out_index, out_rgba) if rgba else out_index
+
+    def render_device_timed(self, poses_ptr: int, tics, n: int, index_ptr: int, rgba_ptr: int = 0, stream: int = 0):
+        t = np.ascontiguousarray(tics, dtype=np.uint32)
+        assert len(t) == n
+        _check(_lib.load().b2d_render_device_timed(self._h, poses_ptr, t.ctypes.data, n, index_ptr, rgba_ptr or None, stream or None))
+
     def render_ptr(self, poses_ptr: int, n: int, index_ptr: int, rgba_ptr: int = 0):
         """b2d_render on raw host pointers (e.g. pinned torch tensors)."""
         _check(_lib.load().b2d_render(self._h, poses_ptr, n, index_ptr, rgba_ptr or None))

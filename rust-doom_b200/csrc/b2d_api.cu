@@ -158,18 +158,26 @@ int raster_from_slot(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t
 // device blob in stream order.  Everything this renderer has enqueued so far -- on any stream -- is awaited by `stream`
 // first (the walk/raster events of both worklist slots), and later launches on other streams wait for the upload, so the
 // host never blocks on the device: no cudaDeviceSynchronize in the System::update loop this stands in for.
-int upload_timed_tables(b2d_renderer *r, uint32_t tics, cudaStream_t stream) {
+// the time-dependent tables at `tics`, laid out [tex | sectors | segs | sprites] (timed_bytes)
+void tables_at(const b2d_renderer *r, uint32_t tics, uint8_t *out) {
     const uint8_t *blob = r->h_blob.data();
     const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
-    const int buf = r->timed_next;
-    r->timed_next ^= 1;
-    CU(cudaEventSynchronize(r->timed_copied[buf]));          // the copy issued two uploads ago has read this buffer
-    uint8_t *p = r->h_timed[buf];
-    TexRec *tex = reinterpret_cast<TexRec *>(p);
+    TexRec *tex = reinterpret_cast<TexRec *>(out);
     SectorRec *sectors = reinterpret_cast<SectorRec *>(tex + h[H_NTEX]);
     SegRec *segs = reinterpret_cast<SegRec *>(sectors + h[H_NSECTORS]);
     SpriteRec *sprites = reinterpret_cast<SpriteRec *>(segs + h[H_NSEGS]);
     scene_at_time(blob, tics, tex, sectors, segs, sprites);
+}
+
+int upload_tables(b2d_renderer *r, const uint8_t *tables, cudaStream_t stream) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(r->h_blob.data());
+    const int buf = r->timed_next;
+    r->timed_next ^= 1;
+    CU(cudaEventSynchronize(r->timed_copied[buf]));          // the copy issued two uploads ago has read this buffer
+    uint8_t *p = r->h_timed[buf];
+    std::memcpy(p, tables, r->timed_bytes);
+    const uint8_t *tex = p, *sectors = tex + h[H_NTEX] * sizeof(TexRec), *segs = sectors + h[H_NSECTORS] * sizeof(SectorRec),
+                  *sprites = segs + h[H_NSEGS] * sizeof(SegRec);
     for (int i = 0; i < 2; i++) {
         if (r->walk_done[i]) CU(cudaStreamWaitEvent(stream, r->walk_done[i], 0));
         if (r->raster_done[i]) CU(cudaStreamWaitEvent(stream, r->raster_done[i], 0));
@@ -182,6 +190,41 @@ int upload_timed_tables(b2d_renderer *r, uint32_t tics, cudaStream_t stream) {
     CU(cudaEventRecord(r->timed_copied[buf], stream));
     CU(cudaEventRecord(r->tables_ready, stream));
     r->tables_pending = true;
+    r->cur_tables.assign(tables, tables + r->timed_bytes);
+    return B2D_OK;
+}
+
+int upload_timed_tables(b2d_renderer *r, uint32_t tics, cudaStream_t stream) {
+    r->scratch_tables.resize(r->timed_bytes);
+    tables_at(r, tics, r->scratch_tables.data());
+    return upload_tables(r, r->scratch_tables.data(), stream);
+}
+
+// Per-pose time: poses [i, n) with their tics; makes the tables of tics[i] current on `stream` (uploading only if they
+// differ from what is there) and returns in *end the end of the run of poses that can share this launch: consecutive
+// poses whose tables are byte-identical (equal tics, or different tics that change nothing -- e.g. inside one 8-tic
+// animation frame of a level without light effects or scrolling walls).
+int timed_run(b2d_renderer *r, const uint32_t *tics, size_t i, size_t n, size_t limit, cudaStream_t stream, size_t *end) {
+    if (r->h_blob.empty() || !tics) { *end = n < i + limit ? n : i + limit; return B2D_OK; }
+    r->scratch_tables.resize(r->timed_bytes);
+    tables_at(r, tics[i], r->scratch_tables.data());
+    if (r->cur_tables.size() != r->timed_bytes || std::memcmp(r->cur_tables.data(), r->scratch_tables.data(), r->timed_bytes) != 0) {
+        int rc = upload_tables(r, r->scratch_tables.data(), stream);
+        if (rc != B2D_OK) return rc;
+    }
+    r->tics = tics[i];
+    size_t j = i + 1;
+    uint32_t same = tics[i];
+    while (j < n && j < i + limit) {
+        if (tics[j] != same) {
+            tables_at(r, tics[j], r->scratch_tables.data());
+            if (std::memcmp(r->cur_tables.data(), r->scratch_tables.data(), r->timed_bytes) != 0) break;
+            same = tics[j];
+            r->tics = same;
+        }
+        j++;
+    }
+    *end = j;
     return B2D_OK;
 }
 
@@ -557,6 +600,25 @@ int b2d_render_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, uint8_
                           static_cast<cudaStream_t>(cuda_stream));
 }
 
+int b2d_render_device_timed(b2d_renderer *r, const b2d_pose *d_poses, const uint32_t *tics, size_t n, uint8_t *d_index_fb,
+                            uint32_t *d_rgba_fb, void *cuda_stream) {
+    if (!r || !d_poses || !d_index_fb || !tics) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(r->device));
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    const size_t npix = (size_t)r->view.W * r->view.H;
+    size_t i = 0;
+    while (i < n) {
+        size_t j = i;
+        int rc = timed_run(r, tics, i, n, (size_t)r->max_batch, st, &j);
+        if (rc != B2D_OK) return rc;
+        rc = enqueue_frames(r, reinterpret_cast<const Pose *>(d_poses) + i, (int)(j - i), d_index_fb + i * npix,
+                            d_rgba_fb ? d_rgba_fb + i * npix : nullptr, st);
+        if (rc != B2D_OK) return rc;
+        i = j;
+    }
+    return B2D_OK;
+}
+
 int b2d_walk_device(b2d_renderer *r, const b2d_pose *d_poses, size_t n, void *cuda_stream, int64_t *ticket_out) {
     if (!r || !d_poses || !ticket_out) return fail(B2D_ERR_INVALID_ARG, "null argument");
     if (n == 0 || n > (size_t)r->max_batch) return fail(B2D_ERR_INVALID_ARG, "n must be in 1..max_batch");
@@ -571,6 +633,10 @@ int b2d_raster_device(b2d_renderer *r, int64_t ticket, uint8_t *d_index_fb, uint
 }
 
 int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_fb, uint32_t *rgba_fb) {
+    return b2d_render_timed(r, poses, nullptr, n, index_fb, rgba_fb);
+}
+
+int b2d_render_timed(b2d_renderer *r, const b2d_pose *poses, const uint32_t *tics, size_t n, uint8_t *index_fb, uint32_t *rgba_fb) {
     if (!r || !poses || !index_fb) return fail(B2D_ERR_INVALID_ARG, "null argument");
     if (n == 0) return B2D_OK;
     CU(cudaSetDevice(r->device));
@@ -592,7 +658,10 @@ int b2d_render(b2d_renderer *r, const b2d_pose *poses, size_t n, uint8_t *index_
     size_t done = 0;
     int b = 0;
     while (done < n) {
-        const int cnt = (int)((n - done) < (size_t)r->max_batch ? (n - done) : (size_t)r->max_batch);
+        size_t run_end = done;                                      // per-pose time: a batch ends where the tables change
+        int trc = timed_run(r, tics, done, n, (size_t)r->max_batch, r->render_stream, &run_end);
+        if (trc != B2D_OK) return trc;
+        const int cnt = (int)(run_end - done);
         const int buf = b & 1;
         if (b >= 2) CU(cudaEventSynchronize(r->copied[buf]));       // buffer + pose slot free again
         Pose *hp = r->h_poses + (size_t)buf * r->max_batch;

@@ -60,6 +60,7 @@ struct b2d_renderer {
     bool tables_pending = false;
     int timed_next = 0;
     size_t timed_bytes = 0;
+    std::vector<uint8_t> cur_tables, scratch_tables;      // host copies: tables of the last upload / of a candidate time
     cudaEvent_t masked_done = nullptr;                    // last raster that used the masked-entry arena
     uint32_t *d_masked_counter = nullptr;
     int64_t launches = 0;

@@ -565,3 +565,39 @@ def test_gpu_suite_runs_on_a_supplied_iwad(tmp_path):
                          capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "4 passed" in res.stdout
+
+
+def test_gpu_per_pose_time(b2d):
+    """b2d_render_timed / b2d_render_device_timed (SURVEY 8-f2 'poses (x, y, z, yaw, t)'): every pose carries its own level
+    time.  A sorted timeline, an unsorted one and runs of equal tics, through the host path (small max_batch: runs are also
+    cut by the batch size) and the device path; every frame equals the oracle's frame at that pose's tics."""
+    import torch
+    from rust_doom_b200 import synthwad
+    sc = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(anim=True, mid_pct=15, thing_pct=20))), 0)
+    poses = sample_poses(b2d, sc, 24, 66)
+    oview = render.make_view(320, 200)
+    timelines = [np.arange(24, dtype=np.uint32) * 3,                                   # sorted, changes every pose (light effects)
+                 np.array([0, 0, 0, 9, 9, 9, 9, 17, 17, 5, 5, 5] * 2, dtype=np.uint32),    # runs, not monotone
+                 np.random.default_rng(4).integers(0, 1 << 32, 24, dtype=np.uint64).astype(np.uint32)]
+    r = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=5)
+    for tl in timelines:
+        got = r.render_timed(poses, tl)
+        for i in range(24):
+            want = render.render(sc.blob, oview, poses[i:i + 1], tics=int(tl[i]))[0]
+            assert np.array_equal(got[i], want), "host path: pose %d at tics %d" % (i, int(tl[i]))
+    dp = torch.from_numpy(poses.view(np.int32).reshape(-1, 4).copy()).cuda()
+    out = torch.empty((24, 200, 320), dtype=torch.uint8, device="cuda")
+    r2 = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=24)
+    r2.render_device_timed(dp.data_ptr(), timelines[1], 24, out.data_ptr())
+    torch.cuda.synchronize()
+    assert r2.status() == 0
+    g = out.cpu().numpy()
+    for i in range(24):
+        assert np.array_equal(g[i], render.render(sc.blob, oview, poses[i:i + 1], tics=int(timelines[1][i]))[0]), i
+    # a level without time-dependent content: one launch whatever the tics say
+    plain = b2d.Scene(b2d.Archive.from_bytes(synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(light_fx=False))), 0)
+    r3 = b2d.Renderer(plain, b2d.make_view(320, 200), max_batch=24)
+    p3 = sample_poses(b2d, plain, 24, 67)
+    got = r3.render_timed(p3, timelines[2])
+    assert r3.launch_count == 2
+    _assert_same(render.render(plain.blob, oview, p3, threads=8), got, "static level")
