@@ -230,6 +230,13 @@ int timed_run(b2d_renderer *r, const uint32_t *tics, size_t i, size_t n, size_t 
 
 }  // namespace
 
+int b2d::walk_frames(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t stream, int64_t *ticket_out, bool background) {
+    return walk_into_slot(r, d_poses, n, stream, ticket_out, background);
+}
+int b2d::raster_frames(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t *d_rgba, cudaStream_t stream) {
+    return raster_from_slot(r, ticket, d_index, d_rgba, stream);
+}
+
 // walk -> raster on the caller's stream
 int b2d::enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba,
                         cudaStream_t stream) {

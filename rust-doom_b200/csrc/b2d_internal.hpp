@@ -76,6 +76,9 @@ int fail(int code, const std::string &msg);            // sets the thread-local 
 int cuda_fail(cudaError_t e, const char *what);
 // BSP walk + raster of n device poses into d_index / d_rgba (nullable) on `stream`; not synchronised
 int enqueue_frames(b2d_renderer *r, const Pose *d_poses, int n, uint8_t *d_index, uint32_t *d_rgba, cudaStream_t stream);
+// the two halves (b2d_walk_device / b2d_raster_device): a background walk into a worklist slot, the raster of a ticket
+int walk_frames(b2d_renderer *r, const Pose *d_poses, int n, cudaStream_t stream, int64_t *ticket_out, bool background);
+int raster_frames(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t *d_rgba, cudaStream_t stream);
 }  // namespace b2d
 
 #define B2D_CU(call)                                             \

@@ -147,7 +147,7 @@ struct b2d_comm {
     void *reg[2] = {nullptr, nullptr};
     ncclWindow_t win[2] = {nullptr, nullptr};
     const char *registration = "none";
-    cudaStream_t render_stream = nullptr, gather_stream = nullptr, consume_stream = nullptr;
+    cudaStream_t render_stream = nullptr, gather_stream = nullptr, consume_stream = nullptr, walk_stream = nullptr;
     // copy-engine transport (B2D_GATHER=ce): every rank pushes its slice into the peers' buffers with cudaMemcpyAsync over
     // CUDA-IPC mappings -- no SM is used for the exchange; two tiny NCCL all-reduces per chunk order it across ranks
     bool ce = false;
@@ -308,6 +308,7 @@ int b2d_comm_create(const uint8_t id[B2D_COMM_ID_BYTES], int rank, int world, in
     cudaError_t e = cudaStreamCreateWithFlags(&c->render_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->gather_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->consume_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->walk_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { b2d_comm_destroy(c); return b2d::cuda_fail(e, "cudaStreamCreate"); }
     *out = c;
     return B2D_OK;
@@ -323,6 +324,7 @@ void b2d_comm_destroy(b2d_comm *c) {
     if (c->render_stream) cudaStreamDestroy(c->render_stream);
     if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
     if (c->consume_stream) cudaStreamDestroy(c->consume_stream);
+    if (c->walk_stream) cudaStreamDestroy(c->walk_stream);
     for (cudaStream_t ps : c->push_stream) if (ps) cudaStreamDestroy(ps);
     for (cudaEvent_t e : c->push_done) if (e) cudaEventDestroy(e);
     if (c->push_go) cudaEventDestroy(c->push_go);
@@ -387,6 +389,17 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
         std::memcpy(&c->h_poses[i], &poses[g], sizeof(Pose));
     }
     B2D_CU(cudaMemcpyAsync(c->d_poses, c->h_poses, per * sizeof(Pose), cudaMemcpyHostToDevice, c->render_stream));
+    cudaEvent_t poses_up;
+    B2D_CU(cudaEventCreateWithFlags(&poses_up, cudaEventDisableTiming));
+    B2D_CU(cudaEventRecord(poses_up, c->render_stream));
+    B2D_CU(cudaStreamWaitEvent(c->walk_stream, poses_up, 0));
+    // the BSP walk of chunk k+1 runs as a background grid on its own stream under the raster of chunk k
+    auto chunk_count = [&](size_t k) { const size_t f = k * chunk; return (per - f) < chunk ? (per - f) : chunk; };
+    int64_t ticket = -1;
+    if (do_render) {
+        int wrc = b2d::walk_frames(r, c->d_poses, (int)chunk_count(0), c->walk_stream, &ticket, true);
+        if (wrc != B2D_OK) { cudaEventDestroy(poses_up); return wrc; }
+    }
 
     // events: per buffer "rendered", "gathered", "consumed"; timing pairs per chunk
     cudaEvent_t rendered[2], gathered[2], consumed[2], t_begin, t_end;
@@ -411,8 +424,12 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
         if (k >= 2) B2D_CU(cudaStreamWaitEvent(c->render_stream, consumed[b], 0));     // chunk k-2 has left this buffer
         B2D_CU(cudaEventRecord(rt[2 * k], c->render_stream));
         if (do_render) {
-            result = b2d::enqueue_frames(r, c->d_poses + first, (int)cnt, slice, nullptr, c->render_stream);
+            result = b2d::raster_frames(r, ticket, slice, nullptr, c->render_stream);
             if (result != B2D_OK) break;
+            if (k + 1 < nchunks) {
+                result = b2d::walk_frames(r, c->d_poses + (k + 1) * chunk, (int)chunk_count(k + 1), c->walk_stream, &ticket, true);
+                if (result != B2D_OK) break;
+            }
         }
         B2D_CU(cudaEventRecord(rt[2 * k + 1], c->render_stream));
         B2D_CU(cudaEventRecord(rendered[b], c->render_stream));
@@ -462,6 +479,7 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
         std::strncpy(st.registration, c->registration, sizeof st.registration - 1);
         *stats_out = st;
     }
+    cudaEventDestroy(poses_up);
     for (int i = 0; i < 2; i++) { cudaEventDestroy(rendered[i]); cudaEventDestroy(gathered[i]); cudaEventDestroy(consumed[i]); }
     cudaEventDestroy(t_begin); cudaEventDestroy(t_end);
     for (auto e : rt) cudaEventDestroy(e);
