@@ -22,6 +22,26 @@ namespace b2d {
 namespace {
 
 constexpr unsigned kFull = 0xFFFFFFFFu;
+
+// texel / table loads of the raster: read-only path; B2D_LOAD_EL (A/B, profiles/README.md) asks L1 to keep them
+__device__ __forceinline__ uint32_t tex_ld(const uint8_t *p) {
+#if defined(B2D_LOAD_EL)
+    uint32_t v;
+    asm("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+__device__ __forceinline__ uint32_t tex_ld(const uint32_t *p) {
+#if defined(B2D_LOAD_EL)
+    uint32_t v;
+    asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
 constexpr int kMaskWords = 128;      // up to 4096 columns
 constexpr int kStackDepth = 128;
 
@@ -335,7 +355,13 @@ struct RasterCtx {
 template <bool kRgba>
 __device__ __forceinline__ void put_px(const RasterCtx &c, uint8_t *p8, uint32_t *p32, bool on, uint32_t v) {
     if (on) {
+#if defined(B2D_STORE_CS)
+        __stcs(p8, (uint8_t)v);       // A/B (profiles/README.md): streaming store, keeps frame bytes from displacing texels
+#elif defined(B2D_STORE_WT)
+        __stwt(p8, (uint8_t)v);
+#else
         *p8 = (uint8_t)v;
+#endif
         if (kRgba) *p32 = lds_u32(c.pal_s + 4u * v);
     }
 }
@@ -395,7 +421,7 @@ __device__ __forceinline__ void draw_sky_warp(const RasterCtx &c, int ya, int yb
 #pragma unroll 2
     for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc) {
         const uint32_t r = sc.skyrow[y];                                   // warp-uniform table entry
-        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + (inter ? (r >> 2) * w4 + (r & 3u) : r * T.w)));
+        put_px<kRgba>(c, p8, p32, y >= ya && y < yb, tex_ld(px + (inter ? (r >> 2) * w4 + (r & 3u) : r * T.w)));
     }
 }
 
@@ -437,7 +463,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
 #pragma unroll
             for (int k = 0; k < kBatch; k++) {
                 const uint2 rz = c.rowz[j + k];                               // shared-memory broadcast: one 64-bit word per row
-                v[k] = __ldg(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay));   // always in bounds
+                v[k] = tex_ld(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay));   // always in bounds
             }
             const int y = yc + j;
             store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
@@ -445,7 +471,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         for (; j < rows; j++, p8 += Wc, p32 += Wc) {
             const uint2 rz = c.rowz[j];
             const int y = yc + j;
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay)));
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, tex_ld(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay)));
         }
         __syncwarp();
     }
@@ -464,8 +490,8 @@ __device__ __forceinline__ void wall_fast_loop(const RasterCtx &c, const uint8_t
 #pragma unroll 1
     for (int y = y0; y < y1; y += R, p8 += (size_t)R * Wc, p32 += (size_t)R * Wc) {
         const uint32_t q1 = q + 1u == nq ? 0u : q + 1u;
-        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q * w4));
-        const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(plq + (size_t)q1 * w4));
+        const uint32_t w0 = tex_ld(reinterpret_cast<const uint32_t *>(plq + (size_t)q * w4));
+        const uint32_t w1 = tex_ld(reinterpret_cast<const uint32_t *>(plq + (size_t)q1 * w4));
         if (y >= full_lo && y + R <= full_hi) {
 #pragma unroll
             for (int k = 0; k < R; k++) {
@@ -535,8 +561,8 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
             uint32_t v[kBatch];
             if (__all_sync(kFull, b7 < 8u)) {
                 const uint32_t q0 = r0 >> 2, q1 = next_quad(q0, T.h);
-                const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
-                const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q1 * w4 + colb)));
+                const uint32_t w0 = tex_ld(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
+                const uint32_t w1 = tex_ld(reinterpret_cast<const uint32_t *>(pl + (q1 * w4 + colb)));
 #pragma unroll
                 for (int k = 0; k < kBatch; k++) {
                     v[k] = pick_byte(w0, w1, (acc + (uint32_t)k * tstep) >> 16);
@@ -550,10 +576,10 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
                 const uint32_t acc4 = wall_acc(t4, r4);
                 if (__all_sync(kFull, ((acc + 3u * tstep) >> 16) < 8u && ((acc4 + 3u * tstep) >> 16) < 8u)) {
                     const uint32_t q0 = r0 >> 2, q4 = r4 >> 2;
-                    const uint32_t a0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
-                    const uint32_t a1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (next_quad(q0, T.h) * w4 + colb)));
-                    const uint32_t b0 = __ldg(reinterpret_cast<const uint32_t *>(pl + (q4 * w4 + colb)));
-                    const uint32_t b1 = __ldg(reinterpret_cast<const uint32_t *>(pl + (next_quad(q4, T.h) * w4 + colb)));
+                    const uint32_t a0 = tex_ld(reinterpret_cast<const uint32_t *>(pl + (q0 * w4 + colb)));
+                    const uint32_t a1 = tex_ld(reinterpret_cast<const uint32_t *>(pl + (next_quad(q0, T.h) * w4 + colb)));
+                    const uint32_t b0 = tex_ld(reinterpret_cast<const uint32_t *>(pl + (q4 * w4 + colb)));
+                    const uint32_t b1 = tex_ld(reinterpret_cast<const uint32_t *>(pl + (next_quad(q4, T.h) * w4 + colb)));
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         v[k] = pick_byte(a0, a1, (acc + (uint32_t)k * tstep) >> 16);
@@ -564,7 +590,7 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
 #pragma unroll
                     for (int k = 0; k < kBatch; k++) {
                         const uint32_t rk = wall_row((int32_t)(t + (uint32_t)k * tstep), T.h, T.hmagic, T.hbias);
-                        v[k] = __ldg(pl + ((rk >> 2) * w4 + colb + (rk & 3u)));
+                        v[k] = tex_ld(pl + ((rk >> 2) * w4 + colb + (rk & 3u)));
                     }
                 }
             }
@@ -576,7 +602,7 @@ __device__ __forceinline__ void draw_wall_warp(const RasterCtx &c, const FrameCo
         const uint8_t *px = pl + col;
 #pragma unroll 1
         for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += tstep)
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, __ldg(px + wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w));
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, tex_ld(px + wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w));
     }
 }
 
@@ -691,12 +717,12 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
                 uint32_t v[kBatch], o[kBatch];
                 if (__all_sync(kFull, ((acc + 7u * tstep) >> 16) < 8u)) {
                     const uint32_t o0 = (r0 >> 2) * w4 + colb, o1 = next_quad(r0 >> 2, T.h) * w4 + colb;
-                    const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(pl + o0));
-                    const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t *>(pl + o1));
+                    const uint32_t w0 = tex_ld(reinterpret_cast<const uint32_t *>(pl + o0));
+                    const uint32_t w1 = tex_ld(reinterpret_cast<const uint32_t *>(pl + o1));
                     uint32_t m0 = 0x01010101u, m1 = 0x01010101u;
                     if (has_mask) {
-                        m0 = __ldg(reinterpret_cast<const uint32_t *>(pm + o0));
-                        m1 = __ldg(reinterpret_cast<const uint32_t *>(pm + o1));
+                        m0 = tex_ld(reinterpret_cast<const uint32_t *>(pm + o0));
+                        m1 = tex_ld(reinterpret_cast<const uint32_t *>(pm + o1));
                     }
 #pragma unroll
                     for (int k = 0; k < kBatch; k++) {
@@ -709,8 +735,8 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
                     for (int k = 0; k < kBatch; k++) {
                         const uint32_t rk = wall_row((int32_t)(t + (uint32_t)k * tstep), T.h, T.hmagic, T.hbias);
                         const uint32_t off = (rk >> 2) * w4 + colb + (rk & 3u);
-                        v[k] = __ldg(pl + off);
-                        o[k] = has_mask ? (uint32_t)__ldg(pm + off) : 1u;
+                        v[k] = tex_ld(pl + off);
+                        o[k] = has_mask ? (uint32_t)tex_ld(pm + off) : 1u;
                     }
                 }
 #pragma unroll
@@ -721,8 +747,8 @@ __device__ __noinline__ void masked_pass(const DeviceScene &sc, const View &vw, 
 #pragma unroll 1
             for (int y = y0; y < y1; y++, p8 += Wc, p32 += Wc, t += tstep) {
                 const uint32_t off = wall_row((int32_t)t, T.h, T.hmagic, T.hbias) * T.w + col;
-                const bool on = (uint32_t)(y - ya) < len && (!has_mask || __ldg(pm + off) != 0);
-                put_px<kRgba>(c, p8, p32, on, __ldg(pl + off));
+                const bool on = (uint32_t)(y - ya) < len && (!has_mask || tex_ld(pm + off) != 0);
+                put_px<kRgba>(c, p8, p32, on, tex_ld(pl + off));
             }
         }
     }
