@@ -133,3 +133,34 @@ def test_compiled_cli_sharded_world1(tmp_path):
                          env=dict(os.environ))
     assert res.returncode == 0, res.stdout + res.stderr
     assert "rank 0/1: 10 frames gathered in 3 chunk(s)" in res.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["nccl", "ce"])
+def test_compiled_cli_sharded_two_ranks(tmp_path, transport):
+    """Two processes, two GPUs (skipped on a one-GPU box): the ranks gather each other's frames -- over ncclAllGather and
+    over the copy-engine transport -- and both end with the checksum a single rank computes for the whole pose list."""
+    import os
+    import re
+    import subprocess
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rust_doom_b200 import build, synthwad
+    wad = tmp_path / "t.wad"
+    wad.write_bytes(synthwad.build_iwad(1, ("E1M1",)))
+    exe = build.build_cli()
+    env = dict(os.environ)
+    if transport == "ce":
+        env["B2D_GATHER"] = "ce"
+    base = [exe, "--iwad", str(wad), "--resolution", "640x400", "--poses", "22", "--chunk", "4"]
+    one = subprocess.run(base + ["--world", "1", "--rank", "0", "--id-file", str(tmp_path / "id1")], capture_output=True, text=True, timeout=300)
+    assert one.returncode == 0, one.stdout + one.stderr
+    want = re.search(r"checksum ([0-9a-f]{8})", one.stdout).group(1)
+    procs = [subprocess.Popen(base + ["--world", "2", "--rank", str(r), "--id-file", str(tmp_path / "id2")], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True, env=env) for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    # 22 poses on 2 ranks = 11 per rank; the single-rank run gathers the same 22 frames in the same order
+    got = [re.search(r"checksum ([0-9a-f]{8})", o).group(1) for o in outs]
+    assert got == [want, want], (got, want, outs)
