@@ -17,6 +17,7 @@ for w in "$@"; do
     c4) run c4 $TR bench.py --gpus $N --config c4 --steps 3 --warmup 3 ;;
     c2) run c2 $TR bench.py --gpus $N --steps 30 --warmup 3 ;;
     ref) run ref $TR bench.py --gpus $N --impl reference --steps 5 --warmup 2 ;;
+    test2) timeout 900 python -m pytest tests/test_cli.py -m gpu -q -k "two_ranks or world1" > gpurun_out/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_${TAG}.log ;;
     cli)
       python - <<'PY'
 from rust_doom_b200 import synthwad
