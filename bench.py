@@ -89,6 +89,14 @@ def bench_config(desc, n, world, scene_info, extra=None):
     return c
 
 
+def build_provenance():
+    """Which build of which sources this run measured (rust-doom_b200/libb2d.build.json, written by build())."""
+    from rust_doom_b200 import _lib, build
+    info = build.build_info()
+    info["library"] = os.path.relpath(_lib.LIB_PATH, ROOT)
+    return info
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -602,7 +610,7 @@ def main():
                      "the raster's duration WITH that walk co-resident" if pipelined
                      else "BSP walk then raster of one batch, one stream (b2d_render_device)"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "allgather": allgather}))
+            "cpu_baseline": cpu_baseline, "allgather": allgather, "build": build_provenance()}))
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -17,11 +17,45 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xptxas", "-v" if os.environ.get("B2D_PTXAS_V") else "-warn-spills", "-ldl"]
 
 
+INFO = os.path.join(HERE, "libb2d.build.json")
+
+
+def source_digest() -> str:
+    """sha256 over the library's sources and headers (what a build is a function of, besides the compiler)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(set(SOURCES + HEADERS + ["b2d_thing_table.inc", "b2d_anim_table.inc"])):
+        p = os.path.join(CSRC, f)
+        if os.path.exists(p):
+            h.update(f.encode())
+            with open(p, "rb") as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def build_info() -> dict:
+    """What produced the in-tree libb2d.so (written next to it by build()); bench.py puts it on its JSON line together with
+    whether the sources still match, so a run shows which build of which sources it measured."""
+    import json
+    try:
+        with open(INFO) as f:
+            info = json.load(f)
+    except Exception:  # noqa: BLE001
+        info = {"recorded": False}
+    info["sources_now"] = source_digest()
+    info["sources_match"] = info.get("sources") == info["sources_now"]
+    return info
+
+
 def needs_build() -> bool:
     if not os.path.exists(OUT) or not os.path.exists(os.path.join(HERE, "b2d")):
         return True
     t = os.path.getmtime(OUT)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    if any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS):
+        return True
+    # mtimes do not survive every copy (a snapshot to another box): the recorded source digest decides
+    info = build_info()
+    return bool(info.get("recorded")) and not info["sources_match"]
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -33,6 +67,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(" ".join(cmd))
     subprocess.check_call(cmd)
     build_cli(verbose)
+    import json
+    import socket
+    import time
+    try:
+        ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()[-2:]
+    except Exception:  # noqa: BLE001
+        ver = []
+    with open(INFO, "w") as f:
+        json.dump({"recorded": True, "sources": source_digest(), "nvcc": " | ".join(ver), "flags": " ".join(NVCC_FLAGS),
+                   "host": socket.gethostname(), "when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime())}, f, indent=1)
     return OUT
 
 
