@@ -13,8 +13,96 @@
 
 static_assert(sizeof(b2d_pose) == sizeof(Pose) && sizeof(b2d_view) == sizeof(View), "ABI structs");
 
+#include <cuda.h>
+
 namespace {
 thread_local std::string g_error;
+
+// ---- 4 GiB aligned device memory (driver VMM API, resolved through the runtime: no link-time dependency on libcuda) ----
+struct Vmm {
+    CUresult (*GetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*AddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+    bool ok = false;
+};
+const Vmm &vmm() {
+    static Vmm v;
+    static bool init = false;
+    if (!init) {
+        init = true;
+        auto get = [](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            return cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && *fn;
+        };
+        v.ok = get("cuMemGetAllocationGranularity", (void **)&v.GetGranularity) && get("cuMemAddressReserve", (void **)&v.AddressReserve) &&
+               get("cuMemCreate", (void **)&v.Create) && get("cuMemMap", (void **)&v.Map) && get("cuMemSetAccess", (void **)&v.SetAccess) &&
+               get("cuMemUnmap", (void **)&v.Unmap) && get("cuMemRelease", (void **)&v.Release) && get("cuMemAddressFree", (void **)&v.AddressFree);
+        cudaGetLastError();
+    }
+    return v;
+}
+constexpr size_t k4G = (size_t)1 << 32;
+
+// device memory of `bytes` bytes at an address that is a multiple of 4 GiB
+bool alloc_aligned_4g(b2d_renderer *r, size_t bytes) {
+    const Vmm &v = vmm();
+    if (v.ok && !getenv("B2D_NO_VMM")) {
+        CUmemAllocationProp prop;
+        std::memset(&prop, 0, sizeof prop);
+        prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        prop.location.id = r->device;
+        size_t gran = 0;
+        if (v.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM) == CUDA_SUCCESS && gran) {
+            const size_t size = (bytes + gran - 1) / gran * gran;
+            CUdeviceptr ptr = 0;
+            CUmemGenericAllocationHandle h = 0;
+            if (v.AddressReserve(&ptr, size, k4G, 0, 0) == CUDA_SUCCESS) {
+                if ((ptr & (k4G - 1)) == 0 && v.Create(&h, size, &prop, 0) == CUDA_SUCCESS) {
+                    CUmemAccessDesc acc;
+                    std::memset(&acc, 0, sizeof acc);
+                    acc.location = prop.location;
+                    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+                    if (v.Map(ptr, size, 0, h, 0) == CUDA_SUCCESS) {
+                        if (v.SetAccess(ptr, size, &acc, 1) == CUDA_SUCCESS) {
+                            r->d_lit_flats = reinterpret_cast<uint8_t *>(ptr);
+                            r->lit_flats_bytes = size;
+                            r->lit_flats_handle = (unsigned long long)h;
+                            return true;
+                        }
+                        v.Unmap(ptr, size);
+                    }
+                    v.Release(h);
+                }
+                v.AddressFree(ptr, size);
+            }
+        }
+    }
+    // fall-back: a plain allocation 4 GiB larger than needed always contains an aligned address
+    void *raw = nullptr;
+    if (cudaMalloc(&raw, bytes + k4G) != cudaSuccess) { cudaGetLastError(); return false; }
+    r->d_lit_flats_raw = static_cast<uint8_t *>(raw);
+    r->d_lit_flats = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(raw) + k4G - 1) & ~(uintptr_t)(k4G - 1));
+    r->lit_flats_bytes = 0;
+    return true;
+}
+
+void free_aligned_4g(b2d_renderer *r) {
+    if (r->lit_flats_bytes) {
+        const Vmm &v = vmm();
+        v.Unmap(reinterpret_cast<CUdeviceptr>(r->d_lit_flats), r->lit_flats_bytes);
+        v.Release((CUmemGenericAllocationHandle)r->lit_flats_handle);
+        v.AddressFree(reinterpret_cast<CUdeviceptr>(r->d_lit_flats), r->lit_flats_bytes);
+    } else if (r->d_lit_flats_raw) {
+        cudaFree(r->d_lit_flats_raw);
+    }
+    r->d_lit_flats = nullptr; r->d_lit_flats_raw = nullptr; r->lit_flats_bytes = 0;
+}
 }
 
 namespace b2d {
@@ -81,6 +169,7 @@ void free_renderer(b2d_renderer *r) {
         if (r->timed_copied[i]) cudaEventDestroy(r->timed_copied[i]);
     }
     if (r->d_lit) cudaFree(r->d_lit);
+    free_aligned_4g(r);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
 }
@@ -518,11 +607,12 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     {   // pre-lit texel and flat planes: 32 x (texel bytes + flat bytes)
         const size_t tstride = (h[H_TEXEL_BYTES] + 255u) & ~(size_t)255, fstride = (size_t)h[H_NFLATS] * 4096u;
         if (tstride * 33 > 0xFFFFFFFFull || fstride * 32 > 0xFFFFFFFFull) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level textures too large"); }
-        CUR(cudaMalloc(&r->d_lit, 33 * tstride + 32 * fstride + 256));    // plane 32 of the texels: opacity
+        CUR(cudaMalloc(&r->d_lit, 33 * tstride + 256));                    // plane 32 of the texels: opacity
+        if (!alloc_aligned_4g(r, 32 * fstride + 256)) { free_renderer(r); return fail(B2D_ERR_NO_MEMORY, "no 4 GiB aligned device memory for the pre-lit flats"); }
         CUR(launch_prelight_textures(d.colormap, d.texels, d.tex, (int)h[H_NTEX], r->d_lit, tstride, nullptr));
-        CUR(launch_prelight(d.colormap, d.flats, r->d_lit + 33 * tstride, fstride, fstride, nullptr));
+        CUR(launch_prelight(d.colormap, d.flats, r->d_lit_flats, fstride, fstride, nullptr));
         CUR(cudaDeviceSynchronize());
-        d.lit_texels = r->d_lit; d.lit_flats = r->d_lit + 33 * tstride;
+        d.lit_texels = r->d_lit; d.lit_flats = r->d_lit_flats;           // low 32 address bits of lit_flats are zero
         d.lit_texel_stride = (uint32_t)tstride; d.lit_flat_stride = (uint32_t)fstride;
     }
     d.yslope = r->d_yslope;

@@ -32,7 +32,14 @@ struct b2d_renderer {
     uint16_t *d_skyrow = nullptr;
     int32_t *d_status = nullptr;
     uint32_t *d_masked = nullptr;
-    uint8_t *d_lit = nullptr;       // colormap-applied copies of the texels and flats (32 light rows each)
+    uint8_t *d_lit = nullptr;       // colormap-applied copies of the texels (32 light rows + the opacity plane)
+    // ... and of the flats, in a region whose address is a multiple of 4 GiB: the raster then forms a flat texel's address
+    // as {high word, 32-bit offset} without a 64-bit add (one instruction per flat pixel).  Reserved + mapped through the
+    // driver's virtual-memory API (cuMemAddressReserve takes an alignment); an over-sized cudaMalloc is the fall-back.
+    uint8_t *d_lit_flats = nullptr;
+    size_t lit_flats_bytes = 0;     // mapped size (VMM) or 0
+    unsigned long long lit_flats_handle = 0;
+    uint8_t *d_lit_flats_raw = nullptr;   // fall-back allocation the aligned pointer lies in
     DeviceScene ds{};
     Pose *d_poses = nullptr;
     // two worklist slots: the BSP walk of batch k+1 may run (b2d_walk_device, another stream) while batch k is rastered

@@ -434,7 +434,9 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
     if (!visible) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
     if (flat == kFlatSky) { draw_sky_warp<kRgba, kW>(c, ya, yb); return; }
     if (flat < 0 || flat >= sc.nflats) { fill_void_warp<kRgba, kW>(c, ya, yb); return; }
-    const uint8_t *px = sc.lit_flats;                   // + per-row plane offset + flat offset (row1) + texel
+    // the pre-lit flats start at a multiple of 4 GiB (b2d_api.cu alloc_aligned_4g): a texel's address is {high word,
+    // 32-bit offset} -- no 64-bit add per pixel
+    const uint64_t px_hi = reinterpret_cast<uint64_t>(sc.lit_flats) & 0xFFFFFFFF00000000ull;   // low word is zero: tell the compiler
     const uint32_t habs = plane_habs(h, fc.pose.z);
     bool act = ya < yb;
     int y0 = __reduce_min_sync(kFull, act ? ya : 0x7FFFFFFF);
@@ -463,7 +465,7 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
 #pragma unroll
             for (int k = 0; k < kBatch; k++) {
                 const uint2 rz = c.rowz[j + k];                               // shared-memory broadcast: one 64-bit word per row
-                v[k] = tex_ld(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay));   // always in bounds
+                v[k] = tex_ld(reinterpret_cast<const uint8_t *>(px_hi | flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay)));   // always in bounds
             }
             const int y = yc + j;
             store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
@@ -471,7 +473,8 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         for (; j < rows; j++, p8 += Wc, p32 += Wc) {
             const uint2 rz = c.rowz[j];
             const int y = yc + j;
-            put_px<kRgba>(c, p8, p32, y >= ya && y < yb, tex_ld(px + flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay)));
+            put_px<kRgba>(c, p8, p32, y >= ya && y < yb,
+                          tex_ld(reinterpret_cast<const uint8_t *>(px_hi | flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay))));
         }
         __syncwarp();
     }

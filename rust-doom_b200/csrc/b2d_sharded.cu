@@ -433,7 +433,6 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
         }
         B2D_CU(cudaEventRecord(rt[2 * k + 1], c->render_stream));
         B2D_CU(cudaEventRecord(rendered[b], c->render_stream));
-        cudaStream_t after = c->render_stream;
         if (do_gather) {
             B2D_CU(cudaStreamWaitEvent(c->gather_stream, rendered[b], 0));
             B2D_CU(cudaEventRecord(gt[2 * k], c->gather_stream));
@@ -446,13 +445,11 @@ int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size
             }
             B2D_CU(cudaEventRecord(gt[2 * k + 1], c->gather_stream));
             B2D_CU(cudaEventRecord(gathered[b], c->gather_stream));
-            after = c->gather_stream;
         }
         // consumer of the chunk (gathered: world x cnt frames, rank-major; render only: this rank's cnt frames)
         B2D_CU(cudaStreamWaitEvent(c->consume_stream, do_gather ? gathered[b] : rendered[b], 0));
         if (fn) fn(user, (int)k, first, cnt, do_gather ? c->buf[b] : slice, do_gather ? c->world : 1, c->consume_stream);
         B2D_CU(cudaEventRecord(consumed[b], c->consume_stream));
-        (void)after;
     }
     // the end of the job on this rank: everything on the three streams
     B2D_CU(cudaStreamWaitEvent(c->consume_stream, rendered[(nchunks - 1) & 1], 0));
