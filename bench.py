@@ -323,6 +323,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     cfg = args.config
+    # stdout carries the one JSON line: NCCL's version banner / debug output (NCCL_DEBUG may be set by the box) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

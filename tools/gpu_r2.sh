@@ -11,7 +11,7 @@ for T in $TUNES; do
   echo "tune $T rc=$?"; python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_${TAG}_t$T.json")); r=d["roofline"]
+    d=json.loads([l for l in open("gpurun_out/bench_${TAG}_t$T.json") if l.startswith("{")][-1]); r=d["roofline"]
     print("tune $T: %.0f fps  raster %.4f ms walk %.4f ms  frac %.4f" % (d["value"], r["avg_launch_ms"], r["walk_avg_launch_ms"], r["frac"]))
 except Exception as e: print("tune $T: no result", e)
 PY

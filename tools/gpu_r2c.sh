@@ -6,7 +6,7 @@ tail -3 gpurun_out/pytest_$TAG.log
 run() { name=$1; shift; timeout 600 "$@" > gpurun_out/bench_${TAG}_$name.json 2> gpurun_out/bench_${TAG}_$name.err; echo "$name rc=$?"; python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_${TAG}_$name.json")); r=d.get("roofline") or {}
+    d=json.loads([l for l in open("gpurun_out/bench_${TAG}_$name.json") if l.startswith("{")][-1]); r=d.get("roofline") or {}
     print("$name: %.0f fps  ms/step %.4f raster %s walk %s frac %s" % (d["value"], d["ms_per_step"], r.get("avg_launch_ms"), r.get("walk_avg_launch_ms"), r.get("frac")))
 except Exception as e: print("$name: no result", e)
 PY

@@ -10,7 +10,7 @@ timeout 900 python tools/campaign_gpu.py 300 > gpurun_out/campaign_$TAG.log 2>&1
 run() { name=$1; shift; timeout 900 "$@" > gpurun_out/bench_${TAG}_$name.json 2> gpurun_out/bench_${TAG}_$name.err; echo "$name rc=$?"; python - <<PY
 import json
 try:
-    d=json.load(open("gpurun_out/bench_${TAG}_$name.json")); r=d.get("roofline") or {}; e=d.get("e2e") or {}; c=d.get("cpu_baseline") or {}
+    d=json.loads([l for l in open("gpurun_out/bench_${TAG}_$name.json") if l.startswith("{")][-1]); r=d.get("roofline") or {}; e=d.get("e2e") or {}; c=d.get("cpu_baseline") or {}
     print("$name: %.0f fps  ms/step %.4f raster %s walk %s frac %s e2e %s cpu %s/%s" % (d["value"], d["ms_per_step"], r.get("avg_launch_ms"), r.get("walk_avg_launch_ms"), r.get("frac"), e.get("value"), c.get("value"), c.get("cores")))
 except Exception as e: print("$name: no result", e)
 PY
