@@ -69,6 +69,7 @@ typedef struct b2d_scene_info {
     int32_t has_start;                       /* player-1 start found */
     b2d_pose start;                          /* spawn camera pose (eye = floor + 62) */
     int32_t min_height, max_height;          /* level height range +-512 (visitor.rs:1173-1182) */
+    int32_t n_dynamic;                       /* sectors declared dynamic at creation */
 } b2d_scene_info;
 
 const char *b2d_last_error(void);
@@ -127,6 +128,34 @@ typedef struct b2d_textures {
 } b2d_textures;
 int b2d_scene_create_from_lumps(const b2d_level_lumps *level, const b2d_textures *tex, b2d_scene **out);
 
+/* Moving sectors (doors, lifts, crushers) as a per-batch input.  The reference finds the sectors that may move and their
+ * height ranges when it loads a level (`LevelAnalysis`, wad/src/visitor.rs:316-497; ranges: `DynamicSectorInfo`,
+ * :159-245), attaches every wall quad, flat and decoration to the floor or ceiling object of a sector (:733-836, :957-983,
+ * :1106-1121) and moves those objects from its trigger logic (game/src/level.rs:201-245).  The analysis and the triggers
+ * are gameplay and stay on the host; what the renderer takes is their result: the list of dynamic sectors with their
+ * ranges at scene creation (pieces that can come into existence while a sector moves are resolved then -- the reference
+ * pre-extends its quads over these ranges), and one state per batch: the offset of each moved floor and ceiling from the
+ * height in the level lumps, in map units.  A range is widened to contain the sector's own heights (visitor.rs:232-245).
+ * Every surface then moves rigidly with the object the reference attaches it to. */
+typedef struct b2d_dynamic_sector {
+    int32_t sector;
+    int32_t floor_min, floor_max, ceil_min, ceil_max;
+} b2d_dynamic_sector;
+typedef struct b2d_sector_move {
+    int32_t sector;
+    int32_t floor_offset, ceil_offset;
+} b2d_sector_move;
+int b2d_scene_create_dynamic(const b2d_archive *a, int level_index, const b2d_dynamic_sector *dynamic, size_t n_dynamic,
+                             b2d_scene **out);
+int b2d_scene_create_from_lumps_dynamic(const b2d_level_lumps *level, const b2d_textures *tex,
+                                        const b2d_dynamic_sector *dynamic, size_t n_dynamic, b2d_scene **out);
+/* The state-dependent tables of a scene at level time `tics` with the given sectors moved, laid out
+ * [textures | sectors | segs | sprites | mids] as in the blob (host only, no device needed: what the renderer uploads
+ * before a batch).  out = NULL: only *size_out is set.  A move of an undeclared sector or outside its range (or with the
+ * floor above the ceiling) is B2D_ERR_INVALID_ARG. */
+int b2d_scene_tables_at(const b2d_scene *s, uint32_t tics, const b2d_sector_move *moves, size_t n_moves, void *out,
+                        size_t capacity, size_t *size_out);
+
 int b2d_scene_info_get(const b2d_scene *s, b2d_scene_info *out);
 /* Read-only access to the compiled "B2DS" blob (layout in DESIGN.md); valid until destroy. */
 const void *b2d_scene_blob(const b2d_scene *s, size_t *size_out);
@@ -156,6 +185,11 @@ void b2d_renderer_destroy(b2d_renderer *r);
  * a per-frame System::update loop).  b2d_renderer_set_time additionally waits until the upload has completed. */
 int b2d_renderer_set_time_async(b2d_renderer *r, uint32_t tics, void *cuda_stream);
 int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics);
+/* The state of the moving sectors for the batches enqueued after this call (sectors not listed are at rest; n = 0 puts
+ * everything back).  Stream-ordered like b2d_renderer_set_time_async: the re-derived tables are uploaded behind every
+ * batch already enqueued, the host does not wait.  The plain variant returns when the tables are in place. */
+int b2d_renderer_set_sector_moves_async(b2d_renderer *r, const b2d_sector_move *moves, size_t n, void *cuda_stream);
+int b2d_renderer_set_sector_moves(b2d_renderer *r, const b2d_sector_move *moves, size_t n);
 
 /* Sticky completeness status of everything rendered since the last call (device-resident entry points do not
  * synchronise, so they cannot report it themselves): synchronises the device, returns the OR of

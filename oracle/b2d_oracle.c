@@ -62,7 +62,7 @@ typedef struct {
 
 static int scene_bind(Scene *s, const uint8_t *blob) {
     const uint32_t *h = (const uint32_t *)blob;
-    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 5) return -1;
+    if (h[H_MAGIC] != 0x53443242u || h[H_VERSION] != 6) return -1;
     s->hdr = h;
     s->verts = (const int32_t *)(blob + h[H_OFF_VERTS]);
     s->nodes = (const int32_t *)(blob + h[H_OFF_NODES]);

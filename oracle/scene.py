@@ -11,7 +11,7 @@ reference's one-and-only geometry emitter `LevelWalker` and its visitor in `game
                                               game/src/player.rs:72-92 (camera_height)
 * sky texture per level                       wad/src/meta.rs:156-172, assets/meta/doom.toml:29-68
 
-The blob layout ("B2DS" v5) is the contract shared with the product's scene compiler
+The blob layout ("B2DS" v6) is the contract shared with the product's scene compiler
 (rust-doom_b200/csrc/b2d_scene.cpp, written independently); tests compare the two byte-for-byte.
 All fields are little-endian int32 unless noted.
 
@@ -20,7 +20,7 @@ verts   : {x, y}                                                   8 B
 nodes   : {x, y, dx, dy, rbox[4], lbox[4], rchild, lchild, 0, 0}   64 B  (box = top,bottom,left,right;
           child bit31 = subsector)
 ssectors: {first_seg, num_segs, sector, sprites}                   16 B  (sprites = first | count<<24)
-sprites : {x, y, low, tex, light, sector, 0, 0}                       32 B  decoration things grouped by subsector:
+sprites : {x, y, low, tex, light, sector, hanging, 0}                 32 B  decoration things grouped by subsector:
           billboard of the sprite image's size standing on the floor / hanging from the ceiling
           (visitor.rs:1062-1137), lit by the sector light without contrast
 segs    : {v1, v2, front, flags, uoff, len_q12, texA, tA, hA, texB, tB, hB, light, otop, obot, mid}   64 B
@@ -40,6 +40,17 @@ texels  : u8 row-major, textures back to back (transparent texels stored as 0); 
 flats   : n x 4096 u8
 colormap: 34 x 256 u8 (zero padded if the WAD has fewer)
 palette : 256 x u32  R | G<<8 | B<<16 | 0xFF<<24  from PLAYPAL[0]
+segdyn  : {back, bits} per seg                                     8 B   what apply_moves needs beyond the seg record:
+          back sector (-1 one-sided), bits 1 = lower-unpegged line, 2 = the back ceiling is sky
+dyn     : {sector, floor_min, floor_max, ceil_min, ceil_max, 0, 0, 0}  32 B  the sectors that may move and the height
+          ranges the host's LevelAnalysis found for them (visitor.rs:146-245)
+
+Moving sectors (doors, lifts).  The reference attaches every wall quad, flat and decoration to the floor or
+ceiling *object* of a sector and translates it rigidly with that object's height offset (visitor.rs:733-836 object_id;
+game/src/level.rs:201-245); quads next to a dynamic sector are pre-extended over the sector's height range so that
+nothing opens up while it moves.  Here the same rule is applied to the per-seg pieces: `compile_scene(dynamic=...)`
+resolves, for segs that touch a declared sector, the pieces that can come into existence while it moves, and
+`apply_moves` re-derives the height-dependent records for one state (a floor and a ceiling offset per declared sector).
 """
 from __future__ import annotations
 
@@ -53,13 +64,16 @@ import numpy as np
 from . import wad as W
 
 MAGIC = 0x53443242
-VERSION = 5
+VERSION = 6
 HEADER_WORDS = 64
 (H_MAGIC, H_VERSION, H_TOTAL, H_NVERTS, H_NNODES, H_NSSECTORS, H_NSEGS, H_NSECTORS, H_NTEX, H_NFLATS,
  H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
  H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
  H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES, H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM,
- H_OFF_LIGHTS) = range(38)
+ H_OFF_LIGHTS, H_NDYN, H_OFF_DYN, H_OFF_SEGDYN) = range(41)
+
+SEGDYN_UNPEG_LOWER = 1
+SEGDYN_BACK_SKY = 2
 
 SEG_TWO_SIDED = 1
 SEG_SCROLL = 2            # linedef special 0x30: texture scrolls 35 units/s along s (visitor.rs:922)
@@ -227,10 +241,27 @@ def sector_lights_at(blob: bytes, tics: int) -> np.ndarray:
     return out
 
 
-def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int) -> bytes:
+def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int, dynamic=()) -> bytes:
+    """`dynamic`: (sector, floor_min, floor_max, ceil_min, ceil_max) per sector that may move (the ranges are widened to
+    contain the sector's own heights, like visitor.rs:232-245 merge_range)."""
     level = W.Level(archive, level_index)
     nverts, nsegs = len(level.vertices), len(level.segs)
     nsect, nss, nnodes = len(level.sectors), len(level.subsectors), len(level.nodes)
+    dyn: Dict[int, Tuple[int, int, int, int]] = {}
+    for d in dynamic:
+        sec, fmin, fmax, cmin, cmax = (int(v) for v in d)
+        if not 0 <= sec < nsect or sec in dyn:
+            raise W.WadError("dynamic sector %d: out of range or listed twice" % sec)
+        f0, c0 = int(level.sectors[sec]["floor"]), int(level.sectors[sec]["ceil"])
+        dyn[sec] = (min(fmin, fmax, f0), max(fmin, fmax, f0), min(cmin, cmax, c0), max(cmin, cmax, c0))
+
+    def floor_range(sec: int) -> Tuple[int, int]:
+        f0 = int(level.sectors[sec]["floor"])
+        return dyn[sec][0:2] if sec in dyn else (f0, f0)
+
+    def ceil_range(sec: int) -> Tuple[int, int]:
+        c0 = int(level.sectors[sec]["ceil"])
+        return dyn[sec][2:4] if sec in dyn else (c0, c0)
 
     # --- texture / flat id assignment in first-use order -------------------------------------
     tex_ids: Dict[bytes, int] = {}
@@ -343,6 +374,8 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
 
     # --- segs ------------------------------------------------------------------------------------
     segs = np.zeros((nsegs, 16), dtype=np.int32)
+    segdyn = np.zeros((nsegs, 2), dtype=np.int32)
+    segdyn[:, 0] = -1
     mids: List[List[int]] = []
     side_bytes = level.sidedefs.tobytes()
 
@@ -414,16 +447,21 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
             rec[3] = scroll
             rec[6], rec[7], rec[8] = tid, t, fc
             rec[13], rec[14] = fc, ff
+            segdyn[i] = [-1, SEGDYN_UNPEG_LOWER if unpeg_lower else 0]
         else:
             bsec = level.sectors[back]
             bf, bc = int(bsec["floor"]), int(bsec["ceil"])
             back_sky = W.is_sky_flat(raw_name(level.sectors, back, "ceil_tex"))
             rec[3] = SEG_TWO_SIDED | scroll
+            # next to a sector that may move, the pieces that can come into existence are resolved too (the reference
+            # pre-extends the lower quad over the floor ranges, visitor.rs:772-790; the upper one we extend likewise)
+            segdyn[i] = [back, (SEGDYN_UNPEG_LOWER if unpeg_lower else 0) | (SEGDYN_BACK_SKY if back_sky else 0)]
             # upper: exists iff back_ceil < ceil and the back ceiling is not sky (visitor.rs:791-807);
             # Peg::Top if upper-unpegged else Peg::Bottom (t at `high`=ceil: 0 / texh - (ceil-back_ceil)).
             otop = fc
-            if bc < fc and not back_sky:
-                otop = bc
+            if ceil_range(back)[0] < ceil_range(front)[1] and not back_sky:     # = bc < fc for sectors that never move
+                if bc < fc:
+                    otop = bc
                 if unpeg_upper:
                     tid, t = piece(side_name(side, 0), lambda th: 0)
                 else:
@@ -433,18 +471,20 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
             # lower: exists iff back_floor > floor (visitor.rs:772-790); Peg::BottomLower if
             # lower-unpegged (t at `high`=back_floor: texh - (back_floor-floor) + (ceil-floor)) else Top.
             obot = ff
-            if bf > ff:
-                obot = bf
-                if unpeg_lower:
-                    tid, t = piece(side_name(side, 1), lambda th: th - (bf - ff) + (fc - ff))
+            bf_hi, ff_lo = floor_range(back)[1], floor_range(front)[0]
+            if bf_hi > ff_lo:                                 # = bf > ff for sectors that never move
+                if bf > ff:
+                    obot = bf
+                if unpeg_lower:                               # quad height = back_range.1 - front_range.0 (:777-780, :913-917)
+                    tid, t = piece(side_name(side, 1), lambda th: th - (bf_hi - ff_lo) + (fc - ff))
                 else:
                     tid, t = piece(side_name(side, 1), lambda th: 0)
                 rec[9], rec[10] = tid, t
-            rec[11] = obot
+            rec[11] = bf if bf_hi > ff_lo else obot           # anchor of tB: the back floor (moves with it)
             rec[13], rec[14] = otop, obot
             # masked middle (visitor.rs:808-836): between max(floors) and min(ceilings); float pegs clamp the
             # quad to the texture height (visitor.rs:875-885); t at `high`: Top/Floats 0, Bottom texh-height
-            low0, high0 = obot, (bc if bc < fc else fc)
+            low0, high0 = (bf if bf_hi > ff_lo else ff), (bc if bc < fc else fc)
             mname = side_name(side, 2)
             mtid = tex_id(mname) if low0 < high0 else TEX_NONE
             rec[15] = -1
@@ -489,7 +529,7 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
         th = int(tex_list[tid].shape[0])
         sct = level.sectors[sec]
         low = int(sct["ceil"]) - th if hanging else int(sct["floor"])
-        sprite_rows.append((ssid, ti, [int(t["x"]), int(t["y"]), low, tid, sector_light0[sec], sec, 0, 0]))
+        sprite_rows.append((ssid, ti, [int(t["x"]), int(t["y"]), low, tid, sector_light0[sec], sec, 1 if hanging else 0, 0]))
     sprite_rows.sort(key=lambda r: (r[0], r[1]))
     sprites = np.array([r[2] for r in sprite_rows], dtype=np.int64).reshape(-1, 8)
     k = 0
@@ -647,7 +687,8 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
              ("anim", np.array(anim_frames, dtype="<i4").tobytes()),
              ("flatanim", flat_anim_rec.astype("<i4").tobytes()), ("lights", lights.tobytes()),
              ("texels", bytes(texels)), ("flats", b"".join(flat_list)), ("colormap", bytes(colormap)),
-             ("palette", palette.tobytes())]
+             ("palette", palette.tobytes()), ("segdyn", segdyn.astype("<i4").tobytes()),
+             ("dyn", np.array([[sec] + list(dyn[sec]) + [0, 0, 0] for sec in sorted(dyn)], dtype="<i4").reshape(-1, 8).tobytes())]
     off = 4 * HEADER_WORDS
     offs = {}
     for name, data in parts:
@@ -674,11 +715,79 @@ def compile_scene(archive: W.Archive, tex: W.TextureDirectory, level_index: int)
     hdr[H_NSPRITES], hdr[H_OFF_SPRITES] = len(sprite_rows), offs["sprites"]
     hdr[H_NANIM], hdr[H_OFF_ANIM], hdr[H_OFF_FLAT_ANIM] = len(anim_frames), offs["anim"], offs["flatanim"]
     hdr[H_OFF_LIGHTS] = offs["lights"]
+    hdr[H_NDYN], hdr[H_OFF_DYN], hdr[H_OFF_SEGDYN] = len(dyn), offs["dyn"], offs["segdyn"]
     blob = bytearray(total)
     blob[0:4 * HEADER_WORDS] = struct.pack("<%dI" % HEADER_WORDS, *hdr)
     for name, data in parts:
         blob[offs[name]:offs[name] + len(data)] = data
     return bytes(blob)
+
+
+def apply_moves(blob: bytes, moves) -> bytes:
+    """The scene with some of its declared sectors moved: `moves` = (sector, floor_offset, ceil_offset) in map units
+    relative to the heights in the level lumps.  Every record that depends on a height is re-derived the way the
+    reference moves its meshes -- rigidly with the floor / ceiling object they are attached to:
+
+    * sector floor / ceiling (flats, sky)               own floor / ceiling object   visitor.rs:957-983
+    * one-sided wall                                    own floor if the line is lower-unpegged, else own ceiling  :736-740
+    * upper piece                                       back ceiling                 :797
+    * lower piece                                       back floor                   :777
+    * masked middle texture                             own floor if lower-unpegged, else own ceiling   :812-816
+    * decoration                                        floor of its sector, ceiling if it hangs   :1106-1121
+    and the opening of a two-sided seg follows the moved heights (what the depth test leaves visible of the
+    pre-extended quads)."""
+    h = header(blob)
+    out = bytearray(blob)
+    nsect = h[H_NSECTORS]
+    dyn = section(blob, "dyn")
+    ranges = {int(r[0]): [int(v) for v in r[1:5]] for r in dyn}
+    df, dc = np.zeros(nsect, dtype=np.int64), np.zeros(nsect, dtype=np.int64)
+    sectors = section(blob, "sectors").astype(np.int64)
+    for sec, dfl, dcl in moves:
+        sec = int(sec)
+        if sec not in ranges:
+            raise ValueError("sector %d was not declared dynamic" % sec)
+        f1, c1 = int(sectors[sec, 0]) + int(dfl), int(sectors[sec, 1]) + int(dcl)
+        r = ranges[sec]
+        if not (r[0] <= f1 <= r[1] and r[2] <= c1 <= r[3] and f1 <= c1):
+            raise ValueError("sector %d moved outside its declared range" % sec)
+        df[sec], dc[sec] = int(dfl), int(dcl)
+    sectors[:, 0] += df
+    sectors[:, 1] += dc
+    segs = section(blob, "segs").astype(np.int64)
+    segdyn = section(blob, "segdyn")
+    mids = section(blob, "mids").astype(np.int64)
+    for i in range(len(segs)):
+        S = segs[i]
+        if S[3] & SEG_INVALID:
+            continue
+        f, b, bits = int(S[2]), int(segdyn[i, 0]), int(segdyn[i, 1])
+        own = df[f] if bits & SEGDYN_UNPEG_LOWER else dc[f]
+        if not (S[3] & SEG_TWO_SIDED):
+            S[8] += own
+            S[13], S[14] = sectors[f, 1], sectors[f, 0]
+            continue
+        S[8] += dc[b]
+        S[11] += df[b]
+        ff, fc, bf, bc = sectors[f, 0], sectors[f, 1], sectors[b, 0], sectors[b, 1]
+        S[13] = bc if (bc < fc and not bits & SEGDYN_BACK_SKY) else fc
+        S[14] = bf if bf > ff else ff
+        if S[15] >= 0:
+            mids[S[15], 2] += own
+            mids[S[15], 3] += own
+    sprites = section(blob, "sprites").astype(np.int64)
+    for i in range(len(sprites)):
+        sec = int(sprites[i, 5])
+        sprites[i, 2] += dc[sec] if sprites[i, 6] else df[sec]
+
+    def put(off, a):
+        data = a.astype("<i4").tobytes()
+        out[off:off + len(data)] = data
+    put(h[H_OFF_SECTORS], sectors)
+    put(h[H_OFF_SEGS], segs)
+    put(h[H_OFF_MIDS], mids)
+    put(h[H_OFF_SPRITES], sprites)
+    return bytes(out)
 
 
 def header(blob: bytes) -> List[int]:
@@ -706,4 +815,8 @@ def section(blob: bytes, which: str) -> np.ndarray:
         return arr(h[H_OFF_MIDS], h[H_NMIDS], 8)
     if which == "sprites":
         return arr(h[H_OFF_SPRITES], h[H_NSPRITES], 8)
+    if which == "segdyn":
+        return arr(h[H_OFF_SEGDYN], h[H_NSEGS], 2)
+    if which == "dyn":
+        return arr(h[H_OFF_DYN], h[H_NDYN], 8)
     raise KeyError(which)

@@ -112,11 +112,29 @@ class Archive:
             pass
 
 
+def _dynamic_array(dynamic):
+    d = list(dynamic)
+    arr = (_lib.DynamicSector * max(len(d), 1))()
+    for i, (sec, fmin, fmax, cmin, cmax) in enumerate(d):
+        arr[i] = _lib.DynamicSector(int(sec), int(fmin), int(fmax), int(cmin), int(cmax))
+    return arr, len(d)
+
+
+def _moves_array(moves):
+    m = list(moves)
+    arr = (_lib.SectorMove * max(len(m), 1))()
+    for i, (sec, dfl, dcl) in enumerate(m):
+        arr[i] = _lib.SectorMove(int(sec), int(dfl), int(dcl))
+    return arr, len(m)
+
+
 class Scene:
-    def __init__(self, archive: Optional[Archive], level_index: int = 0, _handle=None):
+    def __init__(self, archive: Optional[Archive], level_index: int = 0, _handle=None, dynamic=()):
+        """`dynamic`: (sector, floor_min, floor_max, ceil_min, ceil_max) per sector that may move (b2d_scene_create_dynamic)"""
         h = _handle if _handle is not None else ctypes.c_void_p()
         if _handle is None:
-            _check(_lib.load().b2d_scene_create(archive._h, level_index, ctypes.byref(h)))
+            arr, n = _dynamic_array(dynamic)
+            _check(_lib.load().b2d_scene_create_dynamic(archive._h, level_index, arr, n, ctypes.byref(h)))
         self._h = h
         info = _lib.SceneInfo()
         _check(_lib.load().b2d_scene_info_get(self._h, ctypes.byref(info)))
@@ -125,7 +143,7 @@ class Scene:
     LUMP_ORDER = ("things", "linedefs", "sidedefs", "vertexes", "segs", "ssectors", "nodes", "sectors")
 
     @classmethod
-    def from_lumps(cls, name: bytes, lumps, textures, flats, colormaps, palette: bytes) -> "Scene":
+    def from_lumps(cls, name: bytes, lumps, textures, flats, colormaps, palette: bytes, dynamic=()) -> "Scene":
         """b2d_scene_create_from_lumps: the scene from buffers a host that has already parsed the WAD owns
         (game::WadSystem's pub fields).  lumps: dict of the eight raw level lumps (bytes); textures: iterable of
         (name, uint16 array [h, w], hi byte != 0 = transparent); flats: iterable of (name, 4096 bytes); colormaps:
@@ -156,9 +174,20 @@ class Scene:
         t = _lib.Textures(imgs, len(tex), fds, len(fl), ctypes.addressof(cmb) if cmb is not None else None, len(cm) // 256,
                           ctypes.addressof(pal))
         h = ctypes.c_void_p()
-        _check(_lib.load().b2d_scene_create_from_lumps(ctypes.byref(ll), ctypes.byref(t), ctypes.byref(h)))
+        arr, n = _dynamic_array(dynamic)
+        _check(_lib.load().b2d_scene_create_from_lumps_dynamic(ctypes.byref(ll), ctypes.byref(t), arr, n, ctypes.byref(h)))
         del keep
         return cls(None, 0, _handle=h)
+
+    def tables_at(self, tics: int = 0, moves=()) -> bytes:
+        """b2d_scene_tables_at: the state-dependent tables [textures | sectors | segs | sprites | mids] at level time `tics`
+        with `moves` = (sector, floor_offset, ceil_offset) applied (host only)."""
+        arr, n = _moves_array(moves)
+        size = ctypes.c_size_t()
+        _check(_lib.load().b2d_scene_tables_at(self._h, tics, arr, n, None, 0, ctypes.byref(size)))
+        buf = ctypes.create_string_buffer(max(size.value, 1))
+        _check(_lib.load().b2d_scene_tables_at(self._h, tics, arr, n, buf, size.value, ctypes.byref(size)))
+        return buf.raw[:size.value]
 
     @property
     def blob(self) -> bytes:
@@ -275,6 +304,16 @@ class Renderer:
     def set_time_async(self, tics: int, stream: int = 0):
         """Same, without blocking the host: the table upload is ordered on `stream` (a cudaStream_t as int)."""
         _check(_lib.load().b2d_renderer_set_time_async(self._h, int(tics) & 0xFFFFFFFF, ctypes.c_void_p(stream)))
+
+    def set_sector_moves(self, moves=(), stream: Optional[int] = None):
+        """State of the moving sectors for the batches rendered afterwards: (sector, floor_offset, ceil_offset) in map
+        units relative to the level lumps; sectors not listed are at rest.  With `stream` (a cudaStream_t as int) the
+        host does not wait for the table upload (b2d_renderer_set_sector_moves_async)."""
+        arr, n = _moves_array(moves)
+        if stream is None:
+            _check(_lib.load().b2d_renderer_set_sector_moves(self._h, arr, n))
+        else:
+            _check(_lib.load().b2d_renderer_set_sector_moves_async(self._h, arr, n, ctypes.c_void_p(stream)))
 
     def status(self) -> int:
         """Sticky completeness bits of everything rendered since the last call (0 = every frame complete); synchronises

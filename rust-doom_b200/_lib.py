@@ -22,12 +22,23 @@ class SceneInfo(ctypes.Structure):
                 ("n_segs", ctypes.c_int32), ("n_sectors", ctypes.c_int32), ("n_textures", ctypes.c_int32),
                 ("n_flats", ctypes.c_int32), ("n_masked_mids", ctypes.c_int32), ("n_sprites", ctypes.c_int32),
                 ("blob_bytes", ctypes.c_int32), ("has_start", ctypes.c_int32),
-                ("start", Pose), ("min_height", ctypes.c_int32), ("max_height", ctypes.c_int32)]
+                ("start", Pose), ("min_height", ctypes.c_int32), ("max_height", ctypes.c_int32),
+                ("n_dynamic", ctypes.c_int32)]
+
+
+class DynamicSector(ctypes.Structure):
+    _fields_ = [("sector", ctypes.c_int32), ("floor_min", ctypes.c_int32), ("floor_max", ctypes.c_int32),
+                ("ceil_min", ctypes.c_int32), ("ceil_max", ctypes.c_int32)]
+
+
+class SectorMove(ctypes.Structure):
+    _fields_ = [("sector", ctypes.c_int32), ("floor_offset", ctypes.c_int32), ("ceil_offset", ctypes.c_int32)]
 
 
 EXPORTS = [
     "b2d_last_error", "b2d_archive_open", "b2d_archive_open_memory", "b2d_archive_open_files", "b2d_archive_open_memory_files", "b2d_archive_num_levels",
-    "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_create_from_lumps", "b2d_scene_info_get",
+    "b2d_archive_level_name", "b2d_archive_close", "b2d_wad_name", "b2d_scene_create", "b2d_scene_create_from_lumps", "b2d_scene_create_dynamic",
+    "b2d_scene_create_from_lumps_dynamic", "b2d_scene_tables_at", "b2d_renderer_set_sector_moves", "b2d_renderer_set_sector_moves_async", "b2d_scene_info_get",
     "b2d_scene_blob", "b2d_scene_sector_at", "b2d_scene_destroy", "b2d_view_init", "b2d_renderer_create",
     "b2d_renderer_destroy", "b2d_renderer_set_time", "b2d_renderer_set_time_async", "b2d_renderer_status", "b2d_render", "b2d_render_device",
     "b2d_render_timed", "b2d_render_device_timed", "b2d_walk_device",
@@ -103,6 +114,12 @@ def load() -> ctypes.CDLL:
     L.b2d_wad_name.argtypes = [vp, cs, ctypes.c_char_p]
     L.b2d_scene_create.argtypes = [vp, ci, ctypes.POINTER(vp)]
     L.b2d_scene_create_from_lumps.argtypes = [ctypes.POINTER(LevelLumps), ctypes.POINTER(Textures), ctypes.POINTER(vp)]
+    L.b2d_scene_create_dynamic.argtypes = [vp, ci, ctypes.POINTER(DynamicSector), cs, ctypes.POINTER(vp)]
+    L.b2d_scene_create_from_lumps_dynamic.argtypes = [ctypes.POINTER(LevelLumps), ctypes.POINTER(Textures), ctypes.POINTER(DynamicSector), cs,
+                                                      ctypes.POINTER(vp)]
+    L.b2d_scene_tables_at.argtypes = [vp, ctypes.c_uint32, ctypes.POINTER(SectorMove), cs, vp, cs, ctypes.POINTER(cs)]
+    L.b2d_renderer_set_sector_moves.argtypes = [vp, ctypes.POINTER(SectorMove), cs]
+    L.b2d_renderer_set_sector_moves_async.argtypes = [vp, ctypes.POINTER(SectorMove), cs, vp]
     L.b2d_scene_info_get.argtypes = [vp, ctypes.POINTER(SceneInfo)]
     L.b2d_scene_blob.argtypes = [vp, ctypes.POINTER(cs)]
     L.b2d_scene_blob.restype = vp

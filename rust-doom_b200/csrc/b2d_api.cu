@@ -129,7 +129,7 @@ int guarded(Fn fn) {
     try {
         return fn();
     } catch (const WadError &e) {
-        return fail(e.code == kErrIo ? B2D_ERR_IO : B2D_ERR_CORRUPT_WAD, e.what());
+        return fail(e.code == kErrIo ? B2D_ERR_IO : e.code == kErrArg ? B2D_ERR_INVALID_ARG : B2D_ERR_CORRUPT_WAD, e.what());
     } catch (const std::bad_alloc &) {
         return fail(B2D_ERR_NO_MEMORY, "out of host memory");
     } catch (const std::exception &e) {
@@ -247,15 +247,26 @@ int raster_from_slot(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t
 // device blob in stream order.  Everything this renderer has enqueued so far -- on any stream -- is awaited by `stream`
 // first (the walk/raster events of both worklist slots), and later launches on other streams wait for the upload, so the
 // host never blocks on the device: no cudaDeviceSynchronize in the System::update loop this stands in for.
-// the time-dependent tables at `tics`, laid out [tex | sectors | segs | sprites] (timed_bytes)
-void tables_at(const b2d_renderer *r, uint32_t tics, uint8_t *out) {
-    const uint8_t *blob = r->h_blob.data();
+// the state-dependent tables (level time `tics`, sector offsets), laid out [tex | sectors | segs | sprites | mids]
+size_t state_table_bytes(const uint8_t *blob) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    return h[H_NTEX] * sizeof(TexRec) + h[H_NSECTORS] * sizeof(SectorRec) + h[H_NSEGS] * sizeof(SegRec) +
+           h[H_NSPRITES] * sizeof(SpriteRec) + h[H_NMIDS] * sizeof(MidRec);
+}
+
+void state_tables(const uint8_t *blob, uint32_t tics, const int32_t *floor_off, const int32_t *ceil_off, uint8_t *out) {
     const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
     TexRec *tex = reinterpret_cast<TexRec *>(out);
     SectorRec *sectors = reinterpret_cast<SectorRec *>(tex + h[H_NTEX]);
     SegRec *segs = reinterpret_cast<SegRec *>(sectors + h[H_NSECTORS]);
     SpriteRec *sprites = reinterpret_cast<SpriteRec *>(segs + h[H_NSEGS]);
-    scene_at_time(blob, tics, tex, sectors, segs, sprites);
+    MidRec *mids = reinterpret_cast<MidRec *>(sprites + h[H_NSPRITES]);
+    scene_at_time(blob, tics, tex, sectors, segs, sprites, mids, floor_off, ceil_off);
+}
+
+void tables_at(const b2d_renderer *r, uint32_t tics, uint8_t *out) {
+    const bool moved = !r->floor_off.empty();
+    state_tables(r->h_blob.data(), tics, moved ? r->floor_off.data() : nullptr, moved ? r->ceil_off.data() : nullptr, out);
 }
 
 int upload_tables(b2d_renderer *r, const uint8_t *tables, cudaStream_t stream) {
@@ -266,7 +277,7 @@ int upload_tables(b2d_renderer *r, const uint8_t *tables, cudaStream_t stream) {
     uint8_t *p = r->h_timed[buf];
     std::memcpy(p, tables, r->timed_bytes);
     const uint8_t *tex = p, *sectors = tex + h[H_NTEX] * sizeof(TexRec), *segs = sectors + h[H_NSECTORS] * sizeof(SectorRec),
-                  *sprites = segs + h[H_NSEGS] * sizeof(SegRec);
+                  *sprites = segs + h[H_NSEGS] * sizeof(SegRec), *mids = sprites + h[H_NSPRITES] * sizeof(SpriteRec);
     for (int i = 0; i < 2; i++) {
         if (r->walk_done[i]) CU(cudaStreamWaitEvent(stream, r->walk_done[i], 0));
         if (r->raster_done[i]) CU(cudaStreamWaitEvent(stream, r->raster_done[i], 0));
@@ -276,6 +287,8 @@ int upload_tables(b2d_renderer *r, const uint8_t *tables, cudaStream_t stream) {
     CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_SEGS], segs, h[H_NSEGS] * sizeof(SegRec), cudaMemcpyHostToDevice, stream));
     if (h[H_NSPRITES])
         CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_SPRITES], sprites, h[H_NSPRITES] * sizeof(SpriteRec), cudaMemcpyHostToDevice, stream));
+    if (h[H_NMIDS] && h[H_NDYN])        // masked middle textures only move with their sector
+        CU(cudaMemcpyAsync(r->d_blob + h[H_OFF_MIDS], mids, h[H_NMIDS] * sizeof(MidRec), cudaMemcpyHostToDevice, stream));
     CU(cudaEventRecord(r->timed_copied[buf], stream));
     CU(cudaEventRecord(r->tables_ready, stream));
     r->tables_pending = true;
@@ -432,24 +445,63 @@ void fill_scene_info(b2d_scene *s) {
     i.start.z = (int32_t)h[H_START_Z] * 65536;
     i.start.angle = (uint32_t)(((uint64_t)h[H_START_ANGLE] << 32) / 360u);
     i.min_height = (int32_t)h[H_MIN_H]; i.max_height = (int32_t)h[H_MAX_H];
+    i.n_dynamic = (int32_t)h[H_NDYN];
 }
 }  // namespace
 
-int b2d_scene_create(const b2d_archive *a, int level_index, b2d_scene **out) {
-    if (!a || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+namespace {
+std::vector<DynRec> dyn_list(const b2d_dynamic_sector *dyn, size_t n) {
+    std::vector<DynRec> v(n);
+    for (size_t i = 0; i < n; i++) {
+        v[i] = DynRec{};
+        v[i].sector = dyn[i].sector;
+        v[i].floor_min = dyn[i].floor_min; v[i].floor_max = dyn[i].floor_max;
+        v[i].ceil_min = dyn[i].ceil_min; v[i].ceil_max = dyn[i].ceil_max;
+    }
+    return v;
+}
+}  // namespace
+
+int b2d_scene_create_dynamic(const b2d_archive *a, int level_index, const b2d_dynamic_sector *dyn, size_t n_dyn, b2d_scene **out) {
+    if (!a || !out || (n_dyn && !dyn)) return fail(B2D_ERR_INVALID_ARG, "null argument");
     return guarded([&] {
         auto s = std::make_unique<b2d_scene>();
         TextureDirectory td = TextureDirectory::load(*a->wad);
         s->level = Level::load(*a->wad, level_index);
-        s->blob = compile_scene(s->level, td);
+        s->blob = compile_scene(s->level, td, dyn_list(dyn, n_dyn));
         fill_scene_info(s.get());
         *out = s.release();
         return B2D_OK;
     });
 }
 
+int b2d_scene_create(const b2d_archive *a, int level_index, b2d_scene **out) {
+    return b2d_scene_create_dynamic(a, level_index, nullptr, 0, out);
+}
+
 int b2d_scene_create_from_lumps(const b2d_level_lumps *lv, const b2d_textures *tex, b2d_scene **out) {
-    if (!lv || !tex || !out) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    return b2d_scene_create_from_lumps_dynamic(lv, tex, nullptr, 0, out);
+}
+
+int b2d_scene_tables_at(const b2d_scene *s, uint32_t tics, const b2d_sector_move *moves, size_t n_moves, void *out,
+                        size_t capacity, size_t *size_out) {
+    if (!s || (n_moves && !moves)) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    const size_t need = state_table_bytes(s->blob.data());
+    if (size_out) *size_out = need;
+    if (!out) return B2D_OK;
+    if (capacity < need) return fail(B2D_ERR_INVALID_ARG, "buffer too small for the tables");
+    std::vector<int32_t> fo, co;
+    if (n_moves) {
+        if (const char *why = expand_moves(s->blob.data(), reinterpret_cast<const SectorMove *>(moves), n_moves, fo, co))
+            return fail(B2D_ERR_INVALID_ARG, why);
+    }
+    state_tables(s->blob.data(), tics, n_moves ? fo.data() : nullptr, n_moves ? co.data() : nullptr, static_cast<uint8_t *>(out));
+    return B2D_OK;
+}
+
+int b2d_scene_create_from_lumps_dynamic(const b2d_level_lumps *lv, const b2d_textures *tex, const b2d_dynamic_sector *dyn,
+                                        size_t n_dyn, b2d_scene **out) {
+    if (!lv || !tex || !out || (n_dyn && !dyn)) return fail(B2D_ERR_INVALID_ARG, "null argument");
     if ((tex->n_textures && !tex->textures) || (tex->n_flats && !tex->flats) || (tex->n_colormaps && !tex->colormaps))
         return fail(B2D_ERR_INVALID_ARG, "null texture table");
     return guarded([&] {
@@ -483,7 +535,7 @@ int b2d_scene_create_from_lumps(const b2d_level_lumps *lv, const b2d_textures *t
             td.palettes.resize(1);
             std::memcpy(td.palettes[0].data(), tex->palette, 768);
         }
-        s->blob = compile_scene(s->level, td);
+        s->blob = compile_scene(s->level, td, dyn_list(dyn, n_dyn));
         fill_scene_info(s.get());
         *out = s.release();
         return B2D_OK;
@@ -633,8 +685,7 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     if (walk_smem_per_warp(d) > 227 * 1024) { free_renderer(r); return fail(B2D_ERR_INVALID_ARG, "level too large for the BSP-walk kernel's shared memory"); }
     if (scene_is_timed(s->blob.data())) {
         r->h_blob = s->blob;
-        r->timed_bytes = h[H_NTEX] * sizeof(TexRec) + h[H_NSECTORS] * sizeof(SectorRec) + h[H_NSEGS] * sizeof(SegRec) +
-                         h[H_NSPRITES] * sizeof(SpriteRec);
+        r->timed_bytes = state_table_bytes(r->h_blob.data());
         for (int i = 0; i < 2; i++) {
             CUR(cudaMallocHost(&r->h_timed[i], r->timed_bytes ? r->timed_bytes : 1));
             CUR(cudaEventCreateWithFlags(&r->timed_copied[i], cudaEventDisableTiming));
@@ -664,6 +715,36 @@ int b2d_renderer_set_time_async(b2d_renderer *r, uint32_t tics, void *cuda_strea
     int rc = upload_timed_tables(r, tics, static_cast<cudaStream_t>(cuda_stream));
     if (rc == B2D_OK) r->tics = tics;
     return rc;
+}
+
+int b2d_renderer_set_sector_moves_async(b2d_renderer *r, const b2d_sector_move *moves, size_t n, void *cuda_stream) {
+    if (!r || (n && !moves)) return fail(B2D_ERR_INVALID_ARG, "null argument");
+    if (r->h_blob.empty()) {
+        if (n == 0) return B2D_OK;
+        return fail(B2D_ERR_INVALID_ARG, "the scene declares no dynamic sectors");
+    }
+    static_assert(sizeof(b2d_sector_move) == sizeof(SectorMove), "ABI record");
+    std::vector<int32_t> fo, co;
+    if (const char *why = expand_moves(r->h_blob.data(), reinterpret_cast<const SectorMove *>(moves), n, fo, co))
+        return fail(B2D_ERR_INVALID_ARG, why);
+    bool any = false;
+    for (size_t i = 0; i < fo.size(); i++) any |= fo[i] != 0 || co[i] != 0;
+    if (!any) { fo.clear(); co.clear(); }
+    if (fo == r->floor_off && co == r->ceil_off) return B2D_OK;
+    r->floor_off.swap(fo);
+    r->ceil_off.swap(co);
+    CU(cudaSetDevice(r->device));
+    return upload_timed_tables(r, r->tics, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int b2d_renderer_set_sector_moves(b2d_renderer *r, const b2d_sector_move *moves, size_t n) {
+    int rc = b2d_renderer_set_sector_moves_async(r, moves, n, nullptr);
+    if (rc != B2D_OK) return rc;
+    if (r->tables_pending) {
+        CU(cudaEventSynchronize(r->tables_ready));
+        r->tables_pending = false;
+    }
+    return B2D_OK;
 }
 
 int b2d_renderer_set_time(b2d_renderer *r, uint32_t tics) {

@@ -67,6 +67,7 @@ struct b2d_renderer {
     bool tables_pending = false;
     int timed_next = 0;
     size_t timed_bytes = 0;
+    std::vector<int32_t> floor_off, ceil_off;             // state of the moving sectors (one offset per sector; empty = at rest)
     std::vector<uint8_t> cur_tables, scratch_tables;      // host copies: tables of the last upload / of a candidate time
     cudaEvent_t masked_done = nullptr;                    // last raster that used the masked-entry arena
     uint32_t *d_masked_counter = nullptr;

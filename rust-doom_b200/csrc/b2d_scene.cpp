@@ -138,13 +138,38 @@ int sector_at(const Level &lv, double x, double y, int *subsector_out) {
     return sector;
 }
 
-std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &td, int level_index) {
-    return compile_scene(Level::load(wad, level_index), td);
+std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &td, int level_index,
+                                   const std::vector<DynRec> &dynamic) {
+    return compile_scene(Level::load(wad, level_index), td, dynamic);
 }
 
-std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) {
+std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td, const std::vector<DynRec> &dynamic) {
     const int nverts = (int)lv.vertices.size(), nsegs = (int)lv.segs.size();
     const int nsect = (int)lv.sectors.size(), nss = (int)lv.subsectors.size(), nnodes = (int)lv.nodes.size();
+
+    // sectors that may move and their height ranges, widened to contain the heights in the lumps (visitor.rs:232-245)
+    std::vector<DynRec> dyn;
+    std::vector<int> dyn_of((size_t)nsect, -1);
+    for (const DynRec &d : dynamic) {
+        if (d.sector < 0 || d.sector >= nsect || dyn_of[(size_t)d.sector] >= 0)
+            throw WadError(kErrArg, "dynamic sector out of range or listed twice");
+        const Sector &sc = lv.sectors[(size_t)d.sector];
+        DynRec n{};
+        n.sector = d.sector;
+        n.floor_min = std::min({d.floor_min, d.floor_max, (int32_t)sc.floor});
+        n.floor_max = std::max({d.floor_min, d.floor_max, (int32_t)sc.floor});
+        n.ceil_min = std::min({d.ceil_min, d.ceil_max, (int32_t)sc.ceil});
+        n.ceil_max = std::max({d.ceil_min, d.ceil_max, (int32_t)sc.ceil});
+        dyn_of[(size_t)d.sector] = (int)dyn.size();
+        dyn.push_back(n);
+    }
+    std::sort(dyn.begin(), dyn.end(), [](const DynRec &a, const DynRec &b) { return a.sector < b.sector; });
+    for (size_t i = 0; i < dyn.size(); i++) dyn_of[(size_t)dyn[i].sector] = (int)i;
+    auto floor_lo = [&](int s) { return dyn_of[(size_t)s] >= 0 ? dyn[(size_t)dyn_of[(size_t)s]].floor_min : (int32_t)lv.sectors[(size_t)s].floor; };
+    auto floor_hi = [&](int s) { return dyn_of[(size_t)s] >= 0 ? dyn[(size_t)dyn_of[(size_t)s]].floor_max : (int32_t)lv.sectors[(size_t)s].floor; };
+    auto ceil_lo = [&](int s) { return dyn_of[(size_t)s] >= 0 ? dyn[(size_t)dyn_of[(size_t)s]].ceil_min : (int32_t)lv.sectors[(size_t)s].ceil; };
+    auto ceil_hi = [&](int s) { return dyn_of[(size_t)s] >= 0 ? dyn[(size_t)dyn_of[(size_t)s]].ceil_max : (int32_t)lv.sectors[(size_t)s].ceil; };
+    std::vector<SegDynRec> segdyn((size_t)nsegs, SegDynRec{-1, 0});
 
     // ids are handed out in first-use order: sky, then segs (A before B), flats by sector order
     std::unordered_map<Name, int, NameHash> tex_ids, flat_ids;
@@ -310,28 +335,35 @@ std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) 
             else piece(sd.middle, r.texA, r.tA, [&](int32_t) { return 0; });
             r.hA = fc;
             r.otop = fc; r.obot = ff;
+            segdyn[(size_t)i] = SegDynRec{-1, unpeg_lower ? kSegDynUnpegLower : 0};
         } else {
             const Sector &bs = lv.sectors[(size_t)back];
             const int32_t bf = bs.floor, bc = bs.ceil;
+            const bool back_sky = is_sky_flat(bs.ceil_tex);
             r.flags = kSegTwoSided | scroll;
+            segdyn[(size_t)i] = SegDynRec{back, (unpeg_lower ? kSegDynUnpegLower : 0) | (back_sky ? kSegDynBackSky : 0)};
             r.otop = fc;
-            if (bc < fc && !is_sky_flat(bs.ceil_tex)) {                          // visitor.rs:791-807
-                r.otop = bc;
+            // next to a sector that may move, a piece that can come into existence is resolved as well (the
+            // reference pre-extends the lower quad over the floor ranges, visitor.rs:772-790; the upper likewise here)
+            if (ceil_lo(back) < ceil_hi(front) && !back_sky) {                   // visitor.rs:791-807 (= bc < fc when static)
+                if (bc < fc) r.otop = bc;
                 if (unpeg_upper) piece(sd.upper, r.texA, r.tA, [&](int32_t) { return 0; });
                 else piece(sd.upper, r.texA, r.tA, [&](int32_t th) { return th - (fc - bc); });
             }
             r.hA = fc;
             r.obot = ff;
-            if (bf > ff) {                                                       // visitor.rs:772-790
-                r.obot = bf;
-                if (unpeg_lower)
-                    piece(sd.lower, r.texB, r.tB, [&](int32_t th) { return th - (bf - ff) + (fc - ff); });
+            const int32_t bf_hi = floor_hi(back), ff_lo = floor_lo(front);
+            const bool lower = bf_hi > ff_lo;                                    // visitor.rs:772 (= bf > ff when static)
+            if (lower) {
+                if (bf > ff) r.obot = bf;
+                if (unpeg_lower)             // quad height = back_range.1 - front_range.0 (visitor.rs:777-780, 913-917)
+                    piece(sd.lower, r.texB, r.tB, [&](int32_t th) { return th - (bf_hi - ff_lo) + (fc - ff); });
                 else piece(sd.lower, r.texB, r.tB, [&](int32_t) { return 0; });
             }
-            r.hB = r.obot;
+            r.hB = lower ? bf : r.obot;          // anchor of tB: the back floor (the piece moves with it)
             // masked middle (visitor.rs:808-836): spans max(floors)..min(ceilings); float pegs clamp the quad to
             // the texture height (visitor.rs:875-885); t at `high`: Top/Floats 0, Bottom texh-height (:909-919)
-            const int32_t low0 = r.obot, high0 = bc < fc ? bc : fc;
+            const int32_t low0 = lower ? bf : ff, high0 = bc < fc ? bc : fc;
             int32_t mtex = low0 < high0 ? tex_id(sd.middle) : kTexNone;
             if (mtex >= 0) {
                 const int32_t th = tex_list[(size_t)mtex]->h;
@@ -380,6 +412,7 @@ std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) 
         row.rec.tex = tid;
         row.rec.light = sectors[(size_t)sec].light;
         row.rec.sector = sec;
+        row.rec.hanging = meta->hanging ? 1 : 0;
         sprite_rows.push_back(row);
     }
     std::stable_sort(sprite_rows.begin(), sprite_rows.end(),
@@ -556,6 +589,9 @@ std::vector<uint8_t> compile_scene(const Level &lv, const TextureDirectory &td) 
     hdr[H_OFF_FLATS] = w.append(flats.data(), flats.size());
     hdr[H_OFF_COLORMAP] = w.append(colormap.data(), colormap.size());
     hdr[H_OFF_PALETTE] = w.append(palette.data(), palette.size() * 4);
+    hdr[H_OFF_SEGDYN] = w.append(segdyn.data(), segdyn.size() * sizeof(SegDynRec));
+    hdr[H_OFF_DYN] = w.append(dyn.data(), dyn.size() * sizeof(DynRec));
+    hdr[H_NDYN] = (uint32_t)dyn.size();
     hdr[H_TOTAL] = (uint32_t)w.bytes.size();
     hdr[H_ROOT] = nnodes > 0 ? (uint32_t)(nnodes - 1) : kLeaf;
     hdr[H_SKY_TEX] = (uint32_t)sky_tex;

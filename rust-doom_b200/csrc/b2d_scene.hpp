@@ -18,7 +18,7 @@
 namespace b2d {
 
 constexpr uint32_t kSceneMagic = 0x53443242u;   // "B2DS"
-constexpr uint32_t kSceneVersion = 5;
+constexpr uint32_t kSceneVersion = 6;
 constexpr uint32_t kLeaf = 0x80000000u;
 
 enum HeaderField : int {
@@ -26,7 +26,7 @@ enum HeaderField : int {
     H_OFF_VERTS, H_OFF_NODES, H_OFF_SSECTORS, H_OFF_SEGS, H_OFF_SECTORS, H_OFF_TEX, H_OFF_TEXELS,
     H_TEXEL_BYTES, H_OFF_FLATS, H_OFF_COLORMAP, H_OFF_PALETTE, H_ROOT, H_SKY_TEX, H_START_X, H_START_Y,
     H_START_Z, H_START_ANGLE, H_HAS_START, H_MIN_H, H_MAX_H, H_NMIDS, H_OFF_MIDS, H_NSPRITES, H_OFF_SPRITES,
-    H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM, H_OFF_LIGHTS, H_COUNT = 64
+    H_NANIM, H_OFF_ANIM, H_OFF_FLAT_ANIM, H_OFF_LIGHTS, H_NDYN, H_OFF_DYN, H_OFF_SEGDYN, H_COUNT = 64
 };
 
 // 64-byte records; all int32.
@@ -34,7 +34,7 @@ struct NodeRec { int32_t x, y, dx, dy, rbox[4], lbox[4]; uint32_t child[2]; int3
 struct SSectorRec { int32_t first_seg, num_segs, sector, sprites; };   // sprites = first | count << 24
 // decoration thing: billboard of its sprite image's size, centred on (x,y), bottom edge at `low`
 // (floor, or ceiling - height for hanging things; visitor.rs:1062-1137), lit by the sector light
-struct SpriteRec { int32_t x, y, low, tex, light, sector, pad[2]; };
+struct SpriteRec { int32_t x, y, low, tex, light, sector, hanging, pad; };
 struct SegRec {
     int32_t v1, v2, front, flags;
     int32_t uoff, len_q12;
@@ -52,6 +52,14 @@ struct FlatAnimRec { int32_t anim_first, anim_nk; };
 // sector light effect (wad/src/light.rs:5-25): kind 0 none, 1 glow, 2 random, 3 alternate
 struct LightRec { uint32_t kind; float level, alt, speed, duration, sync; uint32_t pad[2]; };
 constexpr uint32_t kLightNone = 0, kLightGlow = 1, kLightRandom = 2, kLightAlternate = 3;
+// what scene_at_state needs beyond the seg record: back sector (-1 = one-sided) and pegging / sky bits
+struct SegDynRec { int32_t back, bits; };
+constexpr int32_t kSegDynUnpegLower = 1, kSegDynBackSky = 2;
+// a sector that may move, with the height ranges the host's LevelAnalysis found (visitor.rs:146-245)
+struct DynRec { int32_t sector, floor_min, floor_max, ceil_min, ceil_max, pad[3]; };
+// one state of a moving sector: offsets in map units relative to the heights in the level lumps
+struct SectorMove { int32_t sector, floor_offset, ceil_offset; };
+static_assert(sizeof(SegDynRec) == 8 && sizeof(DynRec) == 32 && sizeof(SectorMove) == 12, "record layout");
 static_assert(sizeof(NodeRec) == 64 && sizeof(SegRec) == 64 && sizeof(SectorRec) == 32 &&
               sizeof(TexRec) == 32 && sizeof(SSectorRec) == 16 && sizeof(MidRec) == 32 &&
               sizeof(SpriteRec) == 32 && sizeof(LightRec) == 32, "record layout");
@@ -108,7 +116,7 @@ inline uint8_t light_byte_at(const LightRec &L, uint32_t tics) {
 
 inline bool scene_is_timed(const uint8_t *blob) {
     const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
-    if (h[H_NANIM] > 0) return true;
+    if (h[H_NANIM] > 0 || h[H_NDYN] > 0) return true;      // sectors that may move: their tables are state too
     const LightRec *lights = reinterpret_cast<const LightRec *>(blob + h[H_OFF_LIGHTS]);
     for (uint32_t i = 0; i < h[H_NSECTORS]; i++)
         if (lights[i].kind != kLightNone) return true;
@@ -118,8 +126,16 @@ inline bool scene_is_timed(const uint8_t *blob) {
     return false;
 }
 
+// `floor_off` / `ceil_off`: nullptr, or one offset per sector (map units) -- the state of the moving sectors.
+// The reference attaches every wall quad, flat and decoration to the floor or the ceiling object of a sector and
+// translates it rigidly with that object (visitor.rs:733-836 object_id, 957-983, 1106-1121; game/src/level.rs:201-245):
+// one-sided wall and masked middle texture -> own floor if the line is lower-unpegged, else own ceiling; upper piece ->
+// back ceiling; lower piece -> back floor; decoration -> floor, or ceiling if it hangs.  The anchors of the pre-resolved
+// pieces move accordingly and the opening of a two-sided seg follows the moved heights (what the depth test leaves
+// visible of the reference's pre-extended quads).  `mids_out` holds H_NMIDS records.
 inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, SectorRec *sectors_out, SegRec *segs_out,
-                          SpriteRec *sprites_out) {
+                          SpriteRec *sprites_out, MidRec *mids_out = nullptr, const int32_t *floor_off = nullptr,
+                          const int32_t *ceil_off = nullptr) {
     const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
     const TexRec *tex = reinterpret_cast<const TexRec *>(blob + h[H_OFF_TEX]);
     const SectorRec *sectors = reinterpret_cast<const SectorRec *>(blob + h[H_OFF_SECTORS]);
@@ -163,10 +179,73 @@ inline void scene_at_time(const uint8_t *blob, uint32_t tics, TexRec *tex_out, S
         const uint32_t f = (uint32_t)sprites[i].sector;
         if (f < nsect && lights[f].kind != kLightNone) sprites_out[i].light = sectors_out[f].light;
     }
+    const MidRec *mids = reinterpret_cast<const MidRec *>(blob + h[H_OFF_MIDS]);
+    if (mids_out)
+        for (uint32_t i = 0; i < h[H_NMIDS]; i++) mids_out[i] = mids[i];
+    if (!floor_off || !ceil_off) return;
+    // ---- moving sectors
+    const SegDynRec *segdyn = reinterpret_cast<const SegDynRec *>(blob + h[H_OFF_SEGDYN]);
+    for (uint32_t i = 0; i < nsect; i++) {
+        sectors_out[i].floor += floor_off[i];
+        sectors_out[i].ceil += ceil_off[i];
+    }
+    for (uint32_t i = 0; i < h[H_NSEGS]; i++) {
+        SegRec &S = segs_out[i];
+        if (S.flags & kSegInvalid) continue;
+        const uint32_t f = (uint32_t)S.front;
+        if (f >= nsect) continue;
+        const int32_t own = (segdyn[i].bits & kSegDynUnpegLower) ? floor_off[f] : ceil_off[f];
+        if (!(S.flags & kSegTwoSided)) {
+            S.hA += own;
+            S.otop = sectors_out[f].ceil;
+            S.obot = sectors_out[f].floor;
+            continue;
+        }
+        const uint32_t b = (uint32_t)segdyn[i].back;
+        if (b >= nsect) continue;
+        S.hA += ceil_off[b];
+        S.hB += floor_off[b];
+        const int32_t ff = sectors_out[f].floor, fc = sectors_out[f].ceil, bf = sectors_out[b].floor, bc = sectors_out[b].ceil;
+        S.otop = (bc < fc && !(segdyn[i].bits & kSegDynBackSky)) ? bc : fc;
+        S.obot = bf > ff ? bf : ff;
+        if (mids_out && S.mid >= 0 && (uint32_t)S.mid < h[H_NMIDS]) {
+            mids_out[S.mid].low += own;
+            mids_out[S.mid].high += own;
+        }
+    }
+    for (uint32_t i = 0; i < h[H_NSPRITES]; i++) {
+        const uint32_t f = (uint32_t)sprites_out[i].sector;
+        if (f < nsect) sprites_out[i].low += sprites_out[i].hanging ? ceil_off[f] : floor_off[f];
+    }
 }
 
-std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &tex, int level_index);
-std::vector<uint8_t> compile_scene(const Level &level, const TextureDirectory &tex);
+// Checks a list of sector moves against the scene's declared dynamic sectors and expands it to one floor and one ceiling
+// offset per sector.  Returns nullptr, or the reason the list is rejected.
+inline const char *expand_moves(const uint8_t *blob, const SectorMove *moves, size_t n, std::vector<int32_t> &floor_off,
+                                std::vector<int32_t> &ceil_off) {
+    const uint32_t *h = reinterpret_cast<const uint32_t *>(blob);
+    const SectorRec *sectors = reinterpret_cast<const SectorRec *>(blob + h[H_OFF_SECTORS]);
+    const DynRec *dyn = reinterpret_cast<const DynRec *>(blob + h[H_OFF_DYN]);
+    floor_off.assign(h[H_NSECTORS], 0);
+    ceil_off.assign(h[H_NSECTORS], 0);
+    for (size_t k = 0; k < n; k++) {
+        const DynRec *d = nullptr;
+        for (uint32_t i = 0; i < h[H_NDYN]; i++)
+            if (dyn[i].sector == moves[k].sector) { d = &dyn[i]; break; }
+        if (!d) return "a moved sector was not declared dynamic when the scene was created";
+        const int64_t f1 = (int64_t)sectors[d->sector].floor + moves[k].floor_offset;
+        const int64_t c1 = (int64_t)sectors[d->sector].ceil + moves[k].ceil_offset;
+        if (f1 < d->floor_min || f1 > d->floor_max || c1 < d->ceil_min || c1 > d->ceil_max || f1 > c1)
+            return "a sector is moved outside its declared height range";
+        floor_off[(size_t)d->sector] = moves[k].floor_offset;
+        ceil_off[(size_t)d->sector] = moves[k].ceil_offset;
+    }
+    return nullptr;
+}
+
+std::vector<uint8_t> compile_scene(const Archive &wad, const TextureDirectory &tex, int level_index,
+                                   const std::vector<DynRec> &dynamic = {});
+std::vector<uint8_t> compile_scene(const Level &level, const TextureDirectory &tex, const std::vector<DynRec> &dynamic = {});
 
 // LevelWalker::sector_at on the raw level (visitor.rs:1028-1060); -1 if outside.
 int sector_at(const Level &level, double x, double y, int *subsector_out = nullptr);

@@ -22,7 +22,7 @@ struct WadError : std::runtime_error {
     int code;
     WadError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
-constexpr int kErrCorrupt = -1, kErrIo = -2;
+constexpr int kErrCorrupt = -1, kErrIo = -2, kErrArg = -4;
 
 using Name = std::array<uint8_t, 8>;
 Name make_name(const uint8_t *bytes, size_t size);   // WadName::from_bytes; throws WadError

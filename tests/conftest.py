@@ -79,7 +79,7 @@ def hostcheck():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOSTCHECK_SO, HOSTCHECK_SRC])
     lib = ctypes.CDLL(HOSTCHECK_SO)
 
-    def run(blob: bytes, view, poses: np.ndarray, tics: int = 0):
+    def run(blob: bytes, view, poses: np.ndarray, tics: int = 0, moves=()):
         n = len(poses)
         nsegs = int(np.frombuffer(blob, dtype="<u4", count=32)[6])
         fb = np.empty((n, view.height, view.width), np.uint8)
@@ -87,10 +87,12 @@ def hostcheck():
         ids = np.full((n, max(nsegs, 1)), -1, np.int32)
         buf = (ctypes.c_char * len(blob)).from_buffer_copy(blob)
         poses = np.ascontiguousarray(poses)
-        lib.hostcheck_render_t(ctypes.c_void_p(ctypes.addressof(buf)), ctypes.byref(view),
-                               ctypes.c_void_p(poses.ctypes.data), n, ctypes.c_void_p(fb.ctypes.data),
-                               ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(ids.ctypes.data), ids.shape[1],
-                               ctypes.c_uint32(int(tics) & 0xFFFFFFFF))
+        mv = np.array([tuple(int(v) for v in m) for m in moves], dtype=np.int32).reshape(-1, 3)
+        rc = lib.hostcheck_render_m(ctypes.c_void_p(ctypes.addressof(buf)), ctypes.byref(view),
+                                    ctypes.c_void_p(poses.ctypes.data), n, ctypes.c_void_p(fb.ctypes.data),
+                                    ctypes.c_void_p(counts.ctypes.data), ctypes.c_void_p(ids.ctypes.data), ids.shape[1],
+                                    ctypes.c_uint32(int(tics) & 0xFFFFFFFF), ctypes.c_void_p(mv.ctypes.data if len(mv) else None), len(mv))
+        assert rc == 0, "hostcheck rejected the sector moves"
         return fb, counts, ids
 
     run.lib = lib

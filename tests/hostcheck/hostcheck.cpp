@@ -445,7 +445,8 @@ void raster(const HostScene &sc, const View &vw, const FrameConst &fc, const std
 }  // namespace
 
 static int render_impl(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
-                       int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics) {
+                       int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics, const SectorMove *moves = nullptr,
+                       int n_moves = 0) {
     HostScene sc = bind(blob);
     LitPlanes lit;
     build_lit(sc, lit);                // from the blob's own table: set_time only re-points records
@@ -455,9 +456,14 @@ static int render_impl(const uint8_t *blob, const View *vw, const Pose *poses, i
     std::vector<SectorRec> sectors_t((size_t)sc.hdr[H_NSECTORS]);
     std::vector<SegRec> segs_t((size_t)sc.nsegs);
     std::vector<SpriteRec> sprites_t((size_t)sc.nsprites);
+    std::vector<MidRec> mids_t((size_t)sc.hdr[H_NMIDS]);
+    std::vector<int32_t> floor_off, ceil_off;             // the moving sectors' state (b2d_renderer_set_sector_moves)
+    if (n_moves > 0 && expand_moves(blob, moves, (size_t)n_moves, floor_off, ceil_off)) return -1;
     if (scene_is_timed(blob)) {          // tic 0 included: a frame name with k > 0 shows the group's frame 0
-        scene_at_time(blob, tics, tex_t.data(), sectors_t.data(), segs_t.data(), sprites_t.data());
+        scene_at_time(blob, tics, tex_t.data(), sectors_t.data(), segs_t.data(), sprites_t.data(), mids_t.data(),
+                      n_moves > 0 ? floor_off.data() : nullptr, n_moves > 0 ? ceil_off.data() : nullptr);
         sc.tex = tex_t.data(); sc.sectors = sectors_t.data(); sc.segs = segs_t.data(); sc.sprites = sprites_t.data();
+        sc.mids = mids_t.data();
     }
     std::vector<uint32_t> yslope((size_t)vw->H);
     for (int y = 0; y < vw->H; y++) yslope[(size_t)y] = yslope_entry(y, *vw);
@@ -484,6 +490,11 @@ extern "C" int hostcheck_render(const uint8_t *blob, const View *vw, const Pose 
 extern "C" int hostcheck_render_t(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
                                   int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics) {
     return render_impl(blob, vw, poses, n, fb, counts, seg_ids, stride, tics);
+}
+
+extern "C" int hostcheck_render_m(const uint8_t *blob, const View *vw, const Pose *poses, int n, uint8_t *fb,
+                                  int32_t *counts, int32_t *seg_ids, int stride, uint32_t tics, const SectorMove *moves, int n_moves) {
+    return render_impl(blob, vw, poses, n, fb, counts, seg_ids, stride, tics, moves, n_moves);
 }
 
 // the product's light-effect evaluation (scene_at_time): light byte per sector at `tics`, -1 without effect

@@ -53,11 +53,22 @@ def _sector_at_vec(level: W.Level, px: np.ndarray, py: np.ndarray) -> np.ndarray
 
 def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width: int, height: int,
            x: float, y: float, z: float, angle_deg: float, fov_deg: float = 65.0, focal2=None,
-           tics: int = 0, cols=None, debug: bool = False):
+           tics: int = 0, cols=None, debug: bool = False, dynamic=(), moves=()):
     """`cols`: optional subset of screen columns to cast (the result then has shape (height, len(cols))); `debug`: also
     return, per pixel, which image / texel / colormap row / surface produced it (for classifying differences)."""
     level = W.Level(archive, level_index)
     from oracle.anim_table import FLATS as ANIM_FLATS, WALLS as ANIM_WALLS
+    # moving sectors, literally as the reference builds and moves its meshes: quads pre-extended over the declared height
+    # ranges (visitor.rs:146-155, 733-790), every quad / flat / decoration translated with the floor or ceiling object it
+    # is attached to (game/src/level.rs:201-245), the depth test (= nearest hit) sorting out what is visible
+    nsec_ = len(level.sectors)
+    rng = [[int(level.sectors[i]["floor"])] * 2 + [int(level.sectors[i]["ceil"])] * 2 for i in range(nsec_)]
+    for d in dynamic:
+        sec_, f0_, c0_ = int(d[0]), rng[int(d[0])][0], rng[int(d[0])][2]
+        rng[sec_] = [min(int(d[1]), int(d[2]), f0_), max(int(d[1]), int(d[2]), f0_), min(int(d[3]), int(d[4]), c0_), max(int(d[3]), int(d[4]), c0_)]
+    dfl, dcl = [0.0] * nsec_, [0.0] * nsec_
+    for m_ in moves:
+        dfl[int(m_[0])], dcl[int(m_[0])] = float(m_[1]), float(m_[2])
 
     def anim_name(name, groups, table):
         """static.vert:23-39 with u_time = tics/35: frame_index = floor(mod(u_time / (8/35), n)), added to the atlas
@@ -225,35 +236,41 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         lb = sector_byte[front] if has_effect[front] else W.light_byte(int(fsec["light"]), contrast)
         back_side = level.seg_back_sidedef_index(sg)
         back = int(level.sidedefs[back_side]["sector"]) if back_side >= 0 else -1
-        pieces = []                                         # (low, high, texture name or 'SKY', t at high)
+        pieces = []                                         # (low, high, texture name or 'SKY', t at high[, object offset])
+        maxh = float(rng[front][3] - rng[front][0])         # SectorInfo::max_height
         if back < 0:
             name = side_name(side, 2)
             img = tex.textures.get(name)
             th = img.shape[0] if img is not None else 0
-            pieces.append((ff, fc, name, (th - (fc - ff)) if unpeg_lower else 0.0))
+            if unpeg_lower:
+                pieces.append((ff, ff + maxh, name, th - maxh, dfl[front]))
+            else:
+                pieces.append((fc - maxh, fc, name, 0.0, dcl[front]))
             if W.is_sky_flat(ceil_name[front]):
-                pieces.append((fc, float(max_h), "SKY", 0.0))
+                pieces.append((fc, float(max_h), "SKY", 0.0, dcl[front]))
             if W.is_sky_flat(floor_name[front]):
-                pieces.append((float(min_h), ff, "SKY", 0.0))
+                pieces.append((float(min_h), ff, "SKY", 0.0, dfl[front]))
         else:
             bsec = secs[back]
             bf, bc = float(bsec["floor"]), float(bsec["ceil"])
             if W.is_sky_flat(ceil_name[front]) and not W.is_sky_flat(ceil_name[back]):
-                pieces.append((fc, float(max_h), "SKY", 0.0))
+                pieces.append((fc, float(max_h), "SKY", 0.0, dcl[front]))
             if W.is_sky_flat(floor_name[front]) and not W.is_sky_flat(floor_name[back]):
-                pieces.append((float(min_h), ff, "SKY", 0.0))
-            if bf > ff:
+                pieces.append((float(min_h), ff, "SKY", 0.0, dfl[front]))
+            lower_exists = rng[back][1] > rng[front][0]
+            if lower_exists:
                 name = side_name(side, 1)
                 img = tex.textures.get(name)
                 th = img.shape[0] if img is not None else 0
-                pieces.append((ff, bf, name, (th - (bf - ff) + (fc - ff)) if unpeg_lower else 0.0))
+                qh = float(rng[back][1] - rng[front][0])
+                pieces.append((bf - qh, bf, name, (th - qh + (fc - ff)) if unpeg_lower else 0.0, dfl[back]))
             if bc < fc and not W.is_sky_flat(ceil_name[back]):
                 name = side_name(side, 0)
                 img = tex.textures.get(name)
                 th = img.shape[0] if img is not None else 0
-                pieces.append((bc, fc, name, 0.0 if unpeg_upper else (th - (fc - bc))))
+                pieces.append((bc, fc, name, 0.0 if unpeg_upper else (th - (fc - bc)), dcl[back]))
             # middle (visitor.rs:808-836,875-919): drawn last, so lower/upper win at equal depth (IfLess)
-            low0, high0 = (bf if bf > ff else ff), (bc if bc < fc else fc)
+            low0, high0 = (bf if lower_exists else ff), (bc if bc < fc else fc)
             mname = side_name(side, 2)
             mimg = None if W.is_untextured(mname) else tex.textures.get(mname)
             if mimg is not None and low0 < high0:
@@ -267,10 +284,11 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
                     low, high = low0 + yoff, low0 + th + yoff
                 elif peg == "bottomfloat":
                     low, high = high0 + yoff - th, high0 + yoff
-                pieces.append((low, high, mname, (th - (high - low)) if peg == "bottom" else 0.0))
-        for pi, (low, high, name, t_high) in enumerate(pieces):
+                pieces.append((low, high, mname, (th - (high - low)) if peg == "bottom" else 0.0, dfl[front] if unpeg_lower else dcl[front]))
+        for pi, (low, high, name, t_high, obj_off) in enumerate(pieces):
             if low >= high:
                 continue
+            low, high = low + obj_off, high + obj_off
             hit = ok & (hz >= low) & (hz < high) & (t < best_t)
             if not hit.any():
                 continue
@@ -319,7 +337,7 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         if img is None:
             continue
         sh, sw = img.shape
-        low = float(secs[sec]["ceil"]) - sh if hanging else float(secs[sec]["floor"])
+        low = float(secs[sec]["ceil"]) - sh + dcl[sec] if hanging else float(secs[sec]["floor"]) + dfl[sec]
         tx0, ty0 = float(th["x"]) - x, float(th["y"]) - y
         cz = tx0 * fx + ty0 * fy                              # view depth of the thing
         cx = tx0 * rx + ty0 * ry                              # offset to the right
@@ -349,8 +367,8 @@ def render(archive: W.Archive, tex: W.TextureDirectory, level_index: int, width:
         d_surf[idx] = 1000000 + int(th["x"]) * 65536 + int(th["y"])
 
     # ---- flats: one horizontal plane per distinct height -------------------------------------------------
-    floor_h = np.array([min_h if W.is_sky_flat(floor_name[i]) else int(secs[i]["floor"]) for i in range(len(secs))], dtype=np.float64)
-    ceil_h = np.array([max_h if W.is_sky_flat(ceil_name[i]) else int(secs[i]["ceil"]) for i in range(len(secs))], dtype=np.float64)
+    floor_h = np.array([(min_h if W.is_sky_flat(floor_name[i]) else int(secs[i]["floor"])) + dfl[i] for i in range(len(secs))], dtype=np.float64)
+    ceil_h = np.array([(max_h if W.is_sky_flat(ceil_name[i]) else int(secs[i]["ceil"])) + dcl[i] for i in range(len(secs))], dtype=np.float64)
     sec_light = np.array(sector_byte, dtype=np.float64)
     for is_ceiling, heights in ((False, floor_h), (True, ceil_h)):
         for h in np.unique(heights):

@@ -355,6 +355,61 @@ def test_gpu_animated_and_scrolling(b2d):
     _assert_same(render.render(sc.blob, render.make_view(1920, 1080), poses[:4], threads=8, tics=1001), r2.render(poses[:4]), "1080p")
 
 
+def test_gpu_moving_sectors(b2d):
+    """Doors / lifts as a per-batch state: b2d_renderer_set_sector_moves re-derives the height-dependent
+    tables on the host and uploads them in stream order; the frames equal the oracle's render of its own scene with the
+    same moves applied (oracle/scene.py apply_moves); moves compose with the level time; going back to rest restores the
+    rest frames; the async variant orders the upload between two batches without a host wait."""
+    import torch
+    from oracle import scene as S, wad as W
+    from rust_doom_b200 import synthwad
+    from tests.refcheck import moves as MV
+    data = synthwad.build_iwad(1, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=30, thing_pct=50, anim=True))
+    a = W.Archive(data)
+    tex = W.TextureDirectory(a)
+    level = W.Level(a, 0)
+    dyn, mv = MV.pick(level, 5, 16)
+    oblob = S.compile_scene(a, tex, 0, dynamic=dyn)                  # the oracle's own scene
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=dyn)
+    assert sc.blob == oblob
+    poses = sample_poses(b2d, sc, 40, 17)
+    oview = render.make_view(320, 200)
+    r = b2d.Renderer(sc, b2d.make_view(320, 200), max_batch=16)
+    rest = r.render(poses)
+    _assert_same(render.render(oblob, oview, poses, threads=8), rest, "at rest")
+    changed = 0
+    for k, (tics, seed) in enumerate(((0, 5), (9, 6), (1000, 7), (0, 8))):
+        moves = mv if k == 0 else MV.state(level, dyn, seed, hole_free=False)     # any state inside the declared ranges
+        r.set_time(tics)
+        r.set_sector_moves(moves)
+        got = r.render(poses)
+        _assert_same(render.render(S.apply_moves(oblob, moves), oview, poses, threads=8, tics=tics), got, "moves %d" % k)
+        changed += int((got != rest).sum())
+    assert changed > 100000, "the moves never changed a pixel"
+    r.set_time(0)
+    r.set_sector_moves(())
+    _assert_same(rest, r.render(poses), "back at rest")
+    assert r.status() == 0
+    # stream order: batch at rest, moves, batch moved -- no host synchronisation in between
+    dp = torch.from_numpy(poses[:16].view(np.int32).reshape(-1, 4).copy()).cuda()
+    out0 = torch.empty((16, 200, 320), dtype=torch.uint8, device="cuda")
+    out1 = torch.empty_like(out0)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        r.render_device(dp.data_ptr(), 16, out0.data_ptr(), stream=st.cuda_stream)
+        r.set_sector_moves(mv, stream=st.cuda_stream)
+        r.render_device(dp.data_ptr(), 16, out1.data_ptr(), stream=st.cuda_stream)
+    st.synchronize()
+    _assert_same(rest[:16], out0.cpu().numpy(), "batch before the moves")
+    _assert_same(render.render(S.apply_moves(oblob, mv), oview, poses[:16], threads=8), out1.cpu().numpy(), "batch after the moves")
+    with pytest.raises(b2d.B2dError):
+        r.set_sector_moves([(dyn[0][0], 5000, 0)])
+    # 1080p, the benchmark resolution
+    r2 = b2d.Renderer(sc, b2d.make_view(1920, 1080), max_batch=4)
+    r2.set_sector_moves(mv)
+    _assert_same(render.render(S.apply_moves(oblob, mv), render.make_view(1920, 1080), poses[:4], threads=8), r2.render(poses[:4]), "1080p moved")
+
+
 def test_gpu_odd_texture_sizes(b2d):
     """Wall textures whose height is not a multiple of 4 / whose width is not a power of two (row-major pre-lit
     layout, magic floor-mod) mixed with 4-row interleaved ones."""

@@ -251,3 +251,45 @@ def test_every_frame_name_of_a_group_shows_the_same_image(b2d, hostcheck):
         assert np.array_equal(a, b), "oracle: a k > 0 frame name rendered differently at tic %d" % tics
         ha, _, _ = hostcheck(sc_k.blob, pv, poses, tics=tics)
         assert np.array_equal(ha, a), "product tables differ from the oracle at tic %d" % tics
+
+
+def test_hostcheck_moving_sectors(b2d, hostcheck):
+    """Doors / lifts: the product's re-derivation of the height-dependent tables (scene_at_time with the
+    sector offsets) under the kernels' algorithms, against the oracle rendering its own scene with the same moves applied
+    by the numpy restatement (oracle/scene.py apply_moves) -- including closed doors (ceiling on the floor), states the
+    reference itself cannot show without holes, level time on top, and eye points inside moved sectors."""
+    from oracle import scene as S, wad as W
+    from rust_doom_b200 import synthwad
+    from tests.refcheck import moves as MV
+    data = synthwad.build_iwad(2, ("E1M1",), cfg=synthwad.SynthConfig(mid_pct=30, thing_pct=50, anim=True))
+    a = W.Archive(data)
+    tex = W.TextureDirectory(a)
+    level = W.Level(a, 0)
+    dyn = MV.declare(level, 3, 20)
+    # a door: one more sector whose ceiling can come all the way down to its floor
+    door = next(i for i in range(len(level.sectors)) if i not in {d[0] for d in dyn}
+                and int(level.sectors[i]["ceil"]) - int(level.sectors[i]["floor"]) >= 64)
+    f0, c0 = int(level.sectors[door]["floor"]), int(level.sectors[door]["ceil"])
+    dyn.append((door, f0, f0, f0, c0))
+    oblob = S.compile_scene(a, tex, 0, dynamic=dyn)
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=dyn)
+    assert sc.blob == oblob
+    poses = sample_poses(b2d, sc, 24, 5)
+    view, oview = b2d.make_view(320, 200), render.make_view(320, 200)
+    rest = render.render(oblob, oview, poses, threads=4)
+    changed = 0
+    for k, tics in enumerate((0, 0, 9, 1000)):
+        moves = MV.state(level, dyn[:-1], 40 + k, hole_free=False) + [(door, 0, -(c0 - f0) if k % 2 == 0 else -((c0 - f0) // 2))]
+        ofb = render.render(S.apply_moves(oblob, moves), oview, poses, threads=4, tics=tics)
+        hfb, counts, _ = hostcheck(oblob, view, poses, tics=tics, moves=moves)
+        bad = [(i, int((ofb[i] != hfb[i]).sum())) for i in range(len(poses)) if not np.array_equal(ofb[i], hfb[i])]
+        assert not bad, "state %d: frames differ (index, pixels): %s" % (k, bad[:5])
+        assert (counts >= 0).all()
+        changed += int((ofb != rest).sum())
+    assert changed > 100000, "the moves never changed a pixel"
+    hfb, _, _ = hostcheck(oblob, view, poses, moves=())
+    assert np.array_equal(hfb, rest)
+    mv1080 = MV.state(level, dyn[:-1], 50, hole_free=False)
+    o = render.render(S.apply_moves(oblob, mv1080), render.make_view(1920, 1080), poses[:2], threads=2)
+    hfb, _, _ = hostcheck(oblob, b2d.make_view(1920, 1080), poses[:2], moves=mv1080)
+    assert np.array_equal(o, hfb)

@@ -295,3 +295,95 @@ def test_last_player_start_wins(b2d):
     sc = b2d.Scene(b2d.Archive.from_bytes(bytes(data)), 0)
     assert sc.blob == ob
     assert sc.info.has_start and sc.info.start.x == (x - 32) * 65536 and sc.info.start.y == y * 65536
+
+
+def _moving_case(seed, cfg):
+    from rust_doom_b200 import synthwad
+    from tests.refcheck import moves as MV
+    data = synthwad.build_iwad(seed, ("E1M1",), cfg=synthwad.SynthConfig(**cfg))
+    a = W.Archive(data)
+    tex = W.TextureDirectory(a)
+    dyn, mv = MV.pick(W.Level(a, 0), seed + 100, 12)
+    return data, a, tex, dyn, mv
+
+
+def _state_tables(blob):
+    """[textures | sectors | segs | sprites | mids] of a blob, as b2d_scene_tables_at lays them out"""
+    h = S.header(blob)
+    spans = [(h[S.H_OFF_TEX], h[S.H_NTEX] * 32), (h[S.H_OFF_SECTORS], h[S.H_NSECTORS] * 32), (h[S.H_OFF_SEGS], h[S.H_NSEGS] * 64),
+             (h[S.H_OFF_SPRITES], h[S.H_NSPRITES] * 32), (h[S.H_OFF_MIDS], h[S.H_NMIDS] * 32)]
+    return b"".join(blob[o:o + n] for o, n in spans)
+
+
+@pytest.mark.parametrize("seed", [1, 9])
+def test_dynamic_sectors_compile_and_move_like_the_oracle(b2d, seed):
+    """Moving sectors: the product's scene compiler given the dynamic-sector list, and its re-derivation
+    of the height-dependent tables for one state, are byte-identical to the oracle's numpy restatement."""
+    data, a, tex, dyn, mv = _moving_case(seed, dict(mid_pct=30, thing_pct=50))
+    ob = S.compile_scene(a, tex, 0, dynamic=dyn)
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=dyn)
+    assert sc.blob == ob and sc.info.n_dynamic == len(dyn)
+    assert S.header(ob)[S.H_NDYN] == len(dyn)
+    # declaring sectors resolves more pieces (textures of walls that only appear while a sector moves), never fewer
+    static = S.compile_scene(a, tex, 0)
+    assert S.header(ob)[S.H_NTEX] >= S.header(static)[S.H_NTEX]
+    assert (S.section(ob, "sectors") == S.section(static, "sectors")).all()
+    moved = S.apply_moves(ob, mv)
+    assert sc.tables_at(0, mv) == _state_tables(moved)
+    assert sc.tables_at(0, ()) == _state_tables(ob)
+    assert moved != ob and S.apply_moves(ob, ()) == ob
+    # rest heights + offsets, openings follow
+    s0, s1 = S.section(ob, "sectors"), S.section(moved, "sectors")
+    for sec, dfl, dcl in mv:
+        assert s1[sec, 0] == s0[sec, 0] + dfl and s1[sec, 1] == s0[sec, 1] + dcl
+    segs, segdyn = S.section(moved, "segs"), S.section(ob, "segdyn")
+    for i in range(len(segs)):
+        if segs[i, 3] & S.SEG_INVALID:
+            continue
+        f, b = int(segs[i, 2]), int(segdyn[i, 0])
+        if b < 0:
+            assert (segs[i, 13], segs[i, 14]) == (s1[f, 1], s1[f, 0])
+        else:
+            assert segs[i, 14] == max(s1[f, 0], s1[b, 0]) and segs[i, 13] <= s1[f, 1]
+
+
+def test_dynamic_sector_arguments_are_checked(b2d):
+    data, a, tex, dyn, mv = _moving_case(3, {})
+    arch = b2d.Archive.from_bytes(data)
+    sc = b2d.Scene(arch, 0, dynamic=dyn)
+    undeclared = next(i for i in range(sc.info.n_sectors) if i not in {d[0] for d in dyn})
+    with pytest.raises(b2d.B2dError):
+        sc.tables_at(0, [(undeclared, 1, 0)])                       # not declared dynamic
+    with pytest.raises(b2d.B2dError):
+        sc.tables_at(0, [(dyn[0][0], 4000, 0)])                     # outside the declared range
+    with pytest.raises(ValueError):
+        S.apply_moves(sc.blob, [(undeclared, 1, 0)])
+    with pytest.raises(ValueError):
+        S.apply_moves(sc.blob, [(dyn[0][0], 4000, 0)])
+    with pytest.raises(b2d.B2dError):
+        b2d.Scene(arch, 0, dynamic=[dyn[0], dyn[0]])                # listed twice
+    with pytest.raises(b2d.B2dError):
+        b2d.Scene(arch, 0, dynamic=[(100000, 0, 0, 0, 0)])
+    with pytest.raises(W.WadError):
+        S.compile_scene(a, tex, 0, dynamic=[dyn[0], dyn[0]])
+    # the lumps entry point takes the same list
+    lv = W.Level(a, 0)
+    assert b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=dyn).blob == S.compile_scene(a, tex, 0, dynamic=dyn)
+    del lv
+
+
+def test_time_and_moves_compose(b2d):
+    """Level time and sector state are one table set: animation / light effects at `tics` plus the moved heights."""
+    data, a, tex, dyn, mv = _moving_case(5, dict(mid_pct=20, thing_pct=30, anim=True))
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=dyn)
+    ob = S.compile_scene(a, tex, 0, dynamic=dyn)
+    h = S.header(ob)
+    for tics in (0, 9, 1000):
+        t0, t1 = sc.tables_at(tics, ()), sc.tables_at(tics, mv)
+        # texture records do not depend on heights; sectors / segs / sprites / mids differ exactly where apply_moves says
+        ntex = h[S.H_NTEX] * 32
+        assert t0[:ntex] == t1[:ntex]
+        rest, moved = _state_tables(ob), _state_tables(S.apply_moves(ob, mv))
+        a0, a1 = np.frombuffer(t0, np.int32), np.frombuffer(t1, np.int32)
+        r0, r1 = np.frombuffer(rest, np.int32), np.frombuffer(moved, np.int32)
+        assert ((a1 - a0) == (r1 - r0)).all()
