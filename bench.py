@@ -309,7 +309,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5", "4k", "rich"])
     ap.add_argument("--poses", type=int, default=0, help="poses per map / per job (0 = the configuration's own count)")
     ap.add_argument("--chunk", type=int, default=256, help="c5: frames per rank per all-gather chunk")
-    ap.add_argument("--transports", default="window", help="c5: comma list of exchange transports to run: window,register,plain,ce")
+    ap.add_argument("--transports", default="ce", help="c5: comma list of exchange transports to run: ce (the library's default: copy engines "
+                    "over CUDA-IPC mappings), window / register / plain (ncclAllGather on ncclMemAlloc window / registered / plain buffers)")
     ap.add_argument("--batch", type=int, default=0, help="c3/c4/4k/rich: frames per launch (0 = 500)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -374,7 +375,8 @@ def main():
         #   window  ncclAllGather in place on ncclMemAlloc buffers registered as a symmetric window (NCCL >= 2.27)
         #   plain   ncclAllGather in place on cudaMalloc buffers, no registration
         #   ce      copy engines: every rank pushes its slice into the peers' buffers over CUDA-IPC mappings
-        env_of = {"window": {}, "register": {"B2D_NCCL_NO_WINDOW": "1"}, "plain": {"B2D_NCCL_NO_REGISTER": "1"}, "ce": {"B2D_GATHER": "ce"}}
+        env_of = {"window": {"B2D_GATHER": "nccl"}, "register": {"B2D_GATHER": "nccl", "B2D_NCCL_NO_WINDOW": "1"},
+                  "plain": {"B2D_GATHER": "nccl", "B2D_NCCL_NO_REGISTER": "1"}, "ce": {}}
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()

@@ -258,7 +258,7 @@ typedef struct b2d_sharded_stats {
     double render_ms, gather_ms;    /* sums of the per-chunk kernel / ncclAllGather times (they overlap each other) */
     int64_t frames_local, frames_gathered, chunks, chunk_frames;
     int64_t bytes_received;         /* (world-1)/world of the gathered bytes */
-    char registration[64];          /* how the gather buffers were registered with NCCL */
+    char registration[64];          /* exchange transport / how the gather buffers were registered with NCCL */
 } b2d_sharded_stats;
 
 /* Called on the host once per chunk, right after the chunk's work has been ENQUEUED: d_frames holds `ranks` x

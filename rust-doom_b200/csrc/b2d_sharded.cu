@@ -183,8 +183,11 @@ int ensure_buffers(b2d_comm *c, size_t bytes) {
     if (c->buf_bytes >= bytes) return B2D_OK;
     Nccl &n = nccl();
     release_buffers(c);
+    // exchange transport: the copy engines over CUDA-IPC peer mappings unless B2D_GATHER=nccl asks for ncclAllGather
+    // (measured on 8 B200: 746 GB/s received per rank against 620-655 with NCCL's kernels, profiles/README.md); if any
+    // rank cannot map a peer's buffer, all ranks agree to fall back to NCCL below
     const char *tr = getenv("B2D_GATHER");
-    c->ce = tr && std::strcmp(tr, "ce") == 0 && c->world > 1 && n.AllReduce;
+    c->ce = !(tr && std::strcmp(tr, "nccl") == 0) && c->world > 1 && n.AllReduce;
     const bool want_reg = !getenv("B2D_NCCL_NO_REGISTER") && !c->ce;      // IPC needs plain cudaMalloc memory
     c->nccl_mem = want_reg && n.MemAlloc && n.MemFree;
     c->registration = "none";
@@ -229,16 +232,37 @@ int ensure_buffers(b2d_comm *c, size_t bytes) {
         B2D_CU(cudaStreamSynchronize(c->gather_stream));
         B2D_CU(cudaMemcpy(all.data(), d_h, all.size(), cudaMemcpyDeviceToHost));
         cudaFree(d_h);
+        int32_t mapped = 1;
         for (int i = 0; i < 2; i++) {
             c->peer[i].assign((size_t)c->world, nullptr);
-            for (int q = 0; q < c->world; q++) {
+            for (int q = 0; q < c->world && mapped; q++) {
                 if (q == c->rank) { c->peer[i][(size_t)q] = c->buf[i]; continue; }
                 cudaIpcMemHandle_t h;
                 std::memcpy(&h, &all[((size_t)q * 2 + (size_t)i) * hb], hb);
                 void *p = nullptr;
-                B2D_CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+                if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { mapped = 0; cudaGetLastError(); break; }
                 c->peer[i][(size_t)q] = static_cast<uint8_t *>(p);
             }
+        }
+        // every rank must have mapped every peer, or nobody uses the mappings (minimum over ranks = sum of the failures == 0)
+        int32_t failures = mapped ? 0 : 1, *d_flag = nullptr;
+        B2D_CU(cudaMalloc(&d_flag, sizeof(int32_t)));
+        B2D_CU(cudaMemcpy(d_flag, &failures, sizeof failures, cudaMemcpyHostToDevice));
+        nrc = n.AllReduce(d_flag, d_flag, 1, kNcclInt32, kNcclSum, c->comm, c->gather_stream);
+        if (nrc != 0) { cudaFree(d_flag); return nccl_fail(nrc, "ncclAllReduce (ipc agreement)"); }
+        B2D_CU(cudaStreamSynchronize(c->gather_stream));
+        B2D_CU(cudaMemcpy(&failures, d_flag, sizeof failures, cudaMemcpyDeviceToHost));
+        cudaFree(d_flag);
+        if (failures) {
+            for (int i = 0; i < 2; i++) {
+                for (size_t q = 0; q < c->peer[i].size(); q++)
+                    if ((int)q != c->rank && c->peer[i][q]) cudaIpcCloseMemHandle(c->peer[i][q]);
+                c->peer[i].clear();
+            }
+            c->ce = false;
+            c->registration = "none (peers not mappable: ncclAllGather, plain buffers)";
+            c->buf_bytes = bytes;
+            return B2D_OK;
         }
         if (c->push_stream.empty()) {
             c->push_stream.resize((size_t)c->world, nullptr);
@@ -252,7 +276,7 @@ int ensure_buffers(b2d_comm *c, size_t bytes) {
             B2D_CU(cudaMalloc(&c->d_token, sizeof(int32_t)));
             B2D_CU(cudaMemset(c->d_token, 0, sizeof(int32_t)));
         }
-        c->registration = "copy engines: cudaMemcpyAsync pushes over CUDA-IPC peer mappings";
+        c->registration = "copy engines: cudaMemcpyAsync over CUDA-IPC peer mappings";
     }
     c->buf_bytes = bytes;
     return B2D_OK;

@@ -151,8 +151,7 @@ def test_compiled_cli_sharded_two_ranks(tmp_path, transport):
     wad.write_bytes(synthwad.build_iwad(1, ("E1M1",)))
     exe = build.build_cli()
     env = dict(os.environ)
-    if transport == "ce":
-        env["B2D_GATHER"] = "ce"
+    env["B2D_GATHER"] = "nccl" if transport == "nccl" else "ce"          # ce (copy engines over CUDA IPC) is the default
     base = [exe, "--iwad", str(wad), "--resolution", "640x400", "--poses", "22", "--chunk", "4"]
     one = subprocess.run(base + ["--world", "1", "--rank", "0", "--id-file", str(tmp_path / "id1")], capture_output=True, text=True, timeout=300)
     assert one.returncode == 0, one.stdout + one.stderr
