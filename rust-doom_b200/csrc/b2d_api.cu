@@ -230,7 +230,21 @@ int raster_from_slot(b2d_renderer *r, int64_t ticket, uint8_t *d_index, uint32_t
         for (auto &e : ev) CU(cudaEventCreate(&e));
         CU(cudaEventRecord(ev[0], stream));
     }
+    if (r->l2_window_bytes) {      // B2D_L2PERSIST (A/B): the pre-lit planes are a persisting L2 window for the raster's loads
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = r->d_lit;
+        av.accessPolicyWindow.num_bytes = r->l2_window_bytes;
+        av.accessPolicyWindow.hitRatio = r->l2_hit_ratio;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CU(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     CU(launch_raster(r->ds, r->view, r->d_frames[slot], r->d_work[slot], r->stride, r->slot_n[slot], d_index, d_rgba, stream));
+    if (r->l2_window_bytes) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        CU(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     if (r->profiling) {
         CU(cudaEventRecord(ev[1], stream));
         for (auto e : ev) r->prof_events.push_back(e);
@@ -664,6 +678,17 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
         CUR(launch_prelight_textures(d.colormap, d.texels, d.tex, (int)h[H_NTEX], r->d_lit, tstride, nullptr));
         CUR(launch_prelight(d.colormap, d.flats, r->d_lit_flats, fstride, fstride, nullptr));
         CUR(cudaDeviceSynchronize());
+        if (getenv("B2D_L2PERSIST")) {      // texel planes only (one window per launch; the flats are a separate mapping)
+            cudaDeviceProp prop;
+            CUR(cudaGetDeviceProperties(&prop, device));
+            const size_t want = 33 * (size_t)tstride;
+            const size_t carve = std::min<size_t>(want, (size_t)prop.persistingL2CacheMaxSize);
+            if (carve && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) {
+                r->l2_window_bytes = std::min<size_t>(want, (size_t)prop.accessPolicyMaxWindowSize);
+                r->l2_hit_ratio = (float)std::min(1.0, (double)carve / (double)r->l2_window_bytes);
+            }
+            cudaGetLastError();
+        }
         d.lit_texels = r->d_lit; d.lit_flats = r->d_lit_flats;           // low 32 address bits of lit_flats are zero
         d.lit_texel_stride = (uint32_t)tstride; d.lit_flat_stride = (uint32_t)fstride;
     }

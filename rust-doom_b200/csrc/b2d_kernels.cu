@@ -24,8 +24,20 @@ namespace {
 constexpr unsigned kFull = 0xFFFFFFFFu;
 
 // texel / table loads of the raster: read-only path; B2D_LOAD_EL (A/B, profiles/README.md) asks L1 to keep them
+#if defined(B2D_LOAD_L2EL)
+// A/B: ask L2 to keep the pre-lit planes (a 2 GB/ms write stream passes through the same L2)
+__device__ __forceinline__ uint64_t l2_keep_policy() {
+    uint64_t pol;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#endif
 __device__ __forceinline__ uint32_t tex_ld(const uint8_t *p) {
-#if defined(B2D_LOAD_EL)
+#if defined(B2D_LOAD_L2EL)
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u8 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_keep_policy()));
+    return v;
+#elif defined(B2D_LOAD_EL)
     uint32_t v;
     asm("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
@@ -34,7 +46,11 @@ __device__ __forceinline__ uint32_t tex_ld(const uint8_t *p) {
 #endif
 }
 __device__ __forceinline__ uint32_t tex_ld(const uint32_t *p) {
-#if defined(B2D_LOAD_EL)
+#if defined(B2D_LOAD_L2EL)
+    uint32_t v;
+    asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(l2_keep_policy()));
+    return v;
+#elif defined(B2D_LOAD_EL)
     uint32_t v;
     asm("ld.global.nc.L1::evict_last.u32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
