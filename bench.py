@@ -319,6 +319,9 @@ def main():
                     help="c2: one b2d_render_device call per step (BSP walk, then raster of the same batch, one stream) instead of "
                          "the default b2d_walk_device / b2d_raster_device pair on two streams (the walk of the next batch runs as a "
                          "one-CTA-per-SM background grid under this batch's raster)")
+    ap.add_argument("--raster-streams", type=int, default=2, choices=[1, 2],
+                    help="c2, pipelined step: 2 = consecutive batches raster on two alternating streams into two output buffers, so the "
+                         "first CTAs of batch k+1 fill the SMs that the last CTAs of batch k leave idle (1 = one stream, one buffer)")
     ap.add_argument("--rgba", action="store_true", help="c2: also materialise RGBA8 frames in HBM (5 B/pixel; not the headline config)")
     ap.add_argument("--gather-frames", type=int, default=0, help="c2, N>1: frames per rank in a separate all-gather timing (0 = off; see --config c5)")
     args = ap.parse_args()
@@ -498,31 +501,55 @@ def main():
     view = b2d.make_view(width, height)
     r = b2d.Renderer(scene, view, device=local_rank, max_batch=n)
     d_poses = torch.from_numpy(poses_np.view(np.int32).reshape(-1, 4).copy()).to(dev)
-    d_index = torch.empty((n, height, width), dtype=torch.uint8, device=dev)
-    d_rgba = torch.empty((n, height, width), dtype=torch.int32, device=dev) if args.rgba else None
-    stream = torch.cuda.current_stream().cuda_stream
-
     pipelined = not args.no_pipeline
+    nbuf = args.raster_streams if pipelined else 1
+    d_index_all = [torch.empty((n, height, width), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+    d_rgba_all = [torch.empty((n, height, width), dtype=torch.int32, device=dev) if args.rgba else None for _ in range(nbuf)]
+    d_index, d_rgba = d_index_all[0], d_rgba_all[0]
+    main_stream = torch.cuda.current_stream()
+    stream = main_stream.cuda_stream
+
     walk_stream = torch.cuda.Stream(device=dev, priority=-1) if pipelined else None
+    raster_streams = [torch.cuda.Stream(device=dev) for _ in range(nbuf)] if pipelined and nbuf > 1 else None
     pending = [r.walk_device(d_poses.data_ptr(), n, walk_stream.cuda_stream)] if pipelined else None
+    turn = [0]
 
     def step():
         if pipelined:
-            r.raster_device(pending[0], d_index.data_ptr(), d_rgba.data_ptr() if args.rgba else 0, stream)
+            b = turn[0] % nbuf
+            turn[0] += 1
+            rs = raster_streams[b].cuda_stream if raster_streams else stream
+            r.raster_device(pending[0], d_index_all[b].data_ptr(), d_rgba_all[b].data_ptr() if args.rgba else 0, rs)
             pending[0] = r.walk_device(d_poses.data_ptr(), n, walk_stream.cuda_stream)
         else:
             r.render_device(d_poses.data_ptr(), n, d_index.data_ptr(), d_rgba.data_ptr() if args.rgba else 0, stream)
 
-    for _ in range(args.warmup):
+    def join():                                 # the main stream waits for everything the steps enqueued elsewhere
+        if raster_streams:
+            for t in raster_streams:
+                main_stream.wait_stream(t)
+
+    def fork():                                 # ... and the side streams start behind the main stream
+        if raster_streams:
+            for t in raster_streams:
+                t.wait_stream(main_stream)
+
+    fork()
+    for _ in range(max(args.warmup, nbuf)):
         step()
+    join()
     barrier()
-    # parity spot check inside the run: one frame of this batch against the oracle
+    # parity spot check inside the run: one frame of this batch (of every output buffer) against the oracle rendering the
+    # scene its own loader and compiler produce from the same WAD bytes
     if rank == 0:
-        from oracle import render as orender
+        from oracle import render as orender, scene as oscene, wad as owad
+        oarch = owad.Archive(open(iwad, "rb").read() if iwad else build_wad(*maps[0][:3]))
+        oblob = oscene.compile_scene(oarch, owad.TextureDirectory(oarch), 0)
         probe = n // 2
-        ofb = orender.render(scene.blob, orender.make_view(width, height), poses_np[probe:probe + 1])
-        if not np.array_equal(d_index[probe].cpu().numpy(), ofb[0]):
-            raise SystemExit("parity check failed: GPU frame differs from the oracle")
+        ofb = orender.render(oblob, orender.make_view(width, height), poses_np[probe:probe + 1])
+        for buf in d_index_all:
+            if not np.array_equal(buf[probe].cpu().numpy(), ofb[0]):
+                raise SystemExit("parity check failed: GPU frame differs from the oracle")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -533,8 +560,10 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork()
     for _ in range(args.steps):
         step()
+    join()
     e1.record()
     barrier()
     if pipelined:                              # the walk issued by the last step belongs to a step that never comes
@@ -552,10 +581,27 @@ def main():
     value = world * n * args.steps / (ms_total / 1e3)
 
     alg_bytes = float(n) * npix * (5 if args.rgba else 1)
-    roofline = roofline_of(raster_ms / max(batches, 1), alg_bytes, walk_ms / max(batches, 1),
+    overlapped = raster_streams is not None
+    # rasters of consecutive batches on alternating streams overlap (head of k+1 in the tail of k), so an event pair around
+    # one launch also spans its wait for SMs: the kernel's duration in the timed region is then the region over its launches
+    per_launch = ms_total / args.steps if overlapped else raster_ms / max(batches, 1)
+    roofline = roofline_of(per_launch, alg_bytes, walk_ms / max(batches, 1),
                            "index-only output (no RGBA materialised); the raster kernel is instruction-issue / L1 bound, not HBM bound "
-                           "(DESIGN.md 5-6, profiles/README.md)", "b2d_raster_kernel<%s>" % ("rgba" if args.rgba else "index"),
-                           None if args.rgba else ncu_traffic())
+                           "(DESIGN.md 5-6, profiles/README.md)" +
+                           ("; avg_launch_ms = timed region / raster launches: the rasters run back to back on two streams, overlapping by "
+                            "their tails, with the next batch's BSP walk co-resident" if overlapped else ""),
+                           "b2d_raster_kernel<%s>" % ("rgba" if args.rgba else "index"), None if args.rgba else ncu_traffic())
+    if pipelined:        # the same kernel timed alone, outside the timed region: one stream, walk first, nothing co-resident
+        r.profile(True)
+        r.profile_read()
+        for _ in range(10):
+            r.render_device(d_poses.data_ptr(), n, d_index.data_ptr(), d_rgba.data_ptr() if args.rgba else 0, stream)
+        torch.cuda.synchronize()
+        _, alone_ms, alone_n = r.profile_read()
+        r.profile(False)
+        alone = max_over_ranks(alone_ms / max(alone_n, 1))
+        roofline["alone_avg_launch_ms"] = alone
+        roofline["alone_frac"] = alg_bytes / (alone / 1e3) / 1e9 / roofline["peak"]
 
     # ------------------------------------------------------------------ end to end (host buffers)
     e2e = None
@@ -609,10 +655,11 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": bench_config(desc + (", + RGBA8 framebuffer" if args.rgba else ""), n, world, scene.info),
-            "step": ("raster of this batch + BSP walk of the NEXT batch on two streams (b2d_walk_device / b2d_raster_device): every step "
-                     "runs one walk and one raster of 1000 poses, the walk as a background grid under the raster; roofline.avg_launch_ms is "
-                     "the raster's duration WITH that walk co-resident" if pipelined
-                     else "BSP walk then raster of one batch, one stream (b2d_render_device)"),
+            "step": ("raster of this batch + BSP walk of the NEXT batch (b2d_walk_device / b2d_raster_device): every step runs one walk "
+                     "and one raster of 1000 poses, the walk as a background grid under the raster" +
+                     ("; rasters alternate between two streams and two output buffers (the first CTAs of batch k+1 use the SMs the "
+                      "last CTAs of batch k leave idle)" if overlapped else "; roofline.avg_launch_ms is the raster's duration WITH that walk co-resident")
+                     if pipelined else "BSP walk then raster of one batch, one stream (b2d_render_device)"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
             "cpu_baseline": cpu_baseline, "allgather": allgather, "build": build_provenance()}))
     if world > 1:

@@ -20,6 +20,9 @@ for rep in a b; do
   for v in stcs l2el l2elcs el; do B2D_LIB=$D/libb2d_$v.so run ${v}_$rep python bench.py $Q; done
 done
 run pipe_base python bench.py $P
+run pipe_base_1stream python bench.py $P --raster-streams 1
+run pipe_base_b python bench.py $P
+run pipe_base_1stream_b python bench.py $P --raster-streams 1
 B2D_L2PERSIST=1 run pipe_persist python bench.py $P
 for v in stcs l2el l2elcs; do B2D_LIB=$D/libb2d_$v.so run pipe_$v python bench.py $P; done
 for v in base stcs l2elcs; do
