@@ -389,8 +389,13 @@ __host__ __device__ __forceinline__ bool tex_interleaved(const TexRec &T) { retu
 // form serialises load -> lookup -> store and leaves the LSU idle while each warp waits).  `full` (warp-uniform)
 // says every lane owns all rows of the batch, so the stores need no predicate.
 constexpr int kBatch = 8;
+#if defined(B2D_FLAT_BATCH)
+constexpr int kFlatBatch = B2D_FLAT_BATCH;     // A/B: gathers in flight per warp in the flat loop
+#else
+constexpr int kFlatBatch = 8;
+#endif
 
-template <bool kRgba, int kW>
+template <bool kRgba, int kW, int kBatch = ::b2d::kBatch>
 __device__ __forceinline__ void store_batch(const RasterCtx &c, uint8_t *p8, uint32_t *p32, const uint32_t (&v)[kBatch],
                                             int y, int ya, int yb, bool full) {
     const int Wc = kW ? kW : c.W;
@@ -476,15 +481,15 @@ __device__ __forceinline__ void draw_plane_warp(const RasterCtx &c, const FrameC
         __syncwarp();
         const int rows = min(32, y1 - yc);
         int j = 0;
-        for (; j + kBatch <= rows; j += kBatch, p8 += (size_t)kBatch * Wc, p32 += (size_t)kBatch * Wc) {
-            uint32_t v[kBatch];
+        for (; j + kFlatBatch <= rows; j += kFlatBatch, p8 += (size_t)kFlatBatch * Wc, p32 += (size_t)kFlatBatch * Wc) {
+            uint32_t v[kFlatBatch];
 #pragma unroll
-            for (int k = 0; k < kBatch; k++) {
+            for (int k = 0; k < kFlatBatch; k++) {
                 const uint2 rz = c.rowz[j + k];                               // shared-memory broadcast: one 64-bit word per row
                 v[k] = tex_ld(reinterpret_cast<const uint8_t *>(px_hi | flat_offset(rz.y, bu + rz.x * ax, bv + rz.x * ay)));   // always in bounds
             }
             const int y = yc + j;
-            store_batch<kRgba, kW>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kBatch <= full_hi);
+            store_batch<kRgba, kW, kFlatBatch>(c, p8, p32, v, y, ya, yb, y >= full_lo && y + kFlatBatch <= full_hi);
         }
         for (; j < rows; j++, p8 += Wc, p32 += Wc) {
             const uint2 rz = c.rowz[j];
@@ -977,17 +982,21 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     // 32 warps resident per SM.  Strips differ a lot in cost; with several warps per CTA the finished warps' slots
     // stay empty until the slowest warp of the CTA is done (1-warp CTAs: +10 % over 2 or 4, 8 and 16 lose more).
     // The frame width is a compile-time constant for the benchmark resolutions (immediate store offsets).
-    constexpr int kWarps = 1;
+#if defined(B2D_RASTER_WARPS)         // A/B: more resident warps per SM at fewer registers per thread
+    constexpr int kWarps = B2D_RASTER_WARPS, kMinBlocks = B2D_RASTER_MINBLOCKS;
+#else
+    constexpr int kWarps = 1, kMinBlocks = 32;
+#endif
     const long long total_warps = (long long)n * strips;
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
     static const bool generic_w = getenv("B2D_RASTER_GENERIC_W") != nullptr;   // A/B knob for profiles/README.md
     const bool w1920 = vw.W == 1920 && !generic_w;
 #define B2D_RASTER_GO(RGBA, KW) do { \
     if ((sc.nmids > 0 || sc.nsprites > 0) && sc.masked_list) \
-        b2d_raster_kernel<RGBA, 32 / kWarps, KW, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
+        b2d_raster_kernel<RGBA, kMinBlocks, KW, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); \
     else \
-        b2d_raster_kernel<RGBA, 32 / kWarps, KW, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
+        b2d_raster_kernel<RGBA, kMinBlocks, KW, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); } while (0)
     if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
     else {
