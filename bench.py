@@ -320,7 +320,7 @@ def main():
                          "the default b2d_walk_device / b2d_raster_device pair on two streams (the walk of the next batch runs as a "
                          "one-CTA-per-SM background grid under this batch's raster)")
     ap.add_argument("--raster-streams", type=int, default=2, choices=[1, 2],
-                    help="c2, pipelined step: 2 = consecutive batches raster on two alternating streams into two output buffers, so the "
+                    help="pipelined step (c2) / map jobs (c3, c4, 4k, rich): 2 = consecutive batches raster on two alternating streams into two output buffers, so the "
                          "first CTAs of batch k+1 fill the SMs that the last CTAs of batch k leave idle (1 = one stream, one buffer)")
     ap.add_argument("--rgba", action="store_true", help="c2: also materialise RGBA8 frames in HBM (5 B/pixel; not the headline config)")
     ap.add_argument("--gather-frames", type=int, default=0, help="c2, N>1: frames per rank in a separate all-gather timing (0 = off; see --config c5)")
@@ -451,7 +451,7 @@ def main():
             tot = {"ms_per_pass": 0.0, "raster_ms_per_pass": 0.0, "walk_ms_per_pass": 0.0, "frames_per_pass": 0, "launches": 0, "status_bits": 0}
             bad = 0
             for sc, ps in zip(scenes, poses):
-                r1 = jobs.run_maps([sc], [ps], width, height, local_rank, batch, steps, args.warmup, False)
+                r1 = jobs.run_maps([sc], [ps], width, height, local_rank, batch, steps, args.warmup, False, args.raster_streams)
                 bad += verify_maps(r1, [sc], [ps], width, height)
                 for k in tot:
                     tot[k] += r1[k]
@@ -459,7 +459,7 @@ def main():
                 torch.cuda.empty_cache()
             res = tot
         else:
-            res = jobs.run_maps(scenes, poses, width, height, local_rank, batch, steps, args.warmup, cfg == "c3")
+            res = jobs.run_maps(scenes, poses, width, height, local_rank, batch, steps, args.warmup, cfg == "c3", args.raster_streams)
             bad = verify_maps(res, scenes, poses, width, height)
         clocks = sampler.stop() if rank == 0 else None
         if bad or res["status_bits"]:
@@ -471,7 +471,9 @@ def main():
         total_frames = float(frames.item())
         value = total_frames / (ms / 1e3)
         roof = roofline_of(res["raster_ms_per_pass"], float(res["frames_per_pass"]) * npix, res["walk_ms_per_pass"],
-                           "this rank's raster launches of one pass (sum) vs the index bytes they write; index-only output")
+                           "this rank's raster launches of one pass vs the index bytes they write; index-only output" +
+                           ("; the launches alternate between two streams and overlap by their tails, with the next launch's BSP walk "
+                            "co-resident: their time is the pass" if args.raster_streams > 1 else " (sum of the per-launch event pairs)"))
         if rank == 0:
             print(json.dumps({
                 "metric": METRIC if height == 1080 else METRIC.replace("1920x1080", "%dx%d" % (width, height)),
@@ -480,6 +482,7 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": bench_config(desc, n, world, scenes[0].info,
                                        {"maps_this_rank": len(scenes), "batch": batch,
+                                        "raster_streams": args.raster_streams,
                                         "step": "one pass over every map of the rank (%s)" % ("batches interleaved across the maps' renderers" if cfg == "c3" else "map after map")}),
                 "clocks": clocks, "gpu_launches": int(res["launches"]), "roofline": roof,
                 "parity": "one probe frame per map bit-exact vs the oracle"}))

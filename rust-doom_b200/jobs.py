@@ -188,10 +188,13 @@ def map_assignment(n_maps: int, world: int) -> List[List[int]]:
 
 
 def run_maps(scenes: Sequence[Scene], poses: Sequence[np.ndarray], width: int, height: int, local_rank: int,
-             batch: int, steps: int, warmup: int, interleave: bool) -> Dict[str, object]:
+             batch: int, steps: int, warmup: int, interleave: bool, raster_streams: int = 2) -> Dict[str, object]:
     """Device-resident render of several maps on one GPU.  interleave=True: one pass = every map's pose list in batches
     of `batch`, round-robin over the maps (c3: 'one scene handle per map, batches interleaved'); False: map after map
-    (c4).  Returns total / raster / walk milliseconds per pass (CUDA events) and the renderers (for parity probes)."""
+    (c4).  raster_streams=2: consecutive launches raster on two alternating streams (they write disjoint frames), so the
+    first CTAs of launch i+1 use the SMs the last CTAs of launch i leave idle.  Returns total / raster / walk milliseconds
+    per pass (CUDA events; with two raster streams the per-launch event pairs also span a launch's wait for SMs, so
+    raster_ms_per_pass is then the pass itself) and the renderers (for parity probes)."""
     import torch
     dev = torch.device("cuda", local_rank)
     view = make_view(width, height)
@@ -201,7 +204,8 @@ def run_maps(scenes: Sequence[Scene], poses: Sequence[np.ndarray], width: int, h
     nmax = max((len(p) for p in poses), default=0)
     # one output buffer per map (c3 keeps all nine resident: 9 x 2.07 GB at 1080p x 1000)
     outs = [torch.empty((len(p), height, width), dtype=torch.uint8, device=dev) for p in poses]
-    stream = torch.cuda.current_stream().cuda_stream
+    main_stream = torch.cuda.current_stream()
+    side = [torch.cuda.Stream(device=dev) for _ in range(2)] if raster_streams > 1 else None
 
     # the launches of one pass, in order: (map, first pose, count); c3 interleaves the maps batch by batch
     items = []
@@ -222,11 +226,18 @@ def run_maps(scenes: Sequence[Scene], poses: Sequence[np.ndarray], width: int, h
 
     def one_pass():
         # pipelined like bench.py's c2 step: the BSP walk of item i+1 (a background grid) runs under the raster of item i
+        if side:
+            for t in side:
+                t.wait_stream(main_stream)
         ticket = walk(0)
         for i, (m, b0, cnt) in enumerate(items):
-            rs[m].raster_device(ticket, outs[m].data_ptr() + npix * b0, 0, stream)
+            st = side[i & 1] if side else main_stream
+            rs[m].raster_device(ticket, outs[m].data_ptr() + npix * b0, 0, st.cuda_stream)
             if i + 1 < len(items):
                 ticket = walk(i + 1)
+        if side:
+            for t in side:
+                main_stream.wait_stream(t)
 
     for _ in range(max(warmup, 1)):
         one_pass()
@@ -250,6 +261,8 @@ def run_maps(scenes: Sequence[Scene], poses: Sequence[np.ndarray], width: int, h
     status = 0
     for r in rs:
         status |= r.status()
-    return {"ms_per_pass": e0.elapsed_time(e1) / steps, "raster_ms_per_pass": raster / steps, "walk_ms_per_pass": walk / steps,
+    ms_pass = e0.elapsed_time(e1) / steps
+    return {"ms_per_pass": ms_pass, "raster_ms_per_pass": ms_pass if side else raster / steps, "walk_ms_per_pass": walk / steps,
+            "raster_streams": 2 if side else 1,
             "frames_per_pass": int(sum(len(p) for p in poses)), "launches": sum(r.launch_count for r in rs) - launches0,
             "renderers": rs, "outs": outs, "status_bits": status}
