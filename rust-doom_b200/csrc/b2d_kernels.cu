@@ -991,13 +991,21 @@ cudaError_t launch_raster(const DeviceScene &sc, const View &vw, const FrameCons
     const int nblocks = (int)((total_warps + kWarps - 1) / kWarps);
     static const bool generic_w = getenv("B2D_RASTER_GENERIC_W") != nullptr;   // A/B knob for profiles/README.md
     const bool w1920 = vw.W == 1920 && !generic_w;
+    // B2D_CARVEOUT=<percent of the SM's L1/shared array given to shared memory> (A/B): the raster uses ~300 B of it per warp
+    static const int carve = getenv("B2D_CARVEOUT") ? atoi(getenv("B2D_CARVEOUT")) : -1;
 #define B2D_RASTER_GO(RGBA, KW) do { \
-    if ((sc.nmids > 0 || sc.nsprites > 0) && sc.masked_list) \
+    if ((sc.nmids > 0 || sc.nsprites > 0) && sc.masked_list) { \
+        static const bool once = carve >= 0 && cudaFuncSetAttribute(b2d_raster_kernel<RGBA, kMinBlocks, KW, kWarps, true>, \
+                                                                     cudaFuncAttributePreferredSharedMemoryCarveout, carve) == cudaSuccess; \
+        (void)once; \
         b2d_raster_kernel<RGBA, kMinBlocks, KW, kWarps, true><<<nblocks, kWarps * 32, 0, stream>>>( \
             sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); \
-    else \
+    } else { \
+        static const bool once = carve >= 0 && cudaFuncSetAttribute(b2d_raster_kernel<RGBA, kMinBlocks, KW, kWarps, false>, \
+                                                                     cudaFuncAttributePreferredSharedMemoryCarveout, carve) == cudaSuccess; \
+        (void)once; \
         b2d_raster_kernel<RGBA, kMinBlocks, KW, kWarps, false><<<nblocks, kWarps * 32, 0, stream>>>( \
-            sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); } while (0)
+            sc, vw, d_frames, d_work, stride, n, strips, d_index_fb, d_rgba); } } while (0)
     if (d_rgba) { if (w1920) B2D_RASTER_GO(true, 1920); else B2D_RASTER_GO(true, 0); }
     else {
         const bool w3840 = vw.W == 3840 && !generic_w;      // BASELINE.json's 4K configuration (index frames only)
