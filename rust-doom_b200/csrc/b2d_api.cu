@@ -169,6 +169,7 @@ void free_renderer(b2d_renderer *r) {
         if (r->timed_copied[i]) cudaEventDestroy(r->timed_copied[i]);
     }
     if (r->d_lit) cudaFree(r->d_lit);
+    if (r->d_walk_static) cudaFree(r->d_walk_static);
     free_aligned_4g(r);
     if (r->d_blob) cudaFree(r->d_blob);
     delete r;
@@ -634,6 +635,20 @@ int b2d_renderer_create(const b2d_scene *s, const b2d_view *view, int device, in
     d.verts = reinterpret_cast<const int32_t *>(r->d_blob + h[H_OFF_VERTS]);
     d.nodes = reinterpret_cast<const NodeRec *>(r->d_blob + h[H_OFF_NODES]);
     d.ssectors = reinterpret_cast<const SSectorRec *>(r->d_blob + h[H_OFF_SSECTORS]);
+    {   // the walk kernel's traversal tables in the layout of its shared memory (one cp.async.bulk per CTA)
+        const NodeRec *nodes = reinterpret_cast<const NodeRec *>(s->blob.data() + h[H_OFF_NODES]);
+        std::vector<int32_t> img(8 * (size_t)h[H_NNODES] + 4 * (size_t)h[H_NSSECTORS]);
+        for (uint32_t i = 0; i < h[H_NNODES]; i++) {
+            int32_t *o = &img[8 * (size_t)i];
+            o[0] = nodes[i].x; o[1] = nodes[i].y; o[2] = nodes[i].dx; o[3] = nodes[i].dy;
+            o[4] = (int32_t)nodes[i].child[0]; o[5] = (int32_t)nodes[i].child[1]; o[6] = 0; o[7] = 0;
+        }
+        if (h[H_NSSECTORS])
+            std::memcpy(&img[8 * (size_t)h[H_NNODES]], s->blob.data() + h[H_OFF_SSECTORS], sizeof(SSectorRec) * h[H_NSSECTORS]);
+        CUR(cudaMalloc(&r->d_walk_static, img.size() * 4 + 16));
+        if (!img.empty()) CUR(cudaMemcpy(r->d_walk_static, img.data(), img.size() * 4, cudaMemcpyHostToDevice));
+        d.walk_static = r->d_walk_static;
+    }
     d.segs = reinterpret_cast<const SegRec *>(r->d_blob + h[H_OFF_SEGS]);
     d.sectors = reinterpret_cast<const SectorRec *>(r->d_blob + h[H_OFF_SECTORS]);
     d.tex = reinterpret_cast<const TexRec *>(r->d_blob + h[H_OFF_TEX]);

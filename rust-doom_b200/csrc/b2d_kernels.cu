@@ -130,6 +130,28 @@ __host__ __device__ inline WalkSmem walk_layout(int nverts, int nsegs, int nnode
     return L;
 }
 
+// 1-D bulk copy global -> shared memory through the TMA unit (cp.async.bulk, SASS UBLKCP), completion on an mbarrier.
+// B2D_WALK_NO_BULK (build variant, A/B in profiles/README.md) stages the same bytes with a thread loop instead.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(arrivals));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {      // bounded: a lost copy must not hang the GPU
+    for (int spin = 0; spin < (1 << 24); spin++) {
+        uint32_t done;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: BSP walk -> worklist
 // ------------------------------------------------------------------------------------------------
@@ -146,6 +168,7 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     const WalkSmem L = walk_layout(sc.nverts, sc.nsegs, sc.nnodes, sc.nss, sc.nsprites);
     uint8_t *base = smem;
     __shared__ int s_count, s_status;
+    __shared__ __align__(8) uint64_t s_bar;
     int32_t *tx = reinterpret_cast<int32_t *>(base + L.off_tx);
     int32_t *tz = reinterpret_cast<int32_t *>(base + L.off_tz);
     uint32_t *segr = reinterpret_cast<uint32_t *>(base + L.off_segr);
@@ -161,6 +184,20 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
     // One frame per CTA when the grid has a CTA per frame; a smaller (persistent) grid loops: that is the form for running
     // under another batch's raster -- a CTA per SM keeps the walk's footprint at 1/8 of the register file while it takes
     // a few frame latencies, all hidden behind the raster (launch_walk, B2D_TUNE bit 2).
+    // The traversal tables (node partition lines + children, subsector records) do not depend on the frame: one bulk copy
+    // per CTA brings them into shared memory while the threads are busy with steps 1-3 of the first frame.
+    const uint32_t static_bytes = 32u * (uint32_t)sc.nnodes + 16u * (uint32_t)sc.nss;
+    bool static_pending = false;
+#if !defined(B2D_WALK_NO_BULK)
+    if (static_bytes) {
+        if (tid == 0) mbar_init(&s_bar, 1);
+        __syncthreads();
+        if (tid == 0) bulk_copy_g2s(node_s, sc.walk_static, static_bytes, &s_bar);
+        static_pending = true;
+    }
+#else
+    for (uint32_t i = tid; i < static_bytes / 16u; i += nthr) node_s[i] = reinterpret_cast<const int4 *>(sc.walk_static)[i];
+#endif
     for (int frame = blockIdx.x; frame < n; frame += gridDim.x) {
     FrameConst fc;
     frame_setup(poses[frame], fc);
@@ -197,12 +234,10 @@ b2d_walk_kernel(const __grid_constant__ DeviceScene sc, const __grid_constant__ 
         int lo, hi;
         boxr[i] = box_range(fc, vw, b4, lo, hi) ? pack_range(lo, hi, kVisBit) : 0u;
     }
-    for (int i = tid; i < sc.nnodes; i += nthr) {
-        const NodeRec &N = sc.nodes[i];
-        node_s[2 * i] = make_int4(N.x, N.y, N.dx, N.dy);
-        node_s[2 * i + 1] = make_int4((int)N.child[0], (int)N.child[1], 0, 0);
+    if (static_pending) {                        // first frame of this CTA: the bulk copy has had steps 1-3 to land
+        if (!mbar_wait(&s_bar, 0)) __trap();
+        static_pending = false;
     }
-    for (int i = tid; i < sc.nss; i += nthr) ssec_s[i] = *reinterpret_cast<const int4 *>(&sc.ssectors[i]);
     for (int i = tid; i < sc.nsprites; i += nthr) {          // decoration sprites: exact column interval
         const SpriteRec &P = sc.sprites[i];
         SpriteFrame sp;

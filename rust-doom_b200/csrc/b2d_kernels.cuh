@@ -28,6 +28,8 @@ struct DeviceScene {
     const uint8_t *lit_flats;
     uint32_t lit_texel_stride, lit_flat_stride;
     const uint32_t *palette;     // 256 RGBA8
+    const uint8_t *walk_static;  // the walk's traversal tables as they sit in its shared memory: {x,y,dx,dy,rchild,lchild,0,0}
+                                 // per node (32 B) followed by the SSectorRec array (16 B each); one bulk copy per CTA
     const uint32_t *yslope;      // per view: H entries
     const uint16_t *skyrow;      // per view: H entries, sky texture row of each screen row
     int32_t nverts, nnodes, nss, nsegs, nsectors, ntex, nflats, sky_tex, nmids, nsprites;
