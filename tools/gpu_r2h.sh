@@ -12,11 +12,19 @@ PY
 tail -2 gpurun_out/bench_${TAG}_$name.err; }
 P="--no-e2e --no-cpu-baseline --steps 60 --warmup 3"
 D=$PWD/rust-doom_b200
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$TAG.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_$TAG.log
 timeout 600 python tools/campaign_gpu.py 240 > gpurun_out/campaign_$TAG.log 2>&1; echo "campaign rc=$?"; tail -2 gpurun_out/campaign_$TAG.log
 for rep in a b; do
   run c2_$rep python bench.py $P
   for v in fb16 w2b20 l2el; do B2D_LIB=$D/libb2d_$v.so run c2_${v}_$rep python bench.py $P; done
 done
+Q="--no-e2e --no-cpu-baseline --steps 60 --warmup 3 --no-pipeline"
+for rep in a b; do
+  run seq_$rep python bench.py $Q
+  B2D_LIB=$D/libb2d_nobulk.so run seq_nobulk_$rep python bench.py $Q
+done
+B2D_LIB=$D/libb2d_nobulk.so run c2_nobulk python bench.py $P
+for c in 0 12 25; do B2D_CARVEOUT=$c run c2_carve$c python bench.py $P; B2D_CARVEOUT=$c run seq_carve$c python bench.py $Q; done
 run c3 python bench.py --config c3 --steps 5 --warmup 3
 run c3_1stream python bench.py --config c3 --steps 5 --warmup 3 --raster-streams 1
 run 4k python bench.py --config 4k --steps 20 --warmup 3
