@@ -482,7 +482,7 @@ def main():
                 "dtype": "u8", "data": "synthetic",
                 "config": bench_config(desc, n, world, scenes[0].info,
                                        {"maps_this_rank": len(scenes), "batch": batch,
-                                        "raster_streams": args.raster_streams,
+                                        "raster_streams": res.get("raster_streams", args.raster_streams),
                                         "step": "one pass over every map of the rank (%s)" % ("batches interleaved across the maps' renderers" if cfg == "c3" else "map after map")}),
                 "clocks": clocks, "gpu_launches": int(res["launches"]), "roofline": roof,
                 "parity": "one probe frame per map bit-exact vs the oracle"}))
@@ -505,7 +505,8 @@ def main():
     r = b2d.Renderer(scene, view, device=local_rank, max_batch=n)
     d_poses = torch.from_numpy(poses_np.view(np.int32).reshape(-1, 4).copy()).to(dev)
     pipelined = not args.no_pipeline
-    nbuf = args.raster_streams if pipelined else 1
+    masked = scene.info.n_masked_mids + scene.info.n_sprites > 0      # such rasters are ordered by an event: one stream
+    nbuf = args.raster_streams if pipelined and not masked else 1
     d_index_all = [torch.empty((n, height, width), dtype=torch.uint8, device=dev) for _ in range(nbuf)]
     d_rgba_all = [torch.empty((n, height, width), dtype=torch.int32, device=dev) if args.rgba else None for _ in range(nbuf)]
     d_index, d_rgba = d_index_all[0], d_rgba_all[0]
