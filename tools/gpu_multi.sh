@@ -18,6 +18,9 @@ for w in "$@"; do
     c2) run c2 $TR bench.py --gpus $N --steps 30 --warmup 3 ;;
     d2h) timeout 300 $TR tools/d2h_ceiling.py > gpurun_out/d2h_${TAG}.json 2> gpurun_out/d2h_${TAG}.err; cat gpurun_out/d2h_${TAG}.json
          timeout 300 $TR tools/d2h_ceiling.py --no-numa > gpurun_out/d2h_${TAG}_nonuma.json 2>> gpurun_out/d2h_${TAG}.err; cat gpurun_out/d2h_${TAG}_nonuma.json ;;
+    c5ce) run c5ce $TR bench.py --gpus $N --config c5 --chunk 256 --steps 1 --transports ce ;;
+    c2q) run c2q $TR bench.py --gpus $N --steps 20 --warmup 3 --no-cpu-baseline ;;
+    d2hb) timeout 300 $TR tools/d2h_ceiling.py > gpurun_out/d2h_${TAG}.json 2> gpurun_out/d2h_${TAG}.err; cat gpurun_out/d2h_${TAG}.json ;;
     c2e2e) run c2e2e $TR bench.py --gpus $N --steps 10 --warmup 3 --no-cpu-baseline ;;
     ref) run ref $TR bench.py --gpus $N --impl reference --steps 5 --warmup 2 ;;
     test2) timeout 900 python -m pytest tests/test_cli.py -m gpu -q -k "two_ranks or world1" > gpurun_out/pytest_${TAG}.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_${TAG}.log ;;
