@@ -366,10 +366,16 @@ def test_dynamic_sector_arguments_are_checked(b2d):
         b2d.Scene(arch, 0, dynamic=[(100000, 0, 0, 0, 0)])
     with pytest.raises(W.WadError):
         S.compile_scene(a, tex, 0, dynamic=[dyn[0], dyn[0]])
-    # the lumps entry point takes the same list
-    lv = W.Level(a, 0)
-    assert b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=dyn).blob == S.compile_scene(a, tex, 0, dynamic=dyn)
-    del lv
+    # the lumps entry point (b2d_scene_create_from_lumps_dynamic) takes the same list and compiles the same scene
+    marker = a.levels[0]
+    lumps = {key: a.read(marker + 1 + k) for k, key in enumerate(b2d.Scene.LUMP_ORDER)}
+    from_lumps = b2d.Scene.from_lumps(a.lumps[marker][0], lumps, list(tex.textures.items()), list(tex.flats.items()),
+                                      tex.colormaps, tex.palettes[0], dynamic=dyn)
+    assert from_lumps.blob == S.compile_scene(a, tex, 0, dynamic=dyn) and from_lumps.info.n_dynamic == len(dyn)
+    assert from_lumps.tables_at(7, mv) == sc.tables_at(7, mv)
+    with pytest.raises(b2d.B2dError):
+        b2d.Scene.from_lumps(a.lumps[marker][0], lumps, list(tex.textures.items()), list(tex.flats.items()),
+                             tex.colormaps, tex.palettes[0], dynamic=[(100000, 0, 0, 0, 0)])
 
 
 def test_time_and_moves_compose(b2d):
