@@ -120,3 +120,66 @@ def test_threads_do_not_change_output(oracle_scene):
     a = render.render(oracle_scene, v, poses, threads=1)
     b = render.render(oracle_scene, v, poses, threads=4)
     assert np.array_equal(a, b)
+
+
+def test_micro_level_door_hand_checked():
+    """Moving sectors by hand.  Room B of the micro level is a door: floor 0, ceiling 0 at rest (shut),
+    declared dynamic with the ceiling free to rise to 124.  Seen from room A (eye 60, 128 units in front of the line,
+    fovy 65 deg at 320x200: 157/128 px per unit) the shut door is a wall from 128 down to 0; raised by 72 its face covers
+    128..72 and the opening 72..0 shows room B.  The upper texture is pegged to the door (Peg::Bottom, visitor.rs:797-804):
+    its bottom row stays on the door's lower edge while it rises, i.e. the texture moves with the door."""
+    data = _micro_level(two_sided_flags=0x0004, front=(0, 128), back=(0, 0))
+    a = wad.Archive(data)
+    td = wad.TextureDirectory(a)
+    blob = scene.compile_scene(a, td, 0, dynamic=[(1, 0, 0, 0, 124)])
+    s = scene.section(blob, "segs")[3]
+    assert (s[13], s[14]) == (0, 0) and s[7] == 0 and s[8] == 128          # shut: opening empty; row 0 of the texture at 128
+    v = render.make_view(320, 200)
+    pose = render.make_pose(-128, 128, 60, 0)
+    x, scale = 160, 157.0 / 128.0
+    cm = np.stack([np.frombuffer(td.colormaps[k], np.uint8) for k in range(32)])
+    brick2 = td.textures[wad.wad_name(b"BRICK2")] & 0xFF
+    row = int(math.floor(64 * (255 - wad.light_byte(160, -1)) / 255.0 - 2880.0 / (128 + 90)))
+    col = (8 + 128) % 64
+    rows = {h: math.ceil(100 - (h - 60) * scale - 0.5) for h in (128, 72, 0)}
+    assert rows == {128: 17, 72: 85, 0: 174}
+
+    def texel_ok(value, t):
+        """value is texture row floor(t) -- either neighbour where t falls on a row boundary (the integer pipeline and this
+        float restatement may round an exact boundary differently)"""
+        cands = {int(math.floor(t))} | ({int(math.floor(t - 1e-3)), int(math.floor(t + 1e-3))} if abs(t - round(t)) < 1e-3 else set())
+        return any(value == cm[row][brick2[k % 128, col]] for k in cands)
+
+    shut = render.render(blob, v, pose)[0]
+    for y in range(rows[128], rows[0]):                                      # the whole face, texture top at the ceiling 128
+        hy = 60 - (y + 0.5 - 100) / scale
+        assert texel_ok(shut[y, x], 128 - hy), ("shut", y)
+
+    moved = scene.apply_moves(blob, [(1, 0, 72)])
+    s = scene.section(moved, "segs")[3]
+    assert (s[13], s[14]) == (72, 0) and s[7] == 0 and s[8] == 200          # opening 72..0; the anchor rose with the door
+    assert scene.section(moved, "sectors")[1].tolist()[:2] == [0, 72]
+    opened, hits = render.render(moved, v, pose, seg_hits=True)
+    opened = opened[0]
+    for y in range(rows[128], rows[72]):                                     # the door's face: what was at height h is now at h + 72
+        hy = 60 - (y + 0.5 - 100) / scale
+        assert texel_ok(opened[y, x], 200 - hy), ("raised", y)
+    # the opening shows room B: its far wall (BRICK1, one-sided, 256 units behind the line) between its ceiling 72 and floor 0
+    far = {h: math.ceil(100 - (h - 60) * (157.0 / 384.0) - 0.5) for h in (72, 0)}
+    brick1 = td.textures[wad.wad_name(b"BRICK1")] & 0xFF
+    rowb = int(math.floor(64 * (255 - wad.light_byte(160, -1)) / 255.0 - 2880.0 / (384 + 90)))
+    seen = 0
+    for y in range(far[72], far[0]):
+        hy = 60 - (y + 0.5 - 100) / (157.0 / 384.0)
+        t = int(math.floor(72 - hy))                                         # B's wall is top-pegged to B's (moved) ceiling
+        seen += int(opened[y, x] in cm[max(rowb - 1, 0):rowb + 2][:, brick1[t % 128, :]].ravel())
+    assert seen >= (far[0] - far[72]) - 2, "room B's far wall is not what shows through the opening"
+    assert rows[72] < far[72] and far[0] < rows[0]                           # ... framed by B's ceiling above and floor below
+    # the product's re-derivation gives the same records
+    import rust_doom_b200 as b2d
+    sc = b2d.Scene(b2d.Archive.from_bytes(data), 0, dynamic=[(1, 0, 0, 0, 124)])
+    assert sc.blob == blob
+    h = scene.header(blob)
+    segs_off = h[scene.H_NTEX] * 32 + h[scene.H_NSECTORS] * 32
+    got = np.frombuffer(sc.tables_at(0, [(1, 0, 72)]), np.int32)[segs_off // 4:][3 * 16:4 * 16]
+    assert got.tolist() == scene.section(moved, "segs")[3].tolist()
