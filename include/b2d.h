@@ -229,7 +229,8 @@ int b2d_palette_lut_device(b2d_renderer *r, const uint8_t *d_index, uint32_t *d_
  * its own `cuda_stream`.  The two calls are ordered through events, not by the streams: with two streams the walk of
  * batch k+1 overlaps the raster of batch k.  b2d_walk_device launches the walk as a background grid (one CTA per SM
  * looping over the frames): it then takes several frame latencies instead of one (~0.7 ms for 1000 frames) but leaves
- * 7/8 of the registers to the raster it runs under.  At
+ * 7/8 of the registers to the raster it runs under.  Rasters of consecutive batches may go to two alternating
+ * streams (and output buffers): the first CTAs of batch k+1 then fill the SMs the last CTAs of batch k leave idle.  At
  * most two batches can be walked and not yet rastered; tickets are rastered once.  d_poses is read by the walk
  * only.  Levels with masked middle textures or sprites share one arena of deferred entries per renderer: their rasters are
  * ordered one after the other through an event, whatever streams they are enqueued on.  Replaces nothing in the reference (its render loop is synchronous, engine/src/renderer.rs:62-175). */
@@ -272,7 +273,11 @@ typedef void (*b2d_chunk_fn)(void *user, int chunk_index, size_t first_local_pos
  * per = ceil(n_total/world); rank q renders block q (a short last block is padded by repeating the last pose) in
  * chunks of min(chunk_frames, max_batch) frames, each chunk rastered straight into this rank's slice of the
  * all-gather buffer (no staging copy) and gathered in place on a second stream while the next chunk renders; the
- * consumer callback (nullable) runs on a third.  Synchronous: returns when this rank's part is complete. */
+ * consumer callback (nullable) runs on a third.  Transport of the exchange: by default every rank pushes its slice into the
+ * peers' buffers with the copy engines over CUDA-IPC mappings (ordered across ranks by two 4-byte ncclAllReduce per
+ * chunk); if any rank cannot map a peer's buffer all ranks fall back, together, to an in-place ncclAllGather, which
+ * B2D_GATHER=nccl also selects (buffers then from ncclMemAlloc, registered with the communicator where NCCL offers it).
+ * stats_out->registration names what was used.  Synchronous: returns when this rank's part is complete. */
 int b2d_render_sharded(b2d_renderer *r, b2d_comm *c, const b2d_pose *poses, size_t n_total, size_t chunk_frames,
                        int mode, b2d_chunk_fn fn, void *user, b2d_sharded_stats *stats_out);
 
