@@ -332,6 +332,14 @@ def test_dynamic_sectors_compile_and_move_like_the_oracle(b2d, seed):
     assert sc.tables_at(0, mv) == _state_tables(moved)
     assert sc.tables_at(0, ()) == _state_tables(ob)
     assert moved != ob and S.apply_moves(ob, ()) == ob
+    from tests.refcheck import moves as MV
+    level = W.Level(a, 0)
+    for k in range(25):                                  # more states of the same declaration, any height inside the ranges
+        st = MV.state(level, dyn, 1000 * seed + k, hole_free=False)
+        assert sc.tables_at(k, st) == sc.tables_at(k, list(reversed(st)))            # order of the list does not matter
+        got = np.frombuffer(sc.tables_at(0, st), np.int32)
+        want = np.frombuffer(_state_tables(S.apply_moves(ob, st)), np.int32)
+        assert (got == want).all(), "state %d" % k
     # rest heights + offsets, openings follow
     s0, s1 = S.section(ob, "sectors"), S.section(moved, "sectors")
     for sec, dfl, dcl in mv:
