@@ -99,6 +99,20 @@ def test_oracle_agrees_with_raycaster_at_1920x1080(synth_wad, oracle_scene):
     assert t.px == 2 * 480 * 1080
 
 
+def test_oracle_agrees_with_raycaster_at_3840x2160(synth_wad, oracle_scene):
+    """BASELINE.json's 4K configuration: every sixteenth column of one 3840x2160 frame."""
+    a = wad.Archive(synth_wad)
+    tex = wad.TextureDirectory(a)
+    level = wad.Level(a, 0)
+    cols = np.arange(0, 3840, 16)
+    t = Tally()
+    for pose in _poses_in(level, False, 1, 49):
+        g, o, kind, dbg = _frame(a, tex, oracle_scene, 3840, 2160, pose, cols=cols)
+        t.add(g, o, dbg, pose)
+    t.check()
+    assert t.px == 240 * 2160
+
+
 def test_masked_middle_textures_agree_with_raycaster():
     """Two-sided middle textures with holes (visitor.rs:808-836; transparent texels discarded,
     static.frag:21-22): the oracle's deferred back-to-front pass vs rays that pass through the holes."""
